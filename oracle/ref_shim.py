@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE -- not product code.  Only tests/, oracle/gen_golden.py and
+bench.py's reference/cpu_baseline legs may import this.
+
+Imports the reference's OWN `ImportanceRenderer` (renderer.py:260-704) and `NeRFDecoder`
+(triplane.py:267-316), unmodified, from /root/reference under shims, so that golden vectors can be
+generated from the real reference code on the CPU of THIS container.  It cannot
+travel: /root/reference does not exist on the GPU box, where `available()` is False and the
+restatement in oracle/port.py (validated against this module here) is the checker.
+
+Shims (none of them touches reference arithmetic except #1, which replaces an absent dependency):
+ 1. pytorch3d.ops.knn.knn_points -> brute-force K=1 squared-L2 argmin, d2 = (dx*dx + dy*dy) + dz*dz
+    in fp32, smallest index on ties.  pytorch3d is not vendored and its version is unpinned
+    (README.md:48), so this formula IS our statement of its semantics ("parity unpinned").
+ 2. spconv / spconv.pytorch -> constructor-only stubs (the sparse convs are outside the hot-path
+    scope; the three densified volumes are inputs).
+ 3. torch.Tensor.cuda -> identity, torch.cuda.current_device -> 0 (the reference hard-codes .cuda()).
+ 4. renderer.read_pickle / SMPL_to_tensor -> return the synthetic SMPL-shaped model.
+ 5. imageio -> empty stub (imported, unused, by triplane.py:27).
+ 6. ImportanceRenderer.encoder_3d -> a module doing exactly renderer.py:764,773,782,794-795 on the
+    three supplied dense volumes.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF_ROOT = '/root/reference/sherf'
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, 'training', 'volumetric_rendering'))
+
+
+def knn_points_bruteforce(p1, p2, K=1, chunk=4096, **_):
+    """Stand-in for pytorch3d.ops.knn.knn_points (call sites renderer.py:315,564,627)."""
+    assert K == 1 and p1.shape[0] == 1 and p2.shape[0] == 1
+    q, v = p1[0], p2[0]
+    vx, vy, vz = v[:, 0][None], v[:, 1][None], v[:, 2][None]
+    d2_out = torch.empty(q.shape[0], dtype=torch.float32)
+    id_out = torch.empty(q.shape[0], dtype=torch.long)
+    for s in range(0, q.shape[0], chunk):
+        c = q[s:s + chunk]
+        dx = c[:, 0:1] - vx
+        dy = c[:, 1:2] - vy
+        dz = c[:, 2:3] - vz
+        d2 = (dx * dx + dy * dy) + dz * dz
+        m, i = torch.min(d2, dim=1)
+        # torch.min returns *a* minimal index; force the smallest one for determinism
+        first = (d2 == m[:, None]).float().argmax(dim=1)
+        d2_out[s:s + chunk] = m
+        id_out[s:s + chunk] = first
+    return d2_out.view(1, -1, 1), id_out.view(1, -1, 1), None
+
+
+class DenseVolumeGather(nn.Module):
+    """Shim 6: the gather half of SparseConvNet.forward (renderer.py:762-797)."""
+
+    def forward(self, volumes, grid):
+        feats = [F.grid_sample(v, grid, padding_mode='zeros', align_corners=True) for v in volumes]
+        feats = torch.cat(feats, dim=1)
+        return feats.view(feats.size(0), -1, feats.size(4)).transpose(1, 2)
+
+
+_loaded = None
+
+
+def load(smpl_model_torch: dict):
+    """Returns (renderer_module, triplane_NeRFDecoder_class). Idempotent."""
+    global _loaded
+    if _loaded is not None:
+        _loaded[0]._SYNTH_SMPL = smpl_model_torch
+        return _loaded[0], _loaded[1]
+    if not available():
+        raise RuntimeError('reference tree not present (expected on the GPU box); use oracle.port')
+    sys.dont_write_bytecode = True          # /root/reference is read-only
+
+    knn_mod = types.ModuleType('pytorch3d.ops.knn'); knn_mod.knn_points = knn_points_bruteforce
+    ops_mod = types.ModuleType('pytorch3d.ops'); ops_mod.knn = knn_mod
+    p3d = types.ModuleType('pytorch3d'); p3d.ops = ops_mod
+    sys.modules.update({'pytorch3d': p3d, 'pytorch3d.ops': ops_mod, 'pytorch3d.ops.knn': knn_mod})
+
+    class _Ctor(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+    class _Seq(nn.Sequential):
+        pass
+    sp = types.ModuleType('spconv.pytorch')
+    sp.SparseSequential, sp.SubMConv3d, sp.SparseConv3d = _Seq, _Ctor, _Ctor
+    core = types.ModuleType('spconv.core'); core.SparseConvTensor = object
+    sp.core = core
+    spr = types.ModuleType('spconv'); spr.pytorch = sp; spr.core = core
+    sys.modules.update({'spconv': spr, 'spconv.pytorch': sp, 'spconv.core': core})
+    sys.modules.setdefault('imageio', types.ModuleType('imageio'))
+
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.cuda.current_device = lambda: 0
+
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    from training.volumetric_rendering import renderer as ref_renderer   # noqa: E402
+    ref_renderer._SYNTH_SMPL = smpl_model_torch
+    ref_renderer.read_pickle = lambda path: ref_renderer._SYNTH_SMPL
+    ref_renderer.SMPL_to_tensor = lambda params, device: params
+
+    # NeRFDecoder lives in triplane.py, whose module-level imports pull in the StyleGAN backbone and
+    # torchvision; exec only the class body's source region is not allowed (no copying), so import it.
+    try:
+        from training import triplane as ref_triplane
+        decoder_cls = ref_triplane.NeRFDecoder
+    except Exception as e:                                               # pragma: no cover
+        raise RuntimeError(f'could not import reference triplane.py under shims: {e}')
+    _loaded = (ref_renderer, decoder_cls)
+    return _loaded
+
+
+def build_reference(smpl_model_torch: dict, seed: int = 0):
+    """Reference ImportanceRenderer(use_trans=True, use_NeRF_decoder=True) + NeRFDecoder(32), default torch init under `seed`."""
+    ref_renderer, decoder_cls = load(smpl_model_torch)
+    torch.manual_seed(seed)
+    ren = ref_renderer.ImportanceRenderer(use_1d_feature=True, use_2d_feature=True, use_3d_feature=True,
+                                          use_trans=True, use_NeRF_decoder=True)
+    ren.encoder_3d = DenseVolumeGather()
+    dec = decoder_cls(32)
+    return ren.eval(), dec.eval()
+
+
+@torch.no_grad()
+def render(ren, dec, scene: dict):
+    """One call of the reference forward on a synthetic scene (synthetic.make_scene)."""
+    return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None,
+               scene['obs_sp_input'], dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'],
+               scene['input_data'], scene['rendering_options'])
