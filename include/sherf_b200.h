@@ -1,0 +1,195 @@
+/*
+ * sherf_b200 -- C ABI of the B200-native SHERF volumetric render hot path.
+ *
+ * The reference has no FFI for this path: it is Python calling torch ops.  The boundary a
+ * maintainer binds instead is ImportanceRenderer.forward
+ *   /root/reference/sherf/training/volumetric_rendering/renderer.py:286-398
+ * plus NeRFDecoder.forward
+ *   /root/reference/sherf/training/triplane.py:285-316
+ * Every entry point below names the reference lines it replaces.  All pointers are DEVICE
+ * pointers to contiguous fp32 / int32 arrays unless marked "host"; the library BORROWS them for
+ * the duration of one call and owns nothing but the caller-provided scratch arena.  Batch is 1
+ * per call (the reference renderer only works for per-GPU batch 1, renderer.py:320-321).
+ * All functions return 0 on success or a negative SHERF_E_* code and never throw;
+ * sherf_last_error() returns a thread-local description.  Kernels are enqueued on `stream`
+ * (a cudaStream_t passed as void*), nothing synchronises the device except where noted.
+ */
+#ifndef SHERF_B200_H
+#define SHERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHERF_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SHERF_API __attribute__((visibility("default")))
+#else
+#define SHERF_API
+#endif
+#define SHERF_NUM_JOINTS 24
+#define SHERF_NUM_LEVELS 3
+
+enum {
+  SHERF_OK = 0,
+  SHERF_E_INVALID = -1,   /* bad argument (null pointer, unsupported shape / option) */
+  SHERF_E_SCRATCH = -2,   /* scratch arena too small */
+  SHERF_E_CUDA = -3,      /* a CUDA runtime call failed; see sherf_last_error() */
+  SHERF_E_UNSUPPORTED = -4
+};
+
+/* MLP arithmetic.  FP32 = CUDA-core fp32 FMA (parity mode, the reference disables TF32,
+ * training_loop.py:169-171).  TF32 / TF32X3 = tcgen05 tensor-core paths. */
+enum { SHERF_MLP_FP32 = 0, SHERF_MLP_TF32 = 1, SHERF_MLP_TF32X3 = 2 };
+
+/* The SMPL body model the reference loads in ImportanceRenderer.__init__ (renderer.py:282-284,
+ * SMPL_to_tensor renderer.py:65-74). */
+typedef struct SherfSmplModel {
+  const float* v_template;   /* [V,3] */
+  const float* shapedirs;    /* [V,3,10] */
+  const float* posedirs;     /* [V,3,207] */
+  const float* j_regressor;  /* [24,V] dense */
+  const float* weights;      /* [V,24] */
+  int32_t parents[SHERF_NUM_JOINTS]; /* host; kintree_table[0], parents[0] ignored */
+  int32_t n_verts;           /* V (6890) */
+} SherfSmplModel;
+
+/* One `params` dict of the dataset (RenderPeople_dataset.py:195-204). */
+typedef struct SherfPose {
+  const float* poses;   /* [72] axis-angle */
+  const float* shapes;  /* [10] */
+  const float* R;       /* [3,3] row-major; smpl = (world - Th) @ R */
+  const float* Th;      /* [3] */
+} SherfPose;
+
+/* Per-frame inputs = the non-ray entries of `input_data` (RenderPeople_dataset.py:362-391) and
+ * obs_sp_input (triplane.py:174-217). */
+typedef struct SherfFrame {
+  SherfPose target;            /* input_data['params'] */
+  SherfPose canonical;         /* input_data['t_params'] (R, Th unused, as in the reference) */
+  SherfPose obs;               /* input_data['obs_params'] */
+  const float* vertices;       /* [V,3] posed target vertices, world space */
+  const float* t_vertices;     /* [V,3] canonical ("big pose") vertices */
+  const float* t_world_bounds; /* [2,3] tri-plane box (renderer.py:239) */
+  const float* obs_K;          /* [3,3] observation camera (renderer.py:686-699) */
+  const float* obs_R;          /* [3,3] */
+  const float* obs_T;          /* [3] */
+  const float* sp_bounds;      /* [2,3] obs_sp_input['bounds'][0] (renderer.py:548) */
+  int32_t out_sh[3];           /* host; obs_sp_input['out_sh'] (z,y,x) (renderer.py:552) */
+} SherfFrame;
+
+/* Feature tensors in the layouts the reference hands to forward() (NCHW / NCDHW, batch 1). */
+typedef struct SherfScene {
+  const float* planes;     /* [3,plane_ch,plane_h,plane_w]  renderer.py:234-243 */
+  int32_t plane_ch, plane_h, plane_w;
+  const float* obs_img;    /* [3,img_h,img_w]               renderer.py:336 */
+  int32_t img_h, img_w;
+  const float* obs_feat;   /* [feat_ch,feat_h,feat_w]       renderer.py:333 */
+  int32_t feat_ch, feat_h, feat_w;
+  const float* vol[SHERF_NUM_LEVELS];      /* dense [C,D,H,W] pyramid levels, renderer.py:762-782 */
+  int32_t vol_ch[SHERF_NUM_LEVELS];
+  int32_t vol_dim[SHERF_NUM_LEVELS][3];    /* D,H,W */
+} SherfScene;
+
+/* Hot-path parameters, PyTorch layouts ([out,in] row-major weights).  Names = checkpoint names
+ * (SURVEY.md 8b): renderer.* from renderer.py:271-276, decoder.* from triplane.py:267-283. */
+typedef struct SherfWeights {
+  const float *proj_w, *proj_b;         /* renderer.conv1d_projection   [96,192(,1)], [96]  */
+  const float *reproj_w, *reproj_b;     /* renderer.conv1d_reprojection [32,96(,1)],  [32]  */
+  const float *ln1_w, *ln1_b;           /* transformer.layers.0.0.fn.norm               [32] */
+  const float *qkv_w;                   /* ...0.0.fn.fn.to_qkv.weight  [144,32] (no bias)    */
+  const float *attn_out_w, *attn_out_b; /* ...0.0.fn.fn.to_out.0       [32,48], [32]         */
+  const float *ln2_w, *ln2_b;           /* ...0.1.fn.norm                               [32] */
+  const float *ff1_w, *ff1_b;           /* ...0.1.fn.fn.net.0          [32,32], [32]         */
+  const float *ff2_w, *ff2_b;           /* ...0.1.fn.fn.net.3          [32,32], [32]         */
+  const float *pts_w[8], *pts_b[8];     /* decoder.pts_linears.{0..7}: [128,71],[128,128]x4,[128,199],[128,128]x2 */
+  const float *alpha_w, *alpha_b;       /* decoder.alpha_linear   [1,128], [1]   */
+  const float *feature_w, *feature_b;   /* decoder.feature_linear [128,128], [128] */
+  const float *views_w, *views_b;       /* decoder.views_linear   [64,187], [64] */
+  const float *rgb_w, *rgb_b;           /* decoder.rgb_linear     [3,64], [3]    */
+} SherfWeights;
+
+/* Rays of one view (RenderPeople_dataset.py:14-27,129-134). */
+typedef struct SherfRays {
+  const float* origins;  /* [N,3] */
+  const float* dirs;     /* [N,3] un-normalised */
+  const float* near_;    /* [N] */
+  const float* far_;     /* [N] */
+  int32_t n_rays;        /* N */
+  int32_t n_samples;     /* S = rendering_options['depth_resolution'] (2..256) */
+} SherfRays;
+
+/* rendering_options subset used by the path (train.py:328-351, ray_marcher.py:25-64). */
+typedef struct SherfOptions {
+  int32_t white_back;        /* ray_marcher.py:59 */
+  int32_t mlp_precision;     /* SHERF_MLP_* */
+  float depth_clamp_min;     /* used only if use_external_clamp != 0: global min/max of ALL depths of the */
+  float depth_clamp_max;     /*   full (unsharded) view, ray_marcher.py:57 -- needed when rays are sharded */
+  int32_t use_external_clamp;
+  const float* density_noise; /* optional [N*S] additive sigma noise, already scaled (renderer.py:435-436); NULL = none */
+} SherfOptions;
+
+/* Outputs of forward (renderer.py:398): rgb in (-1,1), depth, accumulated weight. */
+typedef struct SherfOut {
+  float* rgb;    /* [N,3] */
+  float* depth;  /* [N]   */
+  float* acc;    /* [N]   */
+} SherfOut;
+
+/* Optional stage-wise taps for parity tests (any pointer may be NULL).  Point-indexed arrays are
+ * in compaction order = row-major order of surviving samples (renderer.py:320-321); the caller
+ * sizes them for N*S points or reads n_points from a previous call. */
+typedef struct SherfDebug {
+  int32_t* sample_vid;   /* [N*S] nearest posed-vertex id of every sample within the cull radius, -1 otherwise */
+  int32_t* point_sample; /* [P] flat sample index n*S+i of each surviving point */
+  int32_t* point_vid3;   /* [P] nearest canonical vertex (renderer.py:627) */
+  float* point_can;      /* [P,3] canonical position (renderer.py:615) */
+  float* point_cdir;     /* [P,3] canonical view direction (renderer.py:618) */
+  float* point_uv;       /* [P,2] observation-image pixel coordinates (renderer.py:699) */
+  float* point_feat;     /* [P,384] tri(3x32) | f2d(96) | f3d_raw(192) (renderer.py:340, :794, :402) */
+  float* point_tok;      /* [P,64] tokens 0,1 after the transformer (renderer.py:427) */
+  float* point_sigma;    /* [P] (triplane.py:302) */
+  float* point_rgb;      /* [P,3] (triplane.py:314) */
+  int64_t max_points;    /* capacity of the point-indexed arrays */
+} SherfDebug;
+
+/* Bytes of scratch sherf_render_forward needs for an (N rays, S samples) call on `scene` (only its
+ * shape fields are read).  The arena holds the per-frame tables, channels-last copies of the feature
+ * tensors, per-sample bookkeeping and the activation buffers of one chunk of surviving points. */
+SHERF_API size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_verts);
+
+/* Replaces ImportanceRenderer.forward (renderer.py:286-398) including the decoder call
+ * (triplane.py:285-316) and the ray marcher (ray_marcher.py:25-64).
+ * Synchronises `stream` once internally (to size the point stage).  n_points_out (host, optional)
+ * receives the number of samples that survived the 5 cm cull. */
+SHERF_API int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene,
+                         const SherfWeights* weights, const SherfRays* rays, const SherfOptions* opts,
+                         const SherfOut* out, const SherfDebug* debug /* may be NULL */,
+                         void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out);
+
+/* Replaces get_transform_params_torch (renderer.py:129-157) for one pose: writes the 24 rigid
+ * transforms A[24,4,4] (device).  Exposed for tests and for the dataset-side SMPL forward. */
+SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* pose, float* A_out /* [24,16] device */,
+                         void* scratch, size_t scratch_bytes, void* stream);
+
+/* Global depth-clamp range of a full view: min/max over all rays of the first/last sample depth
+ * (ray_marcher.py:57 via math_utils.py:101-118).  Host results; synchronises the stream. */
+SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */, float* max_out /* host */,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
+SHERF_API const char* sherf_last_error(void);
+SHERF_API int sherf_abi_version(void);
+/* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */
+SHERF_API int64_t sherf_last_launch_count(void);
+/* Device time (ms) of the named stage of the last forward on this thread, measured with CUDA events when
+ * sherf_set_profiling(1) was called; stages: 0 prologue, 1 cull+compact, 2 warp+gather, 3 mlp, 4 composite. */
+SHERF_API void sherf_set_profiling(int enabled);
+SHERF_API float sherf_last_stage_ms(int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHERF_B200_H */

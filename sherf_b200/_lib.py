@@ -1,0 +1,115 @@
+"""ctypes binding of libsherf_b200.so (include/sherf_b200.h).  No fallback: if the library is missing or
+fails to load, every product entry point raises -- there is deliberately no CPU / PyTorch path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_float_p = C.c_void_p          # device pointers travel as plain integers
+c_int_p = C.c_void_p
+
+MLP_FP32, MLP_TF32, MLP_TF32X3 = 0, 1, 2
+
+
+class SherfSmplModel(C.Structure):
+    _fields_ = [('v_template', c_float_p), ('shapedirs', c_float_p), ('posedirs', c_float_p), ('j_regressor', c_float_p),
+                ('weights', c_float_p), ('parents', C.c_int32 * 24), ('n_verts', C.c_int32)]
+
+
+class SherfPose(C.Structure):
+    _fields_ = [('poses', c_float_p), ('shapes', c_float_p), ('R', c_float_p), ('Th', c_float_p)]
+
+
+class SherfFrame(C.Structure):
+    _fields_ = [('target', SherfPose), ('canonical', SherfPose), ('obs', SherfPose), ('vertices', c_float_p),
+                ('t_vertices', c_float_p), ('t_world_bounds', c_float_p), ('obs_K', c_float_p), ('obs_R', c_float_p),
+                ('obs_T', c_float_p), ('sp_bounds', c_float_p), ('out_sh', C.c_int32 * 3)]
+
+
+class SherfScene(C.Structure):
+    _fields_ = [('planes', c_float_p), ('plane_ch', C.c_int32), ('plane_h', C.c_int32), ('plane_w', C.c_int32),
+                ('obs_img', c_float_p), ('img_h', C.c_int32), ('img_w', C.c_int32),
+                ('obs_feat', c_float_p), ('feat_ch', C.c_int32), ('feat_h', C.c_int32), ('feat_w', C.c_int32),
+                ('vol', c_float_p * 3), ('vol_ch', C.c_int32 * 3), ('vol_dim', (C.c_int32 * 3) * 3)]
+
+
+class SherfWeights(C.Structure):
+    _fields_ = [('proj_w', c_float_p), ('proj_b', c_float_p), ('reproj_w', c_float_p), ('reproj_b', c_float_p),
+                ('ln1_w', c_float_p), ('ln1_b', c_float_p), ('qkv_w', c_float_p), ('attn_out_w', c_float_p),
+                ('attn_out_b', c_float_p), ('ln2_w', c_float_p), ('ln2_b', c_float_p), ('ff1_w', c_float_p),
+                ('ff1_b', c_float_p), ('ff2_w', c_float_p), ('ff2_b', c_float_p), ('pts_w', c_float_p * 8),
+                ('pts_b', c_float_p * 8), ('alpha_w', c_float_p), ('alpha_b', c_float_p), ('feature_w', c_float_p),
+                ('feature_b', c_float_p), ('views_w', c_float_p), ('views_b', c_float_p), ('rgb_w', c_float_p),
+                ('rgb_b', c_float_p)]
+
+
+class SherfRays(C.Structure):
+    _fields_ = [('origins', c_float_p), ('dirs', c_float_p), ('near_', c_float_p), ('far_', c_float_p),
+                ('n_rays', C.c_int32), ('n_samples', C.c_int32)]
+
+
+class SherfOptions(C.Structure):
+    _fields_ = [('white_back', C.c_int32), ('mlp_precision', C.c_int32), ('depth_clamp_min', C.c_float),
+                ('depth_clamp_max', C.c_float), ('use_external_clamp', C.c_int32), ('density_noise', c_float_p)]
+
+
+class SherfOut(C.Structure):
+    _fields_ = [('rgb', c_float_p), ('depth', c_float_p), ('acc', c_float_p)]
+
+
+class SherfDebug(C.Structure):
+    _fields_ = [('sample_vid', c_int_p), ('point_sample', c_int_p), ('point_vid3', c_int_p), ('point_can', c_float_p),
+                ('point_cdir', c_float_p), ('point_uv', c_float_p), ('point_feat', c_float_p), ('point_tok', c_float_p),
+                ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64)]
+
+
+EXPORTS = ['sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+           'sherf_abi_version', 'sherf_last_launch_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Returns the loaded library; raises RuntimeError (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} not found: build it with `python -m sherf_b200.build` (or __graft_entry__.build()); '
+                           'sherf_b200 has no CPU or PyTorch fallback')
+    lib = C.CDLL(path)
+    lib.sherf_scratch_bytes.restype = C.c_size_t
+    lib.sherf_scratch_bytes.argtypes = [C.POINTER(SherfScene), C.c_int32, C.c_int32, C.c_int32]
+    lib.sherf_render_forward.restype = C.c_int
+    lib.sherf_render_forward.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfFrame), C.POINTER(SherfScene),
+                                         C.POINTER(SherfWeights), C.POINTER(SherfRays), C.POINTER(SherfOptions),
+                                         C.POINTER(SherfOut), C.POINTER(SherfDebug), C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.POINTER(C.c_int64)]
+    lib.sherf_lbs_transforms.restype = C.c_int
+    lib.sherf_lbs_transforms.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfPose), C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]
+    lib.sherf_depth_range.restype = C.c_int
+    lib.sherf_depth_range.argtypes = [C.POINTER(SherfRays), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_size_t,
+                                      C.c_void_p]
+    lib.sherf_last_error.restype = C.c_char_p
+    lib.sherf_abi_version.restype = C.c_int
+    lib.sherf_last_launch_count.restype = C.c_int64
+    lib.sherf_set_profiling.argtypes = [C.c_int]
+    lib.sherf_last_stage_ms.restype = C.c_float
+    lib.sherf_last_stage_ms.argtypes = [C.c_int]
+    if lib.sherf_abi_version() != 1:
+        raise RuntimeError('libsherf_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f'sherf_b200 error {rc}: {load().sherf_last_error().decode()}')

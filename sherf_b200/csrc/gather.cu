@@ -1,0 +1,271 @@
+// Stage 2: per surviving point -- inverse-LBS warp to canonical space, canonical -> observation warp
+// (exact unbounded nearest canonical vertex), projection, and the three hierarchical feature gathers.
+// One warp per point, lane = channel, so every tap is one coalesced 128 B line of a channels-last copy
+// of the feature tensor.  Replaces renderer.py:323-350 (minus conv1d_projection) and :402 (sample_from_planes).
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace sherf {
+
+// [C][M] (channel-major, the reference's NCHW/NCDHW) -> [M][C] channels-last; 32x32 smem tiles.
+__global__ void k_to_channels_last(const float* __restrict__ in, float* __restrict__ out, int C, int64_t M) {
+  __shared__ float tile[32][33];
+  const int64_t m0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t m = m0 + tx;
+    tile[r][tx] = (c < C && m < M) ? in[(size_t)c * M + m] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t m = m0 + r;
+    const int c = c0 + tx;
+    if (c < C && m < M) out[(size_t)m * C + c] = tile[tx][r];
+  }
+}
+
+
+__device__ __forceinline__ void warp_lexmin(float& d, int& id) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float od = __shfl_xor_sync(0xffffffffu, d, o);
+    int oi = __shfl_xor_sync(0xffffffffu, id, o);
+    if (od < d || (od == d && oi < id)) { d = od; id = oi; }
+  }
+}
+
+// Exact K=1 search, no radius bound (renderer.py:627): box of Chebyshev radius r around the query's cell, lanes
+// take rows of the box; r doubles until every unsearched cell is provably farther than the best hit.
+__device__ int nn_unbounded(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
+                            float qx, float qy, float qz, int lane) {
+  const int cx = min(max(grid_coord(qx, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int cy = min(max(grid_coord(qy, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int cz = min(max(grid_coord(qz, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  float best = 3.0e38f;
+  int bid = 0x7fffffff;
+  for (int r = 1;; r *= 2) {
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dim[0] - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dim[1] - 1);
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dim[2] - 1);
+    const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+    for (int rr = lane; rr < nrows; rr += 32) {
+      const int z = z0 + rr / ny, y = y0 + rr % ny;
+      const int row = (z * g.dim[1] + y) * g.dim[0];
+      const int b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+      for (int k = b; k < e; ++k) {
+        const float4 v = gv[k];
+        const float d2 = dist2_xyz(qx, qy, qz, v.x, v.y, v.z);
+        const int id = __float_as_int(v.w);
+        if (d2 < best || (d2 == best && id < bid)) { best = d2; bid = id; }
+      }
+    }
+    warp_lexmin(best, bid);
+    // distance from q to the nearest face of the searched box that still has grid cells behind it
+    float m = 3.0e38f;
+    if (cx - r > 0) m = fminf(m, qx - (g.origin[0] + (float)(cx - r) * g.cell));
+    if (cx + r < g.dim[0] - 1) m = fminf(m, (g.origin[0] + (float)(cx + r + 1) * g.cell) - qx);
+    if (cy - r > 0) m = fminf(m, qy - (g.origin[1] + (float)(cy - r) * g.cell));
+    if (cy + r < g.dim[1] - 1) m = fminf(m, (g.origin[1] + (float)(cy + r + 1) * g.cell) - qy);
+    if (cz - r > 0) m = fminf(m, qz - (g.origin[2] + (float)(cz - r) * g.cell));
+    if (cz + r < g.dim[2] - 1) m = fminf(m, (g.origin[2] + (float)(cz + r + 1) * g.cell) - qz);
+    if (m > 1.0e38f) break;                       // whole grid searched
+    const float ms = m - 1.0e-4f * g.cell;        // guard band for fp32 rounding of d2 / face positions
+    if (ms > 0.f && best < ms * ms) break;
+  }
+  return bid;
+}
+
+__device__ __forceinline__ void apply_warp(const VertexWarp* __restrict__ Tp, float p[3], float d[3], bool with_dir) {
+  // broadcast loads: every lane reads the same 144 B record
+  const float4* r4 = reinterpret_cast<const float4*>(Tp);
+  float w[36];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { float4 v = r4[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+  float a[3] = {p[0] - w[9], p[1] - w[10], p[2] - w[11]};
+  float c[3];
+  mat3_vec(w, a, c);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { c[k] = c[k] + w[12 + k]; c[k] = c[k] + w[15 + k]; c[k] = c[k] + w[18 + k]; }
+  const float* Af = w + 21;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = (Af[4 * k] * c[0] + Af[4 * k + 1] * c[1] + Af[4 * k + 2] * c[2]) + Af[4 * k + 3];
+  if (with_dir) {
+    float e[3];
+    mat3_vec(w, d, e);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = Af[4 * k] * e[0] + Af[4 * k + 1] * e[1] + Af[4 * k + 2] * e[2];
+  }
+}
+
+struct Tap2 { int x0, y0; float wnw, wne, wsw, wse; };
+__device__ __forceinline__ Tap2 make_tap2(float ix, float iy) {
+  Tap2 t;
+  const float fx = floorf(ix), fy = floorf(iy);
+  t.x0 = (int)fx; t.y0 = (int)fy;
+  const float ax = ix - fx, ay = iy - fy, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+  t.wnw = bx * by; t.wne = ax * by; t.wsw = bx * ay; t.wse = ax * ay;
+  return t;
+}
+// bilinear, zeros padding; base -> [H][W][C] channels-last, returns channel `c`
+__device__ __forceinline__ float bilerp_cl(const float* __restrict__ base, int H, int W, int C, const Tap2& t, int c) {
+  const bool xl = t.x0 >= 0 && t.x0 < W, xr = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const bool yt = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  const float* r0 = base + ((size_t)t.y0 * W + t.x0) * C + c;
+  const float* r1 = r0 + (size_t)W * C;
+  const float vnw = (yt && xl) ? __ldg(r0) : 0.f;
+  const float vne = (yt && xr) ? __ldg(r0 + C) : 0.f;
+  const float vsw = (yb && xl) ? __ldg(r1) : 0.f;
+  const float vse = (yb && xr) ? __ldg(r1 + C) : 0.f;
+  return ((vnw * t.wnw + vne * t.wne) + vsw * t.wsw) + vse * t.wse;
+}
+
+__global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
+  __shared__ FrameConst fc;
+  for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int lp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); lp < P.np; lp += warps_total) {
+    const int64_t gp = P.p0 + lp;
+    const int s = P.point_sample[gp];
+    const int n = s / P.S, i = s - n * P.S;
+    // ---- re-derive the SMPL-space query exactly as the cull did (renderer.py:304-310) ----
+    const float t = sample_depth(P.nearv[n], P.farv[n], i, P.S);
+    float dray[3] = {P.dirs[n * 3], P.dirs[n * 3 + 1], P.dirs[n * 3 + 2]};
+    float pw[3], q[3], vd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pw[k] = __fsub_rn(mul_add_sep(t, dray[k], P.origins[n * 3 + k]), fc.Th_tgt[k]);
+    rowvec_mat3(pw, fc.R_tgt, q);
+    rowvec_mat3(dray, fc.R_tgt, vd);
+    // ---- target -> canonical (renderer.py:558-621) ----
+    float can[3] = {q[0], q[1], q[2]}, cdir[3] = {vd[0], vd[1], vd[2]};
+    apply_warp(P.T1 + P.point_vid[gp], can, cdir, true);
+    // ---- canonical -> observation -> pixel (renderer.py:623-704) ----
+    const int vid3 = nn_unbounded(fc.g3, P.g3_start, P.g3_verts, can[0], can[1], can[2], lane);
+    float ps[3] = {can[0], can[1], can[2]}, dummy[3] = {0.f, 0.f, 0.f};
+    apply_warp(P.T3 + vid3, ps, dummy, false);
+    float world[3], cam[3], pix[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      world[k] = (ps[0] * fc.Rinv_obs[k] + ps[1] * fc.Rinv_obs[3 + k] + ps[2] * fc.Rinv_obs[6 + k]) + fc.Th_obs[k];
+    mat3_vec(fc.camR, world, cam);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cam[k] += fc.camT[k];
+    mat3_vec(fc.camK, cam, pix);
+    const float zz = pix[2] + 1e-5f;
+    const float u = pix[0] / zz, v = pix[1] / zz;
+
+    float* comb = P.comb + (size_t)lp * 288;
+    float* f3 = P.f3raw + (size_t)lp * 192;
+    float* dbgf = (P.dbg_feat && gp < P.dbg_max) ? P.dbg_feat + (size_t)gp * 384 : nullptr;
+
+    // ---- pixel-aligned 2-D features (renderer.py:331-340) ----
+    {
+      const float gx = 2.0f * u / (float)P.img_w - 1.0f, gy = 2.0f * v / (float)P.img_h - 1.0f;
+      const Tap2 tf = make_tap2((gx + 1.f) * 0.5f * (float)(P.feat_w - 1), (gy + 1.f) * 0.5f * (float)(P.feat_h - 1));
+      const float f0 = bilerp_cl(P.feat_cl, P.feat_h, P.feat_w, P.feat_ch, tf, lane);
+      const float f1 = bilerp_cl(P.feat_cl, P.feat_h, P.feat_w, P.feat_ch, tf, lane + 32);
+      const Tap2 ti = make_tap2((gx + 1.f) * 0.5f * (float)(P.img_w - 1), (gy + 1.f) * 0.5f * (float)(P.img_h - 1));
+      float rgbc = 0.f;
+      if (lane < 3) {   // NCHW image: channel plane `lane`
+        const float* pl = P.img + (size_t)lane * P.img_h * P.img_w;
+        const bool xl = ti.x0 >= 0 && ti.x0 < P.img_w, xr = ti.x0 + 1 >= 0 && ti.x0 + 1 < P.img_w;
+        const bool yt = ti.y0 >= 0 && ti.y0 < P.img_h, yb = ti.y0 + 1 >= 0 && ti.y0 + 1 < P.img_h;
+        const float* r0 = pl + (size_t)ti.y0 * P.img_w + ti.x0;
+        const float vnw = (yt && xl) ? __ldg(r0) : 0.f, vne = (yt && xr) ? __ldg(r0 + 1) : 0.f;
+        const float vsw = (yb && xl) ? __ldg(r0 + P.img_w) : 0.f, vse = (yb && xr) ? __ldg(r0 + P.img_w + 1) : 0.f;
+        rgbc = ((vnw * ti.wnw + vne * ti.wne) + vsw * ti.wsw) + vse * ti.wse;
+      }
+      // rgb_enc (num_freqs=5) truncated to its first 32 outputs (renderer.py:339, :900-916)
+      const int e = lane - 3;
+      const int m = e >= 0 ? e / 3 : 0, c = e >= 0 ? e - 3 * m : lane;
+      const float xc = __shfl_sync(0xffffffffu, rgbc, c);
+      const float enc = lane < 3 ? xc : sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+      comb[0 * 96 + 32 + lane] = f0;
+      comb[1 * 96 + 32 + lane] = f1;
+      comb[2 * 96 + 32 + lane] = enc;
+      if (dbgf) { dbgf[96 + lane] = f0; dbgf[128 + lane] = f1; dbgf[160 + lane] = enc; }
+    }
+    // ---- tri-plane features (renderer.py:234-243), align_corners=False ----
+    {
+      float cn[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cn[k] = 2.f * (can[k] - fc.twb_min[k]) / (fc.twb_max[k] - fc.twb_min[k]) - 1.f;
+      const float px[3] = {cn[0], cn[0], cn[2]}, py[3] = {cn[1], cn[2], cn[1]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const Tap2 tp = make_tap2(((px[k] + 1.f) * (float)P.plane_w - 1.f) * 0.5f, ((py[k] + 1.f) * (float)P.plane_h - 1.f) * 0.5f);
+        const float val = bilerp_cl(P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32, P.plane_h, P.plane_w, 32, tp, lane);
+        comb[k * 96 + lane] = val;
+        if (dbgf) dbgf[k * 32 + lane] = val;
+      }
+    }
+    // ---- 3-D pyramid (renderer.py:544-556, :762-797), align_corners=True ----
+    {
+      float gn[3];   // normalised (x, y, z)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        // dhw axis a = 2-k holds coordinate k; out_sh is (z,y,x)
+        gn[k] = ((can[k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
+      }
+      int coff = 0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const int D = P.vol_d[l], H = P.vol_h[l], W = P.vol_w[l], C = P.vol_ch[l];
+        const float ix = (gn[0] + 1.f) * 0.5f * (float)(W - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(H - 1),
+                    iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+        const float ax = ix - fx, ay = iy - fy, az = iz - fz, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy, bz = (fz + 1.f) - iz;
+        const float wgt[8] = {bx * by * bz, ax * by * bz, bx * ay * bz, ax * ay * bz, bx * by * az, ax * by * az, bx * ay * az, ax * ay * az};
+        const float* vol = P.vol_cl[l];
+        for (int c = lane; c < C; c += 32) {
+          float acc = 0.f;
+#pragma unroll
+          for (int tcorner = 0; tcorner < 8; ++tcorner) {
+            const int xx = x0 + (tcorner & 1), yy = y0 + ((tcorner >> 1) & 1), zz2 = z0 + (tcorner >> 2);
+            const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz2 >= 0 && zz2 < D;
+            const float val = ok ? __ldg(vol + (((size_t)zz2 * H + yy) * W + xx) * C + c) : 0.f;
+            acc += val * wgt[tcorner];
+          }
+          f3[coff + c] = acc;
+          if (dbgf) dbgf[192 + coff + c] = acc;
+        }
+        coff += C;
+      }
+    }
+    if (lane < 8) {
+      float gval = 0.f;   // select chain instead of dynamic indexing (keeps the vectors in registers)
+      if (lane == 0) gval = can[0]; else if (lane == 1) gval = can[1]; else if (lane == 2) gval = can[2];
+      else if (lane == 3) gval = cdir[0]; else if (lane == 4) gval = cdir[1]; else if (lane == 5) gval = cdir[2];
+      P.geo[(size_t)lp * 8 + lane] = gval;
+    }
+    if (lane == 0 && gp < P.dbg_max) {
+      if (P.dbg_vid3) P.dbg_vid3[gp] = vid3;
+      if (P.dbg_can) { P.dbg_can[gp * 3] = can[0]; P.dbg_can[gp * 3 + 1] = can[1]; P.dbg_can[gp * 3 + 2] = can[2]; }
+      if (P.dbg_cdir) { P.dbg_cdir[gp * 3] = cdir[0]; P.dbg_cdir[gp * 3 + 1] = cdir[1]; P.dbg_cdir[gp * 3 + 2] = cdir[2]; }
+      if (P.dbg_uv) { P.dbg_uv[gp * 2] = u; P.dbg_uv[gp * 2 + 1] = v; }
+    }
+  }
+}
+
+int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st) {
+  dim3 grid((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32));
+  k_to_channels_last<<<grid, 256, 0, st>>>(in, out, C, M);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+int run_point_gather(const GatherParams& P, cudaStream_t st) {
+  if (P.np <= 0) return SHERF_OK;
+  const int blocks = min(ceil_div(P.np, 8), 148 * 16);
+  k_point_gather<<<blocks, 256, 0, st>>>(P);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+}  // namespace sherf

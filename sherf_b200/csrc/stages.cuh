@@ -1,0 +1,73 @@
+// Stage parameter blocks and host-side launchers shared between the .cu files.
+#pragma once
+#include "common.cuh"
+
+namespace sherf {
+
+struct GatherParams {
+  // rays
+  const float *origins, *dirs, *nearv, *farv;
+  int S;
+  // compacted points of this chunk
+  const int *point_sample, *point_vid;
+  int64_t p0; int np;
+  // frame
+  const FrameConst* fc;
+  const VertexWarp *T1, *T3;
+  const int* g3_start; const float4* g3_verts;
+  // channels-last features
+  const float* planes_cl; int plane_h, plane_w;            // [3][H][W][32]
+  const float* feat_cl; int feat_h, feat_w, feat_ch;       // [fh][fw][64]
+  const float* img; int img_h, img_w;                      // [3][H][W] (NCHW, 3 channels only)
+  const float* vol_cl[3]; int vol_ch[3]; int vol_d[3], vol_h[3], vol_w[3];
+  // outputs (chunk-relative rows)
+  float* comb;      // [np][288]: token k at k*96: tri_k(32) | f2d_k(32) | (f3d_k written by the projection GEMM)
+  float* f3raw;     // [np][192]
+  float* geo;       // [np][8]: can xyz, cdir xyz, 0, 0
+  // optional taps (absolute point index)
+  int* dbg_vid3; float *dbg_can, *dbg_cdir, *dbg_uv, *dbg_feat; int64_t dbg_max;
+};
+
+int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
+int run_point_gather(const GatherParams& P, cudaStream_t st);
+int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* ray_start, int64_t* total_dev,
+             int* point_sample, int* point_vid, cudaStream_t st);
+
+// Row-major activation buffers of one chunk of `cap` points (fp32).
+struct ChunkBuffers {
+  int cap;
+  float *comb;   // [cap][288]   token k at k*96: tri_k | f2d_k | f3d_k
+  float *f3raw;  // [cap][192]
+  float *geo;    // [cap][8]
+  float *tok;    // [3cap][32]   conv1d_reprojection output
+  float *ln;     // [3cap][32]
+  float *qkv;    // [3cap][144]
+  float *att;    // [3cap][48]
+  float *tok2;   // [3cap][32]
+  float *ffh;    // [3cap][32]
+  float *tok3;   // [3cap][32]
+  float *x;      // [cap][72]    PE6(can) | tok0 | 0
+  float *h1, *h2;// [cap][128]
+  float *hb;     // [cap][200]   x | h (skip concat, triplane.py:299-300)
+  float *fv;     // [cap][188]   feature | PE4(dir) | tok1 | 0
+  float *vh;     // [cap][64]
+};
+size_t chunk_buffer_floats(int cap);
+void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb);
+
+// Packed (transposed, zero-padded) weights: Wt[kp][np], kp = round_up(K,16), np = round_up(N,32).
+struct PackedLayer { const float* wt; const float* bias; int K, N, kp, np; };
+struct PackedWeights {
+  PackedLayer proj, reproj, qkv, attn_out, ff1, ff2, pts[8], feature, views;
+};
+size_t packed_weight_floats();
+int run_pack_weights(const SherfWeights& w, float* base, PackedWeights& pw, cudaStream_t st);
+
+// The fusion / transformer / decoder stack on one chunk (fp32 CUDA-core path).  renderer.py:350,423-432; triplane.py:285-316
+int run_mlp_fp32(const SherfWeights& w, const PackedWeights& pw, const ChunkBuffers& cb, int np, int64_t p0,
+                 float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st);
+
+int run_composite(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample,
+                  const float* sigma, const float* rgb, const float* noise, int white_back, const SherfOut& out, cudaStream_t st);
+
+}  // namespace sherf

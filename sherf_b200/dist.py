@@ -1,0 +1,83 @@
+"""Multi-GPU ray sharding.  Rays are independent; the only cross-ray coupling in the reference is the
+global depth clamp `torch.min(depths) / torch.max(depths)` (ray_marcher.py:57), which every rank computes from the
+replicated near/far.  One process per GPU renders an interleaved set of ray tiles and the rendered tiles
+(rgb 3 + depth 1 + acc 1 = 20 B per ray) are exchanged with exactly ONE all-gather; nothing else crosses ranks.
+The reference has no such path (its evaluation runs on rank 0 only, training_loop.py:311-328).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+TILE = 256          # consecutive rays per tile; tiles are dealt round-robin so that body / background pixels balance
+
+
+def shard_indices(n_rays: int, rank: int, world: int, tile: int = TILE, device='cpu') -> torch.Tensor:
+    """Ray indices owned by `rank`: tiles t with t % world == rank, in ascending order."""
+    idx = torch.arange(n_rays, device=device)
+    return idx[(idx // tile) % world == rank]
+
+
+def padded_shard_size(n_rays: int, world: int, tile: int = TILE) -> int:
+    """Largest shard over all ranks (ranks pad to it so one fixed-size all-gather suffices)."""
+    n_tiles = (n_rays + tile - 1) // tile
+    most = (n_tiles + world - 1) // world
+    return most * tile
+
+
+def depth_range(near: torch.Tensor, far: torch.Tensor, n_samples: int):
+    """(min, max) over ALL sample depths of the full view, bit-identical to torch.min/max(depths_coarse):
+    t_0 = near + 0 * (far - near) = near and t_{S-1} = near + 1 * (far - near) (math_utils.py:101-118), t monotone in i."""
+    first = near.float().reshape(-1)
+    last = first + (far.float().reshape(-1) - first)
+    lo = torch.minimum(first, last).min()
+    hi = torch.maximum(first, last).max()
+    return float(lo), float(hi)
+
+
+def shard_scene(scene: dict, rank: int, world: int, tile: int = TILE):
+    """A shallow copy of a scene dict (synthetic.make_scene layout) that carries only `rank`'s rays."""
+    n = scene['ray_origins'].shape[1]
+    idx = shard_indices(n, rank, world, tile, device=scene['ray_origins'].device)
+    sh = dict(scene)
+    for k in ('ray_origins', 'ray_directions', 'near', 'far'):
+        sh[k] = scene[k][:, idx].contiguous()
+    return sh, idx
+
+
+def all_gather_tiles(local: torch.Tensor, n_rays: int, group=None, tile: int = TILE) -> torch.Tensor:
+    """local: [n_local, C] rendered values of this rank's rays (shard_indices order).  Returns the full [n_rays, C]
+    on every rank using a single all_gather of equally padded shards."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    pad = padded_shard_size(n_rays, world, tile)
+    buf = local.new_zeros(pad, local.shape[1])
+    buf[:local.shape[0]] = local
+    gathered = local.new_empty(world * pad, local.shape[1])
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    full = local.new_empty(n_rays, local.shape[1])
+    for r in range(world):
+        idx = shard_indices(n_rays, r, world, tile, device=local.device)
+        full[idx] = gathered[r * pad:r * pad + idx.numel()]
+    assert shard_indices(n_rays, rank, world, tile).numel() == local.shape[0]
+    return full
+
+
+def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE):
+    """Every rank holds the replicated scene, renders its ray tiles through the CUDA path and receives the full image.
+    Returns (rgb[1,N,3], depth[1,N,1], acc[1,N,1]) on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = scene['ray_origins'].shape[1]
+    S = int(scene['rendering_options']['depth_resolution'])
+    clamp = depth_range(scene['near'], scene['far'], S)
+    sh, idx = shard_scene(scene, rank, world, tile)
+    if idx.numel() > 0:
+        rgb, depth, acc = renderer(sh['planes'], sh['obs_input_img'], sh['obs_input_feature'], sh['volumes'], None,
+                                   sh['obs_sp_input'], decoder, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'],
+                                   sh['input_data'], sh['rendering_options'], depth_clamp=clamp)
+        local = torch.cat([rgb[0], depth[0], acc[0]], dim=-1)
+    else:
+        local = scene['ray_origins'].new_zeros(0, 5)
+    full = all_gather_tiles(local, n, group, tile)
+    return full[None, :, :3], full[None, :, 3:4], full[None, :, 4:5]

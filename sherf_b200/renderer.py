@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's `training.volumetric_rendering.renderer` for the render hot path.
+
+`ImportanceRenderer` keeps the reference's constructor kwargs, parameter / buffer names and forward signature
+(/root/reference/sherf/training/volumetric_rendering/renderer.py:260-286,398) so checkpoints resume by name and
+`TriPlaneGenerator.synthesis` (triplane.py:156-157) can call it unchanged -- but forward() does no torch math: it
+packs raw device pointers into the C-ABI structs of include/sherf_b200.h and calls libsherf_b200.so (hand-written
+sm_100a CUDA).  PyTorch is the container for device memory, streams and parameters only.  There is no CPU or
+eager fallback: without the library, or on a CPU tensor, forward() raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pickle
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3}
+
+
+def read_pickle(pkl_path):
+    """Same contract as renderer.py:34-38 (latin1 unpickle of the SMPL model)."""
+    with open(pkl_path, 'rb') as f:
+        u = pickle._Unpickler(f)
+        u.encoding = 'latin1'
+        return u.load()
+
+
+def SMPL_to_tensor(params, device):
+    """Same contract as renderer.py:65-74; additionally accepts an already-dense J_regressor."""
+    out = dict(params)
+    for key in ['v_template', 'shapedirs', 'J_regressor', 'kintree_table', 'f', 'weights', 'posedirs']:
+        val = params[key]
+        if key == 'J_regressor' and hasattr(val, 'toarray'):
+            val = val.toarray()
+        if torch.is_tensor(val):
+            t = val
+        else:
+            t = torch.tensor(np.array(val).astype(float))
+        out[key] = t.to(dtype=torch.long if key in ('kintree_table', 'f') else torch.float32, device=device)
+    return out
+
+
+# ---- parameter containers whose attribute paths reproduce the checkpoint names ----------------------
+class PositionalEncoding(nn.Module):
+    """Buffers only (_freqs, _phases; renderer.py:875-898).  The encoding itself runs inside the CUDA kernels."""
+
+    def __init__(self, num_freqs=6, d_in=3, include_input=True):
+        super().__init__()
+        self.num_freqs, self.d_in, self.include_input = num_freqs, d_in, include_input
+        self.d_out = num_freqs * 2 * d_in + (d_in if include_input else 0)
+        freqs = 2. ** torch.linspace(0., num_freqs - 1, steps=num_freqs)
+        self.register_buffer('_freqs', torch.repeat_interleave(freqs, 2).view(1, -1, 1))
+        ph = torch.zeros(2 * num_freqs)
+        ph[1::2] = torch.pi * 0.5
+        self.register_buffer('_phases', ph.view(1, -1, 1))
+
+
+class _Fn(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class _PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.scale = heads, dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(0.))
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.), nn.Linear(hidden, dim), nn.Dropout(0.))
+
+
+class Transformer(nn.Module):
+    """Parameters of renderer.py:980-993: layers.0.{0,1}.fn.{norm, fn.(to_qkv|to_out.0|net.0|net.3)}."""
+
+    def __init__(self, dim=32, depth=1, heads=3, dim_head=16, mlp_dim=32, dropout=0.):
+        super().__init__()
+        assert (dim, depth, heads, dim_head, mlp_dim) == (32, 1, 3, 16, 32), 'the CUDA path is built for SHERF\'s fixed transformer'
+        self.layers = nn.ModuleList([nn.ModuleList([_Fn(_PreNorm(dim, _Attention(dim, heads, dim_head))),
+                                                    _Fn(_PreNorm(dim, _FeedForward(dim, mlp_dim)))])])
+
+
+class _SpConvParam(nn.Module):
+    """Weight container for a spconv (Sub)MConv3d: KRSC layout [out, k, k, k, in] (spconv 2.3.3), no bias."""
+
+    def __init__(self, cin, cout, k=3):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, k, k, k, cin))
+        nn.init.kaiming_uniform_(self.weight.view(cout, -1), a=5 ** 0.5)
+
+
+def _sp_block(cin, cout, n):
+    mods = []
+    for i in range(n):
+        mods += [_SpConvParam(cin if i == 0 else cout, cout), nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01), nn.ReLU()]
+    return nn.Sequential(*mods)
+
+
+class SparseConvNet(nn.Module):
+    """Parameter names of renderer.py:708-742.  The sparse 3-D encoder itself is SURVEY.md 8(f) rank 1 ("next"); this
+    round the renderer consumes the three densified pyramid levels directly."""
+
+    def __init__(self, num_layers=4):
+        super().__init__()
+        self.num_layers = num_layers
+        self.conv0, self.down0 = _sp_block(32, 32, 2), _sp_block(32, 32, 1)
+        self.conv1, self.down1 = _sp_block(32, 32, 2), _sp_block(32, 64, 1)
+        self.conv2, self.down2 = _sp_block(64, 64, 3), _sp_block(64, 96, 1)
+        self.conv3, self.down3 = _sp_block(96, 96, 3), _sp_block(96, 96, 1)
+        self.conv4 = _sp_block(96, 96, 3)
+
+
+# ---- pointer plumbing -------------------------------------------------------------------------------------------
+def _dev32(t: torch.Tensor, device) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t))
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class ImportanceRenderer(nn.Module):
+    def __init__(self, use_1d_feature=True, use_2d_feature=True, use_3d_feature=True, use_trans=False, use_NeRF_decoder=False,
+                 smpl_model: dict | None = None, mlp_precision: str = 'fp32'):
+        super().__init__()
+        self.use_1d_feature, self.use_2d_feature, self.use_3d_feature = use_1d_feature, use_2d_feature, use_3d_feature
+        self.use_trans, self.use_NeRF_decoder = use_trans, use_NeRF_decoder
+        self.mlp_precision = mlp_precision
+        self.encoder_3d = SparseConvNet(num_layers=4)
+        self.conv1d_projection = nn.Conv1d(192, 96, 1)
+        if use_1d_feature and use_2d_feature and use_3d_feature:
+            self.conv1d_reprojection = nn.Conv1d(96, 32, 1)
+        elif (use_1d_feature and use_2d_feature) or (use_1d_feature and use_3d_feature) or (use_3d_feature and use_2d_feature):
+            self.conv1d_reprojection = nn.Conv1d(64, 32, 1)
+        self.transformer = None if not use_trans else Transformer(32)
+        self.rgb_enc = PositionalEncoding(num_freqs=5)
+        self.pos_enc = PositionalEncoding(num_freqs=6)
+        self.view_enc = PositionalEncoding(num_freqs=4)
+        # SMPL model: same default location as renderer.py:283; tests and the bench inject a synthetic body.
+        self.SMPL_NEUTRAL = None
+        self._smpl_dev = None
+        if smpl_model is not None:
+            self.set_smpl_model(smpl_model)
+        elif os.path.exists(os.path.join('assets', 'SMPL_NEUTRAL.pkl')):
+            self.set_smpl_model(read_pickle(os.path.join('assets', 'SMPL_NEUTRAL.pkl')))
+        self._scratch = None
+        self._dbg_keep = None
+        self.last_num_points = 0
+        self.last_launches = 0
+
+    # -- configuration ------------------------------------------------------------------------------------------
+    def set_smpl_model(self, model: dict):
+        self.SMPL_NEUTRAL = SMPL_to_tensor(model, device='cpu')
+        self._smpl_dev = None
+
+    def _smpl_struct(self, device):
+        if self.SMPL_NEUTRAL is None:
+            raise RuntimeError('no SMPL model: put assets/SMPL_NEUTRAL.pkl in the cwd or call set_smpl_model()')
+        if self._smpl_dev is None or self._smpl_dev[0] != device:
+            m = self.SMPL_NEUTRAL
+            keep = {k: _dev32(m[k], device) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights')}
+            st = _lib.SherfSmplModel()
+            st.v_template, st.shapedirs, st.posedirs = _ptr(keep['v_template']), _ptr(keep['shapedirs']), _ptr(keep['posedirs'])
+            st.j_regressor, st.weights = _ptr(keep['J_regressor']), _ptr(keep['weights'])
+            par = m['kintree_table'][0].tolist()
+            for j in range(24):
+                st.parents[j] = 0 if j == 0 else int(par[j])
+            st.n_verts = keep['v_template'].shape[0]
+            self._smpl_dev = (device, keep, st)
+        return self._smpl_dev[2]
+
+    def _check_supported(self):
+        if not (self.use_1d_feature and self.use_2d_feature and self.use_3d_feature and self.use_trans and self.use_NeRF_decoder):
+            raise NotImplementedError('sherf_b200 implements the configuration every shipped SHERF script uses: '
+                                      'use_1d/2d/3d_feature, use_trans and use_nerf_decoder all True')
+
+    def _weights_struct(self, decoder, device, keep):
+        w = _lib.SherfWeights()
+
+        def P(t):
+            t = _dev32(t, device)
+            keep.append(t)
+            return _ptr(t)
+        w.proj_w, w.proj_b = P(self.conv1d_projection.weight), P(self.conv1d_projection.bias)
+        w.reproj_w, w.reproj_b = P(self.conv1d_reprojection.weight), P(self.conv1d_reprojection.bias)
+        att, ff = self.transformer.layers[0][0].fn, self.transformer.layers[0][1].fn
+        w.ln1_w, w.ln1_b, w.qkv_w = P(att.norm.weight), P(att.norm.bias), P(att.fn.to_qkv.weight)
+        w.attn_out_w, w.attn_out_b = P(att.fn.to_out[0].weight), P(att.fn.to_out[0].bias)
+        w.ln2_w, w.ln2_b = P(ff.norm.weight), P(ff.norm.bias)
+        w.ff1_w, w.ff1_b = P(ff.fn.net[0].weight), P(ff.fn.net[0].bias)
+        w.ff2_w, w.ff2_b = P(ff.fn.net[3].weight), P(ff.fn.net[3].bias)
+        for i in range(8):
+            w.pts_w[i], w.pts_b[i] = P(decoder.pts_linears[i].weight), P(decoder.pts_linears[i].bias)
+        w.alpha_w, w.alpha_b = P(decoder.alpha_linear.weight), P(decoder.alpha_linear.bias)
+        w.feature_w, w.feature_b = P(decoder.feature_linear.weight), P(decoder.feature_linear.bias)
+        w.views_w, w.views_b = P(decoder.views_linear.weight), P(decoder.views_linear.bias)
+        w.rgb_w, w.rgb_b = P(decoder.rgb_linear.weight), P(decoder.rgb_linear.bias)
+        return w
+
+    @staticmethod
+    def _pose_struct(params, device, keep):
+        p = _lib.SherfPose()
+        for name in ('poses', 'shapes', 'R', 'Th'):
+            t = _dev32(params[name], device).reshape(-1)
+            keep.append(t)
+            setattr(p, name, _ptr(t))
+        return p
+
+    # -- the hot path ----------------------------------------------------------------------------------------------
+    def forward(self, planes, obs_input_img, obs_input_feature, canonical_sp_conv_volume, obs_smpl_vertex_mask, obs_sp_input,
+                decoder, ray_origins, ray_directions, near, far, input_data, rendering_options, debug: dict | None = None,
+                depth_clamp: tuple | None = None):
+        """Same positional signature and return value as renderer.py:286,398:
+        (rgb[B,N,3] in (-1,1), depth[B,N,1], acc[B,N,1]).  `canonical_sp_conv_volume` is the list of the three densified
+        pyramid levels [1,32,D/2..], [1,64,D/4..], [1,96,D/8..] (what SparseConvNet.forward densifies at renderer.py:762-782).
+        Extra keyword-only hooks: `debug` (dict filled with stage-wise tensors) and `depth_clamp` ((min,max) of the full
+        view's depths when this call renders a shard of its rays, ray_marcher.py:57)."""
+        self._check_supported()
+        lib = _lib.load()
+        device = ray_origins.device
+        if device.type != 'cuda':
+            raise RuntimeError('sherf_b200.ImportanceRenderer runs on CUDA tensors only (no CPU fallback)')
+        if ray_origins.shape[0] != 1:
+            raise NotImplementedError('per-GPU batch must be 1, as in the reference (renderer.py:320-321)')
+        if rendering_options.get('depth_resolution_importance', 0) > 0:
+            raise NotImplementedError('importance pass: dead code in the reference (renderer.py:376,383), SURVEY.md a13')
+        if rendering_options.get('clamp_mode', 'relu') != 'relu':
+            raise NotImplementedError("only clamp_mode='relu' (train.py:332)")
+        if rendering_options.get('disparity_space_sampling', False):
+            raise NotImplementedError('disparity_space_sampling')
+        if not isinstance(canonical_sp_conv_volume, (list, tuple)) or len(canonical_sp_conv_volume) != 3:
+            raise NotImplementedError('pass the three densified pyramid levels; the sparse 3-D encoder is a "next" row (SURVEY 8f)')
+        keep = []
+        N = ray_origins.shape[1]
+        S = int(rendering_options['depth_resolution'])
+        with torch.cuda.device(device):
+            smpl = self._smpl_struct(device)
+            fr = _lib.SherfFrame()
+            fr.target = self._pose_struct(input_data['params'], device, keep)
+            fr.canonical = self._pose_struct(input_data['t_params'], device, keep)
+            fr.obs = self._pose_struct(input_data['obs_params'], device, keep)
+            for name, key in (('vertices', 'vertices'), ('t_vertices', 't_vertices'), ('t_world_bounds', 't_world_bounds'),
+                              ('obs_K', 'obs_K_all'), ('obs_R', 'obs_R_all'), ('obs_T', 'obs_T_all')):
+                t = _dev32(input_data[key], device).reshape(-1)
+                keep.append(t)
+                setattr(fr, name, _ptr(t))
+            t = _dev32(obs_sp_input['bounds'], device).reshape(-1)
+            keep.append(t)
+            fr.sp_bounds = _ptr(t)
+            for i in range(3):
+                fr.out_sh[i] = int(obs_sp_input['out_sh'][i])
+
+            sc = _lib.SherfScene()
+            pl = _dev32(planes, device); keep.append(pl)
+            assert pl.dim() == 5 and pl.shape[0] == 1 and pl.shape[1] == 3, 'planes must be [1,3,C,H,W]'
+            sc.planes, sc.plane_ch, sc.plane_h, sc.plane_w = _ptr(pl), pl.shape[2], pl.shape[3], pl.shape[4]
+            im = _dev32(obs_input_img, device); keep.append(im)
+            sc.obs_img, sc.img_h, sc.img_w = _ptr(im), im.shape[-2], im.shape[-1]
+            ft = _dev32(obs_input_feature, device); keep.append(ft)
+            sc.obs_feat, sc.feat_ch, sc.feat_h, sc.feat_w = _ptr(ft), ft.shape[-3], ft.shape[-2], ft.shape[-1]
+            for l, v in enumerate(canonical_sp_conv_volume):
+                v = _dev32(v, device); keep.append(v)
+                sc.vol[l], sc.vol_ch[l] = _ptr(v), v.shape[1]
+                for a in range(3):
+                    sc.vol_dim[l][a] = v.shape[2 + a]
+
+            w = self._weights_struct(decoder, device, keep)
+            rays = _lib.SherfRays()
+            ro, rd = _dev32(ray_origins, device).reshape(-1), _dev32(ray_directions, device).reshape(-1)
+            nr, fa = _dev32(near, device).reshape(-1), _dev32(far, device).reshape(-1)
+            keep += [ro, rd, nr, fa]
+            rays.origins, rays.dirs, rays.near_, rays.far_, rays.n_rays, rays.n_samples = _ptr(ro), _ptr(rd), _ptr(nr), _ptr(fa), N, S
+
+            opts = _lib.SherfOptions()
+            opts.white_back = int(bool(rendering_options.get('white_back', False)))
+            opts.mlp_precision = PRECISIONS[self.mlp_precision]
+            if depth_clamp is not None:
+                opts.use_external_clamp, opts.depth_clamp_min, opts.depth_clamp_max = 1, float(depth_clamp[0]), float(depth_clamp[1])
+            noise_scale = float(rendering_options.get('density_noise', 0) or 0)
+            if noise_scale > 0:
+                # renderer.py:435-436; drawn per SAMPLE here (the reference draws per surviving point), same distribution
+                nz = torch.randn(N * S, device=device, dtype=torch.float32) * noise_scale
+                keep.append(nz)
+                opts.density_noise = _ptr(nz)
+
+            rgb = torch.empty(1, N, 3, device=device, dtype=torch.float32)
+            depth = torch.empty(1, N, 1, device=device, dtype=torch.float32)
+            acc = torch.empty(1, N, 1, device=device, dtype=torch.float32)
+            out = _lib.SherfOut(_ptr(rgb), _ptr(depth), _ptr(acc))
+
+            need = lib.sherf_scratch_bytes(C.byref(sc), N, S, smpl.n_verts)
+            if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
+                self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+
+            dbg_p = None
+            if debug is not None:
+                NS = N * S
+                d = _lib.SherfDebug()
+                bufs = {
+                    'sample_vid': torch.empty(NS, dtype=torch.int32, device=device),
+                    'point_sample': torch.empty(NS, dtype=torch.int32, device=device),
+                    'point_vid3': torch.empty(NS, dtype=torch.int32, device=device),
+                    'point_can': torch.empty(NS, 3, device=device), 'point_cdir': torch.empty(NS, 3, device=device),
+                    'point_uv': torch.empty(NS, 2, device=device), 'point_sigma': torch.empty(NS, device=device),
+                    'point_rgb': torch.empty(NS, 3, device=device), 'point_tok': torch.empty(NS, 64, device=device),
+                }
+                cap_feat = min(NS, int(debug.get('max_feat_points', NS)))
+                bufs['point_feat'] = torch.empty(cap_feat, 384, device=device)
+                for k, v in bufs.items():
+                    setattr(d, k, _ptr(v))
+                d.max_points = cap_feat
+                dbg_p = C.byref(d)
+                self._dbg_keep = (d, bufs)
+
+            npts = C.c_int64(0)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            rc = lib.sherf_render_forward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(opts),
+                                          C.byref(out), dbg_p, self._scratch.data_ptr(), self._scratch.numel(), stream,
+                                          C.byref(npts))
+            _lib.check(rc)
+            self.last_num_points = int(npts.value)
+            self.last_launches = int(lib.sherf_last_launch_count())
+            if debug is not None:
+                Pn = min(self.last_num_points, self._dbg_keep[0].max_points)
+                for k, v in self._dbg_keep[1].items():
+                    debug[k] = v if k == 'sample_vid' else v[:Pn]
+                debug['num_points'] = self.last_num_points
+            # the C side only borrowed the pointers for the call; outputs are ordered after it on the same stream
+            del keep
+        return rgb, depth, acc

@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads here (no GPU), exports every symbol the header declares,
+the ctypes mirrors match the C struct layouts, and the product modules refuse to run without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+from sherf_b200 import _lib, build
+
+HEADER = os.path.join(ROOT, 'include', 'sherf_b200.h')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    build.build_library()
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(sherf_[a-z_0-9]+)\s*\(', src)))
+
+
+def test_exports_every_declared_symbol(lib):
+    names = declared_functions()
+    assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in the header but not exported'
+    assert lib.sherf_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    structs = ['SherfSmplModel', 'SherfPose', 'SherfFrame', 'SherfScene', 'SherfWeights', 'SherfRays', 'SherfOptions', 'SherfOut',
+               'SherfDebug']
+    prog = '#include <stdio.h>\n#include "sherf_b200.h"\nint main(){' + ''.join(
+        f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + 'return 0;}'
+    c = tmp_path / 'sz.c'
+    c.write_text(prog)
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', '-I', os.path.dirname(HEADER), str(c), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    sizes = dict(l.split() for l in out.strip().splitlines())
+    for s in structs:
+        assert int(sizes[s]) == ctypes.sizeof(getattr(_lib, s)), s
+
+
+def test_scratch_bytes_and_argument_validation(lib):
+    sc = _lib.SherfScene()
+    sc.plane_ch, sc.plane_h, sc.plane_w = 32, 256, 256
+    sc.img_h = sc.img_w = 64
+    sc.feat_ch, sc.feat_h, sc.feat_w = 64, 32, 32
+    for l, (c, d) in enumerate(zip((32, 64, 96), ((48, 176, 192), (24, 88, 96), (12, 44, 48)))):
+        sc.vol_ch[l] = c
+        for a in range(3):
+            sc.vol_dim[l][a] = d[a]
+    small = lib.sherf_scratch_bytes(ctypes.byref(sc), 4096, 16, 6890)
+    big = lib.sherf_scratch_bytes(ctypes.byref(sc), 512 * 512, 64, 6890)
+    assert 0 < small < big < 8 << 30
+    assert lib.sherf_scratch_bytes(ctypes.byref(sc), 0, 16, 6890) == 0
+    rc = lib.sherf_render_forward(None, None, None, None, None, None, None, None, None, 0, None, None)
+    assert rc == -1 and b'null' in lib.sherf_last_error()
+
+
+def test_no_cpu_fallback(smpl_model):
+    from sherf_b200 import synthetic as S
+    from sherf_b200.triplane import hot_path_modules
+    ren, dec = hot_path_modules(smpl_model)
+    scene = S.make_scene(S.SceneSpec(H=4, W=4, samples=4), smpl_model)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'], dec,
+            scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'], scene['rendering_options'])
+    with pytest.raises(RuntimeError):
+        dec(torch.zeros(1, 39), torch.zeros(3, 1, 32), torch.zeros(1, 27))
+
+
+def test_checkpoint_names_match_reference_contract(smpl_model):
+    """resume copies parameters by name with require_all=True."""
+    from sherf_b200.triplane import hot_path_modules
+    ren, dec = hot_path_modules(smpl_model)
+    names = set(ren.state_dict().keys())
+    for n in ['conv1d_projection.weight', 'conv1d_projection.bias', 'conv1d_reprojection.weight', 'conv1d_reprojection.bias',
+              'transformer.layers.0.0.fn.norm.weight', 'transformer.layers.0.0.fn.fn.to_qkv.weight',
+              'transformer.layers.0.0.fn.fn.to_out.0.weight', 'transformer.layers.0.0.fn.fn.to_out.0.bias',
+              'transformer.layers.0.1.fn.norm.bias', 'transformer.layers.0.1.fn.fn.net.0.weight',
+              'transformer.layers.0.1.fn.fn.net.3.bias', 'rgb_enc._freqs', 'pos_enc._phases', 'view_enc._freqs',
+              'encoder_3d.conv0.0.weight', 'encoder_3d.conv0.1.running_mean', 'encoder_3d.down3.0.weight', 'encoder_3d.conv4.6.weight']:
+        assert n in names, n
+    assert ren.state_dict()['conv1d_projection.weight'].shape == (96, 192, 1)
+    dn = dec.state_dict()
+    assert dn['pts_linears.0.weight'].shape == (128, 71) and dn['pts_linears.5.weight'].shape == (128, 199)
+    assert dn['views_linear.weight'].shape == (64, 187) and dn['alpha_linear.weight'].shape == (1, 128)
+    n_hot = sum(v.numel() for k, v in ren.state_dict().items() if k.startswith(('conv1d', 'transformer'))) + sum(
+        p.numel() for p in dec.parameters())
+    assert n_hot == 192804                                                       # SURVEY.md section 7 "hard parts"

@@ -1,0 +1,78 @@
+"""CPU tests of the checker itself: oracle/port.py against the golden fixtures made from the reference's own code,
+and (only where /root/reference is mounted) against the live shimmed reference on a fresh scene."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from sherf_b200 import synthetic as S
+from oracle import port, ref_shim
+from oracle.gen_golden import checksum
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+def test_port_matches_reference_golden(case, smpl_model, smpl_model_t):
+    g = load_golden(case)
+    scene = S.make_scene(g['scene_spec'], smpl_model)
+    assert checksum(scene) == str(g['input_sha256']), 'synthetic scene is not bit-reproducible from its seed'
+    rgb, depth, acc, st = port.render_forward(g['weights'], smpl_model_t, scene, return_stages=True)
+    N, S_ = scene['ray_origins'].shape[1], g['scene_spec'].samples
+    gold_mask = np.unpackbits(g['mask_bits'])[:N * S_].astype(bool)
+    assert np.array_equal(st['mask'].numpy(), gold_mask)                      # bit-exact cull mask
+    assert np.array_equal(st['id1'][st['sel']].numpy(), g['id1'].astype(np.int64))
+    assert np.array_equal(st['id3'].numpy(), g['id3'].astype(np.int64))
+    assert np.abs(st['can'].numpy() - g['can']).max() <= 2e-6
+    assert np.abs(st['cdir'].numpy() - g['cdir']).max() <= 2e-6
+    assert np.abs(st['uv'].numpy() - g['uv']).max() <= 5e-4
+    k = g['f2d_head'].shape[0]
+    assert np.abs(st['f2d'][:k].numpy() - g['f2d_head']).max() <= 5e-4     # = uv error x gradient of the N(0,1) map
+    assert np.abs(st['f3d_raw'][:k].numpy() - g['f3raw_head']).max() <= 5e-4     # voxel-coordinate rounding x gradient of the N(0,1) volume
+    assert np.abs(st['tok_post'][:k, :2].reshape(k, 64).numpy() - g['tok01_head']).max() <= 5e-4
+    assert np.abs(st['sigma'].numpy() - g['sigma']).max() <= 1e-3
+    assert np.abs(st['rgb'].numpy() - g['rgb_pts']).max() <= 1e-5
+    assert np.abs(rgb[0].numpy() - g['rgb']).max() <= 1e-5
+    assert np.abs(acc[0].numpy() - g['acc']).max() <= 1e-5
+    assert np.abs(depth[0].numpy() - g['depth']).max() <= 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree is only mounted in the build container')
+def test_port_matches_live_reference(smpl_model, smpl_model_t):
+    ren, dec = ref_shim.build_reference(smpl_model_t, seed=4)
+    with torch.no_grad():
+        dec.alpha_linear.weight *= 30
+        dec.alpha_linear.bias += 2.0
+    scene = S.make_scene(S.SceneSpec(H=20, W=28, samples=12, seed=9, random_global_R=True), smpl_model)
+    ref = ref_shim.render(ren, dec, scene)
+    got = port.render_forward(port.hot_path_state_dict(ren, dec), smpl_model_t, scene)
+    for a, b in zip(ref, got):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 1e-5
+    assert float(ref[2].max()) > 0.2          # the body is actually visible
+
+
+def test_knn_tie_break_smallest_index():
+    v = torch.tensor([[0., 0, 0], [1, 0, 0], [1, 0, 0], [0, 0, 0]])
+    q = torch.tensor([[0.1, 0, 0], [0.9, 0, 0], [0.5, 0, 0]])
+    d2, idx = port.knn1(q, v)
+    assert idx.tolist() == [0, 1, 0]
+    d2s, idxs, _ = ref_shim.knn_points_bruteforce(q[None], v[None])
+    assert idxs[0, :, 0].tolist() == [0, 1, 0] and torch.equal(d2s[0, :, 0], d2)
+
+
+def test_positional_encoding_layout():
+    x = torch.tensor([[0.3, -0.2, 0.7]])
+    e = port.positional_encoding(x, 2)[0]
+    want = torch.cat([x[0], torch.sin(x[0]), torch.sin(x[0] + torch.pi * 0.5), torch.sin(2 * x[0]), torch.sin(2 * x[0] + torch.pi * 0.5)])
+    assert torch.allclose(e, want, atol=1e-7)
+
+
+def test_composite_background_and_clamp():
+    depths = port.sample_depths(torch.tensor([0.0, 2.0]), torch.tensor([1.0, 3.0]), 4)
+    colors = torch.zeros(2, 4, 3)
+    sigma = torch.full((2, 4), -80.0)
+    sigma[1, 1] = 50.0
+    colors[1, 1] = torch.tensor([0.2, 0.4, 0.6])
+    rgb, depth, w = port.composite(colors, sigma, depths, torch.tensor([[0., 0, 1], [0, 0, 2]]), white_back=False)
+    assert torch.all(rgb[0] == -1) and float(depth[0]) == 3.0           # empty ray: nan -> inf -> clamp to max(depths)
+    assert float(w[1].sum()) == pytest.approx(1.0, abs=1e-6)
+    assert torch.allclose(rgb[1], torch.tensor([0.2, 0.4, 0.6]) * 2 - 1, atol=1e-5)
