@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Bench of the SHERF render hot path (ImportanceRenderer.forward + NeRFDecoder + ray marcher) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path over N_gpus novel views of BASELINE.json configs[1]
+(512x512 RenderPeople-shape, 64 samples/ray, one subject / one observation), synthetic seeded inputs.
+With N > 1 (torchrun, one rank per GPU) every view's rays are dealt to all ranks in interleaved tiles and each
+view ends with ONE all-gather of the rendered tiles (weak scaling: N views on N GPUs).
+Prints one JSON line (see README / DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, S = 512, 512, 64
+WORKLOAD = 'configs[1]: 512x512 RenderPeople-shape, 64 samples/ray, 1 subject novel view'
+FLOP_PER_POINT = 429_248          # MLP MACs x 2 per decoded (surviving) sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='sherf_b200', choices=['sherf_b200', 'reference'])
+    ap.add_argument('--precision', default='fp32')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tensor_tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'src': 'measured (MEASURED_PEAKS.json, bf16 sustained)'}
+    return {'hbm_gbs': 6650.0, 'tensor_tflops': 1400.0, 'src': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_views(n_views, model):
+    """One subject / observation, n_views novel target cameras.  Returns (base scene, list of per-view ray dicts), CPU tensors."""
+    from sherf_b200 import synthetic as SY
+    base = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0, cam_azim_deg=25.0), model)
+    views = [{k: base[k] for k in ('ray_origins', 'ray_directions', 'near', 'far')}]
+    for v in range(1, n_views):
+        sc = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0, cam_azim_deg=25.0 + 360.0 * v / n_views), model)
+        views.append({k: sc[k] for k in ('ray_origins', 'ray_directions', 'near', 'far')})
+    return base, views
+
+
+def cpu_port_rate(model, n_rays_target, threads):
+    """Times oracle/port.py (CPU restatement of the reference path) on a strided subset of the same 512x512x64 rays."""
+    import torch
+    from sherf_b200 import synthetic as SY
+    from sherf_b200.triplane import hot_path_modules
+    from oracle import port
+    torch.set_num_threads(threads)
+    base = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0), model)
+    stride = max(1, int(round((H * W / n_rays_target) ** 0.5)))
+    idx = (torch.arange(0, H, stride)[:, None] * W + torch.arange(0, W, stride)[None, :]).reshape(-1)
+    sub = dict(base)
+    for k in ('ray_origins', 'ray_directions', 'near', 'far'):
+        sub[k] = base[k][:, idx].contiguous()
+    ren, dec = hot_path_modules(model, seed=0, dense_sigma=True)
+    wts = port.hot_path_state_dict(ren, dec)
+    mt = SY.smpl_model_to_torch(model)
+    t0 = time.perf_counter()
+    port.render_forward(wts, mt, sub)
+    dt = time.perf_counter() - t0
+    n = idx.numel() * S
+    return n / dt, dt, f'{idx.numel()} rays (every {stride}th pixel in x and y of the 512x512 view) x {S} samples = {n} ray-samples'
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference is Python + pytorch3d/spconv (absent) and cannot be
+    installed or shipped to the GPU box, so this times oracle/port.py (kind 'port') with all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from sherf_b200 import synthetic as SY
+    model = SY.make_smpl_model(0)
+    threads = os.cpu_count() or 1
+    budget = 150.0 / max(1, args.steps + args.warmup)                 # seconds per step
+    n_rays = int(min(16384, max(256, budget * 9000 / S)))             # ~9e3 ray-samples/s/8 cores measured in the build container
+    rates, last = [], None
+    for i in range(args.warmup + args.steps):
+        rate, dt, sample = cpu_port_rate(model, n_rays, threads)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+        last = sample
+    value = sum(r for r, _ in rates) / len(rates)
+    line = {
+        'impl': 'reference', 'metric': 'ray_samples_per_sec', 'value': value, 'unit': 'ray-samples/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(d for _, d in rates) / len(rates), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'step': 'bounded sample: ' + last},
+        'cpu_baseline': {'value': value, 'unit': 'ray-samples/s', 'cores': threads, 'kind': 'port', 'sample': last},
+        'e2e': {'value': value, 'unit': 'ray-samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from sherf_b200 import synthetic as SY, _lib
+    from sherf_b200 import dist as sd
+    from sherf_b200.triplane import hot_path_modules
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    lib.sherf_set_profiling(1)
+
+    model = SY.make_smpl_model(0)
+    base, views = make_views(world, model)
+    ren, dec = hot_path_modules(model, seed=0, mlp_precision=args.precision, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+
+    def mv(x):
+        if torch.is_tensor(x):
+            return x.to(dev)
+        if isinstance(x, dict):
+            return {k: mv(v) for k, v in x.items()}
+        if isinstance(x, list):
+            return [mv(v) for v in x]
+        return x
+    scene = {k: mv(v) for k, v in base.items()}
+    N = H * W
+    clamp = [sd.depth_range(v['near'], v['far'], S) for v in views]
+    # this rank's tiles of every view (device resident for `value`, pinned host copies for `e2e`)
+    idx = sd.shard_indices(N, rank, world)
+    shard_host = [{k: v[k][:, idx].contiguous().pin_memory() for k in v} for v in views]
+    shard_dev = [{k: t.to(dev) for k, t in sh.items()} for sh in shard_host]
+    pose_host = {k: base['input_data'][k] for k in ('vertices',)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                   # > 126 MB L2
+
+    def render(sh, v):
+        return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+                   dec, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'], scene['input_data'], scene['rendering_options'],
+                   depth_clamp=clamp[v] if world > 1 else None)
+
+    stage_ms = [0.0] * 5
+    launches = [0]
+    points = [0]
+
+    def step_device():
+        outs = []
+        for v in range(world):
+            rgb, depth, acc = render(shard_dev[v], v)
+            for s_ in range(5):
+                stage_ms[s_] += lib.sherf_last_stage_ms(s_)
+            launches[0] += ren.last_launches
+            points[0] += ren.last_num_points
+            local = torch.cat([rgb[0], depth[0], acc[0]], -1)
+            outs.append(sd.all_gather_tiles(local, N) if world > 1 else local)
+        return outs
+
+    def step_e2e(host_out):
+        for v in range(world):
+            sh = {k: t.to(dev, non_blocking=True) for k, t in shard_host[v].items()}
+            scene['input_data']['vertices'] = pose_host['vertices'].to(dev, non_blocking=True)
+            rgb, depth, acc = render(sh, v)
+            local = torch.cat([rgb[0], depth[0], acc[0]], -1)
+            full = sd.all_gather_tiles(local, N) if world > 1 else local
+            host_out[v].copy_(full, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps (outside the events)."""
+        tot = 0.0
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / k
+
+    for _ in range(args.warmup):
+        step_device()
+    stage_ms[:] = [0.0] * 5
+    launches[0] = 0
+    points[0] = 0
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    ms = timed(step_device, args.steps)
+    barrier()
+    clk = clocks.stop()
+    host_out = [torch.empty(N, 5).pin_memory() for _ in range(world)]
+    for _ in range(args.warmup):
+        step_e2e(host_out)
+    barrier()
+    ms_e2e = timed(lambda: step_e2e(host_out), args.steps)
+    barrier()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        samples_per_step = world * N * S
+        calls = args.steps * world
+        mlp_ms = stage_ms[3] / calls
+        p_call = points[0] / calls
+        ach_tflops = p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        h2d = sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * world
+        line = {
+            'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'views_per_step': world,
+                       'parallelism': f'ray-tiles x{world}, one all-gather of rendered tiles per view' if world > 1 else 'single GPU',
+                       'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if world > 1 else p_call,
+                       'l2': 'explicit 256 MiB flush between timed steps (outside the events); working set > 126 MB L2'},
+            'e2e': {'value': samples_per_step / (ms_e2e * 1e-3), 'unit': 'ray-samples/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': world * N * 5 * 4, 'ms_per_step': ms_e2e,
+                    'note': 'per step: pinned-host rays/near/far/vertices -> device, ImportanceRenderer.forward via the C ABI, rendered rgb+depth+acc -> pinned host'},
+            'gpu_launches': launches[0],
+            'clocks': clk,
+            'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite'])},
+            'roofline': {'bound': 'tensor', 'kernel': 'MLP stage (k_sgemm fp32 CUDA-core layers)' if args.precision == 'fp32' else 'MLP stage',
+                         'achieved': ach_tflops, 'peak': pk['tensor_tflops'], 'unit': 'TFLOP/s', 'frac': ach_tflops / pk['tensor_tflops'],
+                         'traffic': None, 'peak_source': pk['src'],
+                         'algorithmic': f'{FLOP_PER_POINT} FLOP per surviving sample x {p_call:.0f} samples per call'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, dt, sample = cpu_port_rate(model, 4096, threads)
+            line['cpu_baseline'] = {'value': rate, 'unit': 'ray-samples/s', 'cores': threads, 'kind': 'port', 'sample': sample, 'seconds': dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

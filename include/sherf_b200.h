@@ -153,7 +153,8 @@ typedef struct SherfDebug {
   float* point_tok;      /* [P,64] tokens 0,1 after the transformer (renderer.py:427) */
   float* point_sigma;    /* [P] (triplane.py:302) */
   float* point_rgb;      /* [P,3] (triplane.py:314) */
-  int64_t max_points;    /* capacity of the point-indexed arrays */
+  int64_t max_points;    /* capacity (in points) of the point-indexed arrays except point_feat */
+  int64_t max_feat_points; /* capacity (in points) of point_feat */
 } SherfDebug;
 
 /* Bytes of scratch sherf_render_forward needs for an (N rays, S samples) call on `scene` (only its

@@ -112,7 +112,7 @@ def positional_encoding(x, num_freqs):
     phases[1::2] = torch.pi * 0.5
     phases = phases.view(1, -1, 1)
     e = x.unsqueeze(1).repeat(1, num_freqs * 2, 1)
-    e = torch.sin(torch.addcmul(phases, e, freqs)).view(x.shape[0], -1)
+    e = torch.sin(torch.addcmul(phases, e, freqs)).view(x.shape[0], num_freqs * 2 * x.shape[1])
     return torch.cat((x, e), dim=-1)
 
 
@@ -264,6 +264,12 @@ def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool =
     st = cull(scene, S)
     N = st['depths'].shape[0]
     sel = st['mask'].nonzero()[:, 0]                                              # row-major [N,S] order
+    if sel.numel() == 0:                                                          # nothing within 5 cm: every sample keeps sigma = -80
+        rgb, depth, wts = composite(torch.zeros(N, S, 3), torch.full((N, S), -80.0), st['depths'], scene['ray_directions'][0],
+                                    opts['white_back'])
+        out = (rgb[None], depth[None], wts.sum(1, keepdim=True)[None])
+        st.update({'sel': sel})
+        return out + (st,) if return_stages else out
     q, vdir, vid = st['q'][sel], st['vdir'][sel], st['id1'][sel]
     can, cdir = warp_to_canonical(smpl, idt['params'], idt['t_params'], q, vdir, vid)
     world, id3 = warp_to_observation(smpl, idt['obs_params'], idt['t_params'], idt['t_vertices'][0], can)

@@ -62,7 +62,7 @@ class SherfOut(C.Structure):
 class SherfDebug(C.Structure):
     _fields_ = [('sample_vid', c_int_p), ('point_sample', c_int_p), ('point_vid3', c_int_p), ('point_can', c_float_p),
                 ('point_cdir', c_float_p), ('point_uv', c_float_p), ('point_feat', c_float_p), ('point_tok', c_float_p),
-                ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64)]
+                ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64), ('max_feat_points', C.c_int64)]
 
 
 EXPORTS = ['sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',

@@ -223,6 +223,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     G.dbg_vid3 = dbg ? dbg->point_vid3 : nullptr; G.dbg_can = dbg ? dbg->point_can : nullptr;
     G.dbg_cdir = dbg ? dbg->point_cdir : nullptr; G.dbg_uv = dbg ? dbg->point_uv : nullptr;
     G.dbg_feat = dbg ? dbg->point_feat : nullptr; G.dbg_max = dbg ? dbg->max_points : 0;
+    G.dbg_feat_max = dbg ? dbg->max_feat_points : 0;
     RC(run_point_gather(G, st));
     if (single) tm.mark(3);
     RC(run_mlp_fp32(*weights, pw, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
 
     float* comb = P.comb + (size_t)lp * 288;
     float* f3 = P.f3raw + (size_t)lp * 192;
-    float* dbgf = (P.dbg_feat && gp < P.dbg_max) ? P.dbg_feat + (size_t)gp * 384 : nullptr;
+    float* dbgf = (P.dbg_feat && gp < P.dbg_feat_max) ? P.dbg_feat + (size_t)gp * 384 : nullptr;
 
     // ---- pixel-aligned 2-D features (renderer.py:331-340) ----
     {

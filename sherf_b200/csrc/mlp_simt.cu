@@ -247,23 +247,23 @@ __global__ void k_decoder_inputs(const float* __restrict__ geo, const float* __r
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= np) return;
   const float g = lane < 8 ? geo[(size_t)p * 8 + lane] : 0.f;
+  // broadcast the six geometry values with full-warp shuffles BEFORE any divergent code
+  float gv[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) gv[k] = __shfl_sync(0xffffffffu, g, k);
   // positional encodings: out[0:3] = v ; out[3 + m*3 + c] = sin(phase(m) + v[c] * 2^(m/2))       renderer.py:900-916
+  auto pe = [&](int e, float v0, float v1, float v2) -> float {
+    if (e < 3) return e == 0 ? v0 : (e == 1 ? v1 : v2);
+    const int m = (e - 3) / 3, c = (e - 3) - 3 * m;
+    const float vv = c == 0 ? v0 : (c == 1 ? v1 : v2);
+    return sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(vv, (float)(1 << (m >> 1)))));
+  };
   for (int e = lane; e < 39; e += 32) {
-    float val;
-    if (e < 3) val = __shfl_sync(__activemask(), g, e);
-    else { const int m = (e - 3) / 3, c = (e - 3) % 3; const float vv = __shfl_sync(__activemask(), g, c);
-           val = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(vv, (float)(1 << (m >> 1))))); }
+    const float val = pe(e, gv[0], gv[1], gv[2]);
     x[(size_t)p * 72 + e] = val;
     hb[(size_t)p * 200 + e] = val;
   }
-  if (lane < 27) {
-    const int e = lane;
-    float val;
-    if (e < 3) val = __shfl_sync(__activemask(), g, 3 + e);
-    else { const int m = (e - 3) / 3, c = (e - 3) % 3; const float vv = __shfl_sync(__activemask(), g, 3 + c);
-           val = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(vv, (float)(1 << (m >> 1))))); }
-    fv[(size_t)p * 188 + 128 + e] = val;
-  }
+  if (lane < 27) fv[(size_t)p * 188 + 128 + lane] = pe(lane, gv[3], gv[4], gv[5]);
   const float t0 = tok3[(size_t)(p * 3 + 0) * 32 + lane], t1 = tok3[(size_t)(p * 3 + 1) * 32 + lane];
   x[(size_t)p * 72 + 39 + lane] = t0;
   hb[(size_t)p * 200 + 39 + lane] = t0;

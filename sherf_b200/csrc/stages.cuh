@@ -25,7 +25,7 @@ struct GatherParams {
   float* f3raw;     // [np][192]
   float* geo;       // [np][8]: can xyz, cdir xyz, 0, 0
   // optional taps (absolute point index)
-  int* dbg_vid3; float *dbg_can, *dbg_cdir, *dbg_uv, *dbg_feat; int64_t dbg_max;
+  int* dbg_vid3; float *dbg_can, *dbg_cdir, *dbg_uv, *dbg_feat; int64_t dbg_max, dbg_feat_max;
 };
 
 int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);

@@ -328,7 +328,8 @@ class ImportanceRenderer(nn.Module):
                 bufs['point_feat'] = torch.empty(cap_feat, 384, device=device)
                 for k, v in bufs.items():
                     setattr(d, k, _ptr(v))
-                d.max_points = cap_feat
+                d.max_points = NS
+                d.max_feat_points = cap_feat
                 dbg_p = C.byref(d)
                 self._dbg_keep = (d, bufs)
 
@@ -341,9 +342,9 @@ class ImportanceRenderer(nn.Module):
             self.last_num_points = int(npts.value)
             self.last_launches = int(lib.sherf_last_launch_count())
             if debug is not None:
-                Pn = min(self.last_num_points, self._dbg_keep[0].max_points)
+                Pn = self.last_num_points
                 for k, v in self._dbg_keep[1].items():
-                    debug[k] = v if k == 'sample_vid' else v[:Pn]
+                    debug[k] = v if k == 'sample_vid' else v[:min(Pn, v.shape[0])]
                 debug['num_points'] = self.last_num_points
             # the C side only borrowed the pointers for the call; outputs are ordered after it on the same stream
             del keep

@@ -88,7 +88,7 @@ def test_against_reference_golden(case, smpl_model):
 
 EDGE_SPECS = [
     S.SceneSpec(H=16, W=16, samples=2, seed=11),                       # minimum samples per ray
-    S.SceneSpec(H=1, W=1, samples=64, seed=12),                        # a single ray
+    S.SceneSpec(H=2, W=2, samples=64, seed=12),                        # four rays (the half-res feature map is 1x1)
     S.SceneSpec(H=24, W=40, samples=33, seed=13, random_global_R=True),
     S.SceneSpec(H=20, W=20, samples=16, seed=14, cam_dist=40.0),       # body covers < 1 pixel: (almost) nothing survives
 ]
