@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace sherf {
 
@@ -89,20 +90,31 @@ static int chunk_cap(int N, int S) {
   return (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
 }
 
+// Device-time accounting per stage: every begin()/end() pair is a CUDA-event span on the launching stream; spans of
+// the same stage are summed (the point stages run once per chunk).
 struct StageTimer {
-  cudaEvent_t ev[6]; bool on; cudaStream_t st;
-  int init(bool enable, cudaStream_t s) {
-    on = enable; st = s;
-    if (!on) return 0;
-    for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return -1;
-    return 0;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans; bool on = false; cudaStream_t st = nullptr; int open = -1;
+  void init(bool enable, cudaStream_t s) { on = enable; st = s; }
+  void begin(int stage) {
+    if (!on) return;
+    Span sp; sp.stage = stage;
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+    spans.push_back(sp);
   }
-  void mark(int i) { if (on) cudaEventRecord(ev[i], st); }
+  void end() { if (on && !spans.empty()) cudaEventRecord(spans.back().b, st); }
   void finish() {
     if (!on) return;
-    cudaEventSynchronize(ev[5]);
-    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&g_stage_ms[i], ev[i], ev[i + 1]);
-    for (auto& e : ev) cudaEventDestroy(e);
+    for (int i = 0; i < 8; ++i) g_stage_ms[i] = 0.f;
+    if (!spans.empty()) cudaEventSynchronize(spans.back().b);
+    for (auto& sp : spans) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, sp.a, sp.b);
+      g_stage_ms[sp.stage] += ms;
+      cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    spans.clear();
   }
 };
 
@@ -165,10 +177,10 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   if (!scratch || need > a.size) { set_error("scratch arena too small: need %zu bytes, have %zu", need, scratch_bytes); return SHERF_E_SCRATCH; }
   g_launches.n = 0;
   StageTimer tm;
-  if (tm.init(g_profiling != 0, st)) { set_error("cudaEventCreate failed"); return SHERF_E_CUDA; }
+  tm.init(g_profiling != 0, st);
 
   // ---- stage 0: per-frame tables, channels-last feature copies, packed weights ----
-  tm.mark(0);
+  tm.begin(0);
   RC(run_prologue(*smpl, *frame, *rays, *opts, L.ft, st));
   RC(run_to_channels_last(scene->planes, L.planes_cl, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, st));
   RC(run_to_channels_last(scene->planes + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w,
@@ -184,11 +196,14 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   PackedWeights pw;
   RC(run_pack_weights(*weights, L.packed_w, pw, st));
 
+  tm.end();
+
   // ---- stage 1: cull + ordered compaction ----
-  tm.mark(1);
+  tm.begin(1);
   int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
   RC(run_cull(*rays, L.ft, sample_vid, L.ray_count, L.ray_start, L.total, L.point_sample, L.point_vid, st));
   int64_t P = 0;
+  tm.end();
   SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   SHERF_CUDA_OK(cudaStreamSynchronize(st));
   if (n_points_out) *n_points_out = P;
@@ -199,13 +214,6 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   // ---- stages 2+3 per chunk of surviving points: warp + gather, then fusion / transformer / decoder ----
   ChunkBuffers cb;
   carve_chunk_buffers(L.chunk, chunk_cap(N, S), cb);
-  float ms_gather = 0.f, ms_mlp = 0.f;
-  (void)ms_gather; (void)ms_mlp;
-  tm.mark(2);
-  // NOTE: with profiling on and more than one chunk, stage 2 / 3 times are attributed by running all gathers of a
-  // chunk then its MLP; the event split below is exact only for single-chunk frames, so profiling reports 2+3 summed
-  // into stage 3 when P > chunk capacity.
-  const bool single = P <= cb.cap;
   for (int64_t p0 = 0; p0 < P; p0 += cb.cap) {
     const int np = (int)((P - p0 < cb.cap) ? (P - p0) : cb.cap);
     GatherParams G;
@@ -224,11 +232,13 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     G.dbg_cdir = dbg ? dbg->point_cdir : nullptr; G.dbg_uv = dbg ? dbg->point_uv : nullptr;
     G.dbg_feat = dbg ? dbg->point_feat : nullptr; G.dbg_max = dbg ? dbg->max_points : 0;
     G.dbg_feat_max = dbg ? dbg->max_feat_points : 0;
+    tm.begin(2);
     RC(run_point_gather(G, st));
-    if (single) tm.mark(3);
+    tm.end();
+    tm.begin(3);
     RC(run_mlp_fp32(*weights, pw, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
+    tm.end();
   }
-  if (!single || P == 0) tm.mark(3);
   if (dbg && P > 0) {
     const size_t cnt = (size_t)(P < dbg->max_points ? P : dbg->max_points);
     if (dbg->point_sigma) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sigma, L.sigma, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, st));
@@ -236,9 +246,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   }
 
   // ---- stage 4: composite ----
-  tm.mark(4);
+  tm.begin(4);
   RC(run_composite(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, *out, st));
-  tm.mark(5);
+  tm.end();
   tm.finish();
   g_last_launches = g_launches.n;
   return SHERF_OK;
