@@ -181,6 +181,13 @@ SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* 
 SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */, float* max_out /* host */,
                       void* scratch, size_t scratch_bytes, void* stream);
 
+/* Diagnostic: one linear layer Y[M,N] = act(A[M,K] * W[N,K]^T + bias) on the selected arithmetic (SHERF_MLP_*), the building
+ * block of the fusion / transformer / decoder stack (nn.Linear / Conv1d(k=1) call sites renderer.py:350,424 and
+ * triplane.py:296-312).  act: 0 none, 1 ReLU, 2 GELU(erf).  Tensor-core modes need N % 16 == 0; N, K <= 256.
+ * lda % 4 == 0, A 16-byte aligned.  scratch >= 2.5 MB. */
+SHERF_API int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy,
+                                 int M, int N, int K, int act, void* scratch, size_t scratch_bytes, void* stream);
+
 SHERF_API const char* sherf_last_error(void);
 SHERF_API int sherf_abi_version(void);
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */

@@ -42,6 +42,7 @@ struct Layout {
   int* point_sample; int* point_vid;
   float* sigma; float* rgb;
   float* packed_w;
+  float* canon_w;
   float* chunk;
   float* lbs_joints; float* lbs_pf;
 };
@@ -80,6 +81,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.sigma = a.take<float>(NS);
   L.rgb = a.take<float>(NS * 3);
   L.packed_w = a.take<float>(packed_weight_floats());
+  L.canon_w = a.take<float>(canonical_weight_floats());
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
   return a.off;
@@ -150,7 +152,7 @@ static int validate(const SherfSmplModel* smpl, const SherfFrame* fr, const Sher
               sc->feat_ch, sc->vol_ch[0], sc->vol_ch[1], sc->vol_ch[2]);
     return SHERF_E_UNSUPPORTED;
   }
-  if (opts->mlp_precision != SHERF_MLP_FP32) { set_error("mlp_precision %d not built in this library", opts->mlp_precision); return SHERF_E_UNSUPPORTED; }
+  if (opts->mlp_precision < SHERF_MLP_FP32 || opts->mlp_precision > SHERF_MLP_TF32X3) { set_error("unknown mlp_precision %d", opts->mlp_precision); return SHERF_E_UNSUPPORTED; }
   if (!rays->origins || !rays->dirs || !rays->near_ || !rays->far_ || !out->rgb || !out->depth || !out->acc || !sc->planes ||
       !sc->obs_img || !sc->obs_feat || !sc->vol[0] || !sc->vol[1] || !sc->vol[2] || !smpl->weights || !smpl->posedirs) {
     set_error("null device pointer in arguments");
@@ -194,7 +196,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     RC(run_to_channels_last(scene->vol[l], L.vol_cl[l], scene->vol_ch[l],
                             (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2], st));
   PackedWeights pw;
-  RC(run_pack_weights(*weights, L.packed_w, pw, st));
+  CanonWeights cw;
+  if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, st));
+  else RC(run_pack_canonical(*weights, L.canon_w, cw, st));
 
   tm.end();
 
@@ -236,7 +240,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     RC(run_point_gather(G, st));
     tm.end();
     tm.begin(3);
-    RC(run_mlp_fp32(*weights, pw, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
+    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
     tm.end();
   }
   if (dbg && P > 0) {
@@ -250,6 +254,22 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   RC(run_composite(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, *out, st));
   tm.end();
   tm.finish();
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
+int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N,
+                       int K, int act, void* scratch, size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!A || !W || !Y || !scratch || M <= 0 || N <= 0 || K <= 0 || N > 256 || K > 256) { set_error("bad argument"); return SHERF_E_INVALID; }
+  const size_t need = (size_t)8 * 272 * 272 * sizeof(float) + 512;
+  if (scratch_bytes < need) { set_error("scratch arena too small: need %zu bytes", need); return SHERF_E_SCRATCH; }
+  char* b = (char*)scratch;
+  const size_t mis = ((size_t)b) & 255;
+  if (mis) b += 256 - mis;
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches.n = 0;
+  RC(run_debug_linear(precision, A, lda, W, bias, Y, ldy, M, N, K, act, (float*)b, st));
   g_last_launches = g_launches.n;
   return SHERF_OK;
 }

@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(256) k_sgemm(const GemmArgs g) {
   }
 }
 
-static int launch_gemm(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
-                       const float* Res = nullptr, int ldr = 0, int ygroup = 0, int ygstride = 0) {
+int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
+                       const float* Res, int ldr, int ygroup, int ygstride) {
   GemmArgs g;
   g.A = A; g.lda = lda; g.Wt = L.wt; g.np = L.np; g.bias = L.bias; g.Y = Y; g.ldy = ldy; g.ygroup = ygroup; g.ygstride = ygstride;
   g.Res = Res; g.ldr = ldr; g.act = act; g.M = M; g.N = L.N; g.K = L.K;
@@ -332,40 +332,46 @@ void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb) {
 
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
-int run_mlp_fp32(const SherfWeights& w, const PackedWeights& pw, const ChunkBuffers& cb, int np, int64_t p0,
-                 float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st) {
+int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const ChunkBuffers& cb, int np,
+            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st) {
   if (np <= 0) return SHERF_OK;
   const int rows3 = 3 * np;
+  // one linear layer on the selected arithmetic
+  auto launch_gemm = [&](const PackedLayer& P, const CanonLayer& C, const float* A, int lda, float* Y, int ldy, int M, int act,
+                         cudaStream_t s, const float* Res = nullptr, int ldr = 0, int yg = 0, int ygs = 0) -> int {
+    if (prec == SHERF_MLP_FP32) return launch_simt_linear(P, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
+    return launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, C, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
+  };
   // conv1d_projection 192 -> 96, written as the third 32-wide slice of each token's 96-wide fusion input (renderer.py:350,423)
-  RC(launch_gemm(pw.proj, cb.f3raw, 192, cb.comb + 64, 288, np, ACT_NONE, st, nullptr, 0, 32, 96));
+  RC(launch_gemm(pw.proj, cw.proj, cb.f3raw, 192, cb.comb + 64, 288, np, ACT_NONE, st, nullptr, 0, 32, 96));
   // conv1d_reprojection 96 -> 32 per token (renderer.py:424): rows = (point, token)
-  RC(launch_gemm(pw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
+  RC(launch_gemm(pw.reproj, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
   // transformer layer (renderer.py:980-993): x = attn(LN(x)) + x ; x = ff(LN(x)) + x
   k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok, w.ln1_w, w.ln1_b, cb.ln, rows3);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
+  RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
   k_attention3<<<ceil_div(rows3, 128), 128, 0, st>>>(cb.qkv, cb.att, np);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.attn_out, cb.att, 48, cb.tok2, 32, rows3, ACT_NONE, st, cb.tok, 32));
+  RC(launch_gemm(pw.attn_out, cw.attn_out, cb.att, 48, cb.tok2, 32, rows3, ACT_NONE, st, cb.tok, 32));
   k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok2, w.ln2_w, w.ln2_b, cb.ln, rows3);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.ff1, cb.ln, 32, cb.ffh, 32, rows3, ACT_GELU, st));
-  RC(launch_gemm(pw.ff2, cb.ffh, 32, cb.tok3, 32, rows3, ACT_NONE, st, cb.tok2, 32));
+  RC(launch_gemm(pw.ff1, cw.ff1, cb.ln, 32, cb.ffh, 32, rows3, ACT_GELU, st));
+  RC(launch_gemm(pw.ff2, cw.ff2, cb.ffh, 32, cb.tok3, 32, rows3, ACT_NONE, st, cb.tok2, 32));
   // decoder (triplane.py:285-316)
   k_decoder_inputs<<<ceil_div(np, 8), 256, 0, st>>>(cb.geo, cb.tok3, cb.x, cb.hb, cb.fv, np, dbg_tok, p0, dbg_max);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[2], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[3], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[4], cb.h2, 128, cb.hb + 71, 200, np, ACT_RELU, st));       // skip: h = cat([x, h])  (i == 4)
-  RC(launch_gemm(pw.pts[5], cb.hb, 200, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[6], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[7], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[0], cw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[1], cw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[2], cw.pts[2], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[3], cw.pts[3], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[4], cw.pts[4], cb.h2, 128, cb.hb + 71, 200, np, ACT_RELU, st));       // skip: h = cat([x, h])  (i == 4)
+  RC(launch_gemm(pw.pts[5], cw.pts[5], cb.hb, 200, cb.h1, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[6], cw.pts[6], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+  RC(launch_gemm(pw.pts[7], cw.pts[7], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
   k_alpha<<<ceil_div(np, 8), 256, 0, st>>>(cb.h1, 128, w.alpha_w, w.alpha_b, sigma_out + p0, np);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.feature, cb.h1, 128, cb.fv, 188, np, ACT_NONE, st));
-  RC(launch_gemm(pw.views, cb.fv, 188, cb.vh, 64, np, ACT_RELU, st));
+  RC(launch_gemm(pw.feature, cw.feature, cb.h1, 128, cb.fv, 188, np, ACT_NONE, st));
+  RC(launch_gemm(pw.views, cw.views, cb.fv, 188, cb.vh, 64, np, ACT_RELU, st));
   k_rgb_head<<<ceil_div(np, 8), 256, 0, st>>>(cb.vh, w.rgb_w, w.rgb_b, rgb_out + p0 * 3, np);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;

@@ -1,0 +1,253 @@
+// Tensor-core linear layer for the fusion / transformer / decoder stack: Y = act(A * W^T + b) (+ residual) with
+// tcgen05.mma kind::tf32 (fp32 accumulate in TMEM).  Two arithmetic modes:
+//   TF32   : one MMA per k-step on round-to-nearest TF32 operands                       (fast, ~1e-3 relative)
+//   TF32X3 : error-compensated split  a = a_hi + a_lo, w = w_hi + w_lo;  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi
+//            = fp32-grade products on the tensor cores (the dropped a_lo*w_lo term is 2^-22 relative)
+// Operands sit in shared memory in the K-major no-swizzle canonical layout (8-row x 16-byte core matrices):
+//   A tile  [128 rows x 64 k]  : element (r,k) at (k/4)*2048 + r*16 + (k%4)*4 bytes   (LBO 2048, SBO 128)
+//   W chunk [Np rows  x 64 k]  : element (n,k) at (k/4)*Np*16 + n*16 + (k%4)*4 bytes  (LBO Np*16, SBO 128)
+// Weights are pre-packed in exactly that order in global memory, so a chunk is one contiguous copy.
+#include "common.cuh"
+#include "stages.cuh"
+#include "umma.cuh"
+
+namespace sherf {
+
+constexpr int kKC = 64;                 // k per shared-memory chunk (16 core-matrix columns)
+
+// W[N][K] (PyTorch) -> canonical chunks, hi (tf32-rounded) and lo (tf32-rounded residual) parts.
+struct CanonJob { const float* w; float* hi; float* lo; int N, K, Np, nchunks; };
+struct CanonJobs { CanonJob j[17]; int n; };
+
+__global__ void k_pack_canonical(const CanonJobs jobs) {
+  const CanonJob jb = jobs.j[blockIdx.y];
+  const int total = jb.nchunks * 16 * jb.Np * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 3, n = (i >> 2) % jb.Np, kg = (i >> 2) / jb.Np;     // kg counts core-matrix columns over all chunks
+    const int k = kg * 4 + e;
+    const float v = (n < jb.N && k < jb.K) ? jb.w[(size_t)n * jb.K + k] : 0.f;
+    const float h = umma::to_tf32(v);
+    jb.hi[i] = h;
+    jb.lo[i] = umma::to_tf32(v - h);
+  }
+}
+
+struct UmmaArgs {
+  const float* A; int lda;
+  const float* Whi; const float* Wlo; int Np; int nchunks;
+  const float* bias;
+  float* Y; int ldy; int ygroup, ygstride;
+  const float* Res; int ldr;
+  int act;
+  int M, N, K;
+  uint32_t tmem_cols;
+};
+
+template <int PREC>
+__global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128;
+  const uint32_t a_bytes = 16 * 2048, w_bytes = 16u * g.Np * 16u;
+  float* A_hi = reinterpret_cast<float*>(smem);
+  float* W_hi = reinterpret_cast<float*>(smem + a_bytes);
+  float* A_lo = reinterpret_cast<float*>(smem + a_bytes + w_bytes);
+  float* W_lo = reinterpret_cast<float*>(smem + 2 * a_bytes + w_bytes);
+
+  if (tid == 0) { umma::mbar_init(&mma_bar, 1); umma::fence_mbar_init(); }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, g.tmem_cols);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int r = tid & 127, half = tid >> 7;
+  const bool row_ok = (m0 + r) < g.M;
+  const float* arow = g.A + (size_t)(m0 + r) * g.lda;
+  const uint32_t idesc = umma::make_idesc_tf32(128, g.Np);
+  uint32_t parity = 0;
+  for (int c = 0; c < g.nchunks; ++c) {
+    const int k0 = c * kKC;
+    const int used_kg = min(16, (g.K - k0 + 3) / 4);            // core-matrix columns that hold real k
+    const int mma_steps = (used_kg + 1) / 2;                    // MMA K = 8 = two core-matrix columns
+    if (c > 0) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }
+    // ---- A chunk: global (row-major fp32) -> registers -> tf32 hi/lo -> canonical smem ----
+    for (int kg = half; kg < 2 * mma_steps; kg += 2) {
+      const int k = k0 + kg * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok && k < g.K) {
+        if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(arow + k);
+        else { v.x = arow[k]; if (k + 1 < g.K) v.y = arow[k + 1]; if (k + 2 < g.K) v.z = arow[k + 2]; }
+      }
+      float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
+      *reinterpret_cast<float4*>(A_hi + kg * 512 + r * 4) = h;
+      if (PREC == 3) {
+        float4 l = make_float4(umma::to_tf32(v.x - h.x), umma::to_tf32(v.y - h.y), umma::to_tf32(v.z - h.z), umma::to_tf32(v.w - h.w));
+        *reinterpret_cast<float4*>(A_lo + kg * 512 + r * 4) = l;
+      }
+    }
+    // ---- W chunk: contiguous pre-packed canonical block (only the core-matrix columns the MMAs will read) ----
+    {
+      const int n4 = 2 * mma_steps * g.Np;                      // float4 count
+      const float4* src_hi = reinterpret_cast<const float4*>(g.Whi) + (size_t)c * 16 * g.Np;
+      float4* dst_hi = reinterpret_cast<float4*>(W_hi);
+      for (int i = tid; i < n4; i += 256) dst_hi[i] = __ldg(src_hi + i);
+      if (PREC == 3) {
+        const float4* src_lo = reinterpret_cast<const float4*>(g.Wlo) + (size_t)c * 16 * g.Np;
+        float4* dst_lo = reinterpret_cast<float4*>(W_lo);
+        for (int i = tid; i < n4; i += 256) dst_lo[i] = __ldg(src_lo + i);
+      }
+    }
+    umma::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after_sync();
+      const uint32_t a_hi_s = umma::smem_u32(A_hi), w_hi_s = umma::smem_u32(W_hi);
+      const uint32_t a_lo_s = umma::smem_u32(A_lo), w_lo_s = umma::smem_u32(W_lo);
+      const uint32_t w_lbo = (uint32_t)g.Np * 16u;
+      for (int s = 0; s < mma_steps; ++s) {
+        const uint32_t a_off = (uint32_t)s * 4096u, w_off = (uint32_t)s * 2u * w_lbo;
+        const uint64_t ah = umma::make_smem_desc(a_hi_s + a_off, 2048u, 128u);
+        const uint64_t wh = umma::make_smem_desc(w_hi_s + w_off, w_lbo, 128u);
+        const uint32_t first = (c == 0 && s == 0) ? 0u : 1u;
+        if (PREC == 3) {
+          const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, 2048u, 128u);
+          const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
+          umma::mma_tf32_ss(tmem_base, al, wh, idesc, first);          // small terms first
+          umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
+          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, 1u);
+        } else {
+          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, first);
+        }
+      }
+      umma::mma_commit(&mma_bar);
+    }
+  }
+  umma::mbar_wait(&mma_bar, parity);
+  umma::tc_fence_after_sync();
+
+  // ---- epilogue: TMEM -> registers -> bias / activation / residual -> global.  Warp w reads lane quarter (w & 3). ----
+  {
+    const int q = warp & 3, hsel = warp >> 2;
+    const int m = m0 + 32 * q + lane;
+    const int ncol_half = g.Np / 2;
+    for (int j = 0; j < ncol_half / 8; ++j) {
+      const int c0 = hsel * ncol_half + 8 * j;
+      uint32_t v[8];
+      umma::tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      umma::tmem_ld_wait();
+      if (m < g.M) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = c0 + i;
+          if (n < g.N) {
+            float x = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n) : 0.f);
+            if (g.act == 1) x = fmaxf(x, 0.f);
+            else if (g.act == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+            if (g.Res) x += g.Res[(size_t)m * g.ldr + n];
+            const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
+            g.Y[(size_t)m * g.ldy + col] = x;
+          }
+        }
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+static inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+
+size_t canonical_weight_floats() {
+  const int dims[16][2] = {{96, 192}, {32, 96}, {144, 32}, {32, 48}, {32, 32}, {32, 32}, {128, 71}, {128, 128}, {128, 128},
+                           {128, 128}, {128, 128}, {128, 199}, {128, 128}, {128, 128}, {128, 128}, {64, 187}};
+  size_t t = 0;
+  for (int i = 0; i < 16; ++i) t += (size_t)round_up_i(dims[i][1], kKC) * round_up_i(dims[i][0], 16);
+  return 2 * t;      // hi + lo
+}
+
+int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cudaStream_t st) {
+  CanonJobs jobs;
+  jobs.n = 0;
+  float* cur = base;
+  auto add = [&](CanonLayer& L, const float* W, const float* b, int N, int K) {
+    L.N = N; L.K = K; L.Np = round_up_i(N, 16); L.nchunks = round_up_i(K, kKC) / kKC; L.bias = b;
+    const size_t sz = (size_t)L.nchunks * kKC * L.Np;
+    L.hi = cur; L.lo = cur + sz;
+    CanonJob& j = jobs.j[jobs.n++];
+    j.w = W; j.hi = cur; j.lo = cur + sz; j.N = N; j.K = K; j.Np = L.Np; j.nchunks = L.nchunks;
+    cur += 2 * sz;
+  };
+  add(cw.proj, w.proj_w, w.proj_b, 96, 192);
+  add(cw.reproj, w.reproj_w, w.reproj_b, 32, 96);
+  add(cw.qkv, w.qkv_w, nullptr, 144, 32);
+  add(cw.attn_out, w.attn_out_w, w.attn_out_b, 32, 48);
+  add(cw.ff1, w.ff1_w, w.ff1_b, 32, 32);
+  add(cw.ff2, w.ff2_w, w.ff2_b, 32, 32);
+  const int ptsK[8] = {71, 128, 128, 128, 128, 199, 128, 128};
+  for (int i = 0; i < 8; ++i) add(cw.pts[i], w.pts_w[i], w.pts_b[i], 128, ptsK[i]);
+  add(cw.feature, w.feature_w, w.feature_b, 128, 128);
+  add(cw.views, w.views_w, w.views_b, 64, 187);
+  k_pack_canonical<<<dim3(16, jobs.n), 256, 0, st>>>(jobs);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
+                       const float* Res, int ldr, int ygroup, int ygstride) {
+  UmmaArgs g;
+  g.A = A; g.lda = lda; g.Whi = L.hi; g.Wlo = L.lo; g.Np = L.Np; g.nchunks = L.nchunks; g.bias = L.bias;
+  g.Y = Y; g.ldy = ldy; g.ygroup = ygroup; g.ygstride = ygstride; g.Res = Res; g.ldr = ldr; g.act = act;
+  g.M = M; g.N = L.N; g.K = L.K;
+  uint32_t cols = 32;
+  while ((int)cols < L.Np) cols <<= 1;
+  g.tmem_cols = cols;
+  const size_t smem = (size_t)(prec == 3 ? 2 : 1) * (16 * 2048 + 16 * (size_t)L.Np * 16);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  if (prec == 3) k_umma_linear<3><<<ceil_div(M, 128), 256, smem, st>>>(g);
+  else k_umma_linear<1><<<ceil_div(M, 128), 256, smem, st>>>(g);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+
+// Single linear layer with freshly packed weights (tests / diagnostics).  wscratch: >= 8*272*272 floats.
+__global__ void k_pack_plain(const float* __restrict__ w, float* __restrict__ wt, int N, int K, int kp, int np) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kp * np; i += gridDim.x * blockDim.x) {
+    const int k = i / np, n = i - k * np;
+    wt[i] = (k < K && n < N) ? w[(size_t)n * K + k] : 0.f;
+  }
+}
+
+int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                     int act, float* wscratch, cudaStream_t st) {
+  if (prec == SHERF_MLP_FP32) {
+    PackedLayer L;
+    L.K = K; L.N = N; L.kp = round_up_i(K, 16); L.np = round_up_i(N, 32); L.wt = wscratch; L.bias = bias;
+    k_pack_plain<<<64, 256, 0, st>>>(W, wscratch, N, K, L.kp, L.np);
+    SHERF_LAUNCH_CHECK();
+    return launch_simt_linear(L, A, lda, Y, ldy, M, act, st, nullptr, 0, 0, 0);
+  }
+  if (N % 16 != 0) { set_error("tensor-core linear needs N %% 16 == 0 (got %d)", N); return SHERF_E_INVALID; }
+  CanonJobs jobs;
+  CanonLayer L;
+  L.N = N; L.K = K; L.Np = round_up_i(N, 16); L.nchunks = round_up_i(K, kKC) / kKC; L.bias = bias;
+  const size_t sz = (size_t)L.nchunks * kKC * L.Np;
+  L.hi = wscratch; L.lo = wscratch + sz;
+  jobs.n = 1;
+  jobs.j[0].w = W; jobs.j[0].hi = wscratch; jobs.j[0].lo = wscratch + sz; jobs.j[0].N = N; jobs.j[0].K = K; jobs.j[0].Np = L.Np;
+  jobs.j[0].nchunks = L.nchunks;
+  k_pack_canonical<<<dim3(16, 1), 256, 0, st>>>(jobs);
+  SHERF_LAUNCH_CHECK();
+  return launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, L, A, lda, Y, ldy, M, act, st, nullptr, 0, 0, 0);
+}
+
+}  // namespace sherf

@@ -63,9 +63,23 @@ struct PackedWeights {
 size_t packed_weight_floats();
 int run_pack_weights(const SherfWeights& w, float* base, PackedWeights& pw, cudaStream_t st);
 
-// The fusion / transformer / decoder stack on one chunk (fp32 CUDA-core path).  renderer.py:350,423-432; triplane.py:285-316
-int run_mlp_fp32(const SherfWeights& w, const PackedWeights& pw, const ChunkBuffers& cb, int np, int64_t p0,
-                 float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st);
+// Canonical (UMMA K-major, no-swizzle) tf32 weights for the tensor-core path: hi part and error-compensation lo part.
+struct CanonLayer { const float* hi; const float* lo; const float* bias; int N, K, Np, nchunks; };
+struct CanonWeights { CanonLayer proj, reproj, qkv, attn_out, ff1, ff2, pts[8], feature, views; };
+size_t canonical_weight_floats();
+int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cudaStream_t st);
+int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
+                       const float* Res, int ldr, int ygroup, int ygstride);
+int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
+                       const float* Res, int ldr, int ygroup, int ygstride);
+
+// The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
+// prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 (tcgen05 tensor cores)
+int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const ChunkBuffers& cb, int np,
+            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st);
+
+int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                     int act, float* wscratch, cudaStream_t st);
 
 int run_composite(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample,
                   const float* sigma, const float* rgb, const float* noise, int white_back, const SherfOut& out, cudaStream_t st);

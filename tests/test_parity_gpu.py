@@ -30,12 +30,13 @@ def linf(a, b):
     return float((a.double() - b.double()).abs().max()) if a.numel() else 0.0
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('case', GOLDEN_CASES)
-def test_against_reference_golden(case, smpl_model):
+def test_against_reference_golden(case, precision, smpl_model):
     g = load_golden(case)
     dev = torch.device('cuda:0')
     scene = scene_to(S.make_scene(g['scene_spec'], smpl_model), dev)
-    ren, dec = modules_from_weights(g['weights'], smpl_model)
+    ren, dec = modules_from_weights(g['weights'], smpl_model, mlp_precision=precision)
     ren, dec = ren.to(dev), dec.to(dev)
     dbg = {}
     rgb, depth, acc = run_cuda(ren, dec, scene, debug=dbg)
@@ -72,7 +73,7 @@ def test_against_reference_golden(case, smpl_model):
     e_acc = linf(acc.cpu()[0], torch.from_numpy(g['acc']))
     span = float((scene['far'] - scene['near']).abs().max())
     e_depth = linf(depth.cpu()[0], torch.from_numpy(g['depth'])) / span
-    print(f'\n[{case}] P={dbg["num_points"]} id3-match={rate3:.5f} can={e_can:.2e} dir={e_dir:.2e} uv={e_uv:.2e} f2d={e_f2d:.2e} '
+    print(f'\n[{case} {precision}] P={dbg["num_points"]} id3-match={rate3:.5f} can={e_can:.2e} dir={e_dir:.2e} uv={e_uv:.2e} f2d={e_f2d:.2e} '
           f'f3d={e_f3:.2e} tok={e_tok:.2e} sigma={e_sig:.2e} rgb_pt={e_rgbp:.2e} | rgb={e_rgb:.2e} acc={e_acc:.2e} depth/span={e_depth:.2e}')
     assert rate3 >= 0.999
     assert e_can <= 5e-6 and e_dir <= 5e-6
@@ -84,6 +85,21 @@ def test_against_reference_golden(case, smpl_model):
     assert float(bad) <= 1e-3, f'{float(bad):.4%} of rays exceed 1e-4 (max {e_rgb:.2e})'
     assert e_acc <= 1e-4 or float(bad) > 0
     assert e_depth <= 1e-3
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES[:2])
+def test_tf32_single_pass_quality(case, smpl_model):
+    """Plain TF32 tensor-core MLP: not parity-grade (10-bit mantissa); reported as PSNR against the reference image."""
+    g = load_golden(case)
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(g['scene_spec'], smpl_model), dev)
+    ren, dec = modules_from_weights(g['weights'], smpl_model, mlp_precision='tf32')
+    rgb, depth, acc = run_cuda(ren.to(dev), dec.to(dev), scene)
+    ref = torch.from_numpy(g['rgb'])
+    mse = float(((rgb.cpu()[0] - ref) ** 2).mean())
+    psnr = 10 * np.log10(4.0 / max(mse, 1e-20))              # images span (-1, 1): peak-to-peak 2
+    print(f'\n[{case} tf32] rgb Linf={linf(rgb.cpu()[0], ref):.2e} acc Linf={linf(acc.cpu()[0], torch.from_numpy(g["acc"])):.2e} PSNR={psnr:.1f} dB')
+    assert psnr > 45.0
 
 
 EDGE_SPECS = [
