@@ -38,7 +38,7 @@ struct Arena {
 struct Layout {
   FrameTables ft;
   float* planes_cl; float* feat_cl; float* vol_cl[3];
-  int* sample_vid; int* ray_count; int* ray_start; int64_t* total;
+  int* sample_vid; int* ray_count; int* block_sums; int* ray_start; int64_t* total;
   int* point_sample; int* point_vid;
   float* sigma; float* rgb;
   float* packed_w;
@@ -74,6 +74,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
     L.vol_cl[l] = a.take<float>((size_t)sc.vol_ch[l] * sc.vol_dim[l][0] * sc.vol_dim[l][1] * sc.vol_dim[l][2]);
   L.sample_vid = a.take<int>(NS);
   L.ray_count = a.take<int>(N);
+  L.block_sums = a.take<int>((size_t)N / 1024 + 2);
   L.ray_start = a.take<int>((size_t)N + 1);
   L.total = a.take<int64_t>(1);
   L.point_sample = a.take<int>(NS);
@@ -205,7 +206,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   // ---- stage 1: cull + ordered compaction ----
   tm.begin(1);
   int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
-  RC(run_cull(*rays, L.ft, sample_vid, L.ray_count, L.ray_start, L.total, L.point_sample, L.point_vid, st));
+  RC(run_cull(*rays, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
   int64_t P = 0;
   tm.end();
   SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

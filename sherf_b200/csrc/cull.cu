@@ -70,29 +70,56 @@ __global__ void __launch_bounds__(256) k_cull(const float* __restrict__ origins,
   if (lane == 0) ray_count[n] = count;
 }
 
-// Exclusive scan of ray_count[0..N) -> ray_start[0..N]; single block, thread-serial spans.
-__global__ void __launch_bounds__(1024) k_scan_rays(const int* __restrict__ cnt, int N, int* __restrict__ start, int64_t* total_out) {
-  __shared__ int spart[1024];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int span = (N + nt - 1) / nt;
-  const int b = tid * span, e = min(b + span, N);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += cnt[i];
-  spart[tid] = s;
+// Exclusive scan of ray_count[0..N) -> ray_start[0..N] in two coalesced passes over 1024-ray blocks.
+__global__ void __launch_bounds__(1024) k_ray_block_sums(const int* __restrict__ cnt, int N, int* __restrict__ bsum) {
+  __shared__ int red[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int v = i < N ? cnt[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int x = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = x;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_rays(const int* __restrict__ cnt, const int* __restrict__ bsum, int nblocks, int N,
+                                                    int* __restrict__ start, int64_t* total_out) {
+  __shared__ int red[32];
+  __shared__ int warp_off[32];
+  __shared__ int block_off;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // offset of this block = sum of the preceding block sums (nblocks is small: N / 1024)
+  int pre = 0;
+  for (int b = tid; b < (int)blockIdx.x; b += 1024) pre += bsum[b];
+  for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+  if (lane == 0) red[w] = pre;
   __syncthreads();
   if (tid < 32) {
-    int carry = 0;
-    for (int base = 0; base < nt; base += 32) {
-      int x = spart[base + tid], y = x;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, y, o); if (tid >= o) y += t; }
-      spart[base + tid] = carry + y - x;
-      carry += __shfl_sync(0xffffffffu, y, 31);
-    }
-    if (tid == 0) { start[N] = carry; *total_out = carry; }
+    int x = red[tid];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (tid == 0) block_off = x;
   }
   __syncthreads();
-  int run = spart[tid];
-  for (int i = b; i < e; ++i) { start[i] = run; run += cnt[i]; }
+  const int i = blockIdx.x * 1024 + tid;
+  const int v = i < N ? cnt[i] : 0;
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  __syncthreads();
+  if (lane == 31) red[w] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    const int x = red[tid];
+    int y = x;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, y, o); if (tid >= o) y += t; }
+    warp_off[tid] = y - x;
+  }
+  __syncthreads();
+  const int excl = block_off + warp_off[w] + incl - v;
+  if (i < N) start[i] = excl;
+  if (i == N - 1) { start[N] = excl + v; *total_out = excl + v; }
 }
 
 // Ordered scatter: point_sample[pos] = n*S+i, point_vid[pos] = vid, pos ascending in row-major sample order.
@@ -116,14 +143,17 @@ __global__ void __launch_bounds__(256) k_compact(const int* __restrict__ sample_
   }
 }
 
-int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* ray_start, int64_t* total_dev,
+int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums, int* ray_start, int64_t* total_dev,
              int* point_sample, int* point_vid, cudaStream_t st) {
   const int N = rays.n_rays, S = rays.n_samples;
   const float thr = (float)(0.05 * 0.05);        // `distance < 0.05 ** 2` compares in fp32 (renderer.py:318-319)
   k_cull<<<ceil_div(N, 8), 256, 0, st>>>(rays.origins, rays.dirs, rays.near_, rays.far_, N, S, ft.fc, ft.g1_cell_start, ft.g1_verts,
                                          ft.g1_occ, thr, sample_vid, ray_count);
   SHERF_LAUNCH_CHECK();
-  k_scan_rays<<<1, 1024, 0, st>>>(ray_count, N, ray_start, total_dev);
+  const int nb = ceil_div(N, 1024);
+  k_ray_block_sums<<<nb, 1024, 0, st>>>(ray_count, N, block_sums);
+  SHERF_LAUNCH_CHECK();
+  k_scan_rays<<<nb, 1024, 0, st>>>(ray_count, block_sums, nb, N, ray_start, total_dev);
   SHERF_LAUNCH_CHECK();
   k_compact<<<ceil_div(N, 8), 256, 0, st>>>(sample_vid, ray_start, N, S, point_sample, point_vid);
   SHERF_LAUNCH_CHECK();

@@ -205,38 +205,54 @@ __global__ void k_layernorm32(const float* __restrict__ x, const float* __restri
 }
 
 // 3-token, 3-head (dim 16) attention; thread per (point, head).  qkv rows = p*3+tok, [q(48)|k(48)|v(48)]   renderer.py:966-977
-__global__ void k_attention3(const float* __restrict__ qkv, float* __restrict__ att, int np) {
+__global__ void __launch_bounds__(128) k_attention3(const float* __restrict__ qkv, float* __restrict__ att, int np) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= np * 3) return;
   const int p = idx / 3, h = idx - p * 3;
-  float q[3][16], k[3][16], v[3][16];
+  const float* base = qkv + (size_t)p * 3 * 144 + h * 16;
+  float dots[3][3];
+  {
+    float q[3][16], k[3][16];
 #pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const float4* row = reinterpret_cast<const float4*>(qkv + (size_t)(p * 3 + t) * 144);
+    for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 a = row[(h * 16) / 4 + d4], b = row[(48 + h * 16) / 4 + d4], c = row[(96 + h * 16) / 4 + d4];
-      q[t][d4 * 4] = a.x; q[t][d4 * 4 + 1] = a.y; q[t][d4 * 4 + 2] = a.z; q[t][d4 * 4 + 3] = a.w;
-      k[t][d4 * 4] = b.x; k[t][d4 * 4 + 1] = b.y; k[t][d4 * 4 + 2] = b.z; k[t][d4 * 4 + 3] = b.w;
-      v[t][d4 * 4] = c.x; v[t][d4 * 4 + 1] = c.y; v[t][d4 * 4 + 2] = c.z; v[t][d4 * 4 + 3] = c.w;
-    }
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 a = *reinterpret_cast<const float4*>(base + t * 144 + d4 * 4);
+        const float4 b = *reinterpret_cast<const float4*>(base + t * 144 + 48 + d4 * 4);
+        q[t][d4 * 4] = a.x; q[t][d4 * 4 + 1] = a.y; q[t][d4 * 4 + 2] = a.z; q[t][d4 * 4 + 3] = a.w;
+        k[t][d4 * 4] = b.x; k[t][d4 * 4 + 1] = b.y; k[t][d4 * 4 + 2] = b.z; k[t][d4 * 4 + 3] = b.w;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) s += q[i][d] * k[j][d];
+        dots[i][j] = s * 0.25f;                             // dim_head ** -0.5
+      }
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    float dots[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) s += q[i][d] * k[j][d];
-      dots[j] = s * 0.25f;                                  // dim_head ** -0.5
-    }
-    const float mx = fmaxf(dots[0], fmaxf(dots[1], dots[2]));
-    const float e0 = expf(dots[0] - mx), e1 = expf(dots[1] - mx), e2 = expf(dots[2] - mx);
+    const float mx = fmaxf(dots[i][0], fmaxf(dots[i][1], dots[i][2]));
+    const float e0 = expf(dots[i][0] - mx), e1 = expf(dots[i][1] - mx), e2 = expf(dots[i][2] - mx);
     const float inv = 1.f / (e0 + e1 + e2);
-    float* o = att + (size_t)(p * 3 + i) * 48 + h * 16;
+    dots[i][0] = e0 * inv; dots[i][1] = e1 * inv; dots[i][2] = e2 * inv;
+  }
 #pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = (e0 * inv) * v[0][d] + (e1 * inv) * v[1][d] + (e2 * inv) * v[2][d];
+  for (int d4 = 0; d4 < 4; ++d4) {
+    const float4 v0 = *reinterpret_cast<const float4*>(base + 0 * 144 + 96 + d4 * 4);
+    const float4 v1 = *reinterpret_cast<const float4*>(base + 1 * 144 + 96 + d4 * 4);
+    const float4 v2 = *reinterpret_cast<const float4*>(base + 2 * 144 + 96 + d4 * 4);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float4 o;
+      o.x = dots[i][0] * v0.x + dots[i][1] * v1.x + dots[i][2] * v2.x;
+      o.y = dots[i][0] * v0.y + dots[i][1] * v1.y + dots[i][2] * v2.y;
+      o.z = dots[i][0] * v0.z + dots[i][1] * v1.z + dots[i][2] * v2.z;
+      o.w = dots[i][0] * v0.w + dots[i][1] * v1.w + dots[i][2] * v2.w;
+      *reinterpret_cast<float4*>(att + (size_t)(p * 3 + i) * 48 + h * 16 + d4 * 4) = o;
+    }
   }
 }
 

@@ -43,18 +43,26 @@ struct UmmaArgs {
   uint32_t tmem_cols;
 };
 
+// Padded K-direction stride of the A operand: 2048 B of data + 16 B so that the 8 lanes of a quarter-warp that write 8
+// different core-matrix columns of one row land in 8 different 16-byte bank groups (conflict-free STS.128).
+constexpr uint32_t kALbo = 2064;
+
 template <int PREC>
 __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
+  constexpr int KC = (PREC == 3) ? 32 : 64;          // k per shared-memory chunk
+  constexpr int NKG = KC / 4;                        // core-matrix columns per chunk
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128;
-  const uint32_t a_bytes = 16 * 2048, w_bytes = 16u * g.Np * 16u;
+  const uint32_t a_bytes = NKG * kALbo, w_bytes = (uint32_t)NKG * g.Np * 16u;
   float* A_hi = reinterpret_cast<float*>(smem);
   float* W_hi = reinterpret_cast<float*>(smem + a_bytes);
   float* A_lo = reinterpret_cast<float*>(smem + a_bytes + w_bytes);
   float* W_lo = reinterpret_cast<float*>(smem + 2 * a_bytes + w_bytes);
+  float* stage = reinterpret_cast<float*>(smem);     // output tile, aliases the operands once all MMAs have completed
+  const int sstride = g.Np + 4;
 
   if (tid == 0) { umma::mbar_init(&mma_bar, 1); umma::fence_mbar_init(); }
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, g.tmem_cols);
@@ -63,39 +71,47 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
 
-  const int r = tid & 127, half = tid >> 7;
-  const bool row_ok = (m0 + r) < g.M;
-  const float* arow = g.A + (size_t)(m0 + r) * g.lda;
   const uint32_t idesc = umma::make_idesc_tf32(128, g.Np);
+  const int nchunks = (g.K + KC - 1) / KC;
+  const int kgl = tid & 7, rsub = tid >> 3;          // loader mapping: 8 lanes = 8 consecutive float4 of one row (128 B)
   uint32_t parity = 0;
-  for (int c = 0; c < g.nchunks; ++c) {
-    const int k0 = c * kKC;
-    const int used_kg = min(16, (g.K - k0 + 3) / 4);            // core-matrix columns that hold real k
-    const int mma_steps = (used_kg + 1) / 2;                    // MMA K = 8 = two core-matrix columns
+  for (int c = 0; c < nchunks; ++c) {
+    const int k0 = c * KC;
+    const int used_kg = min(NKG, (g.K - k0 + 3) / 4);
+    const int mma_steps = (used_kg + 1) / 2;         // MMA K = 8 = two core-matrix columns
     if (c > 0) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }
-    // ---- A chunk: global (row-major fp32) -> registers -> tf32 hi/lo -> canonical smem ----
-    for (int kg = half; kg < 2 * mma_steps; kg += 2) {
-      const int k = k0 + kg * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_ok && k < g.K) {
-        if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(arow + k);
-        else { v.x = arow[k]; if (k + 1 < g.K) v.y = arow[k + 1]; if (k + 2 < g.K) v.z = arow[k + 2]; }
-      }
-      float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
-      *reinterpret_cast<float4*>(A_hi + kg * 512 + r * 4) = h;
-      if (PREC == 3) {
-        float4 l = make_float4(umma::to_tf32(v.x - h.x), umma::to_tf32(v.y - h.y), umma::to_tf32(v.z - h.z), umma::to_tf32(v.w - h.w));
-        *reinterpret_cast<float4*>(A_lo + kg * 512 + r * 4) = l;
+    // ---- A chunk: coalesced global reads -> tf32 hi (/lo) -> canonical smem ----
+    for (int kgb = 0; kgb < 2 * mma_steps; kgb += 8) {
+      const int kg = kgb + kgl;
+      if (kg < 2 * mma_steps) {
+        const int k = k0 + kg * 4;
+#pragma unroll
+        for (int rb = 0; rb < 128; rb += 32) {
+          const int row = rb + rsub;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + row < g.M && k < g.K) {
+            const float* ap = g.A + (size_t)(m0 + row) * g.lda + k;
+            if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(ap);
+            else { v.x = ap[0]; if (k + 1 < g.K) v.y = ap[1]; if (k + 2 < g.K) v.z = ap[2]; }
+          }
+          const float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
+          *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_hi) + kg * kALbo + row * 16) = h;
+          if (PREC == 3) {
+            const float4 l = make_float4(umma::to_tf32(v.x - h.x), umma::to_tf32(v.y - h.y), umma::to_tf32(v.z - h.z),
+                                         umma::to_tf32(v.w - h.w));
+            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_lo) + kg * kALbo + row * 16) = l;
+          }
+        }
       }
     }
     // ---- W chunk: contiguous pre-packed canonical block (only the core-matrix columns the MMAs will read) ----
     {
-      const int n4 = 2 * mma_steps * g.Np;                      // float4 count
-      const float4* src_hi = reinterpret_cast<const float4*>(g.Whi) + (size_t)c * 16 * g.Np;
+      const int n4 = 2 * mma_steps * g.Np;
+      const float4* src_hi = reinterpret_cast<const float4*>(g.Whi) + (size_t)c * NKG * g.Np;
       float4* dst_hi = reinterpret_cast<float4*>(W_hi);
       for (int i = tid; i < n4; i += 256) dst_hi[i] = __ldg(src_hi + i);
       if (PREC == 3) {
-        const float4* src_lo = reinterpret_cast<const float4*>(g.Wlo) + (size_t)c * 16 * g.Np;
+        const float4* src_lo = reinterpret_cast<const float4*>(g.Wlo) + (size_t)c * NKG * g.Np;
         float4* dst_lo = reinterpret_cast<float4*>(W_lo);
         for (int i = tid; i < n4; i += 256) dst_lo[i] = __ldg(src_lo + i);
       }
@@ -108,12 +124,12 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
       const uint32_t a_lo_s = umma::smem_u32(A_lo), w_lo_s = umma::smem_u32(W_lo);
       const uint32_t w_lbo = (uint32_t)g.Np * 16u;
       for (int s = 0; s < mma_steps; ++s) {
-        const uint32_t a_off = (uint32_t)s * 4096u, w_off = (uint32_t)s * 2u * w_lbo;
-        const uint64_t ah = umma::make_smem_desc(a_hi_s + a_off, 2048u, 128u);
+        const uint32_t a_off = (uint32_t)s * 2u * kALbo, w_off = (uint32_t)s * 2u * w_lbo;
+        const uint64_t ah = umma::make_smem_desc(a_hi_s + a_off, kALbo, 128u);
         const uint64_t wh = umma::make_smem_desc(w_hi_s + w_off, w_lbo, 128u);
         const uint32_t first = (c == 0 && s == 0) ? 0u : 1u;
         if (PREC == 3) {
-          const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, 2048u, 128u);
+          const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, kALbo, 128u);
           const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
           umma::mma_tf32_ss(tmem_base, al, wh, idesc, first);          // small terms first
           umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
@@ -128,35 +144,52 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   umma::mbar_wait(&mma_bar, parity);
   umma::tc_fence_after_sync();
 
-  // ---- epilogue: TMEM -> registers -> bias / activation / residual -> global.  Warp w reads lane quarter (w & 3). ----
+  // ---- epilogue 1: TMEM -> registers -> bias / activation -> staging tile in smem.  Warp w owns lane quarter (w & 3). ----
   {
     const int q = warp & 3, hsel = warp >> 2;
-    const int m = m0 + 32 * q + lane;
+    const int row = 32 * q + lane;
     const int ncol_half = g.Np / 2;
     for (int j = 0; j < ncol_half / 8; ++j) {
       const int c0 = hsel * ncol_half + 8 * j;
       uint32_t v[8];
       umma::tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
       umma::tmem_ld_wait();
-      if (m < g.M) {
+      float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = c0 + i;
-          if (n < g.N) {
-            float x = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n) : 0.f);
-            if (g.act == 1) x = fmaxf(x, 0.f);
-            else if (g.act == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-            if (g.Res) x += g.Res[(size_t)m * g.ldr + n];
-            const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
-            g.Y[(size_t)m * g.ldy + col] = x;
-          }
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int n = c0 + i;
+        x[i] = __uint_as_float(v[i]) + ((g.bias && n < g.N) ? __ldg(g.bias + n) : 0.f);
+        if (g.act == 1) x[i] = fmaxf(x[i], 0.f);
+        else if (g.act == 2) x[i] = 0.5f * x[i] * (1.f + erff(x[i] * 0.70710678118654752440f));
       }
+      float4* dst = reinterpret_cast<float4*>(stage + (size_t)row * sstride + c0);
+      dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+      dst[1] = make_float4(x[4], x[5], x[6], x[7]);
     }
   }
   umma::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem_base, g.tmem_cols);
+  // ---- epilogue 2: coalesced copy-out (+ residual), consecutive lanes -> consecutive columns of a row ----
+  {
+    const int n4 = g.N / 4;                          // every layer of the stack has N % 16 == 0
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0) && (g.ldy % 4 == 0) && (g.ygroup % 4 == 0) && (g.ygstride % 4 == 0);
+    for (int idx = tid; idx < 128 * n4; idx += 256) {
+      const int row = idx / n4, c4 = idx - row * n4;
+      const int m = m0 + row;
+      if (m >= g.M) continue;
+      const int n = c4 * 4;
+      float4 v = *reinterpret_cast<const float4*>(stage + (size_t)row * sstride + n);
+      if (g.Res) {
+        const float4 rr = *reinterpret_cast<const float4*>(g.Res + (size_t)m * g.ldr + n);
+        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+      }
+      const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
+      float* yp = g.Y + (size_t)m * g.ldy + col;
+      if (vec_ok) *reinterpret_cast<float4*>(yp) = v;
+      else { yp[0] = v.x; yp[1] = v.y; yp[2] = v.z; yp[3] = v.w; }
+    }
+  }
 }
 
 static inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
@@ -205,7 +238,10 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
   uint32_t cols = 32;
   while ((int)cols < L.Np) cols <<= 1;
   g.tmem_cols = cols;
-  const size_t smem = (size_t)(prec == 3 ? 2 : 1) * (16 * 2048 + 16 * (size_t)L.Np * 16);
+  const size_t nkg = prec == 3 ? 8 : 16;
+  const size_t operands = (size_t)(prec == 3 ? 2 : 1) * (nkg * kALbo + nkg * (size_t)L.Np * 16);
+  const size_t staging = (size_t)128 * (L.Np + 4) * sizeof(float);
+  const size_t smem = operands > staging ? operands : staging;
   static bool attr_done = false;
   if (!attr_done) {
     SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

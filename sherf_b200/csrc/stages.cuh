@@ -30,7 +30,7 @@ struct GatherParams {
 
 int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
 int run_point_gather(const GatherParams& P, cudaStream_t st);
-int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* ray_start, int64_t* total_dev,
+int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums, int* ray_start, int64_t* total_dev,
              int* point_sample, int* point_vid, cudaStream_t st);
 
 // Row-major activation buffers of one chunk of `cap` points (fp32).
