@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 namespace sherf {
@@ -43,6 +44,7 @@ struct Layout {
   float* sigma; float* rgb;
   float* packed_w;
   float* canon_w;
+  unsigned char* fused_blob; float* fused_bias;
   float* chunk;
   float* lbs_joints; float* lbs_pf;
 };
@@ -83,6 +85,8 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.rgb = a.take<float>(NS * 3);
   L.packed_w = a.take<float>(packed_weight_floats());
   L.canon_w = a.take<float>(canonical_weight_floats());
+  L.fused_blob = a.take<unsigned char>(fused_blob_bytes());
+  L.fused_bias = a.take<float>(9 * 144);
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
   return a.off;
@@ -200,6 +204,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   CanonWeights cw;
   if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, st));
   else RC(run_pack_canonical(*weights, L.canon_w, cw, st));
+  FusedPlan fplan;
+  const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
+  if (use_fused) RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
 
   tm.end();
 
@@ -241,7 +248,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     RC(run_point_gather(G, st));
     tm.end();
     tm.begin(3);
-    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
+    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
     tm.end();
   }
   if (dbg && P > 0) {

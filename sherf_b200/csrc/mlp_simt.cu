@@ -348,7 +348,7 @@ void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb) {
 
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
-int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const ChunkBuffers& cb, int np,
+int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st) {
   if (np <= 0) return SHERF_OK;
   const int rows3 = 3 * np;
@@ -376,17 +376,22 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   // decoder (triplane.py:285-316)
   k_decoder_inputs<<<ceil_div(np, 8), 256, 0, st>>>(cb.geo, cb.tok3, cb.x, cb.hb, cb.fv, np, dbg_tok, p0, dbg_max);
   SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.pts[0], cw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[1], cw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[2], cw.pts[2], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[3], cw.pts[3], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[4], cw.pts[4], cb.h2, 128, cb.hb + 71, 200, np, ACT_RELU, st));       // skip: h = cat([x, h])  (i == 4)
-  RC(launch_gemm(pw.pts[5], cw.pts[5], cb.hb, 200, cb.h1, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[6], cw.pts[6], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
-  RC(launch_gemm(pw.pts[7], cw.pts[7], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
-  k_alpha<<<ceil_div(np, 8), 256, 0, st>>>(cb.h1, 128, w.alpha_w, w.alpha_b, sigma_out + p0, np);
-  SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.feature, cw.feature, cb.h1, 128, cb.fv, 188, np, ACT_NONE, st));
+  if (fused && prec != SHERF_MLP_FP32) {
+    // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip
+    RC(run_decoder_fused_plan(prec == SHERF_MLP_TF32X3 ? 3 : 1, *fused, cb.x, 72, cb.fv, 188, sigma_out + p0, np, st));
+  } else {
+    RC(launch_gemm(pw.pts[0], cw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[1], cw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[2], cw.pts[2], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[3], cw.pts[3], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[4], cw.pts[4], cb.h2, 128, cb.hb + 71, 200, np, ACT_RELU, st));       // skip: h = cat([x, h])  (i == 4)
+    RC(launch_gemm(pw.pts[5], cw.pts[5], cb.hb, 200, cb.h1, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[6], cw.pts[6], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));
+    RC(launch_gemm(pw.pts[7], cw.pts[7], cb.h2, 128, cb.h1, 128, np, ACT_RELU, st));
+    k_alpha<<<ceil_div(np, 8), 256, 0, st>>>(cb.h1, 128, w.alpha_w, w.alpha_b, sigma_out + p0, np);
+    SHERF_LAUNCH_CHECK();
+    RC(launch_gemm(pw.feature, cw.feature, cb.h1, 128, cb.fv, 188, np, ACT_NONE, st));
+  }
   RC(launch_gemm(pw.views, cw.views, cb.fv, 188, cb.vh, 64, np, ACT_RELU, st));
   k_rgb_head<<<ceil_div(np, 8), 256, 0, st>>>(cb.vh, w.rgb_w, w.rgb_b, rgb_out + p0 * 3, np);
   SHERF_LAUNCH_CHECK();

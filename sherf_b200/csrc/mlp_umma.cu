@@ -49,7 +49,7 @@ constexpr uint32_t kALbo = 2064;
 
 template <int PREC>
 __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
-  constexpr int KC = (PREC == 3) ? 32 : 64;          // k per shared-memory chunk
+  constexpr int KC = (PREC >= 3) ? 32 : 64;          // k per shared-memory chunk
   constexpr int NKG = KC / 4;                        // core-matrix columns per chunk
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mma_bar;
@@ -104,13 +104,30 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         }
       }
     }
+    if (PREC == 4) {
+      // experiment: A_lo goes to TENSOR MEMORY (lane = row, column = k), written row-per-thread with tcgen05.st
+      const int q = warp & 3, hsel = warp >> 2;
+      const int row = 32 * q + lane;
+      for (int kg2 = hsel * (NKG / 2); kg2 < (hsel + 1) * (NKG / 2); kg2 += 2) {
+        uint32_t lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = k0 + kg2 * 4 + e;
+          const float x = (m0 + row < g.M && k < g.K) ? g.A[(size_t)(m0 + row) * g.lda + k] : 0.f;
+          lo[e] = __float_as_uint(umma::to_tf32(x - umma::to_tf32(x)));
+        }
+        umma::tmem_st8(tmem_base + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)(kg2 * 4), lo);
+      }
+      umma::tmem_st_wait();
+      umma::tc_fence_before_sync();
+    }
     // ---- W chunk: contiguous pre-packed canonical block (only the core-matrix columns the MMAs will read) ----
     {
       const int n4 = 2 * mma_steps * g.Np;
       const float4* src_hi = reinterpret_cast<const float4*>(g.Whi) + (size_t)c * NKG * g.Np;
       float4* dst_hi = reinterpret_cast<float4*>(W_hi);
       for (int i = tid; i < n4; i += 256) dst_hi[i] = __ldg(src_hi + i);
-      if (PREC == 3) {
+      if (PREC >= 3) {
         const float4* src_lo = reinterpret_cast<const float4*>(g.Wlo) + (size_t)c * NKG * g.Np;
         float4* dst_lo = reinterpret_cast<float4*>(W_lo);
         for (int i = tid; i < n4; i += 256) dst_lo[i] = __ldg(src_lo + i);
@@ -132,6 +149,11 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
           const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, kALbo, 128u);
           const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
           umma::mma_tf32_ss(tmem_base, al, wh, idesc, first);          // small terms first
+          umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
+          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, 1u);
+        } else if (PREC == 4) {
+          const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
+          umma::mma_tf32_ts(tmem_base, tmem_base + 256u + (uint32_t)(s * 8), wh, idesc, first);
           umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
           umma::mma_tf32_ss(tmem_base, ah, wh, idesc, 1u);
         } else {
@@ -238,8 +260,8 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
   uint32_t cols = 32;
   while ((int)cols < L.Np) cols <<= 1;
   g.tmem_cols = cols;
-  const size_t nkg = prec == 3 ? 8 : 16;
-  const size_t operands = (size_t)(prec == 3 ? 2 : 1) * (nkg * kALbo + nkg * (size_t)L.Np * 16);
+  const size_t nkg = prec >= 3 ? 8 : 16;
+  const size_t operands = (size_t)(prec >= 3 ? 2 : 1) * (nkg * kALbo + nkg * (size_t)L.Np * 16);
   const size_t staging = (size_t)128 * (L.Np + 4) * sizeof(float);
   const size_t smem = operands > staging ? operands : staging;
   static bool attr_done = false;
@@ -248,7 +270,12 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
     SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  if (prec == 3) k_umma_linear<3><<<ceil_div(M, 128), 256, smem, st>>>(g);
+  if (prec == 4) {
+    static bool a4 = false;
+    if (!a4) { SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a4 = true; }
+    g.tmem_cols = 512;
+    k_umma_linear<4><<<ceil_div(M, 128), 256, smem, st>>>(g);
+  } else if (prec == 3) k_umma_linear<3><<<ceil_div(M, 128), 256, smem, st>>>(g);
   else k_umma_linear<1><<<ceil_div(M, 128), 256, smem, st>>>(g);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
@@ -283,7 +310,7 @@ int run_debug_linear(int prec, const float* A, int lda, const float* W, const fl
   jobs.j[0].nchunks = L.nchunks;
   k_pack_canonical<<<dim3(16, 1), 256, 0, st>>>(jobs);
   SHERF_LAUNCH_CHECK();
-  return launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, L, A, lda, Y, ldy, M, act, st, nullptr, 0, 0, 0);
+  return launch_umma_linear(prec == 99 ? 4 : (prec == SHERF_MLP_TF32X3 ? 3 : 1), L, A, lda, Y, ldy, M, act, st, nullptr, 0, 0, 0);
 }
 
 }  // namespace sherf

@@ -73,9 +73,17 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
 int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
                        const float* Res, int ldr, int ygroup, int ygstride);
 
+// Fused tensor-core decoder trunk (decoder_fused.cu)
+struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
+struct FusedSchedule { FusedChunk ch[38]; uint16_t layer_np[9]; uint16_t pad; };
+struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; };
+size_t fused_blob_bytes();
+int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
+int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, float* fv, int ldfv, float* sigma, int np, cudaStream_t st);
+
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
 // prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 (tcgen05 tensor cores)
-int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const ChunkBuffers& cb, int np,
+int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st);
 
 int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,

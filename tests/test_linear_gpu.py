@@ -29,3 +29,19 @@ def test_linear_matches_fp64(precision, N, K):
         err = float(((Y.double() - ref).abs() / scale).max())
         assert torch.isfinite(Y).all()
         assert err <= TOL[precision], f'{precision} N={N} K={K} M={M} act={act}: scaled err {err:.3e}'
+
+
+@pytest.mark.parametrize('N,K', [(128, 128), (128, 71), (64, 187), (32, 48)])
+def test_linear_a_operand_from_tensor_memory(N, K):
+    """The fused decoder keeps the error-compensation (lo) activations in TMEM: validates tcgen05.mma with A from tensor memory."""
+    from sherf_b200 import ops
+    torch.manual_seed(7)
+    dev = torch.device('cuda:0')
+    A = torch.randn(777, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    b = torch.randn(N, device=dev)
+    Y = ops.linear(A, W, b, None, '_tf32x3_tmem_a')
+    ref = A.double() @ W.double().t() + b.double()
+    scale = (A.abs().double() @ W.abs().double().t()).clamp_min(1.0)
+    err = float(((Y.double() - ref).abs() / scale).max())
+    assert err <= TOL['tf32x3'], f'scaled err {err:.3e}'
