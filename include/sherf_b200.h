@@ -188,6 +188,9 @@ SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */
 SHERF_API int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy,
                                  int M, int N, int K, int act, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Diagnostic: device buffer [148*8] of int64 cycle counters filled by the fused decoder kernel (NULL disables). */
+SHERF_API void sherf_debug_set_trace(long long* device_buf);
+
 SHERF_API const char* sherf_last_error(void);
 SHERF_API int sherf_abi_version(void);
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */

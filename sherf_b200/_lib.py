@@ -65,7 +65,7 @@ class SherfDebug(C.Structure):
                 ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64), ('max_feat_points', C.c_int64)]
 
 
-EXPORTS = ['sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+EXPORTS = ['sherf_debug_set_trace', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
 
 _lib = None
@@ -101,6 +101,7 @@ def load():
     lib.sherf_debug_linear.restype = C.c_int
     lib.sherf_debug_linear.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sherf_debug_set_trace.argtypes = [C.c_void_p]
     lib.sherf_last_error.restype = C.c_char_p
     lib.sherf_abi_version.restype = C.c_int
     lib.sherf_last_launch_count.restype = C.c_int64

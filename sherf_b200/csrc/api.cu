@@ -266,6 +266,8 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   return SHERF_OK;
 }
 
+void sherf_debug_set_trace(long long* device_buf) { g_fused_trace = device_buf; }
+
 int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N,
                        int K, int act, void* scratch, size_t scratch_bytes, void* stream) {
   g_err[0] = 0;

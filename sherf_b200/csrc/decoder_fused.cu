@@ -12,13 +12,20 @@
 
 namespace sherf {
 
+// cycle-counter tracing (sherf_debug_set_trace): compile with -DSHERF_FUSED_TRACE to enable
+#ifdef SHERF_FUSED_TRACE
+#define TRACE_CLK() clock64()
+#else
+#define TRACE_CLK() 0LL
+#endif
+
 constexpr int kFusedChunks = 38;
 constexpr int kFusedLayers = 9;
-constexpr int kNst = 3;                                  // weight ring stages
+constexpr int kNst = 3;                                  // weight ring stages (32 k-columns each; a 6 x 16 ring measured slower)
 constexpr uint32_t kLbo = 2064;                          // padded K-direction stride of A operands (bytes)
 constexpr uint32_t kXBytes = 18 * kLbo, kHBytes = 32 * kLbo;
 constexpr uint32_t kStageBytes = 2 * 8 * 144 * 16;       // hi + lo, 8 core-matrix columns, up to 144 rows
-constexpr uint32_t kColD = 0, kColHlo = 160, kColXlo = 288;
+constexpr uint32_t kColD0 = 0, kColD1 = 144, kColHlo = 288, kColXlo = 416;   // 2 x 144 accumulator + 128 H_lo + 72 X_lo = 488 <= 512
 
 static_assert(kFusedChunks == 38 && kFusedLayers == 9, "FusedSchedule (stages.cuh) is sized for 38 chunks / 9 layers");
 
@@ -29,6 +36,7 @@ struct FusedArgs {
   float* fv; int ldfv;                 // feature output -> fv[:, 0:128]
   float* sigma;                        // [np]
   int np;
+  long long* trace;                    // optional [gridDim][8] cycle counters (diagnostics)
   FusedSchedule sch;
 };
 
@@ -43,14 +51,18 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
   unsigned char* H_hi = smem + kXBytes;
   unsigned char* Wst = smem + kXBytes + kHBytes;
   float* s_bias = reinterpret_cast<float*>(Wst + kNst * kStageBytes);
-  __shared__ __align__(8) uint64_t full_bar[kNst], empty_bar[kNst], acc_bar, a_bar;
+  __shared__ __align__(8) uint64_t full_bar[kNst], empty_bar[kNst], acc_bar, x_bar, hchunk_bar[4];
   __shared__ uint32_t tmem_base_s;
+  __shared__ FusedSchedule s_sch;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (int)(sizeof(FusedSchedule) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&s_sch)[i] = reinterpret_cast<const uint32_t*>(&a.sch)[i];
 
   if (tid == 0) {
     for (int s = 0; s < kNst; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
     umma::mbar_init(&acc_bar, 1);
-    umma::mbar_init(&a_bar, 256);
+    umma::mbar_init(&x_bar, 256);
+    for (int j = 0; j < 4; ++j) umma::mbar_init(&hchunk_bar[j], 256);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
@@ -65,52 +77,76 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
     // ===================== TMA weight producer =====================
     if (lane == 0) {
       uint32_t cc = 0;
+      long long t_wait = 0, t0 = TRACE_CLK();
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < kFusedChunks; ++c, ++cc) {
           const int s = cc % kNst;
+          const long long w0 = TRACE_CLK();
           umma::mbar_wait(&empty_bar[s], ((cc / kNst) & 1) ^ 1);
-          const FusedChunk& ch = a.sch.ch[c];
+          t_wait += TRACE_CLK() - w0;
+          const FusedChunk ch = s_sch.ch[c];
           const uint32_t bytes = (PREC == 3) ? ch.w_bytes : ch.w_bytes / 2;      // single-pass TF32 needs the hi half only
           umma::mbar_arrive_expect_tx(&full_bar[s], bytes);
           umma::bulk_g2s(Wst + s * kStageBytes, a.wblob + ch.w_off, bytes, &full_bar[s]);
         }
       }
+      if (a.trace) { a.trace[blockIdx.x * 8 + 0] = t_wait; a.trace[blockIdx.x * 8 + 1] = TRACE_CLK() - t0; }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t cc = 0, par_a = 0;
+      uint32_t cc = 0, par_x = 0, par_h[4] = {0, 0, 0, 0};
+      long long t_op = 0, t_full = 0, t0 = TRACE_CLK();
       const uint32_t x_s = umma::smem_u32(X_hi), h_s = umma::smem_u32(H_hi), w_s = umma::smem_u32(Wst);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < kFusedChunks; ++c, ++cc) {
-          const FusedChunk& ch = a.sch.ch[c];
-          if (ch.first) { umma::mbar_wait(&a_bar, par_a); par_a ^= 1; umma::tc_fence_after_sync(); }
+          const FusedChunk ch = s_sch.ch[c];
+          // operand readiness: X is loaded once per tile; H arrives from the previous layer's epilogue in 32-column chunks
+          const long long w0 = TRACE_CLK();
+          if (ch.src == 0) {
+            if (ch.layer == 0 && ch.first) { umma::mbar_wait(&x_bar, par_x); par_x ^= 1; }
+          } else if ((ch.kg0 & 7) == 0) {                   // first weight chunk that touches a new 32-column block of H
+            const int j = ch.kg0 / 8;
+            umma::mbar_wait(&hchunk_bar[j], par_h[j]);
+            par_h[j] ^= 1;
+          }
           const int s = cc % kNst;
+          const long long w1 = TRACE_CLK();
           umma::mbar_wait(&full_bar[s], (cc / kNst) & 1);
+          t_op += w1 - w0;
+          t_full += TRACE_CLK() - w1;
           umma::tc_fence_after_sync();
-          const uint32_t Np = a.sch.layer_np[ch.layer];
+          const uint32_t Np = s_sch.layer_np[ch.layer];
           const uint32_t idesc = umma::make_idesc_tf32(128, (int)Np);
-          const uint32_t a_base = (ch.src == 0 ? x_s : h_s) + (uint32_t)ch.kg0 * kLbo;
-          const uint32_t alo_col = tmem_base + (ch.src == 0 ? kColXlo : kColHlo) + (uint32_t)ch.kg0 * 4u;
-          const uint32_t w_hi = w_s + (uint32_t)s * kStageBytes, w_lo = w_hi + (uint32_t)ch.nkg * Np * 16u;
+          const uint32_t d_col = tmem_base + ((ch.layer & 1) ? kColD1 : kColD0);      // accumulators alternate per layer
           const uint32_t w_lbo = Np * 16u;
-          for (int st = 0; st < ch.nkg / 2; ++st) {
-            const uint64_t ah = umma::make_smem_desc(a_base + (uint32_t)st * 2u * kLbo, kLbo, 128u);
-            const uint64_t wh = umma::make_smem_desc(w_hi + (uint32_t)st * 2u * w_lbo, w_lbo, 128u);
-            const uint32_t acc = (ch.first && st == 0) ? 0u : 1u;
-            if (PREC == 3) {
-              const uint64_t wl = umma::make_smem_desc(w_lo + (uint32_t)st * 2u * w_lbo, w_lbo, 128u);
-              umma::mma_tf32_ts(tmem_base + kColD, alo_col + (uint32_t)st * 8u, wh, idesc, acc);
-              umma::mma_tf32_ss(tmem_base + kColD, ah, wl, idesc, 1u);
-              umma::mma_tf32_ss(tmem_base + kColD, ah, wh, idesc, 1u);
-            } else {
-              umma::mma_tf32_ss(tmem_base + kColD, ah, wh, idesc, acc);
+          const uint32_t w_hi = w_s + (uint32_t)s * kStageBytes, w_lo = w_hi + (uint32_t)ch.nkg * w_lbo;
+          // descriptors of MMA k-step 0; later steps only advance the 14-bit start-address field (no carry: smem < 256 KB)
+          const uint64_t ah0 = umma::make_smem_desc((ch.src == 0 ? x_s : h_s) + (uint32_t)ch.kg0 * kLbo, kLbo, 128u);
+          const uint64_t wh0 = umma::make_smem_desc(w_hi, w_lbo, 128u);
+          const uint64_t wl0 = umma::make_smem_desc(w_lo, w_lbo, 128u);
+          const uint32_t alo0 = tmem_base + (ch.src == 0 ? kColXlo : kColHlo) + (uint32_t)ch.kg0 * 4u;
+          const uint64_t da = (uint64_t)((2u * kLbo) >> 4), dw = (uint64_t)((2u * w_lbo) >> 4);
+          const int nsteps = ch.nkg >> 1;
+          const uint32_t acc0 = ch.first ? 0u : 1u;
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            if (st < nsteps) {
+              const uint32_t acc = st == 0 ? acc0 : 1u;
+              if (PREC == 3) {
+                umma::mma_tf32_ts(d_col, alo0 + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
+                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
+                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+              } else {
+                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+              }
             }
           }
           umma::mma_commit(&empty_bar[s]);                 // weight stage reusable once these MMAs retire
           if (ch.last) umma::mma_commit(&acc_bar);         // layer accumulator complete
         }
       }
+      if (a.trace) { a.trace[blockIdx.x * 8 + 2] = t_op; a.trace[blockIdx.x * 8 + 3] = t_full; a.trace[blockIdx.x * 8 + 4] = TRACE_CLK() - t0; }
     }
   } else {
     // ===================== tile loader + epilogue (warps 0-7) =====================
@@ -118,83 +154,102 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
     const int row = 32 * q + lane;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     uint32_t par_acc = 0;
+    long long t_acc = 0, t_x = 0, t0 = TRACE_CLK();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long x0 = TRACE_CLK();
       const int m = tile * 128 + row;
       const bool row_ok = m < a.np;
-      // ---- X tile: 72 columns = 18 core-matrix columns; this thread handles 9 of them for its row ----
+      // ---- X tile: 72 columns = 18 core-matrix columns; this thread owns columns [36*hsel, 36*hsel+36) of its row ----
       {
-        const float* xr = a.X + (size_t)m * a.ldx;
-        for (int kg = hsel * 9; kg < hsel * 9 + 9; ++kg) {
-          float4 v = row_ok ? *reinterpret_cast<const float4*>(xr + kg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
-          *reinterpret_cast<float4*>(X_hi + kg * kLbo + row * 16) = h;
+        const float4* xr = reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + 36 * hsel);
+        float4 v[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = row_ok ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t lo[36];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const float4 h = make_float4(umma::to_tf32(v[i].x), umma::to_tf32(v[i].y), umma::to_tf32(v[i].z), umma::to_tf32(v[i].w));
+          *reinterpret_cast<float4*>(X_hi + (9 * hsel + i) * kLbo + row * 16) = h;
+          lo[4 * i + 0] = __float_as_uint(umma::to_tf32(v[i].x - h.x));
+          lo[4 * i + 1] = __float_as_uint(umma::to_tf32(v[i].y - h.y));
+          lo[4 * i + 2] = __float_as_uint(umma::to_tf32(v[i].z - h.z));
+          lo[4 * i + 3] = __float_as_uint(umma::to_tf32(v[i].w - h.w));
         }
         if (PREC == 3) {
-          // lo part, 8 columns per tcgen05.st: thread covers columns [hsel*36, hsel*36+36) -> 4 full groups + a half group;
-          // simpler and exact: hsel 0 writes groups 0..4 (cols 0..39), hsel 1 writes groups 5..8 (cols 40..71)
-          const int g0 = hsel == 0 ? 0 : 5, g1 = hsel == 0 ? 5 : 9;
-          for (int gi = g0; gi < g1; ++gi) {
-            uint32_t lo[8];
+          const uint32_t xlo = tmem_base + lane_base + kColXlo + (uint32_t)(36 * hsel);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = row_ok ? xr[gi * 8 + e] : 0.f;
-              lo[e] = __float_as_uint(umma::to_tf32(x - umma::to_tf32(x)));
-            }
-            umma::tmem_st8(tmem_base + lane_base + kColXlo + (uint32_t)(gi * 8), lo);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const uint32_t t8[8] = {lo[8 * g8], lo[8 * g8 + 1], lo[8 * g8 + 2], lo[8 * g8 + 3], lo[8 * g8 + 4], lo[8 * g8 + 5], lo[8 * g8 + 6], lo[8 * g8 + 7]};
+            umma::tmem_st8(xlo + (uint32_t)(8 * g8), t8);
           }
+          const uint32_t t4[4] = {lo[32], lo[33], lo[34], lo[35]};
+          umma::tmem_st4(xlo + 32u, t4);
           umma::tmem_st_wait();
         }
       }
       umma::fence_proxy_async_smem();
       umma::tc_fence_before_sync();
-      mbar_arrive(&a_bar);
+      mbar_arrive(&x_bar);
+      t_x += TRACE_CLK() - x0;
 
       for (int l = 0; l < kFusedLayers; ++l) {
+        const long long w0 = TRACE_CLK();
         umma::mbar_wait(&acc_bar, par_acc);
+        t_acc += TRACE_CLK() - w0;
         par_acc ^= 1;
         umma::tc_fence_after_sync();
-        const int Np = a.sch.layer_np[l];
-        const int half = Np / 2;
         const float* bl = s_bias + l * 144;
-        for (int j = 0; j < half / 8; ++j) {
-          const int c0 = hsel * half + 8 * j;
-          uint32_t v[8];
-          umma::tmem_ld8(tmem_base + lane_base + kColD + (uint32_t)c0, v);
-          umma::tmem_ld_wait();
-          if (l < kFusedLayers - 1) {
-            float x[8];
-            uint32_t lo[8];
+        const uint32_t d_col = tmem_base + lane_base + ((l & 1) ? kColD1 : kColD0);
+        // all 8 warps sweep the accumulator in 32-column chunks (warp: lane quarter q, 16-column half hsel); after each chunk
+        // the next layer's MMA may consume those 32 k-columns of H while this epilogue continues with the next chunk
+        uint32_t vnext[16];
+        umma::tmem_ld16(d_col + (uint32_t)(16 * hsel), vnext);
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = 32 * j + 16 * hsel;
+          uint32_t v[16];
+          umma::tmem_ld_wait();                             // chunk j has landed (and the previous chunk's tcgen05.st retired below)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 16; ++i) v[i] = vnext[i];
+          if (j < 3) umma::tmem_ld16(d_col + (uint32_t)(c0 + 32), vnext);     // prefetch chunk j+1 while chunk j is processed
+          if (l < kFusedLayers - 1) {
+            float x[16];
+            uint32_t lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
               x[i] = fmaxf(__uint_as_float(v[i]) + bl[c0 + i], 0.f);
               const float h = umma::to_tf32(x[i]);
               lo[i] = __float_as_uint(umma::to_tf32(x[i] - h));
               x[i] = h;
             }
-            *reinterpret_cast<float4*>(H_hi + (c0 / 4) * kLbo + row * 16) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(H_hi + (c0 / 4 + 1) * kLbo + row * 16) = make_float4(x[4], x[5], x[6], x[7]);
-            if (PREC == 3) umma::tmem_st8(tmem_base + lane_base + kColHlo + (uint32_t)c0, lo);
-          } else if (row_ok) {
-            // feature_linear (cols 0..127, no activation) -> fv ; alpha_linear (col 128) -> sigma      triplane.py:302-303
-            if (c0 < 128) {
-              float4* dst = reinterpret_cast<float4*>(a.fv + (size_t)m * a.ldfv + c0);
-              dst[0] = make_float4(__uint_as_float(v[0]) + bl[c0], __uint_as_float(v[1]) + bl[c0 + 1], __uint_as_float(v[2]) + bl[c0 + 2],
-                                   __uint_as_float(v[3]) + bl[c0 + 3]);
-              dst[1] = make_float4(__uint_as_float(v[4]) + bl[c0 + 4], __uint_as_float(v[5]) + bl[c0 + 5], __uint_as_float(v[6]) + bl[c0 + 6],
-                                   __uint_as_float(v[7]) + bl[c0 + 7]);
-            } else if (c0 == 128) {
-              a.sigma[m] = __uint_as_float(v[0]) + bl[128];
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+              *reinterpret_cast<float4*>(H_hi + (c0 / 4 + g4) * kLbo + row * 16) = make_float4(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);
+            if (PREC == 3) {
+              umma::tmem_st16(tmem_base + lane_base + kColHlo + (uint32_t)c0, lo);
+              umma::tmem_st_wait();
             }
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before_sync();
+            mbar_arrive(&hchunk_bar[j]);
+          } else if (row_ok) {
+            // feature_linear (cols 0..127, no activation) -> fv                                        triplane.py:303
+            float4* dst = reinterpret_cast<float4*>(a.fv + (size_t)m * a.ldfv + c0);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+              dst[g4] = make_float4(__uint_as_float(v[4 * g4]) + bl[c0 + 4 * g4], __uint_as_float(v[4 * g4 + 1]) + bl[c0 + 4 * g4 + 1],
+                                    __uint_as_float(v[4 * g4 + 2]) + bl[c0 + 4 * g4 + 2], __uint_as_float(v[4 * g4 + 3]) + bl[c0 + 4 * g4 + 3]);
           }
         }
-        if (l < kFusedLayers - 1) {
-          if (PREC == 3) umma::tmem_st_wait();
-          umma::fence_proxy_async_smem();
-          umma::tc_fence_before_sync();
-          mbar_arrive(&a_bar);
+        if (l == kFusedLayers - 1 && hsel == 0) {
+          // alpha_linear = row 128 of the stacked feature/alpha weight                                  triplane.py:302
+          uint32_t v8[8];
+          umma::tmem_ld8(d_col + 128u, v8);
+          umma::tmem_ld_wait();
+          if (row_ok) a.sigma[m] = __uint_as_float(v8[0]) + bl[128];
         }
       }
     }
+    if (a.trace && tid == 0) { a.trace[blockIdx.x * 8 + 5] = t_acc; a.trace[blockIdx.x * 8 + 6] = t_x; a.trace[blockIdx.x * 8 + 7] = TRACE_CLK() - t0; }
   }
   umma::tc_fence_before_sync();
   __syncthreads();
@@ -232,6 +287,8 @@ __global__ void k_fused_bias(const SherfWeights w, float* bias) {
   else { if (n < 128) v = w.feature_b[n]; else if (n == 128) v = w.alpha_b[0]; }
   bias[l * 144 + n] = v;
 }
+
+long long* g_fused_trace = nullptr;   // set by sherf_debug_set_trace (diagnostics)
 
 size_t fused_blob_bytes() { return (size_t)2 * (128 * (72 + 128 * 4 + 200 + 128 * 2) + 144 * 128) * 4 + 1024; }
 
@@ -277,6 +334,7 @@ int run_decoder_fused(int prec, const FusedSchedule& sch, const unsigned char* b
   if (np <= 0) return SHERF_OK;
   FusedArgs a;
   a.X = X; a.ldx = ldx; a.wblob = blob; a.bias = bias; a.fv = fv; a.ldfv = ldfv; a.sigma = sigma; a.np = np; a.sch = sch;
+  a.trace = g_fused_trace;
   const size_t smem = kXBytes + kHBytes + kNst * kStageBytes + kFusedLayers * 144 * sizeof(float);
   static bool attr_done = false;
   static int num_sms = 148;

@@ -38,8 +38,8 @@ __device__ __forceinline__ void warp_lexmin(float& d, int& id) {
   }
 }
 
-// Exact K=1 search, no radius bound (renderer.py:627): box of Chebyshev radius r around the query's cell, lanes
-// take rows of the box; r doubles until every unsearched cell is provably farther than the best hit.
+// Exact K=1 search, no radius bound (renderer.py:627): box of Chebyshev radius r around the query's cell, one lane per
+// cell of the box; r doubles until every unsearched cell is provably farther than the best hit.
 __device__ int nn_unbounded(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
                             float qx, float qy, float qz, int lane) {
   const int cx = min(max(grid_coord(qx, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
@@ -51,11 +51,11 @@ __device__ int nn_unbounded(const GridDesc& g, const int* __restrict__ cell_star
     const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dim[0] - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dim[1] - 1);
     const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dim[2] - 1);
-    const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
-    for (int rr = lane; rr < nrows; rr += 32) {
-      const int z = z0 + rr / ny, y = y0 + rr % ny;
-      const int row = (z * g.dim[1] + y) * g.dim[0];
-      const int b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncells = nx * ny * (z1 - z0 + 1);
+    for (int cc = lane; cc < ncells; cc += 32) {
+      const int xx = x0 + cc % nx, t = cc / nx;
+      const int cell = ((z0 + t / ny) * g.dim[1] + (y0 + t % ny)) * g.dim[0] + xx;
+      const int b = cell_start[cell], e = cell_start[cell + 1];
       for (int k = b; k < e; ++k) {
         const float4 v = gv[k];
         const float d2 = dist2_xyz(qx, qy, qz, v.x, v.y, v.z);
@@ -101,28 +101,6 @@ __device__ __forceinline__ void apply_warp(const VertexWarp* __restrict__ Tp, fl
   }
 }
 
-struct Tap2 { int x0, y0; float wnw, wne, wsw, wse; };
-__device__ __forceinline__ Tap2 make_tap2(float ix, float iy) {
-  Tap2 t;
-  const float fx = floorf(ix), fy = floorf(iy);
-  t.x0 = (int)fx; t.y0 = (int)fy;
-  const float ax = ix - fx, ay = iy - fy, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
-  t.wnw = bx * by; t.wne = ax * by; t.wsw = bx * ay; t.wse = ax * ay;
-  return t;
-}
-// bilinear, zeros padding; base -> [H][W][C] channels-last, returns channel `c`
-__device__ __forceinline__ float bilerp_cl(const float* __restrict__ base, int H, int W, int C, const Tap2& t, int c) {
-  const bool xl = t.x0 >= 0 && t.x0 < W, xr = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-  const bool yt = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  const float* r0 = base + ((size_t)t.y0 * W + t.x0) * C + c;
-  const float* r1 = r0 + (size_t)W * C;
-  const float vnw = (yt && xl) ? __ldg(r0) : 0.f;
-  const float vne = (yt && xr) ? __ldg(r0 + C) : 0.f;
-  const float vsw = (yb && xl) ? __ldg(r1) : 0.f;
-  const float vse = (yb && xr) ? __ldg(r1 + C) : 0.f;
-  return ((vnw * t.wnw + vne * t.wne) + vsw * t.wsw) + vse * t.wse;
-}
-
 __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
   __shared__ FrameConst fc;
   for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
@@ -163,22 +141,87 @@ __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
     float* f3 = P.f3raw + (size_t)lp * 192;
     float* dbgf = (P.dbg_feat && gp < P.dbg_feat_max) ? P.dbg_feat + (size_t)gp * 384 : nullptr;
 
-    // ---- pixel-aligned 2-D features (renderer.py:331-340) ----
+    // ================= lane-parallel tap setup: every lane prepares ONE 2-D tap and ONE 3-D tap =================
+    // set A (2-D): lanes 0-11 tri-plane (plane k = lane/4), 12-15 observation feature map, 16-19 observation image;
+    //              corner = lane & 3 in grid_sample's accumulation order nw, ne, sw, se                 renderer.py:234-243,331-340
+    // set B (3-D): lanes 0-23 pyramid level lane/8, corner = lane & 7 (bit0 x, bit1 y, bit2 z)          renderer.py:544-556,762-797
+    int offA = -1; float wA = 0.f;
     {
+      float cn[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cn[k] = 2.f * (can[k] - fc.twb_min[k]) / (fc.twb_max[k] - fc.twb_min[k]) - 1.f;
       const float gx = 2.0f * u / (float)P.img_w - 1.0f, gy = 2.0f * v / (float)P.img_h - 1.0f;
-      const Tap2 tf = make_tap2((gx + 1.f) * 0.5f * (float)(P.feat_w - 1), (gy + 1.f) * 0.5f * (float)(P.feat_h - 1));
-      const float f0 = bilerp_cl(P.feat_cl, P.feat_h, P.feat_w, P.feat_ch, tf, lane);
-      const float f1 = bilerp_cl(P.feat_cl, P.feat_h, P.feat_w, P.feat_ch, tf, lane + 32);
-      const Tap2 ti = make_tap2((gx + 1.f) * 0.5f * (float)(P.img_w - 1), (gy + 1.f) * 0.5f * (float)(P.img_h - 1));
-      float rgbc = 0.f;
-      if (lane < 3) {   // NCHW image: channel plane `lane`
-        const float* pl = P.img + (size_t)lane * P.img_h * P.img_w;
-        const bool xl = ti.x0 >= 0 && ti.x0 < P.img_w, xr = ti.x0 + 1 >= 0 && ti.x0 + 1 < P.img_w;
-        const bool yt = ti.y0 >= 0 && ti.y0 < P.img_h, yb = ti.y0 + 1 >= 0 && ti.y0 + 1 < P.img_h;
-        const float* r0 = pl + (size_t)ti.y0 * P.img_w + ti.x0;
-        const float vnw = (yt && xl) ? __ldg(r0) : 0.f, vne = (yt && xr) ? __ldg(r0 + 1) : 0.f;
-        const float vsw = (yb && xl) ? __ldg(r0 + P.img_w) : 0.f, vse = (yb && xr) ? __ldg(r0 + P.img_w + 1) : 0.f;
-        rgbc = ((vnw * ti.wnw + vne * ti.wne) + vsw * ti.wsw) + vse * ti.wse;
+      const int grp = lane >> 2;                                   // 0..2 planes, 3 feature map, 4 image
+      float ix, iy; int W, H, C;
+      if (grp < 3) {                                                // align_corners=False
+        const float px = grp == 2 ? cn[2] : cn[0], py = grp == 1 ? cn[2] : cn[1];
+        W = P.plane_w; H = P.plane_h; C = 32;
+        ix = ((px + 1.f) * (float)W - 1.f) * 0.5f; iy = ((py + 1.f) * (float)H - 1.f) * 0.5f;
+      } else if (grp == 3) {                                        // align_corners=True, uv normalised by the IMAGE size
+        W = P.feat_w; H = P.feat_h; C = P.feat_ch;
+        ix = (gx + 1.f) * 0.5f * (float)(W - 1); iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+      } else {
+        W = P.img_w; H = P.img_h; C = 1;
+        ix = (gx + 1.f) * 0.5f * (float)(W - 1); iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+      }
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int cxb = lane & 1, cyb = (lane >> 1) & 1;
+      const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+      const float wx = cxb ? ix - fx : (fx + 1.f) - ix, wy = cyb ? iy - fy : (fy + 1.f) - iy;
+      wA = wx * wy;
+      if (lane < 20 && xx >= 0 && xx < W && yy >= 0 && yy < H) offA = (yy * W + xx) * C;
+    }
+    int offB = -1; float wB = 0.f;
+    {
+      const int l = lane >> 3;
+      const int D = l == 0 ? P.vol_d[0] : (l == 1 ? P.vol_d[1] : P.vol_d[2]);
+      const int H = l == 0 ? P.vol_h[0] : (l == 1 ? P.vol_h[1] : P.vol_h[2]);
+      const int W = l == 0 ? P.vol_w[0] : (l == 1 ? P.vol_w[1] : P.vol_w[2]);
+      const int C = l == 0 ? P.vol_ch[0] : (l == 1 ? P.vol_ch[1] : P.vol_ch[2]);
+      float gn[3];   // normalised (x, y, z); dhw axis 2-k holds coordinate k, out_sh is (z,y,x)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gn[k] = ((can[k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
+      const float ix = (gn[0] + 1.f) * 0.5f * (float)(W - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(H - 1),
+                  iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
+      const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+      const int bx = lane & 1, by = (lane >> 1) & 1, bz = (lane >> 2) & 1;
+      const int xx = (int)fx + bx, yy = (int)fy + by, zz2 = (int)fz + bz;
+      const float wx = bx ? ix - fx : (fx + 1.f) - ix, wy = by ? iy - fy : (fy + 1.f) - iy, wz = bz ? iz - fz : (fz + 1.f) - iz;
+      wB = wx * wy * wz;
+      if (lane < 24 && xx >= 0 && xx < W && yy >= 0 && yy < H && zz2 >= 0 && zz2 < D) offB = ((zz2 * H + yy) * W + xx) * C;
+    }
+
+    // ================= gathers: lane = channel; tap offsets / weights arrive by shuffle =================
+    // ---- tri-planes ----
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* base = P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int off = __shfl_sync(0xffffffffu, offA, 4 * k + t);
+        const float w = __shfl_sync(0xffffffffu, wA, 4 * k + t);
+        const float val = off >= 0 ? __ldg(base + off) : 0.f;
+        acc = t == 0 ? val * w : acc + val * w;
+      }
+      comb[k * 96 + lane] = acc;
+      if (dbgf) dbgf[k * 32 + lane] = acc;
+    }
+    // ---- pixel-aligned 2-D features + rgb positional encoding ----
+    {
+      float f0 = 0.f, f1 = 0.f, rgbc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int off = __shfl_sync(0xffffffffu, offA, 12 + t);
+        const float w = __shfl_sync(0xffffffffu, wA, 12 + t);
+        const float v0 = off >= 0 ? __ldg(P.feat_cl + off + lane) : 0.f;
+        const float v1 = off >= 0 ? __ldg(P.feat_cl + off + 32 + lane) : 0.f;
+        f0 = t == 0 ? v0 * w : f0 + v0 * w;
+        f1 = t == 0 ? v1 * w : f1 + v1 * w;
+        const int offi = __shfl_sync(0xffffffffu, offA, 16 + t);
+        const float wi = __shfl_sync(0xffffffffu, wA, 16 + t);
+        const float vi = (lane < 3 && offi >= 0) ? __ldg(P.img + (size_t)lane * P.img_h * P.img_w + offi) : 0.f;
+        rgbc = t == 0 ? vi * wi : rgbc + vi * wi;
       }
       // rgb_enc (num_freqs=5) truncated to its first 32 outputs (renderer.py:339, :900-916)
       const int e = lane - 3;
@@ -190,52 +233,29 @@ __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
       comb[2 * 96 + 32 + lane] = enc;
       if (dbgf) { dbgf[96 + lane] = f0; dbgf[128 + lane] = f1; dbgf[160 + lane] = enc; }
     }
-    // ---- tri-plane features (renderer.py:234-243), align_corners=False ----
+    // ---- 3-D pyramid ----
     {
-      float cn[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) cn[k] = 2.f * (can[k] - fc.twb_min[k]) / (fc.twb_max[k] - fc.twb_min[k]) - 1.f;
-      const float px[3] = {cn[0], cn[0], cn[2]}, py[3] = {cn[1], cn[2], cn[1]};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const Tap2 tp = make_tap2(((px[k] + 1.f) * (float)P.plane_w - 1.f) * 0.5f, ((py[k] + 1.f) * (float)P.plane_h - 1.f) * 0.5f);
-        const float val = bilerp_cl(P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32, P.plane_h, P.plane_w, 32, tp, lane);
-        comb[k * 96 + lane] = val;
-        if (dbgf) dbgf[k * 32 + lane] = val;
-      }
-    }
-    // ---- 3-D pyramid (renderer.py:544-556, :762-797), align_corners=True ----
-    {
-      float gn[3];   // normalised (x, y, z)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        // dhw axis a = 2-k holds coordinate k; out_sh is (z,y,x)
-        gn[k] = ((can[k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
-      }
       int coff = 0;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
-        const int D = P.vol_d[l], H = P.vol_h[l], W = P.vol_w[l], C = P.vol_ch[l];
-        const float ix = (gn[0] + 1.f) * 0.5f * (float)(W - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(H - 1),
-                    iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
-        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-        const float ax = ix - fx, ay = iy - fy, az = iz - fz, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy, bz = (fz + 1.f) - iz;
-        const float wgt[8] = {bx * by * bz, ax * by * bz, bx * ay * bz, ax * ay * bz, bx * by * az, ax * by * az, bx * ay * az, ax * ay * az};
-        const float* vol = P.vol_cl[l];
-        for (int c = lane; c < C; c += 32) {
-          float acc = 0.f;
+        int off[8]; float w[8];
 #pragma unroll
-          for (int tcorner = 0; tcorner < 8; ++tcorner) {
-            const int xx = x0 + (tcorner & 1), yy = y0 + ((tcorner >> 1) & 1), zz2 = z0 + (tcorner >> 2);
-            const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz2 >= 0 && zz2 < D;
-            const float val = ok ? __ldg(vol + (((size_t)zz2 * H + yy) * W + xx) * C + c) : 0.f;
-            acc += val * wgt[tcorner];
+        for (int t = 0; t < 8; ++t) { off[t] = __shfl_sync(0xffffffffu, offB, 8 * l + t); w[t] = __shfl_sync(0xffffffffu, wB, 8 * l + t); }
+        const float* vol = P.vol_cl[l] + lane;
+#pragma unroll
+        for (int gsel = 0; gsel < 3; ++gsel) {
+          if (gsel <= l) {                                          // level l has 32*(l+1) channels
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float val = off[t] >= 0 ? __ldg(vol + off[t] + 32 * gsel) : 0.f;
+              acc += val * w[t];
+            }
+            f3[coff + 32 * gsel + lane] = acc;
+            if (dbgf) dbgf[192 + coff + 32 * gsel + lane] = acc;
           }
-          f3[coff + c] = acc;
-          if (dbgf) dbgf[192 + coff + c] = acc;
         }
-        coff += C;
+        coff += 32 * (l + 1);
       }
     }
     if (lane < 8) {

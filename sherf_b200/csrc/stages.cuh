@@ -78,6 +78,7 @@ struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0
 struct FusedSchedule { FusedChunk ch[38]; uint16_t layer_np[9]; uint16_t pad; };
 struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; };
 size_t fused_blob_bytes();
+extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
 int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, float* fv, int ldfv, float* sigma, int np, cudaStream_t st);
 
