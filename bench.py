@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 H, W, S = 512, 512, 64
 WORKLOAD = 'configs[1]: 512x512 RenderPeople-shape, 64 samples/ray, 1 subject novel view'
 FLOP_PER_POINT = 429_248          # MLP MACs x 2 per decoded (surviving) sample
+# the fused tcgen05 decoder kernel covers pts_linears[0..7] + feature_linear + alpha_linear (triplane.py:293-303)
+FLOP_PER_POINT_FUSED = 2 * (71 * 128 + 4 * 128 * 128 + 199 * 128 + 2 * 128 * 128 + 128 * 128 + 128)
+TF32_OVER_BF16 = 0.5              # dense TF32 tensor peak is half the bf16 peak (B200_PROFILING.md table: 1.1 vs 2.25 PF)
 
 
 def parse():
@@ -33,7 +36,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sherf_b200', choices=['sherf_b200', 'reference'])
-    ap.add_argument('--precision', default='fp32')
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32', 'tf32x3'],
+                    help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -126,7 +130,7 @@ def run_reference(args):
     import torch
     from sherf_b200 import synthetic as SY
     model = SY.make_smpl_model(0)
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)      # the chunked brute-force KNN stops scaling (and regresses) beyond ~32 threads
     budget = 150.0 / max(1, args.steps + args.warmup)                 # seconds per step
     n_rays = int(min(16384, max(256, budget * 9000 / S)))             # ~9e3 ray-samples/s/8 cores measured in the build container
     rates, last = [], None
@@ -197,7 +201,7 @@ def main():
                    dec, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'], scene['input_data'], scene['rendering_options'],
                    depth_clamp=clamp[v] if world > 1 else None)
 
-    stage_ms = [0.0] * 5
+    stage_ms = [0.0] * 6
     launches = [0]
     points = [0]
 
@@ -205,7 +209,7 @@ def main():
         outs = []
         for v in range(world):
             rgb, depth, acc = render(shard_dev[v], v)
-            for s_ in range(5):
+            for s_ in range(6):
                 stage_ms[s_] += lib.sherf_last_stage_ms(s_)
             launches[0] += ren.last_launches
             points[0] += ren.last_num_points
@@ -243,7 +247,7 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    stage_ms[:] = [0.0] * 5
+    stage_ms[:] = [0.0] * 6
     launches[0] = 0
     points[0] = 0
     clocks = ClockSampler(local_rank)
@@ -269,12 +273,25 @@ def main():
         calls = args.steps * world
         mlp_ms = stage_ms[3] / calls
         p_call = points[0] / calls
-        ach_tflops = p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        fused_ms = stage_ms[5] / calls
+        if fused_ms > 0:       # tensor-core path: the dominant kernel is the fused decoder trunk (one launch per 131072-point chunk)
+            n_launch = max(1, -(-int(p_call) // 131072))
+            roof_kernel = 'k_decoder_fused (tcgen05 kind::tf32, pts_linears 0-7 + feature/alpha, %d launches per view)' % n_launch
+            ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
+            algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
+            traffic = 67.3e6      # profiles/r1_d_ncu_full_k_decoder_fused.csv: dram read 42.9 MB + write 24.4 MB per launch
+        else:
+            roof_kernel = 'MLP stage (k_sgemm fp32 CUDA-core layers)'
+            ach_tflops = p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+            algo = f'{FLOP_PER_POINT} FLOP per surviving sample x {p_call:.0f} samples per view'
+            traffic = None
+        tf32_peak = pk['tensor_tflops'] * TF32_OVER_BF16
         h2d = sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * world
         line = {
             'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3 (3xTF32 split products, fp32 accumulate; fp32-grade)'}[args.precision],
+            'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'views_per_step': world,
                        'parallelism': f'ray-tiles x{world}, one all-gather of rendered tiles per view' if world > 1 else 'single GPU',
                        'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if world > 1 else p_call,
@@ -284,14 +301,15 @@ def main():
                     'note': 'per step: pinned-host rays/near/far/vertices -> device, ImportanceRenderer.forward via the C ABI, rendered rgb+depth+acc -> pinned host'},
             'gpu_launches': launches[0],
             'clocks': clk,
-            'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite'])},
-            'roofline': {'bound': 'tensor', 'kernel': 'MLP stage (k_sgemm fp32 CUDA-core layers)' if args.precision == 'fp32' else 'MLP stage',
-                         'achieved': ach_tflops, 'peak': pk['tensor_tflops'], 'unit': 'TFLOP/s', 'frac': ach_tflops / pk['tensor_tflops'],
-                         'traffic': None, 'peak_source': pk['src'],
-                         'algorithmic': f'{FLOP_PER_POINT} FLOP per surviving sample x {p_call:.0f} samples per call'},
+            'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite', 'mlp:fused_decoder_kernel'])},
+            'mlp_stage_tflops': p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,
+            'roofline': {'bound': 'tensor', 'kernel': roof_kernel, 'achieved': ach_tflops, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                         'frac': ach_tflops / tf32_peak, 'traffic': traffic,
+                         'peak_source': pk['src'] + ' x 0.5: dense TF32 rate is half the bf16 rate; useful FLOPs counted once although tf32x3 issues 3 MMAs per product',
+                         'algorithmic': algo},
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 32)
             rate, dt, sample = cpu_port_rate(model, 4096, threads)
             line['cpu_baseline'] = {'value': rate, 'unit': 'ray-samples/s', 'cores': threads, 'kind': 'port', 'sample': sample, 'seconds': dt}
         print(json.dumps(line), flush=True)

@@ -109,12 +109,18 @@ struct StageTimer {
     cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
     cudaEventRecord(sp.a, st);
     spans.push_back(sp);
+    open_stack.push_back((int)spans.size() - 1);
   }
-  void end() { if (on && !spans.empty()) cudaEventRecord(spans.back().b, st); }
+  std::vector<int> open_stack;
+  void end() {
+    if (!on || open_stack.empty()) return;
+    cudaEventRecord(spans[open_stack.back()].b, st);
+    open_stack.pop_back();
+  }
   void finish() {
     if (!on) return;
     for (int i = 0; i < 8; ++i) g_stage_ms[i] = 0.f;
-    if (!spans.empty()) cudaEventSynchronize(spans.back().b);
+    cudaStreamSynchronize(st);
     for (auto& sp : spans) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, sp.a, sp.b);
@@ -124,6 +130,10 @@ struct StageTimer {
     spans.clear();
   }
 };
+
+static thread_local StageTimer* g_tm = nullptr;
+static void nested_begin(int stage) { if (g_tm) g_tm->begin(stage); }
+static void nested_end() { if (g_tm) g_tm->end(); }
 
 }  // namespace sherf
 
@@ -185,6 +195,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   g_launches.n = 0;
   StageTimer tm;
   tm.init(g_profiling != 0, st);
+  g_tm = &tm;
 
   // ---- stage 0: per-frame tables, channels-last feature copies, packed weights ----
   tm.begin(0);
@@ -248,7 +259,8 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     RC(run_point_gather(G, st));
     tm.end();
     tm.begin(3);
-    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st));
+    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st,
+               nested_begin, nested_end));
     tm.end();
   }
   if (dbg && P > 0) {
@@ -262,6 +274,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   RC(run_composite(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, *out, st));
   tm.end();
   tm.finish();
+  g_tm = nullptr;
   g_last_launches = g_launches.n;
   return SHERF_OK;
 }

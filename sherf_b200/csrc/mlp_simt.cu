@@ -349,7 +349,8 @@ void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb) {
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
-            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st) {
+            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st, void (*span_begin)(int),
+            void (*span_end)()) {
   if (np <= 0) return SHERF_OK;
   const int rows3 = 3 * np;
   // one linear layer on the selected arithmetic
@@ -378,7 +379,9 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   SHERF_LAUNCH_CHECK();
   if (fused && prec != SHERF_MLP_FP32) {
     // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip
+    if (span_begin) span_begin(5);
     RC(run_decoder_fused_plan(prec == SHERF_MLP_TF32X3 ? 3 : 1, *fused, cb.x, 72, cb.fv, 188, sigma_out + p0, np, st));
+    if (span_end) span_end();
   } else {
     RC(launch_gemm(pw.pts[0], cw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
     RC(launch_gemm(pw.pts[1], cw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));

@@ -85,7 +85,8 @@ int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int 
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
 // prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 (tcgen05 tensor cores)
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
-            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st);
+            int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st,
+            void (*span_begin)(int) = nullptr, void (*span_end)() = nullptr);
 
 int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
                      int act, float* wscratch, cudaStream_t st);
