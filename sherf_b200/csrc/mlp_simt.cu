@@ -288,6 +288,177 @@ __global__ void k_decoder_inputs(const float* __restrict__ geo, const float* __r
   if (dbg_tok && p0 + p < dbg_max) { dbg_tok[(p0 + p) * 64 + lane] = t0; dbg_tok[(p0 + p) * 64 + 32 + lane] = t1; }
 }
 
+// Transformer tail in one pass, thread per (point, query token t in {0,1}) -- token 2 is only ever a key/value source and
+// the decoder never reads its output (triplane.py:288-289).  Per thread: 3-head attention of query t over the 3 tokens,
+// to_out projection + residual, LayerNorm, FeedForward (Linear-GELU-Linear) + residual (renderer.py:966-993), then the
+// decoder inputs: t = 0 -> x = [PE6(can) | tok0], t = 1 -> [PE4(cdir) | tok1] (renderer.py:432, triplane.py:293,308).
+// All fp32 FMA; weights are broadcast from shared memory.
+struct TailParams {
+  const float *qkv, *tok, *geo;                      // [3np][144], [3np][32] (pre-attention tokens), [np][8]
+  const float *wo, *bo, *ln_w, *ln_b, *w1, *b1, *w2, *b2;
+  float *x, *hb, *fv;                                // [np][72], optional [np][200], [np][188]
+  float* dbg_tok; int64_t p0, dbg_max;
+  int np;
+};
+
+__global__ void __launch_bounds__(128) k_transformer_tail(const TailParams P) {
+  __shared__ __align__(16) float s_wo[32 * 48];
+  __shared__ __align__(16) float s_w1[32 * 32];
+  __shared__ __align__(16) float s_w2[32 * 32];
+  __shared__ float s_bo[32], s_lnw[32], s_lnb[32], s_b1[32], s_b2[32];
+  for (int i = threadIdx.x; i < 32 * 48; i += blockDim.x) s_wo[i] = P.wo[i];
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) { s_w1[i] = P.w1[i]; s_w2[i] = P.w2[i]; }
+  if (threadIdx.x < 32) {
+    s_bo[threadIdx.x] = P.bo[threadIdx.x]; s_lnw[threadIdx.x] = P.ln_w[threadIdx.x]; s_lnb[threadIdx.x] = P.ln_b[threadIdx.x];
+    s_b1[threadIdx.x] = P.b1[threadIdx.x]; s_b2[threadIdx.x] = P.b2[threadIdx.x];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // warp-uniform query token: warps alternate t = 0 / 1 over the same 32 points (no divergence, K/V rows shared through L1)
+  const int p = (idx >> 6) * 32 + (idx & 31), t = (idx >> 5) & 1;
+  if (p >= P.np) return;
+  const float* qrow = P.qkv + (size_t)(p * 3 + t) * 144;
+  float out[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) out[o] = s_bo[o];
+#pragma unroll 1
+  for (int h = 0; h < 3; ++h) {
+    float q[16], att[16];
+    float dots[3];
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 a = *reinterpret_cast<const float4*>(qrow + h * 16 + d4 * 4);
+      q[d4 * 4] = a.x; q[d4 * 4 + 1] = a.y; q[d4 * 4 + 2] = a.z; q[d4 * 4 + 3] = a.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* krow = P.qkv + (size_t)(p * 3 + j) * 144 + 48 + h * 16;
+      float sdot = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 b = *reinterpret_cast<const float4*>(krow + d4 * 4);
+        sdot += q[d4 * 4] * b.x; sdot += q[d4 * 4 + 1] * b.y; sdot += q[d4 * 4 + 2] * b.z; sdot += q[d4 * 4 + 3] * b.w;
+      }
+      dots[j] = sdot * 0.25f;                               // dim_head ** -0.5
+    }
+    const float mx = fmaxf(dots[0], fmaxf(dots[1], dots[2]));
+    const float e0 = expf(dots[0] - mx), e1 = expf(dots[1] - mx), e2 = expf(dots[2] - mx);
+    const float inv = 1.f / (e0 + e1 + e2);
+    const float a0 = e0 * inv, a1 = e1 * inv, a2 = e2 * inv;
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 v0 = *reinterpret_cast<const float4*>(P.qkv + (size_t)(p * 3 + 0) * 144 + 96 + h * 16 + d4 * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(P.qkv + (size_t)(p * 3 + 1) * 144 + 96 + h * 16 + d4 * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(P.qkv + (size_t)(p * 3 + 2) * 144 + 96 + h * 16 + d4 * 4);
+      att[d4 * 4 + 0] = a0 * v0.x + a1 * v1.x + a2 * v2.x;
+      att[d4 * 4 + 1] = a0 * v0.y + a1 * v1.y + a2 * v2.y;
+      att[d4 * 4 + 2] = a0 * v0.z + a1 * v1.z + a2 * v2.z;
+      att[d4 * 4 + 3] = a0 * v0.w + a1 * v1.w + a2 * v2.w;
+    }
+    // to_out: out[o] += sum_d att[d] * Wo[o][h*16 + d]
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float4* wr = reinterpret_cast<const float4*>(s_wo + o * 48 + h * 16);
+      float acc = out[o];
+#pragma unroll
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 wv = wr[d4];
+        acc = fmaf(att[d4 * 4], wv.x, acc); acc = fmaf(att[d4 * 4 + 1], wv.y, acc);
+        acc = fmaf(att[d4 * 4 + 2], wv.z, acc); acc = fmaf(att[d4 * 4 + 3], wv.w, acc);
+      }
+      out[o] = acc;
+    }
+  }
+  // residual, LayerNorm (eps 1e-5)
+  float tok2[32], ln[32];
+  {
+    const float4* tr = reinterpret_cast<const float4*>(P.tok + (size_t)(p * 3 + t) * 32);
+    float mean = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 tv = tr[d4];
+      tok2[d4 * 4] = out[d4 * 4] + tv.x; tok2[d4 * 4 + 1] = out[d4 * 4 + 1] + tv.y;
+      tok2[d4 * 4 + 2] = out[d4 * 4 + 2] + tv.z; tok2[d4 * 4 + 3] = out[d4 * 4 + 3] + tv.w;
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) mean += tok2[o];
+    mean *= (1.f / 32.f);
+    float var = 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) { const float d = tok2[o] - mean; var += d * d; }
+    const float rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+    for (int o = 0; o < 32; ++o) ln[o] = (tok2[o] - mean) * rstd * s_lnw[o] + s_lnb[o];
+  }
+  // FeedForward: Linear(32,32) - GELU(erf) - Linear(32,32), + residual
+  float hmid[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const float4* wr = reinterpret_cast<const float4*>(s_w1 + o * 32);
+    float acc = s_b1[o];
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 wv = wr[d4];
+      acc = fmaf(ln[d4 * 4], wv.x, acc); acc = fmaf(ln[d4 * 4 + 1], wv.y, acc);
+      acc = fmaf(ln[d4 * 4 + 2], wv.z, acc); acc = fmaf(ln[d4 * 4 + 3], wv.w, acc);
+    }
+    hmid[o] = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));
+  }
+  float tok3[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const float4* wr = reinterpret_cast<const float4*>(s_w2 + o * 32);
+    float acc = s_b2[o];
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 wv = wr[d4];
+      acc = fmaf(hmid[d4 * 4], wv.x, acc); acc = fmaf(hmid[d4 * 4 + 1], wv.y, acc);
+      acc = fmaf(hmid[d4 * 4 + 2], wv.z, acc); acc = fmaf(hmid[d4 * 4 + 3], wv.w, acc);
+    }
+    tok3[o] = acc + tok2[o];
+  }
+  // decoder inputs, assembled in registers and written with 16-byte stores (rows are 16-byte aligned)
+  const float g0 = P.geo[(size_t)p * 8 + 3 * t], g1 = P.geo[(size_t)p * 8 + 3 * t + 1], g2 = P.geo[(size_t)p * 8 + 3 * t + 2];
+  auto pe = [&](int m, float gv) -> float {
+    return sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(gv, (float)(1 << (m >> 1)))));
+  };
+  if (t == 0) {
+    float vals[72];
+    vals[0] = g0; vals[1] = g1; vals[2] = g2;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) { vals[3 + 3 * m] = pe(m, g0); vals[4 + 3 * m] = pe(m, g1); vals[5 + 3 * m] = pe(m, g2); }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) vals[39 + o] = tok3[o];
+    vals[71] = 0.f;
+    float4* dx = reinterpret_cast<float4*>(P.x + (size_t)p * 72);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) dx[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+    if (P.hb) {
+      float4* dh = reinterpret_cast<float4*>(P.hb + (size_t)p * 200);
+#pragma unroll
+      for (int i = 0; i < 17; ++i) dh[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+      float* dhs = P.hb + (size_t)p * 200;
+      dhs[68] = vals[68]; dhs[69] = vals[69]; dhs[70] = vals[70];      // hb[71..198] belongs to pts_linears[4]'s output
+      dhs[199] = 0.f;
+    }
+  } else {
+    float vals[60];
+    vals[0] = g0; vals[1] = g1; vals[2] = g2;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { vals[3 + 3 * m] = pe(m, g0); vals[4 + 3 * m] = pe(m, g1); vals[5 + 3 * m] = pe(m, g2); }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) vals[27 + o] = tok3[o];
+    vals[59] = 0.f;
+    float4* dv = reinterpret_cast<float4*>(P.fv + (size_t)p * 188 + 128);
+#pragma unroll
+    for (int i = 0; i < 15; ++i) dv[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+  }
+  if (P.dbg_tok && P.p0 + p < P.dbg_max) {
+#pragma unroll
+    for (int o = 0; o < 32; ++o) P.dbg_tok[(P.p0 + p) * 64 + t * 32 + o] = tok3[o];
+  }
+}
+
 // sigma[p] = h[p] . w + b  (alpha_linear, triplane.py:302); warp per row of 128
 __global__ void k_alpha(const float* __restrict__ h, int ldh, const float* __restrict__ w, const float* __restrict__ b,
                         float* __restrict__ sigma, int np) {
@@ -362,21 +533,26 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   // conv1d_projection 192 -> 96, written as the third 32-wide slice of each token's 96-wide fusion input (renderer.py:350,423)
   RC(launch_gemm(pw.proj, cw.proj, cb.f3raw, 192, cb.comb + 64, 288, np, ACT_NONE, st, nullptr, 0, 32, 96));
   // conv1d_reprojection 96 -> 32 per token (renderer.py:424): rows = (point, token)
-  RC(launch_gemm(pw.reproj, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
-  // transformer layer (renderer.py:980-993): x = attn(LN(x)) + x ; x = ff(LN(x)) + x
-  k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok, w.ln1_w, w.ln1_b, cb.ln, rows3);
-  SHERF_LAUNCH_CHECK();
+  if (prec == SHERF_MLP_FP32) {
+    RC(launch_gemm(pw.reproj, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
+    // transformer layer (renderer.py:980-993): x = attn(LN(x)) + x ; x = ff(LN(x)) + x
+    k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok, w.ln1_w, w.ln1_b, cb.ln, rows3);
+    SHERF_LAUNCH_CHECK();
+  } else {
+    // tensor-core path: the first LayerNorm is fused into the reprojection's copy-out
+    RC(launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st, nullptr, 0, 0, 0,
+                          w.ln1_w, w.ln1_b, cb.ln, 32));
+  }
   RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
-  k_attention3<<<ceil_div(rows3, 128), 128, 0, st>>>(cb.qkv, cb.att, np);
-  SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.attn_out, cw.attn_out, cb.att, 48, cb.tok2, 32, rows3, ACT_NONE, st, cb.tok, 32));
-  k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok2, w.ln2_w, w.ln2_b, cb.ln, rows3);
-  SHERF_LAUNCH_CHECK();
-  RC(launch_gemm(pw.ff1, cw.ff1, cb.ln, 32, cb.ffh, 32, rows3, ACT_GELU, st));
-  RC(launch_gemm(pw.ff2, cw.ff2, cb.ffh, 32, cb.tok3, 32, rows3, ACT_NONE, st, cb.tok2, 32));
-  // decoder (triplane.py:285-316)
-  k_decoder_inputs<<<ceil_div(np, 8), 256, 0, st>>>(cb.geo, cb.tok3, cb.x, cb.hb, cb.fv, np, dbg_tok, p0, dbg_max);
-  SHERF_LAUNCH_CHECK();
+  {
+    TailParams T;
+    T.qkv = cb.qkv; T.tok = cb.tok; T.geo = cb.geo;
+    T.wo = w.attn_out_w; T.bo = w.attn_out_b; T.ln_w = w.ln2_w; T.ln_b = w.ln2_b; T.w1 = w.ff1_w; T.b1 = w.ff1_b; T.w2 = w.ff2_w; T.b2 = w.ff2_b;
+    T.x = cb.x; T.hb = (fused && prec != SHERF_MLP_FP32) ? nullptr : cb.hb; T.fv = cb.fv;
+    T.dbg_tok = dbg_tok; T.p0 = p0; T.dbg_max = dbg_max; T.np = np;
+    k_transformer_tail<<<ceil_div(np, 64), 128, 0, st>>>(T);       // 128 threads = 64 points x 2 query tokens
+    SHERF_LAUNCH_CHECK();
+  }
   if (fused && prec != SHERF_MLP_FP32) {
     // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip
     if (span_begin) span_begin(5);

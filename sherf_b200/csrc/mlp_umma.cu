@@ -41,6 +41,7 @@ struct UmmaArgs {
   int act;
   int M, N, K;
   uint32_t tmem_cols;
+  const float *ln_w, *ln_b; float* Y2; int ldy2;      // optional fused LayerNorm(32) of the output rows -> Y2 (N == 32 only)
 };
 
 // Padded K-direction stride of the A operand: 2048 B of data + 16 B so that the 8 lanes of a quarter-warp that write 8
@@ -199,13 +200,29 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
     for (int idx = tid; idx < 128 * n4; idx += 256) {
       const int row = idx / n4, c4 = idx - row * n4;
       const int m = m0 + row;
-      if (m >= g.M) continue;
+      const bool valid = m < g.M;
       const int n = c4 * 4;
       float4 v = *reinterpret_cast<const float4*>(stage + (size_t)row * sstride + n);
-      if (g.Res) {
+      if (g.Res && valid) {
         const float4 rr = *reinterpret_cast<const float4*>(g.Res + (size_t)m * g.ldr + n);
         v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
       }
+      if (g.ln_w) {
+        // LayerNorm over the 32 outputs of this row: the row lives in 8 consecutive lanes (n4 == 8)          renderer.py:931
+        float sum = v.x + v.y + v.z + v.w;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum * (1.f / 32.f);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        float sq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = rsqrtf(sq * (1.f / 32.f) + 1e-5f);
+        if (valid) {
+          const float4 o = make_float4(d0 * rstd * g.ln_w[n] + g.ln_b[n], d1 * rstd * g.ln_w[n + 1] + g.ln_b[n + 1],
+                                       d2 * rstd * g.ln_w[n + 2] + g.ln_b[n + 2], d3 * rstd * g.ln_w[n + 3] + g.ln_b[n + 3]);
+          *reinterpret_cast<float4*>(g.Y2 + (size_t)m * g.ldy2 + n) = o;
+        }
+      }
+      if (!valid) continue;
       const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
       float* yp = g.Y + (size_t)m * g.ldy + col;
       if (vec_ok) *reinterpret_cast<float4*>(yp) = v;
@@ -252,11 +269,12 @@ int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cud
 }
 
 int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
-                       const float* Res, int ldr, int ygroup, int ygstride) {
+                       const float* Res, int ldr, int ygroup, int ygstride, const float* ln_w, const float* ln_b, float* Y2, int ldy2) {
   UmmaArgs g;
   g.A = A; g.lda = lda; g.Whi = L.hi; g.Wlo = L.lo; g.Np = L.Np; g.nchunks = L.nchunks; g.bias = L.bias;
   g.Y = Y; g.ldy = ldy; g.ygroup = ygroup; g.ygstride = ygstride; g.Res = Res; g.ldr = ldr; g.act = act;
   g.M = M; g.N = L.N; g.K = L.K;
+  g.ln_w = (L.N == 32) ? ln_w : nullptr; g.ln_b = ln_b; g.Y2 = Y2; g.ldy2 = ldy2;
   uint32_t cols = 32;
   while ((int)cols < L.Np) cols <<= 1;
   g.tmem_cols = cols;

@@ -69,7 +69,8 @@ struct CanonWeights { CanonLayer proj, reproj, qkv, attn_out, ff1, ff2, pts[8], 
 size_t canonical_weight_floats();
 int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cudaStream_t st);
 int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
-                       const float* Res, int ldr, int ygroup, int ygstride);
+                       const float* Res, int ldr, int ygroup, int ygstride, const float* ln_w = nullptr, const float* ln_b = nullptr,
+                       float* Y2 = nullptr, int ldy2 = 0);
 int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
                        const float* Res, int ldr, int ygroup, int ygstride);
 

@@ -45,22 +45,37 @@ def shard_scene(scene: dict, rank: int, world: int, tile: int = TILE):
     return sh, idx
 
 
+_perm_cache: dict = {}
+
+
+def _gather_permutation(n_rays: int, world: int, tile: int, device) -> torch.Tensor:
+    """perm[ray] = row of that ray in the [world * pad] all-gather buffer (built once per shape, cached)."""
+    key = (n_rays, world, tile, str(device))
+    perm = _perm_cache.get(key)
+    if perm is None:
+        pad = padded_shard_size(n_rays, world, tile)
+        perm = torch.empty(n_rays, dtype=torch.long)
+        for r in range(world):
+            idx = shard_indices(n_rays, r, world, tile)
+            perm[idx] = r * pad + torch.arange(idx.numel())
+        perm = perm.to(device)
+        _perm_cache[key] = perm
+    return perm
+
+
 def all_gather_tiles(local: torch.Tensor, n_rays: int, group=None, tile: int = TILE) -> torch.Tensor:
     """local: [n_local, C] rendered values of this rank's rays (shard_indices order).  Returns the full [n_rays, C]
-    on every rank using a single all_gather of equally padded shards."""
+    on every rank using a single all_gather of equally padded shards followed by one index_select."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     pad = padded_shard_size(n_rays, world, tile)
-    buf = local.new_zeros(pad, local.shape[1])
-    buf[:local.shape[0]] = local
+    if local.shape[0] == pad:
+        buf = local.contiguous()
+    else:
+        buf = local.new_zeros(pad, local.shape[1])
+        buf[:local.shape[0]] = local
     gathered = local.new_empty(world * pad, local.shape[1])
     dist.all_gather_into_tensor(gathered, buf, group=group)
-    full = local.new_empty(n_rays, local.shape[1])
-    for r in range(world):
-        idx = shard_indices(n_rays, r, world, tile, device=local.device)
-        full[idx] = gathered[r * pad:r * pad + idx.numel()]
-    assert shard_indices(n_rays, rank, world, tile).numel() == local.shape[0]
-    return full
+    return gathered.index_select(0, _gather_permutation(n_rays, world, tile, local.device))
 
 
 def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE):
