@@ -44,7 +44,7 @@ struct Layout {
   float* sigma; float* rgb;
   float* packed_w;
   float* canon_w;
-  unsigned char* fused_blob; float* fused_bias;
+  unsigned char* fused_blob; float* fused_bias; float* xf_blob;
   float* chunk;
   float* lbs_joints; float* lbs_pf;
 };
@@ -87,6 +87,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.canon_w = a.take<float>(canonical_weight_floats());
   L.fused_blob = a.take<unsigned char>(fused_blob_bytes());
   L.fused_bias = a.take<float>(9 * 144);
+  L.xf_blob = a.take<float>(xformer_blob_floats());
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
   return a.off;
@@ -217,7 +218,11 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   else RC(run_pack_canonical(*weights, L.canon_w, cw, st));
   FusedPlan fplan;
   const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
-  if (use_fused) RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
+  if (use_fused) {
+    RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
+    fplan.xf_blob = nullptr;
+    if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, st)); fplan.xf_blob = L.xf_blob; }
+  }
 
   tm.end();
 

@@ -543,15 +543,22 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
     RC(launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st, nullptr, 0, 0, 0,
                           w.ln1_w, w.ln1_b, cb.ln, 32));
   }
-  RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
-  {
-    TailParams T;
-    T.qkv = cb.qkv; T.tok = cb.tok; T.geo = cb.geo;
-    T.wo = w.attn_out_w; T.bo = w.attn_out_b; T.ln_w = w.ln2_w; T.ln_b = w.ln2_b; T.w1 = w.ff1_w; T.b1 = w.ff1_b; T.w2 = w.ff2_w; T.b2 = w.ff2_b;
-    T.x = cb.x; T.hb = (fused && prec != SHERF_MLP_FP32) ? nullptr : cb.hb; T.fv = cb.fv;
-    T.dbg_tok = dbg_tok; T.p0 = p0; T.dbg_max = dbg_max; T.np = np;
-    k_transformer_tail<<<ceil_div(np, 64), 128, 0, st>>>(T);       // 128 threads = 64 points x 2 query tokens
-    SHERF_LAUNCH_CHECK();
+  if (fused && prec != SHERF_MLP_FP32 && fused->xf_blob) {
+    // qkv -> attention -> to_out -> LN2 -> FeedForward -> decoder inputs in one persistent tcgen05 kernel (xformer_fused.cu)
+    if (span_begin) span_begin(6);
+    RC(run_xformer_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->xf_blob, cb.ln, cb.tok, cb.geo, cb.x, cb.fv, np, dbg_tok, p0, dbg_max, st));
+    if (span_end) span_end();
+  } else {
+    RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
+    {
+      TailParams T;
+      T.qkv = cb.qkv; T.tok = cb.tok; T.geo = cb.geo;
+      T.wo = w.attn_out_w; T.bo = w.attn_out_b; T.ln_w = w.ln2_w; T.ln_b = w.ln2_b; T.w1 = w.ff1_w; T.b1 = w.ff1_b; T.w2 = w.ff2_w; T.b2 = w.ff2_b;
+      T.x = cb.x; T.hb = (fused && prec != SHERF_MLP_FP32) ? nullptr : cb.hb; T.fv = cb.fv;
+      T.dbg_tok = dbg_tok; T.p0 = p0; T.dbg_max = dbg_max; T.np = np;
+      k_transformer_tail<<<ceil_div(np, 64), 128, 0, st>>>(T);       // 128 threads = 64 points x 2 query tokens
+      SHERF_LAUNCH_CHECK();
+    }
   }
   if (fused && prec != SHERF_MLP_FP32) {
     // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip

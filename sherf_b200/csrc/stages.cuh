@@ -77,11 +77,17 @@ int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
 struct FusedSchedule { FusedChunk ch[38]; uint16_t layer_np[9]; uint16_t pad; };
-struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; };
+struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; };
 size_t fused_blob_bytes();
 extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
 int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, float* fv, int ldfv, float* sigma, int np, cudaStream_t st);
+
+// Fused tensor-core transformer layer + decoder-input assembly (xformer_fused.cu)
+size_t xformer_blob_floats();
+int run_pack_xformer(const SherfWeights& w, float* blob, cudaStream_t st);
+int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const float* ln1, const float* tok, const float* geo, float* x,
+                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st);
 
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
 // prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 (tcgen05 tensor cores)
