@@ -86,7 +86,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.packed_w = a.take<float>(packed_weight_floats());
   L.canon_w = a.take<float>(canonical_weight_floats());
   L.fused_blob = a.take<unsigned char>(fused_blob_bytes());
-  L.fused_bias = a.take<float>(9 * 144);
+  L.fused_bias = a.take<float>(10 * 144);
   L.xf_blob = a.take<float>(xformer_blob_floats());
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));

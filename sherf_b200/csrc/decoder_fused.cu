@@ -1,5 +1,5 @@
-// Fused NeRF-decoder trunk on the tensor cores: pts_linears[0..7] (with the skip concat) + feature_linear + alpha_linear
-// (triplane.py:293-303) for 128-point tiles, one persistent CTA per SM.  Activations never leave the SM:
+// Fused NeRF decoder on the tensor cores: pts_linears[0..7] (with the skip concat), feature_linear + alpha_linear,
+// views_linear (feature | PE4(dir) | tok1) and the rgb head (triplane.py:293-314) for 128-point tiles, one persistent CTA per SM.  Activations never leave the SM:
 //   hi parts   : shared memory, UMMA K-major no-swizzle canonical layout (padded LBO, see mlp_umma.cu)
 //   lo parts   : tensor memory (3xTF32 error compensation), consumed by tcgen05.mma with the A operand in TMEM
 //   accumulator: tensor memory, read back by the epilogue warps (bias + ReLU + tf32 split) straight into the next layer's operands
@@ -19,22 +19,24 @@ namespace sherf {
 #define TRACE_CLK() 0LL
 #endif
 
-constexpr int kFusedChunks = 38;
-constexpr int kFusedLayers = 9;
+constexpr int kFusedChunks = 44;
+constexpr int kFusedLayers = 10;
 constexpr int kNst = 3;                                  // weight ring stages (32 k-columns each; a 6 x 16 ring measured slower)
 constexpr uint32_t kLbo = 2064;                          // padded K-direction stride of A operands (bytes)
 constexpr uint32_t kXBytes = 18 * kLbo, kHBytes = 32 * kLbo;
 constexpr uint32_t kStageBytes = 2 * 8 * 144 * 16;       // hi + lo, 8 core-matrix columns, up to 144 rows
 constexpr uint32_t kColD0 = 0, kColD1 = 144, kColHlo = 288, kColXlo = 416;   // 2 x 144 accumulator + 128 H_lo + 72 X_lo = 488 <= 512
 
-static_assert(kFusedChunks == 38 && kFusedLayers == 9, "FusedSchedule (stages.cuh) is sized for 38 chunks / 9 layers");
+static_assert(kFusedChunks == 44 && kFusedLayers == 10, "FusedSchedule (stages.cuh) is sized for 44 chunks / 10 layers");
 
 struct FusedArgs {
   const float* X; int ldx;             // [np][72] decoder input rows (PE6(can) | tok0 | 0)
   const unsigned char* wblob;          // packed chunks in schedule order
   const float* bias;                   // [9][144] (row 8: feature bias 0..127, alpha bias at 128)
-  float* fv; int ldfv;                 // feature output -> fv[:, 0:128]
+  const float* fv; int ldfv;           // fv[:, 128:188] = PE4(cdir) | tok1 | 0 : the non-feature part of views_linear's input
   float* sigma;                        // [np]
+  float* rgb;                          // [np][3]
+  const float* rgb_w; const float* rgb_b;   // rgb_linear [3][64], [3]
   int np;
   long long* trace;                    // optional [gridDim][8] cycle counters (diagnostics)
   FusedSchedule sch;
@@ -54,6 +56,8 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
   __shared__ __align__(8) uint64_t full_bar[kNst], empty_bar[kNst], acc_bar, x_bar, hchunk_bar[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ FusedSchedule s_sch;
+  __shared__ float s_rgbw[3 * 64 + 4];
+  __shared__ float s_part[128 * 3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < (int)(sizeof(FusedSchedule) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&s_sch)[i] = reinterpret_cast<const uint32_t*>(&a.sch)[i];
@@ -67,6 +71,7 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
   }
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
   for (int i = tid; i < kFusedLayers * 144; i += blockDim.x) s_bias[i] = a.bias[i];
+  for (int i = tid; i < 3 * 64 + 3; i += blockDim.x) s_rgbw[i] = i < 192 ? a.rgb_w[i] : a.rgb_b[i - 192];
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
@@ -202,21 +207,25 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
         const uint32_t d_col = tmem_base + lane_base + ((l & 1) ? kColD1 : kColD0);
         // all 8 warps sweep the accumulator in 32-column chunks (warp: lane quarter q, 16-column half hsel); after each chunk
         // the next layer's MMA may consume those 32 k-columns of H while this epilogue continues with the next chunk
+        const int nchunk = (l == kFusedLayers - 1) ? 2 : 4;        // views_linear has 64 outputs, every other layer 128 (+ alpha)
+        float pr = 0.f, pg = 0.f, pb = 0.f;                         // partial rgb_linear dots (last layer)
         uint32_t vnext[16];
         umma::tmem_ld16(d_col + (uint32_t)(16 * hsel), vnext);
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < nchunk; ++j) {
           const int c0 = 32 * j + 16 * hsel;
           uint32_t v[16];
           umma::tmem_ld_wait();                             // chunk j has landed (and the previous chunk's tcgen05.st retired below)
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = vnext[i];
-          if (j < 3) umma::tmem_ld16(d_col + (uint32_t)(c0 + 32), vnext);     // prefetch chunk j+1 while chunk j is processed
+          if (j + 1 < nchunk) umma::tmem_ld16(d_col + (uint32_t)(c0 + 32), vnext);     // prefetch chunk j+1 while chunk j is processed
           if (l < kFusedLayers - 1) {
+            // pts_linears: bias + ReLU; feature_linear (l == 8): bias only.  Result becomes the next layer's A operand.
             float x[16];
             uint32_t lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              x[i] = fmaxf(__uint_as_float(v[i]) + bl[c0 + i], 0.f);
+              x[i] = __uint_as_float(v[i]) + bl[c0 + i];
+              if (l < 8) x[i] = fmaxf(x[i], 0.f);
               const float h = umma::to_tf32(x[i]);
               lo[i] = __float_as_uint(umma::to_tf32(x[i] - h));
               x[i] = h;
@@ -231,21 +240,63 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
             umma::fence_proxy_async_smem();
             umma::tc_fence_before_sync();
             mbar_arrive(&hchunk_bar[j]);
-          } else if (row_ok) {
-            // feature_linear (cols 0..127, no activation) -> fv                                        triplane.py:303
-            float4* dst = reinterpret_cast<float4*>(a.fv + (size_t)m * a.ldfv + c0);
+          } else {
+            // views_linear: bias + ReLU, then this thread's share of rgb_linear                          triplane.py:310-313
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4)
-              dst[g4] = make_float4(__uint_as_float(v[4 * g4]) + bl[c0 + 4 * g4], __uint_as_float(v[4 * g4 + 1]) + bl[c0 + 4 * g4 + 1],
-                                    __uint_as_float(v[4 * g4 + 2]) + bl[c0 + 4 * g4 + 2], __uint_as_float(v[4 * g4 + 3]) + bl[c0 + 4 * g4 + 3]);
+            for (int i = 0; i < 16; ++i) {
+              const float hv = fmaxf(__uint_as_float(v[i]) + bl[c0 + i], 0.f);
+              pr = fmaf(hv, s_rgbw[c0 + i], pr); pg = fmaf(hv, s_rgbw[64 + c0 + i], pg); pb = fmaf(hv, s_rgbw[128 + c0 + i], pb);
+            }
           }
         }
-        if (l == kFusedLayers - 1 && hsel == 0) {
+        if (l == 5) {
+          // X is dead (its last reader, layer 5, has completed): load V = [PE4(cdir) | tok1 | 0] (60 -> 64 columns) into X's buffers
+          const float4* vr = reinterpret_cast<const float4*>(a.fv + (size_t)m * a.ldfv + 128 + 32 * hsel);
+          float vv[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = row_ok && (hsel == 0 || i < 7);          // columns 60..63 are padding
+            const float4 f = ok ? __ldg(vr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[4 * i] = f.x; vv[4 * i + 1] = f.y; vv[4 * i + 2] = f.z; vv[4 * i + 3] = f.w;
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t lo[16];
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              float h4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float xv = vv[half * 16 + g4 * 4 + e];
+                h4[e] = umma::to_tf32(xv);
+                lo[g4 * 4 + e] = __float_as_uint(umma::to_tf32(xv - h4[e]));
+              }
+              *reinterpret_cast<float4*>(X_hi + (8 * hsel + 4 * half + g4) * kLbo + row * 16) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+            }
+            if (PREC == 3) umma::tmem_st16(tmem_base + lane_base + kColXlo + (uint32_t)(32 * hsel + 16 * half), lo);
+          }
+          if (PREC == 3) umma::tmem_st_wait();
+          umma::fence_proxy_async_smem();
+          umma::tc_fence_before_sync();
+        }
+        if (l == 8 && hsel == 0) {
           // alpha_linear = row 128 of the stacked feature/alpha weight                                  triplane.py:302
           uint32_t v8[8];
           umma::tmem_ld8(d_col + 128u, v8);
           umma::tmem_ld_wait();
           if (row_ok) a.sigma[m] = __uint_as_float(v8[0]) + bl[128];
+        }
+        if (l == kFusedLayers - 1) {
+          // combine the two column halves of the row and apply the sigmoid clamp                       triplane.py:313-314
+          if (hsel == 1) { s_part[row * 3] = pr; s_part[row * 3 + 1] = pg; s_part[row * 3 + 2] = pb; }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (hsel == 0 && row_ok) {
+            const float zr = pr + s_part[row * 3] + s_rgbw[192], zg = pg + s_part[row * 3 + 1] + s_rgbw[193], zb = pb + s_part[row * 3 + 2] + s_rgbw[194];
+            a.rgb[(size_t)m * 3] = (1.f / (1.f + expf(-zr))) * (1.f + 2.f * 0.001f) - 0.001f;
+            a.rgb[(size_t)m * 3 + 1] = (1.f / (1.f + expf(-zg))) * (1.f + 2.f * 0.001f) - 0.001f;
+            a.rgb[(size_t)m * 3 + 2] = (1.f / (1.f + expf(-zb))) * (1.f + 2.f * 0.001f) - 0.001f;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");           // s_part is reused by the next tile
         }
       }
     }
@@ -281,16 +332,17 @@ __global__ void k_pack_fused(const FusedPackJobs jobs, unsigned char* blob) {
 }
 
 __global__ void k_fused_bias(const SherfWeights w, float* bias) {
-  const int l = blockIdx.x, n = threadIdx.x;     // 9 x 144
+  const int l = blockIdx.x, n = threadIdx.x;     // 10 x 144
   float v = 0.f;
   if (l < 8) { if (n < 128) v = w.pts_b[l][n]; }
-  else { if (n < 128) v = w.feature_b[n]; else if (n == 128) v = w.alpha_b[0]; }
+  else if (l == 8) { if (n < 128) v = w.feature_b[n]; else if (n == 128) v = w.alpha_b[0]; }
+  else { if (n < 64) v = w.views_b[n]; }
   bias[l * 144 + n] = v;
 }
 
 long long* g_fused_trace = nullptr;   // set by sherf_debug_set_trace (diagnostics)
 
-size_t fused_blob_bytes() { return (size_t)2 * (128 * (72 + 128 * 4 + 200 + 128 * 2) + 144 * 128) * 4 + 1024; }
+size_t fused_blob_bytes() { return (size_t)2 * (128 * (72 + 128 * 4 + 200 + 128 * 2) + 144 * 128 + 64 * 192) * 4 + 1024; }
 
 int run_pack_fused(const SherfWeights& w, unsigned char* blob, float* bias, FusedSchedule& sch, cudaStream_t st) {
   FusedPackJobs jobs;
@@ -318,10 +370,13 @@ int run_pack_fused(const SherfWeights& w, unsigned char* blob, float* bias, Fuse
   seg(6, w.pts_w[6], nullptr, 128, 128, 128, 0, 128, 1, true, true);
   seg(7, w.pts_w[7], nullptr, 128, 128, 128, 0, 128, 1, true, true);
   seg(8, w.feature_w, w.alpha_w, 128, 144, 128, 0, 128, 1, true, true);
+  seg(9, w.views_w, nullptr, 64, 64, 187, 0, 128, 1, true, false);        // views_linear input = [feature | PE4(dir) | tok1]  triplane.py:308
+  seg(9, w.views_w, nullptr, 64, 64, 187, 128, 59, 0, false, true);       // the 59 non-feature columns come from X's (reused) buffers
   if (c != kFusedChunks) { set_error("internal: fused schedule has %d chunks", c); return SHERF_E_INVALID; }
   for (int l = 0; l < 8; ++l) sch.layer_np[l] = 128;
   sch.layer_np[8] = 144;
-  sch.pad = 0;
+  sch.layer_np[9] = 64;
+  sch.pad[0] = sch.pad[1] = 0;
   k_pack_fused<<<dim3(8, kFusedChunks), 256, 0, st>>>(jobs, blob);
   SHERF_LAUNCH_CHECK();
   k_fused_bias<<<kFusedLayers, 144, 0, st>>>(w, bias);
@@ -329,11 +384,11 @@ int run_pack_fused(const SherfWeights& w, unsigned char* blob, float* bias, Fuse
   return SHERF_OK;
 }
 
-int run_decoder_fused(int prec, const FusedSchedule& sch, const unsigned char* blob, const float* bias, const float* X, int ldx, float* fv,
-                      int ldfv, float* sigma, int np, cudaStream_t st) {
+int run_decoder_fused(int prec, const FusedSchedule& sch, const unsigned char* blob, const float* bias, const float* X, int ldx, const float* fv,
+                      int ldfv, float* sigma, float* rgb, const float* rgb_w, const float* rgb_b, int np, cudaStream_t st) {
   if (np <= 0) return SHERF_OK;
   FusedArgs a;
-  a.X = X; a.ldx = ldx; a.wblob = blob; a.bias = bias; a.fv = fv; a.ldfv = ldfv; a.sigma = sigma; a.np = np; a.sch = sch;
+  a.X = X; a.ldx = ldx; a.wblob = blob; a.bias = bias; a.fv = fv; a.ldfv = ldfv; a.sigma = sigma; a.rgb = rgb; a.rgb_w = rgb_w; a.rgb_b = rgb_b; a.np = np; a.sch = sch;
   a.trace = g_fused_trace;
   const size_t smem = kXBytes + kHBytes + kNst * kStageBytes + kFusedLayers * 144 * sizeof(float);
   static bool attr_done = false;
@@ -363,8 +418,9 @@ int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias,
   return SHERF_OK;
 }
 
-int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, float* fv, int ldfv, float* sigma, int np, cudaStream_t st) {
-  return run_decoder_fused(prec, plan.sch, plan.blob, plan.bias, X, ldx, fv, ldfv, sigma, np, st);
+int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, const float* fv, int ldfv, float* sigma, float* rgb,
+                           const float* rgb_w, const float* rgb_b, int np, cudaStream_t st) {
+  return run_decoder_fused(prec, plan.sch, plan.blob, plan.bias, X, ldx, fv, ldfv, sigma, rgb, rgb_w, rgb_b, np, st);
 }
 
 }  // namespace sherf

@@ -563,8 +563,9 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   if (fused && prec != SHERF_MLP_FP32) {
     // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip
     if (span_begin) span_begin(5);
-    RC(run_decoder_fused_plan(prec == SHERF_MLP_TF32X3 ? 3 : 1, *fused, cb.x, 72, cb.fv, 188, sigma_out + p0, np, st));
+    RC(run_decoder_fused_plan(prec == SHERF_MLP_TF32X3 ? 3 : 1, *fused, cb.x, 72, cb.fv, 188, sigma_out + p0, rgb_out + p0 * 3, w.rgb_w, w.rgb_b, np, st));
     if (span_end) span_end();
+    return SHERF_OK;                 // views_linear + rgb head are part of the fused kernel
   } else {
     RC(launch_gemm(pw.pts[0], cw.pts[0], cb.x, 72, cb.h1, 128, np, ACT_RELU, st));
     RC(launch_gemm(pw.pts[1], cw.pts[1], cb.h1, 128, cb.h2, 128, np, ACT_RELU, st));

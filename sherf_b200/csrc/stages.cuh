@@ -76,12 +76,13 @@ int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, 
 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
-struct FusedSchedule { FusedChunk ch[38]; uint16_t layer_np[9]; uint16_t pad; };
+struct FusedSchedule { FusedChunk ch[44]; uint16_t layer_np[10]; uint16_t pad[2]; };
 struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; };
 size_t fused_blob_bytes();
 extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
-int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, float* fv, int ldfv, float* sigma, int np, cudaStream_t st);
+int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, const float* fv, int ldfv, float* sigma, float* rgb,
+                           const float* rgb_w, const float* rgb_b, int np, cudaStream_t st);
 
 // Fused tensor-core transformer layer + decoder-input assembly (xformer_fused.cu)
 size_t xformer_blob_floats();
