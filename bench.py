@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 H, W, S = 512, 512, 64
 WORKLOAD = 'configs[1]: 512x512 RenderPeople-shape, 64 samples/ray, 1 subject novel view'
 FLOP_PER_POINT = 429_248          # MLP MACs x 2 per decoded (surviving) sample
-# the fused tcgen05 decoder kernel covers pts_linears[0..7] + feature_linear + alpha_linear (triplane.py:293-303)
-FLOP_PER_POINT_FUSED = 2 * (71 * 128 + 4 * 128 * 128 + 199 * 128 + 2 * 128 * 128 + 128 * 128 + 128)
+# the fused tcgen05 decoder kernel covers pts_linears[0..7], feature_linear, alpha_linear, views_linear, rgb_linear (triplane.py:293-314)
+FLOP_PER_POINT_FUSED = 2 * (71 * 128 + 4 * 128 * 128 + 199 * 128 + 2 * 128 * 128 + 128 * 128 + 128 + 187 * 64 + 64 * 3)
 TF32_OVER_BF16 = 0.5              # dense TF32 tensor peak is half the bf16 peak (B200_PROFILING.md table: 1.1 vs 2.25 PF)
 
 
@@ -276,7 +276,7 @@ def main():
         fused_ms = stage_ms[5] / calls
         if fused_ms > 0:       # tensor-core path: the dominant kernel is the fused decoder trunk (one launch per 131072-point chunk)
             n_launch = max(1, -(-int(p_call) // 131072))
-            roof_kernel = 'k_decoder_fused (tcgen05 kind::tf32, pts_linears 0-7 + feature/alpha, %d launches per view)' % n_launch
+            roof_kernel = 'k_decoder_fused (tcgen05 kind::tf32, whole NeRFDecoder: pts_linears 0-7, feature/alpha, views, rgb; %d launches per view)' % n_launch
             ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
             algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
             traffic = 67.3e6      # profiles/r1_d_ncu_full_k_decoder_fused.csv: dram read 42.9 MB + write 24.4 MB per launch

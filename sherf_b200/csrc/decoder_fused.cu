@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "stages.cuh"
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace sherf {
 
@@ -39,6 +40,7 @@ struct FusedArgs {
   const float* rgb_w; const float* rgb_b;   // rgb_linear [3][64], [3]
   int np;
   long long* trace;                    // optional [gridDim][8] cycle counters (diagnostics)
+  int dbg_flags;                       // timing experiments only (SHERF_FUSED_DBG): 1 skip proxy fence, 2 skip st wait
   FusedSchedule sch;
 };
 
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
       if (a.trace) { a.trace[blockIdx.x * 8 + 0] = t_wait; a.trace[blockIdx.x * 8 + 1] = TRACE_CLK() - t0; }
     }
   } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
       uint32_t cc = 0, par_x = 0, par_h[4] = {0, 0, 0, 0};
       long long t_op = 0, t_full = 0, t0 = TRACE_CLK();
       const uint32_t x_s = umma::smem_u32(X_hi), h_s = umma::smem_u32(H_hi), w_s = umma::smem_u32(Wst);
@@ -139,19 +141,20 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
             if (st < nsteps) {
               const uint32_t acc = st == 0 ? acc0 : 1u;
               if (PREC == 3) {
-                umma::mma_tf32_ts(d_col, alo0 + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
-                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
-                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+                umma::mma_tf32_ts_w(d_col, alo0 + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
+                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
+                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
               } else {
-                umma::mma_tf32_ss(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
               }
             }
           }
-          umma::mma_commit(&empty_bar[s]);                 // weight stage reusable once these MMAs retire
-          if (ch.last) umma::mma_commit(&acc_bar);         // layer accumulator complete
+          umma::mma_commit_w(&empty_bar[s]);                 // weight stage reusable once these MMAs retire
+          if (ch.last) umma::mma_commit_w(&acc_bar);         // layer accumulator complete
+          __syncwarp();
         }
       }
-      if (a.trace) { a.trace[blockIdx.x * 8 + 2] = t_op; a.trace[blockIdx.x * 8 + 3] = t_full; a.trace[blockIdx.x * 8 + 4] = TRACE_CLK() - t0; }
+      if (a.trace && lane == 0) { a.trace[blockIdx.x * 8 + 2] = t_op; a.trace[blockIdx.x * 8 + 3] = t_full; a.trace[blockIdx.x * 8 + 4] = TRACE_CLK() - t0; }
     }
   } else {
     // ===================== tile loader + epilogue (warps 0-7) =====================
@@ -235,9 +238,9 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
               *reinterpret_cast<float4*>(H_hi + (c0 / 4 + g4) * kLbo + row * 16) = make_float4(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);
             if (PREC == 3) {
               umma::tmem_st16(tmem_base + lane_base + kColHlo + (uint32_t)c0, lo);
-              umma::tmem_st_wait();
+              if (!(a.dbg_flags & 2)) umma::tmem_st_wait();
             }
-            umma::fence_proxy_async_smem();
+            if (!(a.dbg_flags & 1)) umma::fence_proxy_async_smem();
             umma::tc_fence_before_sync();
             mbar_arrive(&hchunk_bar[j]);
           } else {
@@ -390,6 +393,7 @@ int run_decoder_fused(int prec, const FusedSchedule& sch, const unsigned char* b
   FusedArgs a;
   a.X = X; a.ldx = ldx; a.wblob = blob; a.bias = bias; a.fv = fv; a.ldfv = ldfv; a.sigma = sigma; a.rgb = rgb; a.rgb_w = rgb_w; a.rgb_b = rgb_b; a.np = np; a.sch = sch;
   a.trace = g_fused_trace;
+  { const char* e = getenv("SHERF_FUSED_DBG"); a.dbg_flags = e ? atoi(e) : 0; }
   const size_t smem = kXBytes + kHBytes + kNst * kStageBytes + kFusedLayers * 144 * sizeof(float);
   static bool attr_done = false;
   static int num_sms = 148;

@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
   const int ntiles = (a.np + 127) / 128;
 
   if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
       uint32_t par_a = 0;
       const uint32_t b1s = umma::smem_u32(buf1), b2s = umma::smem_u32(buf2);
       const uint32_t whs = umma::smem_u32(w_hi), wls = whs + xf::kWFloats * 4;
@@ -86,11 +86,11 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
         for (int st = 0; st < nkg / 2; ++st) {
           const uint32_t acc = st == 0 ? 0u : 1u;
           if (PREC == 3) {
-            umma::mma_tf32_ts(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
-            umma::mma_tf32_ss(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
-            umma::mma_tf32_ss(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+            umma::mma_tf32_ts_w(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
+            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
+            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
           } else {
-            umma::mma_tf32_ss(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
           }
         }
       };
@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
             for (int t = 0; t < 2; ++t)
               gemm(b2s + (uint32_t)(t * 8) * xf::kLbo, xf::kLo2 + (uint32_t)(t * 32), xf::kW2, 32, 8, xf::kD4 + (uint32_t)(t * 32));
           }
-          umma::mma_commit(&acc_bar);
+          umma::mma_commit_w(&acc_bar);
+          __syncwarp();
         }
       }
     }
