@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
     }
     umma::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {                                   // converged issuer warp, one elected lane issues
       umma::tc_fence_after_sync();
       const uint32_t a_hi_s = umma::smem_u32(A_hi), w_hi_s = umma::smem_u32(W_hi);
       const uint32_t a_lo_s = umma::smem_u32(A_lo), w_lo_s = umma::smem_u32(W_lo);
@@ -149,19 +149,20 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         if (PREC == 3) {
           const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, kALbo, 128u);
           const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
-          umma::mma_tf32_ss(tmem_base, al, wh, idesc, first);          // small terms first
-          umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
-          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, 1u);
+          umma::mma_tf32_ss_w(tmem_base, al, wh, idesc, first);          // small terms first
+          umma::mma_tf32_ss_w(tmem_base, ah, wl, idesc, 1u);
+          umma::mma_tf32_ss_w(tmem_base, ah, wh, idesc, 1u);
         } else if (PREC == 4) {
           const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
-          umma::mma_tf32_ts(tmem_base, tmem_base + 256u + (uint32_t)(s * 8), wh, idesc, first);
-          umma::mma_tf32_ss(tmem_base, ah, wl, idesc, 1u);
-          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, 1u);
+          umma::mma_tf32_ts_w(tmem_base, tmem_base + 256u + (uint32_t)(s * 8), wh, idesc, first);
+          umma::mma_tf32_ss_w(tmem_base, ah, wl, idesc, 1u);
+          umma::mma_tf32_ss_w(tmem_base, ah, wh, idesc, 1u);
         } else {
-          umma::mma_tf32_ss(tmem_base, ah, wh, idesc, first);
+          umma::mma_tf32_ss_w(tmem_base, ah, wh, idesc, first);
         }
       }
-      umma::mma_commit(&mma_bar);
+      umma::mma_commit_w(&mma_bar);
+      __syncwarp();
     }
   }
   umma::mbar_wait(&mma_bar, parity);
