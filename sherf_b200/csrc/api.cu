@@ -102,17 +102,25 @@ static int chunk_cap(int N, int S) {
 // the same stage are summed (the point stages run once per chunk).
 struct StageTimer {
   struct Span { int stage; cudaEvent_t a, b; };
-  std::vector<Span> spans; bool on = false; cudaStream_t st = nullptr; int open = -1;
-  void init(bool enable, cudaStream_t s) { on = enable; st = s; }
+  std::vector<Span> spans; bool on = false; cudaStream_t st = nullptr;
+  std::vector<int> open_stack;
+  // events are pooled per thread: creating / destroying ~60 events per forward costs more than the stages they time
+  static std::vector<cudaEvent_t>& pool() { static thread_local std::vector<cudaEvent_t> p; return p; }
+  size_t used = 0;
+  cudaEvent_t get_event() {
+    auto& p = pool();
+    if (used == p.size()) { cudaEvent_t e; cudaEventCreate(&e); p.push_back(e); }
+    return p[used++];
+  }
+  void init(bool enable, cudaStream_t s) { on = enable; st = s; used = 0; }
   void begin(int stage) {
     if (!on) return;
     Span sp; sp.stage = stage;
-    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    sp.a = get_event(); sp.b = get_event();
     cudaEventRecord(sp.a, st);
     spans.push_back(sp);
     open_stack.push_back((int)spans.size() - 1);
   }
-  std::vector<int> open_stack;
   void end() {
     if (!on || open_stack.empty()) return;
     cudaEventRecord(spans[open_stack.back()].b, st);
@@ -126,7 +134,6 @@ struct StageTimer {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, sp.a, sp.b);
       g_stage_ms[sp.stage] += ms;
-      cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
     }
     spans.clear();
   }

@@ -4,6 +4,7 @@
 // of the feature tensor.  Replaces renderer.py:323-350 (minus conv1d_projection) and :402 (sample_from_planes).
 #include "common.cuh"
 #include "stages.cuh"
+#include <cstdlib>
 
 namespace sherf {
 
@@ -273,6 +274,257 @@ __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
   }
 }
 
+
+// =====================================================================================================================
+// 4 points per warp: lanes [8g, 8g+8) own point g; lane l8 = lane & 7 owns channels 4*l8 .. 4*l8+3 of every 32-channel
+// group (one 16-byte load per tap).  All geometry / tap-setup instructions therefore serve four points at once.
+// Same arithmetic (and the same operation order per point) as the one-point-per-warp kernel above.
+// =====================================================================================================================
+__device__ __forceinline__ void grp_lexmin(float& d, int& id) {      // reduce over the 8 lanes of a point group
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+    if (od < d || (od == d && oi < id)) { d = od; id = oi; }
+  }
+}
+
+__device__ int nn_unbounded8(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv, float qx, float qy,
+                             float qz, int l8, bool active) {
+  const int cx = min(max(grid_coord(qx, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int cy = min(max(grid_coord(qy, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int cz = min(max(grid_coord(qz, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  float best = 3.0e38f;
+  int bid = 0x7fffffff;
+  (void)active;            // inactive groups shadow a valid point and must still produce a valid vertex id
+  bool done = false;
+  for (int r = 1; __any_sync(0xffffffffu, !done); r *= 2) {
+    if (!done) {
+      const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dim[0] - 1);
+      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dim[1] - 1);
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dim[2] - 1);
+      const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncells = nx * ny * (z1 - z0 + 1);
+      for (int cc = l8; cc < ncells; cc += 8) {
+        const int xx = x0 + cc % nx, t = cc / nx;
+        const int cell = ((z0 + t / ny) * g.dim[1] + (y0 + t % ny)) * g.dim[0] + xx;
+        const int b = cell_start[cell], e = cell_start[cell + 1];
+        for (int k = b; k < e; ++k) {
+          const float4 v = gv[k];
+          const float d2 = dist2_xyz(qx, qy, qz, v.x, v.y, v.z);
+          const int id = __float_as_int(v.w);
+          if (d2 < best || (d2 == best && id < bid)) { best = d2; bid = id; }
+        }
+      }
+    }
+    grp_lexmin(best, bid);
+    if (!done) {
+      float m = 3.0e38f;
+      if (cx - r > 0) m = fminf(m, qx - (g.origin[0] + (float)(cx - r) * g.cell));
+      if (cx + r < g.dim[0] - 1) m = fminf(m, (g.origin[0] + (float)(cx + r + 1) * g.cell) - qx);
+      if (cy - r > 0) m = fminf(m, qy - (g.origin[1] + (float)(cy - r) * g.cell));
+      if (cy + r < g.dim[1] - 1) m = fminf(m, (g.origin[1] + (float)(cy + r + 1) * g.cell) - qy);
+      if (cz - r > 0) m = fminf(m, qz - (g.origin[2] + (float)(cz - r) * g.cell));
+      if (cz + r < g.dim[2] - 1) m = fminf(m, (g.origin[2] + (float)(cz + r + 1) * g.cell) - qz);
+      const float ms = m - 1.0e-4f * g.cell;
+      if (m > 1.0e38f || (ms > 0.f && best < ms * ms)) done = true;
+    }
+  }
+  return bid;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
+  __shared__ FrameConst fc;
+  for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l8 = lane & 7, gbase = lane & 24;
+  const int groups_total = gridDim.x * (blockDim.x >> 3);
+  const int niter = (P.np + groups_total - 1) / groups_total;
+  for (int it = 0; it < niter; ++it) {
+    const int lp_raw = it * groups_total + blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const bool active = lp_raw < P.np;
+    const int lp = active ? lp_raw : P.np - 1;               // inactive groups shadow the last point and store nothing
+    const int64_t gp = P.p0 + lp;
+    const int s = P.point_sample[gp];
+    const int n = s / P.S, i = s - n * P.S;
+    const float t = sample_depth(P.nearv[n], P.farv[n], i, P.S);
+    float dray[3] = {P.dirs[n * 3], P.dirs[n * 3 + 1], P.dirs[n * 3 + 2]};
+    float pw[3], q[3], vd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pw[k] = __fsub_rn(mul_add_sep(t, dray[k], P.origins[n * 3 + k]), fc.Th_tgt[k]);
+    rowvec_mat3(pw, fc.R_tgt, q);
+    rowvec_mat3(dray, fc.R_tgt, vd);
+    float can[3] = {q[0], q[1], q[2]}, cdir[3] = {vd[0], vd[1], vd[2]};
+    apply_warp(P.T1 + P.point_vid[gp], can, cdir, true);
+    const int vid3 = nn_unbounded8(fc.g3, P.g3_start, P.g3_verts, can[0], can[1], can[2], l8, active);
+    float ps[3] = {can[0], can[1], can[2]}, dummy[3] = {0.f, 0.f, 0.f};
+    apply_warp(P.T3 + vid3, ps, dummy, false);
+    float world[3], cam[3], pix[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      world[k] = (ps[0] * fc.Rinv_obs[k] + ps[1] * fc.Rinv_obs[3 + k] + ps[2] * fc.Rinv_obs[6 + k]) + fc.Th_obs[k];
+    mat3_vec(fc.camR, world, cam);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cam[k] += fc.camT[k];
+    mat3_vec(fc.camK, cam, pix);
+    const float zz = pix[2] + 1e-5f;
+    const float u = pix[0] / zz, v = pix[1] / zz;
+
+    // ---- tap setup: lane l8 prepares taps l8, l8+8, l8+16 of set A (20 taps) and of set B (24 taps) ----
+    float cn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cn[k] = 2.f * (can[k] - fc.twb_min[k]) / (fc.twb_max[k] - fc.twb_min[k]) - 1.f;
+    const float gx = 2.0f * u / (float)P.img_w - 1.0f, gy = 2.0f * v / (float)P.img_h - 1.0f;
+    float gn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gn[k] = ((can[k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
+    int offA[3], offB[3];
+    float wA[3], wB[3];
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int tA = l8 + 8 * sl;                              // 0..23 (20..23 unused)
+      {
+        const int grp = tA >> 2;
+        float ix, iy; int W, H, C;
+        if (grp < 3) {
+          const float px = grp == 2 ? cn[2] : cn[0], py = grp == 1 ? cn[2] : cn[1];
+          W = P.plane_w; H = P.plane_h; C = 32;
+          ix = ((px + 1.f) * (float)W - 1.f) * 0.5f; iy = ((py + 1.f) * (float)H - 1.f) * 0.5f;
+        } else if (grp == 3) {
+          W = P.feat_w; H = P.feat_h; C = P.feat_ch;
+          ix = (gx + 1.f) * 0.5f * (float)(W - 1); iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+        } else {
+          W = P.img_w; H = P.img_h; C = 1;
+          ix = (gx + 1.f) * 0.5f * (float)(W - 1); iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+        }
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int cxb = tA & 1, cyb = (tA >> 1) & 1;
+        const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+        const float wx = cxb ? ix - fx : (fx + 1.f) - ix, wy = cyb ? iy - fy : (fy + 1.f) - iy;
+        wA[sl] = wx * wy;
+        offA[sl] = (tA < 20 && xx >= 0 && xx < W && yy >= 0 && yy < H) ? (yy * W + xx) * C : -1;
+      }
+      {
+        const int tB = l8 + 8 * sl;                            // 0..23: level sl, corner l8
+        const int l = sl;
+        const int D = P.vol_d[l], H = P.vol_h[l], W = P.vol_w[l], C = P.vol_ch[l];
+        const float ix = (gn[0] + 1.f) * 0.5f * (float)(W - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(H - 1),
+                    iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int bx = tB & 1, by = (tB >> 1) & 1, bz = (tB >> 2) & 1;
+        const int xx = (int)fx + bx, yy = (int)fy + by, zz2 = (int)fz + bz;
+        const float wx = bx ? ix - fx : (fx + 1.f) - ix, wy = by ? iy - fy : (fy + 1.f) - iy, wz = bz ? iz - fz : (fz + 1.f) - iz;
+        wB[sl] = wx * wy * wz;
+        offB[sl] = (xx >= 0 && xx < W && yy >= 0 && yy < H && zz2 >= 0 && zz2 < D) ? ((zz2 * H + yy) * W + xx) * C : -1;
+      }
+    }
+    auto tapA = [&](int tix, int& off, float& w) {             // tap tix of this point's set A (tix is compile-time after unrolling)
+      off = __shfl_sync(0xffffffffu, offA[tix >> 3], gbase + (tix & 7));
+      w = __shfl_sync(0xffffffffu, wA[tix >> 3], gbase + (tix & 7));
+    };
+    float* comb = P.comb + (size_t)lp * 288;
+    float* f3 = P.f3raw + (size_t)lp * 192;
+    float* dbgf = (DBG && P.dbg_feat && gp < P.dbg_feat_max) ? P.dbg_feat + (size_t)gp * 384 : nullptr;
+    const int c4 = 4 * l8;
+
+    // ---- tri-planes ----
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* base = P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + c4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        int off; float w;
+        tapA(4 * k + tp, off, w);
+        const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp == 0) { acc.x = val.x * w; acc.y = val.y * w; acc.z = val.z * w; acc.w = val.w * w; }
+        else { acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w; }
+      }
+      if (active) *reinterpret_cast<float4*>(comb + k * 96 + c4) = acc;
+      if (DBG && dbgf && active) *reinterpret_cast<float4*>(dbgf + k * 32 + c4) = acc;
+    }
+    // ---- pixel-aligned 2-D features + rgb positional encoding ----
+    {
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+      float rgbc = 0.f;
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        int off; float w;
+        tapA(12 + tp, off, w);
+        const float4 v0 = off >= 0 ? __ldg(reinterpret_cast<const float4*>(P.feat_cl + off + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v1 = off >= 0 ? __ldg(reinterpret_cast<const float4*>(P.feat_cl + off + 32 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp == 0) { f0.x = v0.x * w; f0.y = v0.y * w; f0.z = v0.z * w; f0.w = v0.w * w; f1.x = v1.x * w; f1.y = v1.y * w; f1.z = v1.z * w; f1.w = v1.w * w; }
+        else { f0.x += v0.x * w; f0.y += v0.y * w; f0.z += v0.z * w; f0.w += v0.w * w; f1.x += v1.x * w; f1.y += v1.y * w; f1.z += v1.z * w; f1.w += v1.w * w; }
+        int offi; float wi;
+        tapA(16 + tp, offi, wi);
+        const float vi = (l8 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l8 * P.img_h * P.img_w + offi) : 0.f;
+        rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
+      }
+      // rgb_enc outputs 4*l8 .. 4*l8+3 of the 32 kept ones: [r,g,b, sin(..) ...]                     renderer.py:339,900-916
+      const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
+                  r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
+      float enc[4];
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const int o = c4 + e4;
+        if (o < 3) enc[e4] = o == 0 ? r0 : (o == 1 ? r1 : r2);
+        else {
+          const int e = o - 3, m = e / 3, c = e - 3 * m;
+          const float xc = c == 0 ? r0 : (c == 1 ? r1 : r2);
+          enc[e4] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+        }
+      }
+      if (active) {
+        *reinterpret_cast<float4*>(comb + 0 * 96 + 32 + c4) = f0;
+        *reinterpret_cast<float4*>(comb + 1 * 96 + 32 + c4) = f1;
+        *reinterpret_cast<float4*>(comb + 2 * 96 + 32 + c4) = make_float4(enc[0], enc[1], enc[2], enc[3]);
+        if (DBG && dbgf) {
+          *reinterpret_cast<float4*>(dbgf + 96 + c4) = f0;
+          *reinterpret_cast<float4*>(dbgf + 128 + c4) = f1;
+          *reinterpret_cast<float4*>(dbgf + 160 + c4) = make_float4(enc[0], enc[1], enc[2], enc[3]);
+        }
+      }
+    }
+    // ---- 3-D pyramid ----
+    {
+      int coff = 0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        int off[8]; float w[8];
+#pragma unroll
+        for (int tp = 0; tp < 8; ++tp) { off[tp] = __shfl_sync(0xffffffffu, offB[l], gbase + tp); w[tp] = __shfl_sync(0xffffffffu, wB[l], gbase + tp); }
+        const float* vol = P.vol_cl[l] + c4;
+#pragma unroll
+        for (int gsel = 0; gsel < 3; ++gsel) {
+          if (gsel <= l) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int tp = 0; tp < 8; ++tp) {
+              const float4 val = off[tp] >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + off[tp] + 32 * gsel)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              acc.x += val.x * w[tp]; acc.y += val.y * w[tp]; acc.z += val.z * w[tp]; acc.w += val.w * w[tp];
+            }
+            if (active) *reinterpret_cast<float4*>(f3 + coff + 32 * gsel + c4) = acc;
+            if (DBG && dbgf && active) *reinterpret_cast<float4*>(dbgf + 192 + coff + 32 * gsel + c4) = acc;
+          }
+        }
+        coff += 32 * (l + 1);
+      }
+    }
+    if (active) {
+      float gval = 0.f;
+      if (l8 == 0) gval = can[0]; else if (l8 == 1) gval = can[1]; else if (l8 == 2) gval = can[2];
+      else if (l8 == 3) gval = cdir[0]; else if (l8 == 4) gval = cdir[1]; else if (l8 == 5) gval = cdir[2];
+      P.geo[(size_t)lp * 8 + l8] = gval;
+      if (DBG && l8 == 0 && gp < P.dbg_max) {
+        if (P.dbg_vid3) P.dbg_vid3[gp] = vid3;
+        if (P.dbg_can) { P.dbg_can[gp * 3] = can[0]; P.dbg_can[gp * 3 + 1] = can[1]; P.dbg_can[gp * 3 + 2] = can[2]; }
+        if (P.dbg_cdir) { P.dbg_cdir[gp * 3] = cdir[0]; P.dbg_cdir[gp * 3 + 1] = cdir[1]; P.dbg_cdir[gp * 3 + 2] = cdir[2]; }
+        if (P.dbg_uv) { P.dbg_uv[gp * 2] = u; P.dbg_uv[gp * 2 + 1] = v; }
+      }
+    }
+  }
+}
+
 int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st) {
   dim3 grid((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32));
   k_to_channels_last<<<grid, 256, 0, st>>>(in, out, C, M);
@@ -282,8 +534,15 @@ int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStre
 
 int run_point_gather(const GatherParams& P, cudaStream_t st) {
   if (P.np <= 0) return SHERF_OK;
-  const int blocks = min(ceil_div(P.np, 8), 148 * 16);
-  k_point_gather<<<blocks, 256, 0, st>>>(P);
+  const bool dbg = P.dbg_feat || P.dbg_vid3 || P.dbg_can || P.dbg_cdir || P.dbg_uv;
+  if (getenv("SHERF_GATHER_V1")) {
+    const int blocks = min(ceil_div(P.np, 8), 148 * 16);
+    k_point_gather<<<blocks, 256, 0, st>>>(P);
+  } else {
+    const int blocks = min(ceil_div(P.np, 32), 148 * 8);
+    if (dbg) k_point_gather4<true><<<blocks, 256, 0, st>>>(P);
+    else k_point_gather4<false><<<blocks, 256, 0, st>>>(P);
+  }
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
 }

@@ -196,6 +196,13 @@ class ImportanceRenderer(nn.Module):
                                       'use_1d/2d/3d_feature, use_trans and use_nerf_decoder all True')
 
     def _weights_struct(self, decoder, device, keep):
+        # cache the struct while no parameter has been re-assigned or modified in place (data_ptr / _version signature)
+        params = [p for m in (self.conv1d_projection, self.conv1d_reprojection, self.transformer, decoder) for p in m.parameters()]
+        sig = (str(device), id(decoder)) + tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        cached = getattr(self, '_w_cache', None)
+        if cached is not None and cached[0] == sig:
+            return cached[1]
+        keep = []
         w = _lib.SherfWeights()
 
         def P(t):
@@ -216,6 +223,7 @@ class ImportanceRenderer(nn.Module):
         w.feature_w, w.feature_b = P(decoder.feature_linear.weight), P(decoder.feature_linear.bias)
         w.views_w, w.views_b = P(decoder.views_linear.weight), P(decoder.views_linear.bias)
         w.rgb_w, w.rgb_b = P(decoder.rgb_linear.weight), P(decoder.rgb_linear.bias)
+        self._w_cache = (sig, w, keep)
         return w
 
     @staticmethod
