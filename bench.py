@@ -201,7 +201,7 @@ def main():
                    dec, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'], scene['input_data'], scene['rendering_options'],
                    depth_clamp=clamp[v] if world > 1 else None)
 
-    stage_ms = [0.0] * 6
+    stage_ms = [0.0] * 8
     launches = [0]
     points = [0]
 
@@ -209,7 +209,7 @@ def main():
         outs = []
         for v in range(world):
             rgb, depth, acc = render(shard_dev[v], v)
-            for s_ in range(6):
+            for s_ in range(8):
                 stage_ms[s_] += lib.sherf_last_stage_ms(s_)
             launches[0] += ren.last_launches
             points[0] += ren.last_num_points
@@ -247,7 +247,7 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    stage_ms[:] = [0.0] * 6
+    stage_ms[:] = [0.0] * 8
     launches[0] = 0
     points[0] = 0
     clocks = ClockSampler(local_rank)
@@ -301,7 +301,7 @@ def main():
                     'note': 'per step: pinned-host rays/near/far/vertices -> device, ImportanceRenderer.forward via the C ABI, rendered rgb+depth+acc -> pinned host'},
             'gpu_launches': launches[0],
             'clocks': clk,
-            'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite', 'mlp:fused_decoder_kernel'])},
+            'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite', 'mlp:fused_decoder_kernel', 'mlp:fused_transformer_kernel', 'mlp:fused_fusion_kernel'])},
             'mlp_stage_tflops': p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,
             'roofline': {'bound': 'tensor', 'kernel': roof_kernel, 'achieved': ach_tflops, 'peak': tf32_peak, 'unit': 'TFLOP/s',
                          'frac': ach_tflops / tf32_peak, 'traffic': traffic,

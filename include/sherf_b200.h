@@ -197,7 +197,8 @@ SHERF_API int sherf_abi_version(void);
 SHERF_API int64_t sherf_last_launch_count(void);
 /* Device time (ms) of the named stage of the last forward on this thread, measured with CUDA events when
  * sherf_set_profiling(1) was called; stages: 0 prologue, 1 cull+compact, 2 warp+gather, 3 mlp (whole stage), 4 composite,
- * 5 the fused tcgen05 decoder kernel alone, 6 the fused tcgen05 transformer kernel alone (sub-spans of stage 3; 0 on the fp32 path). */
+ * 5 the fused tcgen05 decoder kernel alone, 6 the fused tcgen05 transformer kernel alone,
+ * 7 the fused tcgen05 feature-fusion kernel alone (sub-spans of stage 3; 0 on the fp32 path). */
 SHERF_API void sherf_set_profiling(int enabled);
 SHERF_API float sherf_last_stage_ms(int stage);
 

@@ -44,7 +44,7 @@ struct Layout {
   float* sigma; float* rgb;
   float* packed_w;
   float* canon_w;
-  unsigned char* fused_blob; float* fused_bias; float* xf_blob;
+  unsigned char* fused_blob; float* fused_bias; float* xf_blob; float* ff_blob;
   float* chunk;
   float* lbs_joints; float* lbs_pf;
 };
@@ -88,6 +88,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.fused_blob = a.take<unsigned char>(fused_blob_bytes());
   L.fused_bias = a.take<float>(10 * 144);
   L.xf_blob = a.take<float>(xformer_blob_floats());
+  L.ff_blob = a.take<float>(fusion_blob_floats());
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
   return a.off;
@@ -228,6 +229,8 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   if (use_fused) {
     RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
     fplan.xf_blob = nullptr;
+    fplan.ff_blob = nullptr;
+    if (!getenv("SHERF_NO_FUSED_FUSION")) { RC(run_pack_fusion(*weights, L.ff_blob, st)); fplan.ff_blob = L.ff_blob; }
     if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, st)); fplan.xf_blob = L.xf_blob; }
   }
 

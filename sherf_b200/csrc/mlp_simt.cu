@@ -530,18 +530,25 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
     if (prec == SHERF_MLP_FP32) return launch_simt_linear(P, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
     return launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, C, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
   };
-  // conv1d_projection 192 -> 96, written as the third 32-wide slice of each token's 96-wide fusion input (renderer.py:350,423)
-  RC(launch_gemm(pw.proj, cw.proj, cb.f3raw, 192, cb.comb + 64, 288, np, ACT_NONE, st, nullptr, 0, 32, 96));
-  // conv1d_reprojection 96 -> 32 per token (renderer.py:424): rows = (point, token)
-  if (prec == SHERF_MLP_FP32) {
-    RC(launch_gemm(pw.reproj, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
-    // transformer layer (renderer.py:980-993): x = attn(LN(x)) + x ; x = ff(LN(x)) + x
-    k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok, w.ln1_w, w.ln1_b, cb.ln, rows3);
-    SHERF_LAUNCH_CHECK();
+  if (fused && prec != SHERF_MLP_FP32 && fused->ff_blob) {
+    // conv1d_projection + conv1d_reprojection + LayerNorm-1 in one persistent tcgen05 kernel (fusion_fused.cu)
+    if (span_begin) span_begin(7);
+    RC(run_fusion_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->ff_blob, cb.f3raw, cb.comb, cb.tok, cb.ln, np, st));
+    if (span_end) span_end();
   } else {
-    // tensor-core path: the first LayerNorm is fused into the reprojection's copy-out
-    RC(launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st, nullptr, 0, 0, 0,
-                          w.ln1_w, w.ln1_b, cb.ln, 32));
+    // conv1d_projection 192 -> 96, written as the third 32-wide slice of each token's 96-wide fusion input (renderer.py:350,423)
+    RC(launch_gemm(pw.proj, cw.proj, cb.f3raw, 192, cb.comb + 64, 288, np, ACT_NONE, st, nullptr, 0, 32, 96));
+    // conv1d_reprojection 96 -> 32 per token (renderer.py:424): rows = (point, token)
+    if (prec == SHERF_MLP_FP32) {
+      RC(launch_gemm(pw.reproj, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st));
+      // transformer layer (renderer.py:980-993): x = attn(LN(x)) + x ; x = ff(LN(x)) + x
+      k_layernorm32<<<ceil_div(rows3, 8), 256, 0, st>>>(cb.tok, w.ln1_w, w.ln1_b, cb.ln, rows3);
+      SHERF_LAUNCH_CHECK();
+    } else {
+      // tensor-core path: the first LayerNorm is fused into the reprojection's copy-out
+      RC(launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, cw.reproj, cb.comb, 96, cb.tok, 32, rows3, ACT_NONE, st, nullptr, 0, 0, 0,
+                            w.ln1_w, w.ln1_b, cb.ln, 32));
+    }
   }
   if (fused && prec != SHERF_MLP_FP32 && fused->xf_blob) {
     // qkv -> attention -> to_out -> LN2 -> FeedForward -> decoder inputs in one persistent tcgen05 kernel (xformer_fused.cu)

@@ -77,12 +77,18 @@ int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
 struct FusedSchedule { FusedChunk ch[44]; uint16_t layer_np[10]; uint16_t pad[2]; };
-struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; };
+struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; const float* ff_blob; };
 size_t fused_blob_bytes();
 extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
 int run_decoder_fused_plan(int prec, const FusedPlan& plan, const float* X, int ldx, const float* fv, int ldfv, float* sigma, float* rgb,
                            const float* rgb_w, const float* rgb_b, int np, cudaStream_t st);
+
+// Fused tensor-core feature fusion: conv1d_projection + conv1d_reprojection + LayerNorm-1 (fusion_fused.cu)
+size_t fusion_blob_floats();
+int run_pack_fusion(const SherfWeights& w, float* blob, cudaStream_t st);
+int run_fusion_fused(int prec, const SherfWeights& w, const float* blob, const float* f3raw, const float* comb, float* tok, float* ln,
+                     int np, cudaStream_t st);
 
 // Fused tensor-core transformer layer + decoder-input assembly (xformer_fused.cu)
 size_t xformer_blob_floats();
