@@ -5,8 +5,11 @@
 
 A step = one pass of the hot path over N_gpus novel views of BASELINE.json configs[1]
 (512x512 RenderPeople-shape, 64 samples/ray, one subject / one observation), synthetic seeded inputs.
-With N > 1 (torchrun, one rank per GPU) every view's rays are dealt to all ranks in interleaved tiles and each
-view ends with ONE all-gather of the rendered tiles (weak scaling: N views on N GPUs).
+With N > 1 (torchrun, one rank per GPU) the step's N x 262 144 rays are sharded across the ranks -- by default at view
+granularity (rank r renders view r: the shard of the ray batch it owns), and the step ends with ONE all-gather of the
+rendered tiles so that every rank holds all N images (weak scaling: N views on N GPUs).  `--shard tiles` instead
+deals every view's rays to all ranks in interleaved 256-ray tiles with one all-gather per view (the single-view
+latency mode of sherf_b200.dist.render_sharded).
 Prints one JSON line (see README / DESIGN.md "Measurement").
 """
 from __future__ import annotations
@@ -39,6 +42,7 @@ def parse():
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32', 'tf32x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='views', choices=['views', 'tiles'], help='N>1: ray-batch sharding granularity')
     return ap.parse_args()
 
 
@@ -190,8 +194,10 @@ def main():
     N = H * W
     clamp = [sd.depth_range(v['near'], v['far'], S) for v in views]
     # this rank's tiles of every view (device resident for `value`, pinned host copies for `e2e`)
-    idx = sd.shard_indices(N, rank, world)
-    shard_host = [{k: v[k][:, idx].contiguous().pin_memory() for k in v} for v in views]
+    by_tiles = world > 1 and args.shard == 'tiles'
+    my_views = list(range(world)) if (by_tiles or world == 1) else [rank]
+    idx = sd.shard_indices(N, rank, world) if by_tiles else torch.arange(N)
+    shard_host = [{k: views[v][k][:, idx].contiguous().pin_memory() for k in views[v]} for v in my_views]
     shard_dev = [{k: t.to(dev) for k, t in sh.items()} for sh in shard_host]
     pose_host = {k: base['input_data'][k] for k in ('vertices',)}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                   # > 126 MB L2
@@ -199,32 +205,44 @@ def main():
     def render(sh, v):
         return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
                    dec, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'], scene['input_data'], scene['rendering_options'],
-                   depth_clamp=clamp[v] if world > 1 else None)
+                   depth_clamp=clamp[v] if by_tiles else None)
 
     stage_ms = [0.0] * 8
     launches = [0]
     points = [0]
 
+    def gather_views(local):
+        """view-granular sharding: one all-gather of the rendered [N,5] tiles -> every rank holds all `world` images"""
+        full = local.new_empty(world * N, 5)
+        dist.all_gather_into_tensor(full, local.contiguous())
+        return full
+
     def step_device():
         outs = []
-        for v in range(world):
-            rgb, depth, acc = render(shard_dev[v], v)
+        for j, v in enumerate(my_views):
+            rgb, depth, acc = render(shard_dev[j], v)
             for s_ in range(8):
                 stage_ms[s_] += lib.sherf_last_stage_ms(s_)
             launches[0] += ren.last_launches
             points[0] += ren.last_num_points
             local = torch.cat([rgb[0], depth[0], acc[0]], -1)
-            outs.append(sd.all_gather_tiles(local, N) if world > 1 else local)
+            outs.append(sd.all_gather_tiles(local, N) if by_tiles else (gather_views(local) if world > 1 else local))
         return outs
 
     def step_e2e(host_out):
-        for v in range(world):
-            sh = {k: t.to(dev, non_blocking=True) for k, t in shard_host[v].items()}
+        for j, v in enumerate(my_views):
+            sh = {k: t.to(dev, non_blocking=True) for k, t in shard_host[j].items()}
             scene['input_data']['vertices'] = pose_host['vertices'].to(dev, non_blocking=True)
             rgb, depth, acc = render(sh, v)
             local = torch.cat([rgb[0], depth[0], acc[0]], -1)
-            full = sd.all_gather_tiles(local, N) if world > 1 else local
-            host_out[v].copy_(full, non_blocking=True)
+            if by_tiles:
+                host_out[v].copy_(sd.all_gather_tiles(local, N), non_blocking=True)
+            elif world > 1:
+                full = gather_views(local)
+                for vv in range(world):
+                    host_out[vv].copy_(full[vv * N:(vv + 1) * N], non_blocking=True)
+            else:
+                host_out[v].copy_(local, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -270,7 +288,7 @@ def main():
     if rank == 0:
         pk = peaks()
         samples_per_step = world * N * S
-        calls = args.steps * world
+        calls = args.steps * len(my_views)
         mlp_ms = stage_ms[3] / calls
         p_call = points[0] / calls
         fused_ms = stage_ms[5] / calls
@@ -286,15 +304,16 @@ def main():
             algo = f'{FLOP_PER_POINT} FLOP per surviving sample x {p_call:.0f} samples per view'
             traffic = None
         tf32_peak = pk['tensor_tflops'] * TF32_OVER_BF16
-        h2d = sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * world
+        h2d = (sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * len(my_views)) * (1 if by_tiles or world == 1 else world)
         line = {
             'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3 (3xTF32 split products, fp32 accumulate; fp32-grade)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'views_per_step': world,
-                       'parallelism': f'ray-tiles x{world}, one all-gather of rendered tiles per view' if world > 1 else 'single GPU',
-                       'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if world > 1 else p_call,
+                       'parallelism': ('single GPU' if world == 1 else (f'256-ray tiles of every view dealt to {world} ranks, one all-gather per view' if by_tiles else
+                                        f'ray batch sharded at view granularity over {world} ranks (1 view each), one all-gather of the rendered tiles per step')),
+                       'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if by_tiles else p_call,
                        'l2': 'explicit 256 MiB flush between timed steps (outside the events); working set > 126 MB L2'},
             'e2e': {'value': samples_per_step / (ms_e2e * 1e-3), 'unit': 'ray-samples/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': world * N * 5 * 4, 'ms_per_step': ms_e2e,
