@@ -46,6 +46,7 @@ struct Layout {
   float* canon_w;
   unsigned char* fused_blob; float* fused_bias; float* xf_blob; float* ff_blob;
   float* chunk;
+  float* gather2;        // second set of gather outputs (comb | f3raw | geo) for the gather / MLP overlap
   float* lbs_joints; float* lbs_pf;
 };
 
@@ -91,6 +92,7 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.ff_blob = a.take<float>(fusion_blob_floats());
   const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
+  L.gather2 = a.take<float>((size_t)cap * (288 + 192 + 8));
   return a.off;
 }
 
@@ -102,7 +104,7 @@ static int chunk_cap(int N, int S) {
 // Device-time accounting per stage: every begin()/end() pair is a CUDA-event span on the launching stream; spans of
 // the same stage are summed (the point stages run once per chunk).
 struct StageTimer {
-  struct Span { int stage; cudaEvent_t a, b; };
+  struct Span { int stage; cudaEvent_t a, b; cudaStream_t s; };
   std::vector<Span> spans; bool on = false; cudaStream_t st = nullptr;
   std::vector<int> open_stack;
   // events are pooled per thread: creating / destroying ~60 events per forward costs more than the stages they time
@@ -114,17 +116,17 @@ struct StageTimer {
     return p[used++];
   }
   void init(bool enable, cudaStream_t s) { on = enable; st = s; used = 0; }
-  void begin(int stage) {
+  void begin(int stage, cudaStream_t on_stream = nullptr) {
     if (!on) return;
-    Span sp; sp.stage = stage;
+    Span sp; sp.stage = stage; sp.s = on_stream ? on_stream : st;
     sp.a = get_event(); sp.b = get_event();
-    cudaEventRecord(sp.a, st);
+    cudaEventRecord(sp.a, sp.s);
     spans.push_back(sp);
     open_stack.push_back((int)spans.size() - 1);
   }
   void end() {
     if (!on || open_stack.empty()) return;
-    cudaEventRecord(spans[open_stack.back()].b, st);
+    cudaEventRecord(spans[open_stack.back()].b, spans[open_stack.back()].s);
     open_stack.pop_back();
   }
   void finish() {
@@ -141,6 +143,23 @@ struct StageTimer {
 };
 
 static thread_local StageTimer* g_tm = nullptr;
+
+// Internal side stream (per host thread): the warp+gather kernel of chunk i+1 runs concurrently with the persistent MLP
+// kernels of chunk i (they leave most issue slots idle and the gather kernel needs no shared memory).
+struct SideStream {
+  cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, gdone[2] = {nullptr, nullptr}, mdone[2] = {nullptr, nullptr}; int dev = -1;
+  int ensure() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return -1;
+    if (s && d == dev) return 0;
+    dev = d;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&gdone[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&mdone[i], cudaEventDisableTiming); }
+    return 0;
+  }
+};
+static thread_local SideStream g_side;
 static void nested_begin(int stage) { if (g_tm) g_tm->begin(stage); }
 static void nested_end() { if (g_tm) g_tm->end(); }
 
@@ -252,8 +271,18 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   // ---- stages 2+3 per chunk of surviving points: warp + gather, then fusion / transformer / decoder ----
   ChunkBuffers cb;
   carve_chunk_buffers(L.chunk, chunk_cap(N, S), cb);
-  for (int64_t p0 = 0; p0 < P; p0 += cb.cap) {
+  ChunkBuffers cbs[2] = {cb, cb};                                   // two sets of gather outputs, everything else shared
+  cbs[1].comb = L.gather2; cbs[1].f3raw = L.gather2 + (size_t)cb.cap * 288; cbs[1].geo = L.gather2 + (size_t)cb.cap * (288 + 192);
+  // measured on B200 (r1): the overlap is neutral (6.98 vs 7.00 ms) -- the gather blocks delay the start of the persistent MLP CTAs
+  // by as much as they hide -- so it is opt-in (SHERF_OVERLAP=1)
+  const bool overlap = P > cb.cap && getenv("SHERF_OVERLAP") && g_side.ensure() == 0;
+  cudaStream_t gs = overlap ? g_side.s : st;
+  if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.fork, 0)); }
+  int ci = 0;
+  for (int64_t p0 = 0; p0 < P; p0 += cb.cap, ++ci) {
     const int np = (int)((P - p0 < cb.cap) ? (P - p0) : cb.cap);
+    const int bsel = overlap ? (ci & 1) : 0;
+    const ChunkBuffers& cbi = cbs[bsel];
     GatherParams G;
     G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = S;
     G.point_sample = L.point_sample; G.point_vid = L.point_vid; G.p0 = p0; G.np = np;
@@ -265,18 +294,22 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
       G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
       G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
     }
-    G.comb = cb.comb; G.f3raw = cb.f3raw; G.geo = cb.geo;
+    G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
     G.dbg_vid3 = dbg ? dbg->point_vid3 : nullptr; G.dbg_can = dbg ? dbg->point_can : nullptr;
     G.dbg_cdir = dbg ? dbg->point_cdir : nullptr; G.dbg_uv = dbg ? dbg->point_uv : nullptr;
     G.dbg_feat = dbg ? dbg->point_feat : nullptr; G.dbg_max = dbg ? dbg->max_points : 0;
     G.dbg_feat_max = dbg ? dbg->max_feat_points : 0;
-    tm.begin(2);
-    RC(run_point_gather(G, st));
+    // gather of chunk ci (side stream): its output buffers must have been released by the MLP of chunk ci-2
+    if (overlap && ci >= 2) SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.mdone[bsel], 0));
+    tm.begin(2, gs);
+    RC(run_point_gather(G, gs));
     tm.end();
+    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.gdone[bsel], gs)); SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.gdone[bsel], 0)); }
     tm.begin(3);
-    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cb, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st,
+    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cbi, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st,
                nested_begin, nested_end));
     tm.end();
+    if (overlap) SHERF_CUDA_OK(cudaEventRecord(g_side.mdone[bsel], st));
   }
   if (dbg && P > 0) {
     const size_t cnt = (size_t)(P < dbg->max_points ? P : dbg->max_points);
