@@ -297,7 +297,7 @@ def main():
             roof_kernel = 'k_decoder_fused (tcgen05 kind::tf32, whole NeRFDecoder: pts_linears 0-7, feature/alpha, views, rgb; %d launches per view)' % n_launch
             ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
             algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
-            traffic = 67.3e6      # profiles/r1_d_ncu_full_k_decoder_fused.csv: dram read 42.9 MB + write 24.4 MB per launch
+            traffic = 87.7e6      # profiles/r1_n_ncu_full_k_decoder_fused.csv: dram read 85.3 MB + write 2.4 MB per 131 072-point launch
         else:
             roof_kernel = 'MLP stage (k_sgemm fp32 CUDA-core layers)'
             ach_tflops = p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0

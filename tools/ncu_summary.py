@@ -1,0 +1,35 @@
+"""Condense an ncu report (--set full, one kernel) into the handful of metrics profiles/*.csv keep.
+
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<tag>_ncu_full_<kernel>.csv
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = [
+    'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic',
+    'launch__grid_size', 'launch__block_size',
+    'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+    'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+]
+
+
+def main(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    names, units, vals = rows[0], rows[1], rows[2]
+    col = {n: i for i, n in enumerate(names)}
+    print('# kernel: %s' % vals[col['Kernel Name']][:120])
+    for k in KEEP:
+        if k in col:
+            print('%s,%s,%s' % (k, vals[col[k]], units[col[k]]))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
