@@ -39,7 +39,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sherf_b200', choices=['sherf_b200', 'reference'])
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32', 'tf32x3'],
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--shard', default='views', choices=['views', 'tiles'], help='N>1: ray-batch sharding granularity')
@@ -308,7 +308,8 @@ def main():
         line = {
             'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3 (3xTF32 split products, fp32 accumulate; fp32-grade)'}[args.precision],
+            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3 (3xTF32 split products, fp32 accumulate; fp32-grade)',
+                                                'bf16x3': 'bf16x3 decoder (bf16 hi/lo split products, 16 significand bits, fp32 accumulate) + tf32x3 fusion/transformer'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'views_per_step': world,
                        'parallelism': ('single GPU' if world == 1 else (f'256-ray tiles of every view dealt to {world} ranks, one all-gather per view' if by_tiles else

@@ -42,8 +42,10 @@ enum {
 };
 
 /* MLP arithmetic.  FP32 = CUDA-core fp32 FMA (parity mode, the reference disables TF32,
- * training_loop.py:169-171).  TF32 / TF32X3 = tcgen05 tensor-core paths. */
-enum { SHERF_MLP_FP32 = 0, SHERF_MLP_TF32 = 1, SHERF_MLP_TF32X3 = 2 };
+ * training_loop.py:169-171).  TF32 / TF32X3 = tcgen05 tensor-core paths (single-pass / error-compensated
+ * 3xTF32).  BF16X3 = 3xTF32 for the fusion conv and the transformer, bf16 split products (a_hi*w_hi +
+ * a_lo*w_hi + a_hi*w_lo, 16 significand bits per operand, fp32 accumulate) for the NeRF decoder. */
+enum { SHERF_MLP_FP32 = 0, SHERF_MLP_TF32 = 1, SHERF_MLP_TF32X3 = 2, SHERF_MLP_BF16X3 = 3 };
 
 /* The SMPL body model the reference loads in ImportanceRenderer.__init__ (renderer.py:282-284,
  * SMPL_to_tensor renderer.py:65-74). */

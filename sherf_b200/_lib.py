@@ -10,7 +10,7 @@ from . import build as _build
 c_float_p = C.c_void_p          # device pointers travel as plain integers
 c_int_p = C.c_void_p
 
-MLP_FP32, MLP_TF32, MLP_TF32X3 = 0, 1, 2
+MLP_FP32, MLP_TF32, MLP_TF32X3, MLP_BF16X3 = 0, 1, 2, 3
 
 
 class SherfSmplModel(C.Structure):

@@ -24,7 +24,16 @@ void set_error(const char* fmt, ...) {
 }
 
 constexpr int kMaxCell = 1 << 18;
-constexpr int kChunkCap = 1 << 17;        // points per MLP chunk (activation buffers are sized for this)
+// points per MLP chunk (activation buffers are sized for this); SHERF_CHUNK_CAP overrides it for tuning experiments
+static size_t chunk_cap_limit() {
+  static size_t cap = 0;
+  if (!cap) {
+    const char* e = getenv("SHERF_CHUNK_CAP");
+    const long v = e ? atol(e) : 0;
+    cap = v >= 128 ? (size_t)(v / 128 * 128) : (size_t)(1 << 17);
+  }
+  return cap;
+}
 
 struct Arena {
   char* base; size_t size; size_t off; bool dry;
@@ -45,6 +54,7 @@ struct Layout {
   float* packed_w;
   float* canon_w;
   unsigned char* fused_blob; float* fused_bias; float* xf_blob; float* ff_blob;
+  unsigned char* pp_blob; float* pp_bias; unsigned char* pp_xv;
   float* chunk;
   float* gather2;        // second set of gather outputs (comb | f3raw | geo) for the gather / MLP overlap
   float* lbs_joints; float* lbs_pf;
@@ -90,15 +100,18 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.fused_bias = a.take<float>(10 * 144);
   L.xf_blob = a.take<float>(xformer_blob_floats());
   L.ff_blob = a.take<float>(fusion_blob_floats());
-  const int cap = (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
+  const int cap = (int)((NS < chunk_cap_limit()) ? ((NS + 127) / 128 * 128) : chunk_cap_limit());
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
+  L.pp_blob = a.take<unsigned char>(pp_blob_bytes());
+  L.pp_bias = a.take<float>(10 * 128);
+  L.pp_xv = a.take<unsigned char>(pp_xv_bytes(cap));
   L.gather2 = a.take<float>((size_t)cap * (288 + 192 + 8));
   return a.off;
 }
 
 static int chunk_cap(int N, int S) {
   const size_t NS = (size_t)N * S;
-  return (int)((NS < (size_t)kChunkCap) ? ((NS + 127) / 128 * 128) : kChunkCap);
+  return (int)((NS < chunk_cap_limit()) ? ((NS + 127) / 128 * 128) : chunk_cap_limit());
 }
 
 // Device-time accounting per stage: every begin()/end() pair is a CUDA-event span on the launching stream; spans of
@@ -195,7 +208,7 @@ static int validate(const SherfSmplModel* smpl, const SherfFrame* fr, const Sher
               sc->feat_ch, sc->vol_ch[0], sc->vol_ch[1], sc->vol_ch[2]);
     return SHERF_E_UNSUPPORTED;
   }
-  if (opts->mlp_precision < SHERF_MLP_FP32 || opts->mlp_precision > SHERF_MLP_TF32X3) { set_error("unknown mlp_precision %d", opts->mlp_precision); return SHERF_E_UNSUPPORTED; }
+  if (opts->mlp_precision < SHERF_MLP_FP32 || opts->mlp_precision > SHERF_MLP_BF16X3) { set_error("unknown mlp_precision %d", opts->mlp_precision); return SHERF_E_UNSUPPORTED; }
   if (!rays->origins || !rays->dirs || !rays->near_ || !rays->far_ || !out->rgb || !out->depth || !out->acc || !sc->planes ||
       !sc->obs_img || !sc->obs_feat || !sc->vol[0] || !sc->vol[1] || !sc->vol[2] || !smpl->weights || !smpl->posedirs) {
     set_error("null device pointer in arguments");
@@ -244,6 +257,8 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, st));
   else RC(run_pack_canonical(*weights, L.canon_w, cw, st));
   FusedPlan fplan;
+  PpPlan pplan;
+  fplan.pp = nullptr;
   const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
   if (use_fused) {
     RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
@@ -251,6 +266,13 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     fplan.ff_blob = nullptr;
     if (!getenv("SHERF_NO_FUSED_FUSION")) { RC(run_pack_fusion(*weights, L.ff_blob, st)); fplan.ff_blob = L.ff_blob; }
     if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, st)); fplan.xf_blob = L.xf_blob; }
+    if (opts->mlp_precision == SHERF_MLP_BF16X3) {
+      RC(run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, st));
+      const int cap = chunk_cap(N, S);
+      pplan.xp = L.pp_xv;
+      pplan.vp = L.pp_xv + (size_t)((cap + 127) / 128) * 40960;
+      fplan.pp = &pplan;
+    }
   }
 
   tm.end();

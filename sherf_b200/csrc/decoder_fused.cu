@@ -39,7 +39,7 @@ struct FusedArgs {
   float* rgb;                          // [np][3]
   const float* rgb_w; const float* rgb_b;   // rgb_linear [3][64], [3]
   int np;
-  long long* trace;                    // optional [gridDim][8] cycle counters (diagnostics)
+  long long* trace;                    // optional [gridDim][16] cycle counters (diagnostics)
   int dbg_flags;                       // timing experiments only (SHERF_FUSED_DBG): 1 skip proxy fence, 2 skip st wait
   FusedSchedule sch;
 };
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
           umma::bulk_g2s(Wst + s * kStageBytes, a.wblob + ch.w_off, bytes, &full_bar[s]);
         }
       }
-      if (a.trace) { a.trace[blockIdx.x * 8 + 0] = t_wait; a.trace[blockIdx.x * 8 + 1] = TRACE_CLK() - t0; }
+      if (a.trace) { a.trace[blockIdx.x * 16 + 0] = t_wait; a.trace[blockIdx.x * 16 + 1] = TRACE_CLK() - t0; }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
           __syncwarp();
         }
       }
-      if (a.trace && lane == 0) { a.trace[blockIdx.x * 8 + 2] = t_op; a.trace[blockIdx.x * 8 + 3] = t_full; a.trace[blockIdx.x * 8 + 4] = TRACE_CLK() - t0; }
+      if (a.trace && lane == 0) { a.trace[blockIdx.x * 16 + 2] = t_op; a.trace[blockIdx.x * 16 + 3] = t_full; a.trace[blockIdx.x * 16 + 4] = TRACE_CLK() - t0; }
     }
   } else {
     // ===================== tile loader + epilogue (warps 0-7) =====================
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
         }
       }
     }
-    if (a.trace && tid == 0) { a.trace[blockIdx.x * 8 + 5] = t_acc; a.trace[blockIdx.x * 8 + 6] = t_x; a.trace[blockIdx.x * 8 + 7] = TRACE_CLK() - t0; }
+    if (a.trace && tid == 0) { a.trace[blockIdx.x * 16 + 5] = t_acc; a.trace[blockIdx.x * 16 + 6] = t_x; a.trace[blockIdx.x * 16 + 7] = TRACE_CLK() - t0; }
   }
   umma::tc_fence_before_sync();
   __syncthreads();

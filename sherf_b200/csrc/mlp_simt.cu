@@ -524,6 +524,9 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
             void (*span_end)()) {
   if (np <= 0) return SHERF_OK;
   const int rows3 = 3 * np;
+  // SHERF_MLP_BF16X3: the decoder runs as bf16 split products (decoder_pp.cu); fusion conv and transformer stay 3xTF32
+  const bool pp = prec == SHERF_MLP_BF16X3 && fused && fused->pp;
+  if (prec == SHERF_MLP_BF16X3) prec = SHERF_MLP_TF32X3;
   // one linear layer on the selected arithmetic
   auto launch_gemm = [&](const PackedLayer& P, const CanonLayer& C, const float* A, int lda, float* Y, int ldy, int M, int act,
                          cudaStream_t s, const float* Res = nullptr, int ldr = 0, int yg = 0, int ygs = 0) -> int {
@@ -566,6 +569,14 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
       k_transformer_tail<<<ceil_div(np, 64), 128, 0, st>>>(T);       // 128 threads = 64 points x 2 query tokens
       SHERF_LAUNCH_CHECK();
     }
+  }
+  if (pp) {
+    // whole NeRFDecoder, two tiles in flight per SM, activations in tensor memory
+    if (span_begin) span_begin(5);
+    RC(run_pack_xv(cb.x, 72, cb.fv, 188, np, fused->pp->xp, fused->pp->vp, st));
+    RC(run_decoder_pp(*fused->pp, w, fused->pp->xp, fused->pp->vp, sigma_out + p0, rgb_out + p0 * 3, np, st));
+    if (span_end) span_end();
+    return SHERF_OK;
   }
   if (fused && prec != SHERF_MLP_FP32) {
     // pts_linears[0..7] + feature_linear + alpha_linear in one persistent tcgen05 kernel, activations on-chip

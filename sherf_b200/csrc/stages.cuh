@@ -77,7 +77,15 @@ int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
 struct FusedSchedule { FusedChunk ch[44]; uint16_t layer_np[10]; uint16_t pad[2]; };
-struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; const float* ff_blob; };
+// Ping-pong bf16x3 decoder (decoder_pp.cu): weight chunk offsets, packed weights / biases, packed X|V input tiles of one chunk
+struct PpPlan { uint32_t w_off[23]; const unsigned char* blob; const float* bias; unsigned char* xp; unsigned char* vp; };
+struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; const float* ff_blob; const PpPlan* pp; };
+size_t pp_blob_bytes();
+size_t pp_xv_bytes(int cap);
+int run_pack_pp(const SherfWeights& w, unsigned char* blob, float* bias, PpPlan& plan, cudaStream_t st);
+int run_pack_xv(const float* x, int ldx, const float* fv, int ldfv, int np, unsigned char* xp, unsigned char* vp, cudaStream_t st);
+int run_decoder_pp(const PpPlan& plan, const SherfWeights& w, const unsigned char* xp, const unsigned char* vp, float* sigma, float* rgb, int np,
+                   cudaStream_t st);
 size_t fused_blob_bytes();
 extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
@@ -97,7 +105,7 @@ int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const 
                       float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st);
 
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
-// prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 (tcgen05 tensor cores)
+// prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 | SHERF_MLP_BF16X3 (tcgen05 tensor cores)
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st,
             void (*span_begin)(int) = nullptr, void (*span_end)() = nullptr);

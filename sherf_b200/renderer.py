@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import _lib
 
-PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3,
+PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3, 'bf16x3': _lib.MLP_BF16X3,
               '_tf32x3_tmem_a': 99}      # diagnostic: 3xTF32 with the A_lo operand in tensor memory (sherf_debug_linear only)
 
 

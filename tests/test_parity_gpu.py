@@ -30,7 +30,7 @@ def linf(a, b):
     return float((a.double() - b.double()).abs().max()) if a.numel() else 0.0
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'bf16x3'])
 @pytest.mark.parametrize('case', GOLDEN_CASES)
 def test_against_reference_golden(case, precision, smpl_model):
     g = load_golden(case)
