@@ -30,6 +30,7 @@ WORKLOAD = 'configs[1]: 512x512 RenderPeople-shape, 64 samples/ray, 1 subject no
 FLOP_PER_POINT = 429_248          # MLP MACs x 2 per decoded (surviving) sample
 # the fused tcgen05 decoder kernel covers pts_linears[0..7], feature_linear, alpha_linear, views_linear, rgb_linear (triplane.py:293-314)
 FLOP_PER_POINT_FUSED = 2 * (71 * 128 + 4 * 128 * 128 + 199 * 128 + 2 * 128 * 128 + 128 * 128 + 128 + 187 * 64 + 64 * 3)
+GATHER_BYTES_PER_POINT = 8752     # tri-plane 1536 + 2-D feature 1024 + rgb 48 + 3-D pyramid 6144 bytes of taps per surviving sample
 TF32_OVER_BF16 = 0.5              # dense TF32 tensor peak is half the bf16 peak (B200_PROFILING.md table: 1.1 vs 2.25 PF)
 
 
@@ -39,7 +40,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sherf_b200', choices=['sherf_b200', 'reference'])
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
+    ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--shard', default='views', choices=['views', 'tiles'], help='N>1: ray-batch sharding granularity')
@@ -292,18 +293,31 @@ def main():
         mlp_ms = stage_ms[3] / calls
         p_call = points[0] / calls
         fused_ms = stage_ms[5] / calls
-        if fused_ms > 0:       # tensor-core path: the dominant kernel is the fused decoder trunk (one launch per 131072-point chunk)
-            n_launch = max(1, -(-int(p_call) // 131072))
+        chunk_cap = int(os.environ.get('SHERF_CHUNK_CAP', 0)) or 524288       # api.cu chunk_cap_limit()
+        n_launch = max(1, -(-int(p_call) // chunk_cap))
+        issued_per_useful = 1
+        if fused_ms > 0 and args.precision == 'bf16x3':
+            # dominant kernel: the ping-pong decoder; its MMAs are kind::f16 (bf16), so the peak is the bf16 one
+            roof_kernel = 'k_decoder_pp (tcgen05 kind::f16 bf16 split products, whole NeRFDecoder, two 128-point tiles in flight per SM; %d launches per view)' % n_launch
+            ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
+            algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
+            traffic = None
+            peak, issued_per_useful = pk['tensor_tflops'], 3
+            peak_src = pk['src'] + ': dense bf16; useful FLOPs counted once although bf16x3 issues 3 MMAs per product (issued_frac counts all three)'
+        elif fused_ms > 0:       # 3xTF32 / TF32 path: the dominant kernel is the fused decoder trunk
             roof_kernel = 'k_decoder_fused (tcgen05 kind::tf32, whole NeRFDecoder: pts_linears 0-7, feature/alpha, views, rgb; %d launches per view)' % n_launch
             ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
             algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
             traffic = 87.7e6      # profiles/r1_n_ncu_full_k_decoder_fused.csv: dram read 85.3 MB + write 2.4 MB per 131 072-point launch
+            peak, issued_per_useful = pk['tensor_tflops'] * TF32_OVER_BF16, (3 if args.precision == 'tf32x3' else 1)
+            peak_src = pk['src'] + ' x 0.5: dense TF32 rate is half the bf16 rate; useful FLOPs counted once although tf32x3 issues 3 MMAs per product'
         else:
             roof_kernel = 'MLP stage (k_sgemm fp32 CUDA-core layers)'
             ach_tflops = p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
             algo = f'{FLOP_PER_POINT} FLOP per surviving sample x {p_call:.0f} samples per view'
             traffic = None
-        tf32_peak = pk['tensor_tflops'] * TF32_OVER_BF16
+            peak = pk['tensor_tflops'] * TF32_OVER_BF16
+            peak_src = pk['src'] + ' x 0.5 (TF32 tensor peak, for reference: this path runs on the CUDA cores)'
         h2d = (sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * len(my_views)) * (1 if by_tiles or world == 1 else world)
         line = {
             'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
@@ -323,10 +337,12 @@ def main():
             'clocks': clk,
             'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite', 'mlp:fused_decoder_kernel', 'mlp:fused_transformer_kernel', 'mlp:fused_fusion_kernel'])},
             'mlp_stage_tflops': p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,
-            'roofline': {'bound': 'tensor', 'kernel': roof_kernel, 'achieved': ach_tflops, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                         'frac': ach_tflops / tf32_peak, 'traffic': traffic,
-                         'peak_source': pk['src'] + ' x 0.5: dense TF32 rate is half the bf16 rate; useful FLOPs counted once although tf32x3 issues 3 MMAs per product',
-                         'algorithmic': algo},
+            'roofline': {'bound': 'tensor', 'kernel': roof_kernel, 'achieved': ach_tflops, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': ach_tflops / peak, 'issued_frac': issued_per_useful * ach_tflops / peak, 'traffic': traffic,
+                         'peak_source': peak_src, 'algorithmic': algo},
+            'decoded_samples_per_sec': points[0] / args.steps * world / (ms * 1e-3),      # surviving samples through the MLP stack (rank 0's count x ranks)
+            'gather_hbm': {'achieved_GBps': p_call * GATHER_BYTES_PER_POINT / (stage_ms[2] / calls * 1e-3) / 1e9 if stage_ms[2] > 0 else None,
+                           'peak_GBps': pk['hbm_gbs'], 'note': 'SURVEY 8(d) algorithmic 8752 B of feature taps per surviving sample / warp+gather stage time (taps are mostly L2 hits, so this can exceed what DRAM moves)'},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)

@@ -30,7 +30,7 @@ static size_t chunk_cap_limit() {
   if (!cap) {
     const char* e = getenv("SHERF_CHUNK_CAP");
     const long v = e ? atol(e) : 0;
-    cap = v >= 128 ? (size_t)(v / 128 * 128) : (size_t)(1 << 17);
+    cap = v >= 128 ? (size_t)(v / 128 * 128) : (size_t)(1 << 19);
   }
   return cap;
 }

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     {
       uint32_t cc = 0, par_x = 0, par_h[4] = {0, 0, 0, 0};
+      const uint32_t el = umma::elect_one();     // one lane issues every MMA / commit of this warp
       long long t_op = 0, t_full = 0, t0 = TRACE_CLK();
       const uint32_t x_s = umma::smem_u32(X_hi), h_s = umma::smem_u32(H_hi), w_s = umma::smem_u32(Wst);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -141,16 +142,16 @@ __global__ void __launch_bounds__(320, 1) k_decoder_fused(const FusedArgs a) {
             if (st < nsteps) {
               const uint32_t acc = st == 0 ? acc0 : 1u;
               if (PREC == 3) {
-                umma::mma_tf32_ts_w(d_col, alo0 + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
-                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
-                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+                umma::mma_tf32_ts_e(d_col, alo0 + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc, el);
+                umma::mma_tf32_ss_e(d_col, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u, el);
+                umma::mma_tf32_ss_e(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u, el);
               } else {
-                umma::mma_tf32_ss_w(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+                umma::mma_tf32_ss_e(d_col, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc, el);
               }
             }
           }
-          umma::mma_commit_w(&empty_bar[s]);                 // weight stage reusable once these MMAs retire
-          if (ch.last) umma::mma_commit_w(&acc_bar);         // layer accumulator complete
+          umma::mma_commit_e(&empty_bar[s], el);                 // weight stage reusable once these MMAs retire
+          if (ch.last) umma::mma_commit_e(&acc_bar, el);         // layer accumulator complete
           __syncwarp();
         }
       }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
   } else if (warp == 8) {
     // ===================== MMA issuer (converged warp) =====================
     const uint32_t sbase = umma::smem_u32(smem);
+    const uint32_t el = umma::elect_one();         // one lane issues every MMA / commit of this warp
     uint32_t cnt = 0, wc = 0, par_t = 0;
     auto gemm = [&](uint32_t a_hi_addr, uint32_t a_lo_col, uint32_t w_hi_addr, uint32_t w_lo_addr, int N, uint32_t dcol, uint32_t acc0) {
       const uint32_t idesc = umma::make_idesc_tf32(128, N);
@@ -91,11 +92,11 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
       for (int st = 0; st < 4; ++st) {                       // 8 core-matrix columns = 4 MMA k-steps
         const uint32_t acc = st == 0 ? acc0 : 1u;
         if (PREC == 3) {
-          umma::mma_tf32_ts_w(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
-          umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
-          umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+          umma::mma_tf32_ts_e(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc, el);
+          umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u, el);
+          umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u, el);
         } else {
-          umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+          umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc, el);
         }
       }
     };
@@ -109,10 +110,10 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
         umma::tc_fence_after_sync();
         const uint32_t w_hi = sbase + ff::kRing + (uint32_t)s * ff::kStage;
         gemm(sbase + (b ? ff::kCh1 : ff::kCh0), b ? ff::kChLo1 : ff::kChLo0, w_hi, w_hi + ff::kStage / 2, 96, ff::kD1, c == 0 ? 0u : 1u);
-        umma::mma_commit_w(&chempty[b]);
-        umma::mma_commit_w(&wempty[s]);
+        umma::mma_commit_e(&chempty[b], el);
+        umma::mma_commit_e(&wempty[s], el);
       }
-      umma::mma_commit_w(&acc1);
+      umma::mma_commit_e(&acc1, el);
       // ---- reprojection per token: D2[:, 32t:+32] = f3d_t * Wr[:,64:96]^T + tri_t * Wr[:,0:32]^T + f2d_t * Wr[:,32:64]^T ----
       umma::mbar_wait(&f3d_ready, par_t);
       umma::tc_fence_after_sync();
@@ -125,10 +126,10 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
           umma::tc_fence_after_sync();
           gemm(sbase + (b ? ff::kCh1 : ff::kCh0), b ? ff::kChLo1 : ff::kChLo0, wr_hi + (uint32_t)(8 * part) * 32u * 16u,
                wr_lo + (uint32_t)(8 * part) * 32u * 16u, 32, ff::kD2 + (uint32_t)(32 * t), 1u);
-          umma::mma_commit_w(&chempty[b]);
+          umma::mma_commit_e(&chempty[b], el);
         }
       }
-      umma::mma_commit_w(&acc2);
+      umma::mma_commit_e(&acc2, el);
       par_t ^= 1;
       __syncwarp();
     }

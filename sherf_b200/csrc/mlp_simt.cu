@@ -556,7 +556,8 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   if (fused && prec != SHERF_MLP_FP32 && fused->xf_blob) {
     // qkv -> attention -> to_out -> LN2 -> FeedForward -> decoder inputs in one persistent tcgen05 kernel (xformer_fused.cu)
     if (span_begin) span_begin(6);
-    RC(run_xformer_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->xf_blob, cb.ln, cb.tok, cb.geo, cb.x, cb.fv, np, dbg_tok, p0, dbg_max, st));
+    RC(run_xformer_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->xf_blob, cb.ln, cb.tok, cb.geo, cb.x, cb.fv, np, dbg_tok, p0, dbg_max, st,
+                         pp ? fused->pp->xp : nullptr, pp ? fused->pp->vp : nullptr));
     if (span_end) span_end();
   } else {
     RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));
@@ -573,7 +574,7 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   if (pp) {
     // whole NeRFDecoder, two tiles in flight per SM, activations in tensor memory
     if (span_begin) span_begin(5);
-    RC(run_pack_xv(cb.x, 72, cb.fv, 188, np, fused->pp->xp, fused->pp->vp, st));
+    if (!fused->xf_blob) RC(run_pack_xv(cb.x, 72, cb.fv, 188, np, fused->pp->xp, fused->pp->vp, st));   // else the transformer kernel wrote the packed tiles
     RC(run_decoder_pp(*fused->pp, w, fused->pp->xp, fused->pp->vp, sigma_out + p0, rgb_out + p0 * 3, np, st));
     if (span_end) span_end();
     return SHERF_OK;

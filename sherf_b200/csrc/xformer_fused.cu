@@ -38,6 +38,7 @@ struct XfArgs {
   const float* wblob;                  // [2][8192] canonical hi | lo
   const float *bo, *ln_w, *ln_b, *b1, *b2;
   float *x, *fv;                       // [np][72], [np][188] (columns 128..187)
+  unsigned char *xp, *vp;              // optional packed bf16 hi/lo tiles for the ping-pong decoder (decoder_pp.cu); replace x / fv
   float* dbg_tok; int64_t p0, dbg_max;
   int np;
 };
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     {
       uint32_t par_a = 0;
+      const uint32_t el = umma::elect_one();       // one lane issues every MMA / commit of this warp
       const uint32_t b1s = umma::smem_u32(buf1), b2s = umma::smem_u32(buf2);
       const uint32_t whs = umma::smem_u32(w_hi), wls = whs + xf::kWFloats * 4;
       // one GEMM block: D[:, dcol:+N] (+)= A[128 x 4*nkg] * W[N x 4*nkg]^T
@@ -86,11 +88,11 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
         for (int st = 0; st < nkg / 2; ++st) {
           const uint32_t acc = st == 0 ? 0u : 1u;
           if (PREC == 3) {
-            umma::mma_tf32_ts_w(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc);
-            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u);
-            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u);
+            umma::mma_tf32_ts_e(tmem_base + dcol, tmem_base + a_lo_col + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc, el);
+            umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u, el);
+            umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u, el);
           } else {
-            umma::mma_tf32_ss_w(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc);
+            umma::mma_tf32_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc, el);
           }
         }
       };
@@ -112,8 +114,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
             for (int t = 0; t < 2; ++t)
               gemm(b2s + (uint32_t)(t * 8) * xf::kLbo, xf::kLo2 + (uint32_t)(t * 32), xf::kW2, 32, 8, xf::kD4 + (uint32_t)(t * 32));
           }
-          umma::mma_commit_w(&acc_bar);
-          __syncwarp();
+          umma::mma_commit_e(&acc_bar, el);
         }
       }
     }
@@ -270,32 +271,66 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
         float tok3[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { tok3[i] = __uint_as_float(o0[i]) + s_b2[i] + tok2[i]; tok3[16 + i] = __uint_as_float(o1[i]) + s_b2[16 + i] + tok2[16 + i]; }
-        if (row_ok) {
-          const float g0 = a.geo[(size_t)m * 8 + 3 * t], g1 = a.geo[(size_t)m * 8 + 3 * t + 1], g2 = a.geo[(size_t)m * 8 + 3 * t + 2];
+        {
+          const float g0 = row_ok ? a.geo[(size_t)m * 8 + 3 * t] : 0.f, g1 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 1] : 0.f,
+                      g2 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 2] : 0.f;
           auto pe = [&](int mm, float gv) -> float { return sinf(__fadd_rn((mm & 1) ? kPi2 : 0.f, __fmul_rn(gv, (float)(1 << (mm >> 1))))); };
+          // packed tile store: 8 consecutive k-columns of this row -> one 16-byte hi and one 16-byte lo chunk (consecutive rows
+          // are consecutive chunks, so a warp writes 512 contiguous bytes per core-matrix column)
+          auto put8 = [&](unsigned char* tile_base, int kg, uint32_t lo_off, const float* v8) {
+            uint4 h, l;
+            umma::split_bf16x2(v8[0], v8[1], h.x, l.x); umma::split_bf16x2(v8[2], v8[3], h.y, l.y);
+            umma::split_bf16x2(v8[4], v8[5], h.z, l.z); umma::split_bf16x2(v8[6], v8[7], h.w, l.w);
+            *reinterpret_cast<uint4*>(tile_base + (size_t)(kg * 128 + row) * 16) = h;
+            *reinterpret_cast<uint4*>(tile_base + lo_off + (size_t)(kg * 128 + row) * 16) = l;
+          };
           if (t == 0) {
-            float vals[72];
+            float vals[80];
             vals[0] = g0; vals[1] = g1; vals[2] = g2;
 #pragma unroll
             for (int mm = 0; mm < 12; ++mm) { vals[3 + 3 * mm] = pe(mm, g0); vals[4 + 3 * mm] = pe(mm, g1); vals[5 + 3 * mm] = pe(mm, g2); }
 #pragma unroll
             for (int o = 0; o < 32; ++o) vals[39 + o] = tok3[o];
-            vals[71] = 0.f;
-            float4* dx = reinterpret_cast<float4*>(a.x + (size_t)m * 72);
 #pragma unroll
-            for (int i = 0; i < 18; ++i) dx[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            for (int o = 71; o < 80; ++o) vals[o] = 0.f;
+            if (a.xp) {
+              if (!row_ok) {
+#pragma unroll
+                for (int o = 0; o < 71; ++o) vals[o] = 0.f;
+              }
+              unsigned char* tb_ = a.xp + (size_t)tile * 40960;
+#pragma unroll
+              for (int kg = 0; kg < 10; ++kg) put8(tb_, kg, 20480u, vals + 8 * kg);
+            } else if (row_ok) {
+              float4* dx = reinterpret_cast<float4*>(a.x + (size_t)m * 72);
+#pragma unroll
+              for (int i = 0; i < 18; ++i) dx[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            }
           } else {
-            float vals[60];
+            float vals[64];
             vals[0] = g0; vals[1] = g1; vals[2] = g2;
 #pragma unroll
             for (int mm = 0; mm < 8; ++mm) { vals[3 + 3 * mm] = pe(mm, g0); vals[4 + 3 * mm] = pe(mm, g1); vals[5 + 3 * mm] = pe(mm, g2); }
 #pragma unroll
             for (int o = 0; o < 32; ++o) vals[27 + o] = tok3[o];
-            vals[59] = 0.f;
-            float4* dv = reinterpret_cast<float4*>(a.fv + (size_t)m * 188 + 128);
 #pragma unroll
-            for (int i = 0; i < 15; ++i) dv[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            for (int o = 59; o < 64; ++o) vals[o] = 0.f;
+            if (a.vp) {
+              if (!row_ok) {
+#pragma unroll
+                for (int o = 0; o < 59; ++o) vals[o] = 0.f;
+              }
+              unsigned char* tb_ = a.vp + (size_t)tile * 32768;
+#pragma unroll
+              for (int kg = 0; kg < 8; ++kg) put8(tb_, kg, 16384u, vals + 8 * kg);
+            } else if (row_ok) {
+              float4* dv = reinterpret_cast<float4*>(a.fv + (size_t)m * 188 + 128);
+#pragma unroll
+              for (int i = 0; i < 15; ++i) dv[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            }
           }
+        }
+        if (row_ok) {
           if (a.dbg_tok && a.p0 + m < a.dbg_max) {
 #pragma unroll
             for (int o = 0; o < 32; ++o) a.dbg_tok[(a.p0 + m) * 64 + t * 32 + o] = tok3[o];
@@ -348,11 +383,11 @@ int run_pack_xformer(const SherfWeights& w, float* blob, cudaStream_t st) {
 }
 
 int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const float* ln1, const float* tok, const float* geo, float* x,
-                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st) {
+                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp) {
   if (np <= 0) return SHERF_OK;
   XfArgs a;
   a.ln1 = ln1; a.tok = tok; a.geo = geo; a.wblob = blob; a.bo = w.attn_out_b; a.ln_w = w.ln2_w; a.ln_b = w.ln2_b; a.b1 = w.ff1_b;
-  a.b2 = w.ff2_b; a.x = x; a.fv = fv; a.dbg_tok = dbg_tok; a.p0 = p0; a.dbg_max = dbg_max; a.np = np;
+  a.b2 = w.ff2_b; a.x = x; a.fv = fv; a.xp = xp; a.vp = vp; a.dbg_tok = dbg_tok; a.p0 = p0; a.dbg_max = dbg_max; a.np = np;
   static bool attr_done = false;
   static int num_sms = 148;
   if (!attr_done) {

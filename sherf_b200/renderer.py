@@ -142,7 +142,7 @@ def _ptr(t: torch.Tensor) -> int:
 
 class ImportanceRenderer(nn.Module):
     def __init__(self, use_1d_feature=True, use_2d_feature=True, use_3d_feature=True, use_trans=False, use_NeRF_decoder=False,
-                 smpl_model: dict | None = None, mlp_precision: str = 'tf32x3'):
+                 smpl_model: dict | None = None, mlp_precision: str = 'bf16x3'):
         super().__init__()
         self.use_1d_feature, self.use_2d_feature, self.use_3d_feature = use_1d_feature, use_2d_feature, use_3d_feature
         self.use_trans, self.use_NeRF_decoder = use_trans, use_NeRF_decoder

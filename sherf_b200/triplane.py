@@ -34,7 +34,7 @@ class NeRFDecoder(nn.Module):
                            'pass it as the `decoder` argument of ImportanceRenderer.forward')
 
 
-def hot_path_modules(smpl_model: dict | None = None, seed: int = 0, mlp_precision: str = 'tf32x3', dense_sigma: bool = False):
+def hot_path_modules(smpl_model: dict | None = None, seed: int = 0, mlp_precision: str = 'bf16x3', dense_sigma: bool = False):
     """(ImportanceRenderer, NeRFDecoder) in the configuration every shipped SHERF script uses (train.py:310-318,
     *.sh: use_trans / use_nerf_decoder True), default PyTorch init under `seed`.  `dense_sigma` rescales the density
     head so that a randomly initialised network renders an opaque body (used by parity tests and the bench so that

@@ -51,7 +51,7 @@ def scene_to(scene, device):
     return {k: mv(v) for k, v in scene.items()}
 
 
-def modules_from_weights(weights, smpl_model, mlp_precision='tf32x3'):
+def modules_from_weights(weights, smpl_model, mlp_precision='bf16x3'):
     """sherf_b200 modules carrying the given hot-path state dict ('renderer.*' / 'decoder.*' names)."""
     from sherf_b200.triplane import hot_path_modules
     ren, dec = hot_path_modules(smpl_model, seed=0, mlp_precision=mlp_precision)

@@ -187,3 +187,27 @@ def test_full_size_properties(smpl_model):
         for k in range(3):
             full[k][:, idx] = o[k]
     assert torch.equal(full[0], rgb) and torch.equal(full[1], depth) and torch.equal(full[2], acc)
+
+
+def test_full_size_precisions_agree(smpl_model):
+    """BASELINE configs[1] size: the tensor-core paths (3xTF32; bf16 split products with two tiles in flight per SM, every
+    tile / slot / tail-tile code path exercised: 6 964 tiles over 148 SMs) against the fp32 CUDA-core path, which the golden
+    fixtures anchor to the reference.  Tolerance: the stated image tolerance divided by ten."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=512, W=512, samples=64, seed=0), smpl_model), dev)
+    outs = {}
+    for prec in ('fp32', 'tf32x3', 'bf16x3'):
+        ren, dec = hot_path_modules(smpl_model, seed=0, mlp_precision=prec, dense_sigma=True)
+        ren, dec = ren.to(dev), dec.to(dev)
+        dbg = {'max_feat_points': 1}
+        outs[prec] = run_cuda(ren, dec, scene, debug=dbg) + (dbg['point_sigma'], dbg['point_rgb'])
+    ref = outs['fp32']
+    for prec in ('tf32x3', 'bf16x3'):
+        o = outs[prec]
+        e_rgb, e_depth, e_acc = linf(o[0], ref[0]), linf(o[1], ref[1]), linf(o[2], ref[2])
+        e_sig = float(((o[3] - ref[3]).abs() / (ref[3].abs() + 1)).max())
+        e_pt = linf(o[4], ref[4])
+        print(f'\n[512x512x64 {prec} vs fp32] rgb={e_rgb:.2e} depth={e_depth:.2e} acc={e_acc:.2e} sigma_rel={e_sig:.2e} rgb_pt={e_pt:.2e}')
+        assert e_rgb <= 1e-5 and e_acc <= 1e-5 and e_depth <= 1e-5
+        assert e_sig <= 1e-4 and e_pt <= 1e-5
