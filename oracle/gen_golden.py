@@ -112,13 +112,57 @@ def run_case(name, cfg, model, model_t):
           f'({os.path.getsize(path) / 1e6:.2f} MB)')
 
 
+IMPORTANCE_CASES = {
+    # SURVEY a13 / BASELINE configs[4] in miniature: coarse + fine importance samples through the REPAIRED fine pass
+    # (oracle/ref_shim.render_importance: the reference's own sample_importance / unify_samples / ray marcher)
+    'importance_28x20x16p12': dict(spec=S.SceneSpec(H=20, W=28, samples=16, seed=9, random_global_R=True), n_importance=12,
+                                   weight_seed=4, u_seed=3),
+}
+
+
+def importance_u(n_rays, n_importance, seed):
+    """The uniform draws standing for torch.rand at renderer.py:526 (CPU generator: identical on every machine)."""
+    return torch.rand(n_rays, n_importance, generator=torch.Generator().manual_seed(seed))
+
+
+def run_importance_case(name, cfg, model, model_t):
+    ren, dec = ref_shim.build_reference(model_t, cfg['weight_seed'])
+    with torch.no_grad():
+        dec.alpha_linear.weight *= 30
+        dec.alpha_linear.bias += 2.0
+    scene = S.make_scene(cfg['spec'], model)
+    scene['rendering_options']['depth_resolution_importance'] = cfg['n_importance']
+    spec = cfg['spec']
+    u = importance_u(spec.H * spec.W, cfg['n_importance'], cfg['u_seed'])
+    rgb, depth, acc, st = ref_shim.render_importance(ren, dec, scene, u, return_stages=True)
+    out = {
+        'spec': np.array([spec.H, spec.W, spec.samples, spec.seed, int(spec.random_global_R), int(spec.white_back)], np.int64),
+        'n_importance': np.int64(cfg['n_importance']), 'u_seed': np.int64(cfg['u_seed']),
+        'weight_seed': np.int64(cfg['weight_seed']), 'input_sha256': np.array(checksum(scene)),
+        'rgb': rgb[0].numpy(), 'depth': depth[0].numpy(), 'acc': acc[0].numpy(),
+        'coarse_weights': st['coarse_weights'].numpy(), 't_fine': st['t_fine'].numpy(),
+        'sigma_coarse': st['sigma_coarse'].numpy(), 'sigma_fine': st['sigma_fine'].numpy(), 'colors_fine': st['colors_fine'].numpy(),
+    }
+    for name_w, t in port.hot_path_state_dict(ren, dec).items():
+        out['w/' + name_w] = t.numpy()
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(f'{name}: N={rgb.shape[1]} S={spec.samples}+{cfg["n_importance"]} fine survivors={int((st["sigma_fine"] != -80).sum())} '
+          f'acc.max={float(acc.max()):.3f} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit('/root/reference not present: fixtures can only be generated where the reference is mounted')
     model = S.make_smpl_model(0)
     model_t = S.smpl_model_to_torch(model)
+    only = sys.argv[1:]
     for name, cfg in CASES.items():
-        run_case(name, cfg, model, model_t)
+        if not only or name in only:
+            run_case(name, cfg, model, model_t)
+    for name, cfg in IMPORTANCE_CASES.items():
+        if not only or name in only:
+            run_importance_case(name, cfg, model, model_t)
 
 
 if __name__ == '__main__':

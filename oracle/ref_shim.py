@@ -136,3 +136,59 @@ def render(ren, dec, scene: dict):
     return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None,
                scene['obs_sp_input'], dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'],
                scene['input_data'], scene['rendering_options'])
+
+
+@torch.no_grad()
+def render_importance(ren, dec, scene: dict, u: torch.Tensor, return_stages: bool = False):
+    """The REPAIRED coarse+fine forward, composed only of the reference's own methods.
+
+    The reference's fine pass (renderer.py:375-393) cannot run: :376 calls the ray marcher without `rays_d` and :383
+    calls `run_model` with the 5-argument EG3D signature.  Repair = fix those two call sites and nothing else:
+      * coarse colours / densities / depths: the reference's forward (:299-371), captured at its ray-marcher call;
+      * coarse weights: the reference's MipRayMarcher2 with `ray_directions` passed (:376 repaired);
+      * fine depths: the reference's sample_importance / sample_pdf (:483-542), with torch.rand (:526) returning `u`;
+      * fine colours / densities: the reference's forward again with sample_stratified returning the fine depths
+        (:383 repaired: the fine points go through the same cull, warps, gathers and decoder, :304-371);
+      * the reference's unify_samples (:446-456) and ray marcher (:393).
+    """
+    opts = scene['rendering_options']
+    n_imp = int(opts['depth_resolution_importance'])
+    opts0 = dict(opts, depth_resolution_importance=0)
+    marcher = ren.ray_marcher
+    cap = []
+
+    class _Tap(nn.Module):
+        def forward(self, colors, densities, depths, rays_d, options):
+            cap.append((colors, densities, depths))
+            return marcher(colors, densities, depths, rays_d, options)
+
+    def fwd():
+        return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None,
+                   scene['obs_sp_input'], dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'],
+                   scene['input_data'], opts0)
+    ren.ray_marcher = _Tap()
+    orig_rand = torch.rand
+    try:
+        fwd()
+        colors_c, dens_c, depths_c = cap[0]
+        weights_c = marcher(colors_c, dens_c, depths_c, scene['ray_directions'], opts)[2]
+        torch.rand = lambda *a, **k: u
+        try:
+            depths_f = ren.sample_importance(depths_c, weights_c, n_imp)
+        finally:
+            torch.rand = orig_rand
+        ren.sample_stratified = lambda *a, **k: depths_f
+        try:
+            fwd()
+        finally:
+            del ren.sample_stratified
+        colors_f, dens_f, _ = cap[1]
+    finally:
+        ren.ray_marcher = marcher
+    all_d, all_c, all_s = ren.unify_samples(depths_c, colors_c, dens_c, depths_f, colors_f, dens_f)
+    rgb, depth, w = marcher(all_c, all_s, all_d, scene['ray_directions'], opts)
+    out = (rgb, depth, w.sum(2))
+    if return_stages:
+        return out + ({'coarse_weights': weights_c[0, :, :, 0], 't_fine': depths_f[0, :, :, 0], 'sigma_fine': dens_f[0, :, :, 0],
+                       'colors_fine': colors_f[0], 'sigma_coarse': dens_c[0, :, :, 0]},)
+    return out

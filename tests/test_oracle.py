@@ -50,6 +50,56 @@ def test_port_matches_live_reference(smpl_model, smpl_model_t):
     assert float(ref[2].max()) > 0.2          # the body is actually visible
 
 
+def test_port_importance_matches_golden(smpl_model, smpl_model_t):
+    """coarse + fine pass.  The fixture comes from the repaired composition of the reference's own
+    sample_importance / sample_pdf / unify_samples / ray marcher (oracle/ref_shim.render_importance)."""
+    from oracle.gen_golden import importance_u
+    g = load_golden('importance_28x20x16p12')
+    scene = S.make_scene(g['scene_spec'], smpl_model)
+    assert checksum(scene) == str(g['input_sha256'])
+    n_imp = int(g['n_importance'])
+    scene['rendering_options']['depth_resolution_importance'] = n_imp
+    u = importance_u(scene['ray_origins'].shape[1], n_imp, int(g['u_seed']))
+    rgb, depth, acc, st = port.render_forward(g['weights'], smpl_model_t, scene, return_stages=True, importance_u=u)
+    assert np.abs(st['coarse_weights'].numpy() - g['coarse_weights']).max() <= 2e-6
+    assert np.abs(st['t_fine'].numpy() - g['t_fine']).max() <= 5e-6
+    assert np.array_equal(st['fine']['mask'].view(-1, n_imp).numpy(), g['sigma_fine'] != -80.0)       # fine cull mask
+    assert np.abs(rgb[0].numpy() - g['rgb']).max() <= 1e-5
+    assert np.abs(acc[0].numpy() - g['acc']).max() <= 1e-5
+    assert np.abs(depth[0].numpy() - g['depth']).max() <= 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree is only mounted in the build container')
+def test_port_importance_matches_live_reference(smpl_model, smpl_model_t):
+    ren, dec = ref_shim.build_reference(smpl_model_t, seed=6)
+    with torch.no_grad():
+        dec.alpha_linear.weight *= 30
+        dec.alpha_linear.bias += 2.0
+    scene = S.make_scene(S.SceneSpec(H=18, W=22, samples=10, seed=17, white_back=True), smpl_model)
+    scene['rendering_options']['depth_resolution_importance'] = 7
+    u = torch.rand(18 * 22, 7, generator=torch.Generator().manual_seed(5))
+    ref = ref_shim.render_importance(ren, dec, scene, u, return_stages=True)
+    got = port.render_forward(port.hot_path_state_dict(ren, dec), smpl_model_t, scene, return_stages=True, importance_u=u)
+    for a, b in zip(ref[:3], got[:3]):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 1e-5
+    assert float((ref[3]['t_fine'] - got[3]['t_fine']).abs().max()) <= 5e-6
+
+
+def test_sample_importance_properties():
+    """Inverse-CDF sampling (renderer.py:483-542): samples stay inside the mid-point bins, follow the weights, and the bin
+    index returned is searchsorted(right=True)."""
+    depths = port.sample_depths(torch.tensor([1.0, 2.0]), torch.tensor([2.0, 4.0]), 8)
+    w = torch.zeros(2, 8)
+    w[0, 3] = 1.0                                   # all the mass on sample 3 of ray 0; ray 1 uniform
+    u = torch.rand(2, 64, generator=torch.Generator().manual_seed(0))
+    t, inds = port.sample_importance(depths, w, 64, u)
+    mid = 0.5 * (depths[:, :-1] + depths[:, 1:])
+    assert torch.all(t >= mid[:, :1] - 1e-6) and torch.all(t <= mid[:, -1:] + 1e-6)
+    assert float(((t[0] > mid[0, 1]) & (t[0] < mid[0, 4])).float().mean()) > 0.9      # smoothing spreads the peak over 3 bins
+    assert int(inds.min()) >= 1 and int(inds.max()) <= 6
+
+
 def test_knn_tie_break_smallest_index():
     v = torch.tensor([[0., 0, 0], [1, 0, 0], [1, 0, 0], [0, 0, 0]])
     q = torch.tensor([[0.1, 0, 0], [0.9, 0, 0], [0.5, 0, 0]])

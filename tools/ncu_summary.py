@@ -1,6 +1,6 @@
 """Condense an ncu report (--set full, one kernel) into the handful of metrics profiles/*.csv keep.
 
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<tag>_ncu_full_<kernel>.csv
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-name-substring] > profiles/<tag>_ncu_full_<kernel>.csv
 """
 import csv
 import io
@@ -20,16 +20,19 @@ KEEP = [
 ]
 
 
-def main(path):
+def main(path, only=None):
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    names, units, vals = rows[0], rows[1], rows[2]
+    names, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(names)}
-    print('# kernel: %s' % vals[col['Kernel Name']][:120])
-    for k in KEEP:
-        if k in col:
-            print('%s,%s,%s' % (k, vals[col[k]], units[col[k]]))
+    for vals in rows[2:]:
+        if len(vals) < len(names) or (only and only not in vals[col['Kernel Name']]):
+            continue
+        print('# kernel: %s' % vals[col['Kernel Name']][:120])
+        for k in KEEP:
+            if k in col:
+                print('%s,%s,%s' % (k, vals[col[k]], units[col[k]]))
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
