@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SHERF_ABI_VERSION 1
+#define SHERF_ABI_VERSION 2
 #if defined(__GNUC__)
 #define SHERF_API __attribute__((visibility("default")))
 #else
@@ -122,6 +122,8 @@ typedef struct SherfRays {
   const float* far_;     /* [N] */
   int32_t n_rays;        /* N */
   int32_t n_samples;     /* S = rendering_options['depth_resolution'] (2..256) */
+  int32_t n_importance;  /* S_f = rendering_options['depth_resolution_importance'] (0 = coarse pass only; else 1..256, needs S >= 3) */
+  int32_t reserved;
 } SherfRays;
 
 /* rendering_options subset used by the path (train.py:328-351, ray_marcher.py:25-64). */
@@ -132,6 +134,9 @@ typedef struct SherfOptions {
   float depth_clamp_max;     /*   full (unsharded) view, ray_marcher.py:57 -- needed when rays are sharded */
   int32_t use_external_clamp;
   const float* density_noise; /* optional [N*S] additive sigma noise, already scaled (renderer.py:435-436); NULL = none */
+  const float* importance_u;  /* [N*S_f] uniform draws in [0,1) standing for torch.rand at renderer.py:526; required when
+                                 n_importance > 0 (the caller owns the RNG, SURVEY.md 8b "RNG") */
+  const float* density_noise_importance; /* optional [N*S_f] additive sigma noise of the fine samples; NULL = none */
 } SherfOptions;
 
 /* Outputs of forward (renderer.py:398): rgb in (-1,1), depth, accumulated weight. */
@@ -157,17 +162,29 @@ typedef struct SherfDebug {
   float* point_rgb;      /* [P,3] (triplane.py:314) */
   int64_t max_points;    /* capacity (in points) of the point-indexed arrays except point_feat */
   int64_t max_feat_points; /* capacity (in points) of point_feat */
+  /* importance (fine) pass taps, dense per sample like the reference's own arrays (renderer.py:364-371, :378): */
+  float* coarse_weights;   /* [N*S]   ray-marcher weights of the coarse pass (renderer.py:376) */
+  float* fine_depths;      /* [N*S_f] importance-sampled depths, in draw order (renderer.py:378) */
+  int32_t* fine_bins;      /* [N*S_f] searchsorted(cdf, u, right=True) (renderer.py:529) */
+  int32_t* fine_sample_vid;/* [N*S_f] nearest posed-vertex id of every fine sample within the cull radius, -1 otherwise */
+  float* fine_sigma;       /* [N*S_f] density, -80 where culled */
+  float* fine_rgb;         /* [N*S_f,3] colour, 0 where culled */
 } SherfDebug;
 
-/* Bytes of scratch sherf_render_forward needs for an (N rays, S samples) call on `scene` (only its
- * shape fields are read).  The arena holds the per-frame tables, channels-last copies of the feature
- * tensors, per-sample bookkeeping and the activation buffers of one chunk of surviving points. */
-SHERF_API size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_verts);
+/* Bytes of scratch sherf_render_forward needs for an (N rays, S coarse + S_f importance samples) call on
+ * `scene` (only its shape fields are read).  The arena holds the per-frame tables, channels-last copies of
+ * the feature tensors, per-sample bookkeeping and the activation buffers of one chunk of surviving points. */
+SHERF_API size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_importance,
+                                     int32_t n_verts);
 
 /* Replaces ImportanceRenderer.forward (renderer.py:286-398) including the decoder call
  * (triplane.py:285-316) and the ray marcher (ray_marcher.py:25-64).
- * Synchronises `stream` once internally (to size the point stage).  n_points_out (host, optional)
- * receives the number of samples that survived the 5 cm cull. */
+ * With rays->n_importance > 0 it also runs the fine pass (renderer.py:373-393: sample_importance :483-542,
+ * unify_samples :446-456) in its REPAIRED form -- the reference's own call sites :376 / :383 cannot execute
+ * (SURVEY.md a13): ray directions are passed to the coarse ray march, and the fine samples go through the same
+ * cull / warp / gather / decoder stages as the coarse ones (oracle/port.py render_forward states the repair).
+ * Synchronises `stream` once per pass internally (to size the point stage).  n_points_out (host, optional)
+ * receives the number of samples (coarse + fine) that survived the 5 cm cull. */
 SHERF_API int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene,
                          const SherfWeights* weights, const SherfRays* rays, const SherfOptions* opts,
                          const SherfOut* out, const SherfDebug* debug /* may be NULL */,
@@ -183,6 +200,11 @@ SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* 
 SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */, float* max_out /* host */,
                       void* scratch, size_t scratch_bytes, void* stream);
 
+/* sample_importance + sample_pdf (renderer.py:483-542) alone, on caller-supplied ray-marcher weights [N*S]
+ * and uniform draws u [N*S_f]: writes the fine depths [N*S_f] and (optional) the searchsorted bin indices. */
+SHERF_API int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out,
+                                            int32_t* bins_out /* may be NULL */, void* stream);
+
 /* Diagnostic: one linear layer Y[M,N] = act(A[M,K] * W[N,K]^T + bias) on the selected arithmetic (SHERF_MLP_*), the building
  * block of the fusion / transformer / decoder stack (nn.Linear / Conv1d(k=1) call sites renderer.py:350,424 and
  * triplane.py:296-312).  act: 0 none, 1 ReLU, 2 GELU(erf).  Tensor-core modes need N % 16 == 0; N, K <= 256.
@@ -197,6 +219,9 @@ SHERF_API const char* sherf_last_error(void);
 SHERF_API int sherf_abi_version(void);
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */
 SHERF_API int64_t sherf_last_launch_count(void);
+/* Number of FINE (importance) samples that survived the cull in the last sherf_render_forward on this thread
+ * (n_points_out reports coarse + fine). */
+SHERF_API int64_t sherf_last_importance_point_count(void);
 /* Device time (ms) of the named stage of the last forward on this thread, measured with CUDA events when
  * sherf_set_profiling(1) was called; stages: 0 prologue, 1 cull+compact, 2 warp+gather, 3 mlp (whole stage), 4 composite,
  * 5 the fused tcgen05 decoder kernel alone, 6 the fused tcgen05 transformer kernel alone,

@@ -11,6 +11,7 @@ c_float_p = C.c_void_p          # device pointers travel as plain integers
 c_int_p = C.c_void_p
 
 MLP_FP32, MLP_TF32, MLP_TF32X3, MLP_BF16X3 = 0, 1, 2, 3
+ABI_VERSION = 2
 
 
 class SherfSmplModel(C.Structure):
@@ -47,12 +48,13 @@ class SherfWeights(C.Structure):
 
 class SherfRays(C.Structure):
     _fields_ = [('origins', c_float_p), ('dirs', c_float_p), ('near_', c_float_p), ('far_', c_float_p),
-                ('n_rays', C.c_int32), ('n_samples', C.c_int32)]
+                ('n_rays', C.c_int32), ('n_samples', C.c_int32), ('n_importance', C.c_int32), ('reserved', C.c_int32)]
 
 
 class SherfOptions(C.Structure):
     _fields_ = [('white_back', C.c_int32), ('mlp_precision', C.c_int32), ('depth_clamp_min', C.c_float),
-                ('depth_clamp_max', C.c_float), ('use_external_clamp', C.c_int32), ('density_noise', c_float_p)]
+                ('depth_clamp_max', C.c_float), ('use_external_clamp', C.c_int32), ('density_noise', c_float_p),
+                ('importance_u', c_float_p), ('density_noise_importance', c_float_p)]
 
 
 class SherfOut(C.Structure):
@@ -62,11 +64,13 @@ class SherfOut(C.Structure):
 class SherfDebug(C.Structure):
     _fields_ = [('sample_vid', c_int_p), ('point_sample', c_int_p), ('point_vid3', c_int_p), ('point_can', c_float_p),
                 ('point_cdir', c_float_p), ('point_uv', c_float_p), ('point_feat', c_float_p), ('point_tok', c_float_p),
-                ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64), ('max_feat_points', C.c_int64)]
+                ('point_sigma', c_float_p), ('point_rgb', c_float_p), ('max_points', C.c_int64), ('max_feat_points', C.c_int64),
+                ('coarse_weights', c_float_p), ('fine_depths', c_float_p), ('fine_bins', c_int_p), ('fine_sample_vid', c_int_p),
+                ('fine_sigma', c_float_p), ('fine_rgb', c_float_p)]
 
 
-EXPORTS = ['sherf_debug_set_trace', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
-           'sherf_abi_version', 'sherf_last_launch_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
+EXPORTS = ['sherf_debug_set_trace', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+           'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
 
 _lib = None
 
@@ -86,7 +90,7 @@ def load():
                            'sherf_b200 has no CPU or PyTorch fallback')
     lib = C.CDLL(path)
     lib.sherf_scratch_bytes.restype = C.c_size_t
-    lib.sherf_scratch_bytes.argtypes = [C.POINTER(SherfScene), C.c_int32, C.c_int32, C.c_int32]
+    lib.sherf_scratch_bytes.argtypes = [C.POINTER(SherfScene), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.sherf_render_forward.restype = C.c_int
     lib.sherf_render_forward.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfFrame), C.POINTER(SherfScene),
                                          C.POINTER(SherfWeights), C.POINTER(SherfRays), C.POINTER(SherfOptions),
@@ -101,14 +105,17 @@ def load():
     lib.sherf_debug_linear.restype = C.c_int
     lib.sherf_debug_linear.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sherf_debug_sample_importance.restype = C.c_int
+    lib.sherf_debug_sample_importance.argtypes = [C.POINTER(SherfRays), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sherf_debug_set_trace.argtypes = [C.c_void_p]
     lib.sherf_last_error.restype = C.c_char_p
     lib.sherf_abi_version.restype = C.c_int
     lib.sherf_last_launch_count.restype = C.c_int64
+    lib.sherf_last_importance_point_count.restype = C.c_int64
     lib.sherf_set_profiling.argtypes = [C.c_int]
     lib.sherf_last_stage_ms.restype = C.c_float
     lib.sherf_last_stage_ms.argtypes = [C.c_int]
-    if lib.sherf_abi_version() != 1:
+    if lib.sherf_abi_version() != ABI_VERSION:
         raise RuntimeError('libsherf_b200.so ABI version mismatch')
     _lib = lib
     return lib

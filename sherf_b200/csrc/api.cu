@@ -13,6 +13,7 @@ namespace sherf {
 thread_local LaunchCounter g_launches;
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_last_launches = 0;
+static thread_local int64_t g_last_fine_points = 0;
 static thread_local int g_profiling = 0;
 static thread_local float g_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -51,6 +52,9 @@ struct Layout {
   int* sample_vid; int* ray_count; int* block_sums; int* ray_start; int64_t* total;
   int* point_sample; int* point_vid;
   float* sigma; float* rgb;
+  // importance (fine) pass bookkeeping, sized N * S_f (absent when S_f == 0)
+  float* fine_depths; int* sample_vid_f; int* ray_count_f; int* ray_start_f; int64_t* total_f; int* point_sample_f; int* point_vid_f;
+  float* sigma_f; float* rgb_f;
   float* packed_w;
   float* canon_w;
   unsigned char* fused_blob; float* fused_bias; float* xf_blob; float* ff_blob;
@@ -60,8 +64,13 @@ struct Layout {
   float* lbs_joints; float* lbs_pf;
 };
 
-static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout& L) {
-  const size_t NS = (size_t)N * S;
+static int chunk_cap(int N, int S, int SF) {
+  const size_t NS = (size_t)N * (S > SF ? S : SF);
+  return (int)((NS < chunk_cap_limit()) ? ((NS + 127) / 128 * 128) : chunk_cap_limit());
+}
+
+static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int SF, int V, Layout& L) {
+  const size_t NS = (size_t)N * S, NF = (size_t)N * SF;
   FrameTables& ft = L.ft;
   ft.fc = a.take<FrameConst>(1);
   ft.A = a.take<float>(3 * kJoints * 16);
@@ -94,24 +103,32 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int V, Layout&
   L.point_vid = a.take<int>(NS);
   L.sigma = a.take<float>(NS);
   L.rgb = a.take<float>(NS * 3);
+  L.fine_depths = nullptr; L.sample_vid_f = nullptr; L.ray_count_f = nullptr; L.ray_start_f = nullptr; L.total_f = nullptr;
+  L.point_sample_f = nullptr; L.point_vid_f = nullptr; L.sigma_f = nullptr; L.rgb_f = nullptr;
+  if (SF > 0) {
+    L.fine_depths = a.take<float>(NF);
+    L.sample_vid_f = a.take<int>(NF);
+    L.ray_count_f = a.take<int>(N);
+    L.ray_start_f = a.take<int>((size_t)N + 1);
+    L.total_f = a.take<int64_t>(1);
+    L.point_sample_f = a.take<int>(NF);
+    L.point_vid_f = a.take<int>(NF);
+    L.sigma_f = a.take<float>(NF);
+    L.rgb_f = a.take<float>(NF * 3);
+  }
   L.packed_w = a.take<float>(packed_weight_floats());
   L.canon_w = a.take<float>(canonical_weight_floats());
   L.fused_blob = a.take<unsigned char>(fused_blob_bytes());
   L.fused_bias = a.take<float>(10 * 144);
   L.xf_blob = a.take<float>(xformer_blob_floats());
   L.ff_blob = a.take<float>(fusion_blob_floats());
-  const int cap = (int)((NS < chunk_cap_limit()) ? ((NS + 127) / 128 * 128) : chunk_cap_limit());
+  const int cap = chunk_cap(N, S, SF);
   L.chunk = a.take<float>(chunk_buffer_floats(cap));
   L.pp_blob = a.take<unsigned char>(pp_blob_bytes());
   L.pp_bias = a.take<float>(10 * 128);
   L.pp_xv = a.take<unsigned char>(pp_xv_bytes(cap));
   L.gather2 = a.take<float>((size_t)cap * (288 + 192 + 8));
   return a.off;
-}
-
-static int chunk_cap(int N, int S) {
-  const size_t NS = (size_t)N * S;
-  return (int)((NS < chunk_cap_limit()) ? ((NS + 127) / 128 * 128) : chunk_cap_limit());
 }
 
 // Device-time accounting per stage: every begin()/end() pair is a CUDA-event span on the launching stream; spans of
@@ -185,14 +202,15 @@ extern "C" {
 int sherf_abi_version(void) { return SHERF_ABI_VERSION; }
 const char* sherf_last_error(void) { return g_err; }
 int64_t sherf_last_launch_count(void) { return g_last_launches; }
+int64_t sherf_last_importance_point_count(void) { return g_last_fine_points; }
 void sherf_set_profiling(int enabled) { g_profiling = enabled; }
 float sherf_last_stage_ms(int stage) { return (stage >= 0 && stage < 8) ? g_stage_ms[stage] : 0.f; }
 
-size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_verts) {
-  if (!scene || n_rays <= 0 || n_samples < 2 || n_verts <= 0) return 0;
+size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_importance, int32_t n_verts) {
+  if (!scene || n_rays <= 0 || n_samples < 2 || n_importance < 0 || n_verts <= 0) return 0;
   Arena a{nullptr, 0, 0, true};
   Layout L;
-  return carve(a, *scene, n_rays, n_samples, n_verts, L) + 512;   // + slack for aligning the caller's base pointer
+  return carve(a, *scene, n_rays, n_samples, n_importance, n_verts, L) + 512;   // + slack for aligning the caller's base pointer
 }
 
 static int validate(const SherfSmplModel* smpl, const SherfFrame* fr, const SherfScene* sc, const SherfWeights* w,
@@ -203,6 +221,13 @@ static int validate(const SherfSmplModel* smpl, const SherfFrame* fr, const Sher
     return SHERF_E_INVALID;
   }
   if ((int64_t)rays->n_rays * rays->n_samples >= (1LL << 31)) { set_error("n_rays * n_samples must be < 2^31"); return SHERF_E_INVALID; }
+  if (rays->n_importance < 0 || rays->n_importance > 256) { set_error("n_importance must be in 0..256 (got %d)", rays->n_importance); return SHERF_E_INVALID; }
+  if (rays->n_importance > 0) {
+    if (rays->n_samples < 3) { set_error("the importance pass needs n_samples >= 3 (sample_pdf bins, renderer.py:498-499)"); return SHERF_E_INVALID; }
+    if (!opts->importance_u) { set_error("n_importance > 0 needs SherfOptions.importance_u (the torch.rand draws of renderer.py:526)"); return SHERF_E_INVALID; }
+    const int64_t smax = rays->n_samples > rays->n_importance ? rays->n_samples : rays->n_importance;
+    if ((int64_t)rays->n_rays * smax >= (1LL << 30)) { set_error("n_rays * max(n_samples, n_importance) must be < 2^30 with the importance pass"); return SHERF_E_INVALID; }
+  }
   if (sc->plane_ch != 32 || sc->feat_ch != 64 || sc->vol_ch[0] != 32 || sc->vol_ch[1] != 64 || sc->vol_ch[2] != 96) {
     set_error("unsupported channel counts (planes %d, feat %d, volumes %d/%d/%d; expected 32, 64, 32/64/96)", sc->plane_ch,
               sc->feat_ch, sc->vol_ch[0], sc->vol_ch[1], sc->vol_ch[2]);
@@ -224,16 +249,17 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
                          const SherfDebug* dbg, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {
   g_err[0] = 0;
   RC(validate(smpl, frame, scene, weights, rays, opts, out));
-  const int N = rays->n_rays, S = rays->n_samples, V = smpl->n_verts;
+  const int N = rays->n_rays, S = rays->n_samples, SF = rays->n_importance, V = smpl->n_verts;
   cudaStream_t st = (cudaStream_t)stream;
   Arena a{(char*)scratch, scratch_bytes, 0, false};
   // align the arena base to 256 B
   const size_t mis = ((size_t)a.base) & 255;
   if (mis) { a.base += 256 - mis; a.size -= 256 - mis; }
   Layout L;
-  const size_t need = carve(a, *scene, N, S, V, L);
+  const size_t need = carve(a, *scene, N, S, SF, V, L);
   if (!scratch || need > a.size) { set_error("scratch arena too small: need %zu bytes, have %zu", need, scratch_bytes); return SHERF_E_SCRATCH; }
   g_launches.n = 0;
+  g_last_fine_points = 0;
   StageTimer tm;
   tm.init(g_profiling != 0, st);
   g_tm = &tm;
@@ -268,7 +294,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, st)); fplan.xf_blob = L.xf_blob; }
     if (opts->mlp_precision == SHERF_MLP_BF16X3) {
       RC(run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, st));
-      const int cap = chunk_cap(N, S);
+      const int cap = chunk_cap(N, S, SF);
       pplan.xp = L.pp_xv;
       pplan.vp = L.pp_xv + (size_t)((cap + 127) / 128) * 40960;
       fplan.pp = &pplan;
@@ -280,7 +306,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   // ---- stage 1: cull + ordered compaction ----
   tm.begin(1);
   int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
-  RC(run_cull(*rays, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
+  RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
   int64_t P = 0;
   tm.end();
   SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -292,59 +318,106 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
 
   // ---- stages 2+3 per chunk of surviving points: warp + gather, then fusion / transformer / decoder ----
   ChunkBuffers cb;
-  carve_chunk_buffers(L.chunk, chunk_cap(N, S), cb);
+  carve_chunk_buffers(L.chunk, chunk_cap(N, S, SF), cb);
   ChunkBuffers cbs[2] = {cb, cb};                                   // two sets of gather outputs, everything else shared
   cbs[1].comb = L.gather2; cbs[1].f3raw = L.gather2 + (size_t)cb.cap * 288; cbs[1].geo = L.gather2 + (size_t)cb.cap * (288 + 192);
-  // measured on B200 (r1): the overlap is neutral (6.98 vs 7.00 ms) -- the gather blocks delay the start of the persistent MLP CTAs
-  // by as much as they hide -- so it is opt-in (SHERF_OVERLAP=1)
-  const bool overlap = P > cb.cap && getenv("SHERF_OVERLAP") && g_side.ensure() == 0;
-  cudaStream_t gs = overlap ? g_side.s : st;
-  if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.fork, 0)); }
-  int ci = 0;
-  for (int64_t p0 = 0; p0 < P; p0 += cb.cap, ++ci) {
-    const int np = (int)((P - p0 < cb.cap) ? (P - p0) : cb.cap);
-    const int bsel = overlap ? (ci & 1) : 0;
-    const ChunkBuffers& cbi = cbs[bsel];
-    GatherParams G;
-    G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = S;
-    G.point_sample = L.point_sample; G.point_vid = L.point_vid; G.p0 = p0; G.np = np;
-    G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
-    G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
-    G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
-    G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;
-    for (int l = 0; l < 3; ++l) {
-      G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
-      G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
+  // One pass over a compacted point list (coarse: stratified depths; fine: importance-sampled depths): renderer.py:323-362
+  auto run_points = [&](const int* point_sample, const int* point_vid, int64_t Pn, int Sn, const float* depths, float* sigma_out, float* rgb_out,
+                        const SherfDebug* d) -> int {
+    // measured on B200 (r1): the overlap is neutral (6.98 vs 7.00 ms) -- the gather blocks delay the start of the persistent MLP CTAs
+    // by as much as they hide -- so it is opt-in (SHERF_OVERLAP=1)
+    const bool overlap = Pn > cb.cap && getenv("SHERF_OVERLAP") && g_side.ensure() == 0;
+    cudaStream_t gs = overlap ? g_side.s : st;
+    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.fork, 0)); }
+    int ci = 0;
+    for (int64_t p0 = 0; p0 < Pn; p0 += cb.cap, ++ci) {
+      const int np = (int)((Pn - p0 < cb.cap) ? (Pn - p0) : cb.cap);
+      const int bsel = overlap ? (ci & 1) : 0;
+      const ChunkBuffers& cbi = cbs[bsel];
+      GatherParams G;
+      G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = Sn; G.depths = depths;
+      G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np;
+      G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
+      G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
+      G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
+      G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;
+      for (int l = 0; l < 3; ++l) {
+        G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
+        G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
+      }
+      G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
+      G.dbg_vid3 = d ? d->point_vid3 : nullptr; G.dbg_can = d ? d->point_can : nullptr;
+      G.dbg_cdir = d ? d->point_cdir : nullptr; G.dbg_uv = d ? d->point_uv : nullptr;
+      G.dbg_feat = d ? d->point_feat : nullptr; G.dbg_max = d ? d->max_points : 0;
+      G.dbg_feat_max = d ? d->max_feat_points : 0;
+      // gather of chunk ci (side stream): its output buffers must have been released by the MLP of chunk ci-2
+      if (overlap && ci >= 2) SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.mdone[bsel], 0));
+      tm.begin(2, gs);
+      RC(run_point_gather(G, gs));
+      tm.end();
+      if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.gdone[bsel], gs)); SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.gdone[bsel], 0)); }
+      tm.begin(3);
+      RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cbi, np, p0, sigma_out, rgb_out, d ? d->point_tok : nullptr,
+                 d ? d->max_points : 0, st, nested_begin, nested_end));
+      tm.end();
+      if (overlap) SHERF_CUDA_OK(cudaEventRecord(g_side.mdone[bsel], st));
     }
-    G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
-    G.dbg_vid3 = dbg ? dbg->point_vid3 : nullptr; G.dbg_can = dbg ? dbg->point_can : nullptr;
-    G.dbg_cdir = dbg ? dbg->point_cdir : nullptr; G.dbg_uv = dbg ? dbg->point_uv : nullptr;
-    G.dbg_feat = dbg ? dbg->point_feat : nullptr; G.dbg_max = dbg ? dbg->max_points : 0;
-    G.dbg_feat_max = dbg ? dbg->max_feat_points : 0;
-    // gather of chunk ci (side stream): its output buffers must have been released by the MLP of chunk ci-2
-    if (overlap && ci >= 2) SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.mdone[bsel], 0));
-    tm.begin(2, gs);
-    RC(run_point_gather(G, gs));
-    tm.end();
-    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.gdone[bsel], gs)); SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.gdone[bsel], 0)); }
-    tm.begin(3);
-    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cbi, np, p0, L.sigma, L.rgb, dbg ? dbg->point_tok : nullptr, dbg ? dbg->max_points : 0, st,
-               nested_begin, nested_end));
-    tm.end();
-    if (overlap) SHERF_CUDA_OK(cudaEventRecord(g_side.mdone[bsel], st));
-  }
+    return SHERF_OK;
+  };
+  RC(run_points(L.point_sample, L.point_vid, P, S, nullptr, L.sigma, L.rgb, dbg));
   if (dbg && P > 0) {
     const size_t cnt = (size_t)(P < dbg->max_points ? P : dbg->max_points);
     if (dbg->point_sigma) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sigma, L.sigma, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, st));
     if (dbg->point_rgb) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_rgb, L.rgb, sizeof(float) * 3 * cnt, cudaMemcpyDeviceToDevice, st));
   }
 
-  // ---- stage 4: composite ----
-  tm.begin(4);
-  RC(run_composite(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, *out, st));
-  tm.end();
+  if (SF == 0) {
+    // ---- stage 4: composite ----
+    tm.begin(4);
+    RC(run_composite(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, *out, st));
+    tm.end();
+  } else {
+    // ---- fine pass (renderer.py:373-393, repaired): coarse weights -> importance depths -> cull / gather / MLP on the fine samples ->
+    //      ray march over the depth-sorted union ----
+    tm.begin(4);
+    RC(run_importance_sample(*rays, L.ray_start, L.point_sample, L.sigma, opts->density_noise, nullptr, opts->importance_u, L.fine_depths,
+                             dbg ? dbg->fine_bins : nullptr, dbg ? dbg->coarse_weights : nullptr, st));
+    tm.end();
+    tm.begin(1);
+    int* vid_f = (dbg && dbg->fine_sample_vid) ? dbg->fine_sample_vid : L.sample_vid_f;
+    RC(run_cull(*rays, SF, L.fine_depths, L.ft, vid_f, L.ray_count_f, L.block_sums, L.ray_start_f, L.total_f, L.point_sample_f, L.point_vid_f, st));
+    tm.end();
+    int64_t PF = 0;
+    SHERF_CUDA_OK(cudaMemcpyAsync(&PF, L.total_f, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SHERF_CUDA_OK(cudaStreamSynchronize(st));
+    if (n_points_out) *n_points_out = P + PF;
+    g_last_fine_points = PF;
+    RC(run_points(L.point_sample_f, L.point_vid_f, PF, SF, L.fine_depths, L.sigma_f, L.rgb_f, nullptr));
+    if (dbg) {
+      if (dbg->fine_depths) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->fine_depths, L.fine_depths, sizeof(float) * (size_t)N * SF, cudaMemcpyDeviceToDevice, st));
+      RC(run_dense_taps(L.point_sample_f, L.sigma_f, L.rgb_f, PF, (int64_t)N * SF, dbg->fine_sigma, dbg->fine_rgb, st));
+    }
+    tm.begin(4);
+    RC(run_composite_merged(*rays, L.ft.fc, sample_vid, L.ray_start, L.sigma, L.rgb, opts->density_noise, L.fine_depths, vid_f, L.ray_start_f,
+                            L.sigma_f, L.rgb_f, opts->density_noise_importance, opts->white_back, *out, st));
+    tm.end();
+  }
   tm.finish();
   g_tm = nullptr;
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
+int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out, int32_t* bins_out,
+                                  void* stream) {
+  g_err[0] = 0;
+  if (!rays || !weights || !u || !t_fine_out || !rays->near_ || !rays->far_) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (rays->n_rays <= 0 || rays->n_samples < 3 || rays->n_samples > 256 || rays->n_importance < 1 || rays->n_importance > 256) {
+    set_error("need n_rays > 0, 3 <= n_samples <= 256, 1 <= n_importance <= 256");
+    return SHERF_E_INVALID;
+  }
+  g_launches.n = 0;
+  RC(run_importance_sample(*rays, nullptr, nullptr, nullptr, nullptr, weights, u, t_fine_out, bins_out, nullptr, (cudaStream_t)stream));
   g_last_launches = g_launches.n;
   return SHERF_OK;
 }

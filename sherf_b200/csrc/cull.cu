@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_cull(const float* __restrict__ origins,
                                               const float* __restrict__ nearv, const float* __restrict__ farv, int N, int S,
                                               const FrameConst* __restrict__ fcp, const int* __restrict__ cell_start,
                                               const float4* __restrict__ gv, const unsigned char* __restrict__ occ, float thr,
-                                              int* __restrict__ sample_vid, int* __restrict__ ray_count) {
+                                              const float* __restrict__ depths, int* __restrict__ sample_vid, int* __restrict__ ray_count) {
   __shared__ FrameConst fc;
   for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)fcp)[i];
   __syncthreads();
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_cull(const float* __restrict__ origins,
     const int i = i0 + lane;
     int vid = -1;
     if (i < S) {
-      const float t = sample_depth(nr, fr, i, S);
+      const float t = depths ? depths[(size_t)n * S + i] : sample_depth(nr, fr, i, S);   // fine pass: importance-sampled depths
       float p[3], q[3];
       p[0] = __fsub_rn(mul_add_sep(t, dx, ox), fc.Th_tgt[0]);
       p[1] = __fsub_rn(mul_add_sep(t, dy, oy), fc.Th_tgt[1]);
@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(256) k_compact(const int* __restrict__ sample_
   }
 }
 
-int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums, int* ray_start, int64_t* total_dev,
-             int* point_sample, int* point_vid, cudaStream_t st) {
-  const int N = rays.n_rays, S = rays.n_samples;
+int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
+             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st) {
+  const int N = rays.n_rays;
   const float thr = (float)(0.05 * 0.05);        // `distance < 0.05 ** 2` compares in fp32 (renderer.py:318-319)
   k_cull<<<ceil_div(N, 8), 256, 0, st>>>(rays.origins, rays.dirs, rays.near_, rays.far_, N, S, ft.fc, ft.g1_cell_start, ft.g1_verts,
-                                         ft.g1_occ, thr, sample_vid, ray_count);
+                                         ft.g1_occ, thr, depths, sample_vid, ray_count);
   SHERF_LAUNCH_CHECK();
   const int nb = ceil_div(N, 1024);
   k_ray_block_sums<<<nb, 1024, 0, st>>>(ray_count, N, block_sums);

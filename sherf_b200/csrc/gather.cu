@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_point_gather(const GatherParams P) {
     const int s = P.point_sample[gp];
     const int n = s / P.S, i = s - n * P.S;
     // ---- re-derive the SMPL-space query exactly as the cull did (renderer.py:304-310) ----
-    const float t = sample_depth(P.nearv[n], P.farv[n], i, P.S);
+    const float t = P.depths ? P.depths[s] : sample_depth(P.nearv[n], P.farv[n], i, P.S);
     float dray[3] = {P.dirs[n * 3], P.dirs[n * 3 + 1], P.dirs[n * 3 + 2]};
     float pw[3], q[3], vd[3];
 #pragma unroll
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
     const int64_t gp = P.p0 + lp;
     const int s = P.point_sample[gp];
     const int n = s / P.S, i = s - n * P.S;
-    const float t = sample_depth(P.nearv[n], P.farv[n], i, P.S);
+    const float t = P.depths ? P.depths[s] : sample_depth(P.nearv[n], P.farv[n], i, P.S);
     float dray[3] = {P.dirs[n * 3], P.dirs[n * 3 + 1], P.dirs[n * 3 + 2]};
     float pw[3], q[3], vd[3];
 #pragma unroll

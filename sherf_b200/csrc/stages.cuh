@@ -8,6 +8,7 @@ struct GatherParams {
   // rays
   const float *origins, *dirs, *nearv, *farv;
   int S;
+  const float* depths;    // NULL: stratified depths from near/far; else explicit per-sample depths [N*S] (importance pass)
   // compacted points of this chunk
   const int *point_sample, *point_vid;
   int64_t p0; int np;
@@ -30,8 +31,9 @@ struct GatherParams {
 
 int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
 int run_point_gather(const GatherParams& P, cudaStream_t st);
-int run_cull(const SherfRays& rays, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums, int* ray_start, int64_t* total_dev,
-             int* point_sample, int* point_vid, cudaStream_t st);
+// S / depths: the sample set to cull -- (rays.n_samples, NULL) for the stratified coarse samples, (rays.n_importance, t_fine) for the fine pass
+int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
+             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st);
 
 // Row-major activation buffers of one chunk of `cap` points (fp32).
 struct ChunkBuffers {
@@ -116,5 +118,15 @@ int run_debug_linear(int prec, const float* A, int lda, const float* W, const fl
 
 int run_composite(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample,
                   const float* sigma, const float* rgb, const float* noise, int white_back, const SherfOut& out, cudaStream_t st);
+
+// Importance (fine) pass, importance.cu (renderer.py:373-393, 446-456, 483-542)
+int run_importance_sample(const SherfRays& rays, const int* ray_start, const int* point_sample, const float* sigma, const float* noise,
+                          const float* w_in, const float* u, float* t_fine, int* bins_out, float* w_out, cudaStream_t st);
+int run_composite_merged(const SherfRays& rays, const FrameConst* fc, const int* vid_c, const int* start_c, const float* sigma_c,
+                         const float* rgb_c, const float* noise_c, const float* t_fine, const int* vid_f, const int* start_f,
+                         const float* sigma_f, const float* rgb_f, const float* noise_f, int white_back, const SherfOut& out,
+                         cudaStream_t st);
+int run_dense_taps(const int* point_sample, const float* sg, const float* c3, int64_t P, int64_t n_dense, float* sigma, float* rgb,
+                   cudaStream_t st);
 
 }  // namespace sherf

@@ -78,9 +78,11 @@ def all_gather_tiles(local: torch.Tensor, n_rays: int, group=None, tile: int = T
     return gathered.index_select(0, _gather_permutation(n_rays, world, tile, local.device))
 
 
-def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE):
+def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE, importance_u: torch.Tensor | None = None):
     """Every rank holds the replicated scene, renders its ray tiles through the CUDA path and receives the full image.
-    Returns (rgb[1,N,3], depth[1,N,1], acc[1,N,1]) on every rank."""
+    Returns (rgb[1,N,3], depth[1,N,1], acc[1,N,1]) on every rank.  `importance_u` ([N,S_f], replicated) holds the
+    importance-pass draws of the FULL view (renderer.py:526); each rank uses the rows of its own rays, so the sharded
+    render equals the single-GPU render of the same draws."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = scene['ray_origins'].shape[1]
@@ -90,7 +92,8 @@ def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE)
     if idx.numel() > 0:
         rgb, depth, acc = renderer(sh['planes'], sh['obs_input_img'], sh['obs_input_feature'], sh['volumes'], None,
                                    sh['obs_sp_input'], decoder, sh['ray_origins'], sh['ray_directions'], sh['near'], sh['far'],
-                                   sh['input_data'], sh['rendering_options'], depth_clamp=clamp)
+                                   sh['input_data'], sh['rendering_options'], depth_clamp=clamp,
+                                   importance_u=None if importance_u is None else importance_u[idx.to(importance_u.device)].contiguous())
         local = torch.cat([rgb[0], depth[0], acc[0]], dim=-1)
     else:
         local = scene['ray_origins'].new_zeros(0, 5)

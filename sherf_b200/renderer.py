@@ -167,6 +167,7 @@ class ImportanceRenderer(nn.Module):
         self._scratch = None
         self._dbg_keep = None
         self.last_num_points = 0
+        self.last_num_fine_points = 0
         self.last_launches = 0
 
     # -- configuration ------------------------------------------------------------------------------------------
@@ -238,12 +239,16 @@ class ImportanceRenderer(nn.Module):
     # -- the hot path ----------------------------------------------------------------------------------------------
     def forward(self, planes, obs_input_img, obs_input_feature, canonical_sp_conv_volume, obs_smpl_vertex_mask, obs_sp_input,
                 decoder, ray_origins, ray_directions, near, far, input_data, rendering_options, debug: dict | None = None,
-                depth_clamp: tuple | None = None):
+                depth_clamp: tuple | None = None, importance_u: torch.Tensor | None = None):
         """Same positional signature and return value as renderer.py:286,398:
         (rgb[B,N,3] in (-1,1), depth[B,N,1], acc[B,N,1]).  `canonical_sp_conv_volume` is the list of the three densified
         pyramid levels [1,32,D/2..], [1,64,D/4..], [1,96,D/8..] (what SparseConvNet.forward densifies at renderer.py:762-782).
-        Extra keyword-only hooks: `debug` (dict filled with stage-wise tensors) and `depth_clamp` ((min,max) of the full
-        view's depths when this call renders a shard of its rays, ray_marcher.py:57)."""
+        Extra keyword-only hooks: `debug` (dict filled with stage-wise tensors), `depth_clamp` ((min,max) of the full
+        view's depths when this call renders a shard of its rays, ray_marcher.py:57) and `importance_u` ([N,S_f] uniform
+        draws replacing the torch.rand of renderer.py:526; drawn here with torch.rand when omitted).
+
+        rendering_options['depth_resolution_importance'] > 0 runs the fine pass of renderer.py:373-393 in its repaired form
+        (the reference's own call sites :376 / :383 cannot execute; see include/sherf_b200.h)."""
         self._check_supported()
         lib = _lib.load()
         device = ray_origins.device
@@ -251,8 +256,6 @@ class ImportanceRenderer(nn.Module):
             raise RuntimeError('sherf_b200.ImportanceRenderer runs on CUDA tensors only (no CPU fallback)')
         if ray_origins.shape[0] != 1:
             raise NotImplementedError('per-GPU batch must be 1, as in the reference (renderer.py:320-321)')
-        if rendering_options.get('depth_resolution_importance', 0) > 0:
-            raise NotImplementedError('importance pass: dead code in the reference (renderer.py:376,383), SURVEY.md a13')
         if rendering_options.get('clamp_mode', 'relu') != 'relu':
             raise NotImplementedError("only clamp_mode='relu' (train.py:332)")
         if rendering_options.get('disparity_space_sampling', False):
@@ -262,6 +265,7 @@ class ImportanceRenderer(nn.Module):
         keep = []
         N = ray_origins.shape[1]
         S = int(rendering_options['depth_resolution'])
+        SF = int(rendering_options.get('depth_resolution_importance', 0) or 0)
         with torch.cuda.device(device):
             smpl = self._smpl_struct(device)
             fr = _lib.SherfFrame()
@@ -299,6 +303,7 @@ class ImportanceRenderer(nn.Module):
             nr, fa = _dev32(near, device).reshape(-1), _dev32(far, device).reshape(-1)
             keep += [ro, rd, nr, fa]
             rays.origins, rays.dirs, rays.near_, rays.far_, rays.n_rays, rays.n_samples = _ptr(ro), _ptr(rd), _ptr(nr), _ptr(fa), N, S
+            rays.n_importance = SF
 
             opts = _lib.SherfOptions()
             opts.white_back = int(bool(rendering_options.get('white_back', False)))
@@ -311,13 +316,22 @@ class ImportanceRenderer(nn.Module):
                 nz = torch.randn(N * S, device=device, dtype=torch.float32) * noise_scale
                 keep.append(nz)
                 opts.density_noise = _ptr(nz)
+                if SF > 0:
+                    nzf = torch.randn(N * SF, device=device, dtype=torch.float32) * noise_scale
+                    keep.append(nzf)
+                    opts.density_noise_importance = _ptr(nzf)
+            if SF > 0:
+                uu = torch.rand(N, SF, device=device) if importance_u is None else _dev32(importance_u, device)      # renderer.py:526
+                assert uu.numel() == N * SF, 'importance_u must be [N, depth_resolution_importance]'
+                keep.append(uu)
+                opts.importance_u = _ptr(uu)
 
             rgb = torch.empty(1, N, 3, device=device, dtype=torch.float32)
             depth = torch.empty(1, N, 1, device=device, dtype=torch.float32)
             acc = torch.empty(1, N, 1, device=device, dtype=torch.float32)
             out = _lib.SherfOut(_ptr(rgb), _ptr(depth), _ptr(acc))
 
-            need = lib.sherf_scratch_bytes(C.byref(sc), N, S, smpl.n_verts)
+            need = lib.sherf_scratch_bytes(C.byref(sc), N, S, SF, smpl.n_verts)
             if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
                 self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
 
@@ -335,6 +349,11 @@ class ImportanceRenderer(nn.Module):
                 }
                 cap_feat = min(NS, int(debug.get('max_feat_points', NS)))
                 bufs['point_feat'] = torch.empty(cap_feat, 384, device=device)
+                if SF > 0:
+                    bufs.update({'coarse_weights': torch.empty(N, S, device=device), 'fine_depths': torch.empty(N, SF, device=device),
+                                 'fine_bins': torch.empty(N, SF, dtype=torch.int32, device=device),
+                                 'fine_sample_vid': torch.empty(N, SF, dtype=torch.int32, device=device),
+                                 'fine_sigma': torch.empty(N, SF, device=device), 'fine_rgb': torch.empty(N, SF, 3, device=device)})
                 for k, v in bufs.items():
                     setattr(d, k, _ptr(v))
                 d.max_points = NS
@@ -348,13 +367,15 @@ class ImportanceRenderer(nn.Module):
                                           C.byref(out), dbg_p, self._scratch.data_ptr(), self._scratch.numel(), stream,
                                           C.byref(npts))
             _lib.check(rc)
-            self.last_num_points = int(npts.value)
+            self.last_num_points = int(npts.value)                               # coarse + fine survivors
+            self.last_num_fine_points = int(lib.sherf_last_importance_point_count())
             self.last_launches = int(lib.sherf_last_launch_count())
             if debug is not None:
-                Pn = self.last_num_points
+                Pn = self.last_num_points - self.last_num_fine_points          # point-indexed taps describe the coarse pass
                 for k, v in self._dbg_keep[1].items():
-                    debug[k] = v if k == 'sample_vid' else v[:min(Pn, v.shape[0])]
-                debug['num_points'] = self.last_num_points
+                    debug[k] = v if (k == 'sample_vid' or k.startswith('fine_') or k == 'coarse_weights') else v[:min(Pn, v.shape[0])]
+                debug['num_points'] = Pn
+                debug['num_fine_points'] = self.last_num_fine_points
             # the C side only borrowed the pointers for the call; outputs are ordered after it on the same stream
             del keep
         return rgb, depth, acc

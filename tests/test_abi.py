@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f'{n} declared in the header but not exported'
-    assert lib.sherf_abi_version() == 1
+    assert lib.sherf_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -59,10 +59,10 @@ def test_scratch_bytes_and_argument_validation(lib):
         sc.vol_ch[l] = c
         for a in range(3):
             sc.vol_dim[l][a] = d[a]
-    small = lib.sherf_scratch_bytes(ctypes.byref(sc), 4096, 16, 6890)
-    big = lib.sherf_scratch_bytes(ctypes.byref(sc), 512 * 512, 64, 6890)
+    small = lib.sherf_scratch_bytes(ctypes.byref(sc), 4096, 16, 0, 6890)
+    big = lib.sherf_scratch_bytes(ctypes.byref(sc), 512 * 512, 64, 0, 6890)
     assert 0 < small < big < 8 << 30
-    assert lib.sherf_scratch_bytes(ctypes.byref(sc), 0, 16, 6890) == 0
+    assert lib.sherf_scratch_bytes(ctypes.byref(sc), 0, 16, 0, 6890) == 0
     rc = lib.sherf_render_forward(None, None, None, None, None, None, None, None, None, 0, None, None)
     assert rc == -1 and b'null' in lib.sherf_last_error()
 

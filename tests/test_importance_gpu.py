@@ -1,0 +1,197 @@
+"""GPU parity tests of the importance (fine) pass, SURVEY.md a13 / BASELINE configs[4]: renderer.py:373-393 in the repaired
+form stated by oracle/port.py (render_forward docstring) and pinned by the composition of the reference's own
+sample_importance / sample_pdf / unify_samples / ray marcher (oracle/ref_shim.render_importance -> tests/golden/importance_*.npz).
+
+Tolerances:
+  sample_pdf alone (same weights, same u): searchsorted bin equal on >= 99.9 % of the draws (the cdf is a float result:
+      torch.sum's summation order is not reproduced, so a draw within an ulp of a cdf entry may land in the neighbouring
+      bin -- the inverse cdf is continuous there), fine depths within 2e-6 * (far - near) everywhere
+  end to end: coarse ray-marcher weights 2e-5, fine depths 1e-4 * span on >= 99.9 % of the draws, fine cull mask equal on
+      >= 99.5 % of the fine samples (5 cm threshold on a float position), final rgb / acc within 1e-4 and depth within
+      1e-3 * span on >= 99 % of the rays (a flipped fine sample changes its ray)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, modules_from_weights, scene_to
+from sherf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(ren, dec, scene, **kw):
+    return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+               dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'],
+               scene['rendering_options'], **kw)
+
+
+@pytest.mark.parametrize('n_rays,S_,SF', [(257, 64, 64), (33, 3, 1), (64, 256, 256), (100, 33, 17), (5, 16, 200)])
+def test_sample_importance_against_torch(n_rays, S_, SF):
+    """sherf_debug_sample_importance == sample_importance + sample_pdf (renderer.py:483-542) on identical weights and draws."""
+    from oracle import port
+    from sherf_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(1000 * S_ + SF)
+    near = torch.rand(n_rays, generator=g) * 2 + 0.5
+    far = near + torch.rand(n_rays, generator=g) * 2 + 0.1
+    w = torch.rand(n_rays, S_, generator=g) ** 8                                  # peaky, like ray-marcher weights
+    w[::5] = 0.0                                                                  # rays that hit nothing: uniform pdf
+    w[1::7, : S_ // 2] = 0.0
+    u = torch.rand(n_rays, SF, generator=g)
+    u[0, 0] = 0.0
+    depths = port.sample_depths(near, far, S_)
+    want_t, want_bins = port.sample_importance(depths, w, SF, u)
+    rays = _lib.SherfRays()
+    nd, fd, wd, ud = near.to(dev), far.to(dev), w.to(dev).contiguous(), u.to(dev).contiguous()
+    t_out = torch.empty(n_rays, SF, device=dev)
+    b_out = torch.empty(n_rays, SF, dtype=torch.int32, device=dev)
+    rays.near_, rays.far_, rays.n_rays, rays.n_samples, rays.n_importance = nd.data_ptr(), fd.data_ptr(), n_rays, S_, SF
+    _lib.check(lib.sherf_debug_sample_importance(C.byref(rays), wd.data_ptr(), ud.data_ptr(), t_out.data_ptr(), b_out.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    same = (b_out.cpu().long() == want_bins).float().mean()
+    err = ((t_out.cpu() - want_t).abs() / (far - near)[:, None]).max()
+    print(f'\n[sample_importance N={n_rays} S={S_} S_f={SF}] bins equal {float(same):.5f}, max |t - torch| / span = {float(err):.2e}')
+    assert float(same) >= 0.999
+    assert float(err) <= 2e-6
+    mid = 0.5 * (depths[:, :-1] + depths[:, 1:])
+    assert torch.all(t_out.cpu() >= mid[:, :1] - 1e-6) and torch.all(t_out.cpu() <= mid[:, -1:] + 1e-6)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_importance_against_reference_golden(precision, smpl_model):
+    from oracle.gen_golden import importance_u
+    g = load_golden('importance_28x20x16p12')
+    dev = torch.device('cuda:0')
+    cpu_scene = S.make_scene(g['scene_spec'], smpl_model)
+    SF = int(g['n_importance'])
+    cpu_scene['rendering_options']['depth_resolution_importance'] = SF
+    scene = scene_to(cpu_scene, dev)
+    N = scene['ray_origins'].shape[1]
+    u = importance_u(N, SF, int(g['u_seed']))
+    ren, dec = modules_from_weights(g['weights'], smpl_model, mlp_precision=precision)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dbg = {}
+    rgb, depth, acc = run_cuda(ren, dec, scene, debug=dbg, importance_u=u.to(dev))
+    torch.cuda.synchronize()
+    span = (cpu_scene['far'] - cpu_scene['near'])[0]                               # [N,1]
+    e_w = float((dbg['coarse_weights'].cpu() - torch.from_numpy(g['coarse_weights'])).abs().max())
+    dt = (dbg['fine_depths'].cpu() - torch.from_numpy(g['t_fine'])).abs() / span
+    gold_mask = torch.from_numpy(g['sigma_fine'] != -80.0)
+    mask = dbg['fine_sample_vid'].cpu() >= 0
+    same_mask = float((mask == gold_mask).float().mean())
+    both = mask & gold_mask & (dt <= 1e-4)
+    sg, sg_g = dbg['fine_sigma'].cpu(), torch.from_numpy(g['sigma_fine'])
+    e_sig = float(((sg - sg_g).abs() / (sg_g.abs() + 1))[both].max()) if both.any() else 0.0
+    e_col = float((dbg['fine_rgb'].cpu() - torch.from_numpy(g['colors_fine'])).abs().amax(-1)[both].max()) if both.any() else 0.0
+    assert torch.all(sg[~mask] == -80.0) and torch.all(dbg['fine_rgb'].cpu()[~mask] == 0)
+    assert dbg['num_fine_points'] == int(mask.sum())
+    bad = ((rgb.cpu()[0] - torch.from_numpy(g['rgb'])).abs().amax(-1) > 1e-4) | ((acc.cpu()[0] - torch.from_numpy(g['acc'])).abs()[:, 0] > 1e-4)
+    bad |= ((depth.cpu()[0] - torch.from_numpy(g['depth'])).abs() / span)[:, 0] > 1e-3
+    print(f'\n[importance golden {precision}] P={dbg["num_points"]}+{dbg["num_fine_points"]} coarse_w={e_w:.2e} t_fine/span max={float(dt.max()):.2e} '
+          f'fine-mask equal={same_mask:.5f} sigma_f={e_sig:.2e} rgb_f={e_col:.2e} | bad rays {float(bad.float().mean()):.4%} '
+          f'rgb max={float((rgb.cpu()[0] - torch.from_numpy(g["rgb"])).abs().max()):.2e}')
+    assert e_w <= 2e-5
+    assert float((dt <= 1e-4).float().mean()) >= 0.999
+    assert same_mask >= 0.995
+    assert e_sig <= 2e-3 and e_col <= 2e-5
+    assert float(bad.float().mean()) <= 0.01
+
+
+IMPORTANCE_EDGE = [
+    (S.SceneSpec(H=12, W=12, samples=3, seed=31), 5),                          # minimum coarse samples: one pdf bin
+    (S.SceneSpec(H=9, W=7, samples=40, seed=32, random_global_R=True, white_back=True), 70),   # S + S_f not a multiple of 32, S_f > S
+    (S.SceneSpec(H=10, W=10, samples=16, seed=33, cam_dist=40.0), 16),         # (almost) nothing survives
+]
+
+
+@pytest.mark.parametrize('spec,SF', IMPORTANCE_EDGE, ids=lambda v: str(v) if isinstance(v, int) else f'{v.H}x{v.W}x{v.samples}')
+def test_importance_against_port_edge_cases(spec, SF, smpl_model, smpl_model_t):
+    from oracle import port
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    ren, dec = hot_path_modules(smpl_model, seed=7, dense_sigma=True)
+    w = port.hot_path_state_dict(ren, dec)
+    cpu_scene = S.make_scene(spec, smpl_model)
+    cpu_scene['rendering_options']['depth_resolution_importance'] = SF
+    N = cpu_scene['ray_origins'].shape[1]
+    u = torch.rand(N, SF, generator=torch.Generator().manual_seed(spec.seed))
+    prgb, pdepth, pacc, st = port.render_forward(w, smpl_model_t, cpu_scene, return_stages=True, importance_u=u)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dbg = {}
+    rgb, depth, acc = run_cuda(ren, dec, scene_to(cpu_scene, dev), debug=dbg, importance_u=u.to(dev))
+    span = (cpu_scene['far'] - cpu_scene['near'])[0].clamp_min(1e-6)
+    dt = (dbg['fine_depths'].cpu() - st['t_fine']).abs() / span
+    mask = dbg['fine_sample_vid'].cpu() >= 0
+    same_mask = float((mask.view(-1) == st['fine']['mask']).float().mean())
+    bad = ((rgb.cpu()[0] - prgb[0]).abs().amax(-1) > 1e-4) | ((acc.cpu()[0] - pacc[0]).abs()[:, 0] > 1e-4)
+    bad |= ((depth.cpu()[0] - pdepth[0]).abs() / span)[:, 0] > 1e-3
+    print(f'\n[importance {spec.H}x{spec.W}x{spec.samples}+{SF}] P={dbg["num_points"]}+{dbg["num_fine_points"]} t_fine/span max={float(dt.max()):.2e} '
+          f'fine-mask equal={same_mask:.5f} bad rays {float(bad.float().mean()):.4%}')
+    assert float((dt <= 1e-4).float().mean()) >= 0.995
+    assert same_mask >= 0.99
+    assert float(bad.float().mean()) <= 0.02
+
+
+def test_importance_empty_scene(smpl_model):
+    """Nothing within 5 cm in either pass: uniform pdf, P = P_f = 0, pure background."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = S.make_scene(S.SceneSpec(H=8, W=8, samples=16, seed=21), smpl_model)
+    scene['ray_origins'] = scene['ray_origins'] + 100.0
+    scene['near'] = torch.zeros_like(scene['near'])
+    scene['far'] = torch.ones_like(scene['far'])
+    scene['rendering_options']['depth_resolution_importance'] = 16
+    ren, dec = hot_path_modules(smpl_model, seed=7, dense_sigma=True)
+    dbg = {}
+    rgb, depth, acc = run_cuda(ren.to(dev), dec.to(dev), scene_to(scene, dev), debug=dbg)
+    assert ren.last_num_points == 0 and ren.last_num_fine_points == 0
+    assert torch.all(acc == 0) and torch.all(rgb == -1.0) and torch.all(depth == 1.0)
+    t = dbg['fine_depths']
+    assert float(t.min()) >= 1.0 / 30 - 1e-6 and float(t.max()) <= 1 - 1.0 / 30 + 1e-6       # inside the mid-point bins of [0,1] x 16
+
+
+def test_importance_full_size_properties(smpl_model):
+    """BASELINE configs[4] size on one GPU (512x512, 64 coarse + 64 fine): determinism for fixed draws, value ranges, rays that
+    hit nothing stay background, the fine pass concentrates samples near the surface, and ray shards (with their rows of the
+    draws) reproduce the full view bit for bit."""
+    from sherf_b200.triplane import hot_path_modules
+    from sherf_b200.dist import shard_scene, depth_range
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=512, W=512, samples=64, seed=0), smpl_model), dev)
+    scene['rendering_options']['depth_resolution_importance'] = 64
+    N = 512 * 512
+    u = torch.rand(N, 64, generator=torch.Generator().manual_seed(0)).to(dev)
+    ren, dec = hot_path_modules(smpl_model, seed=0, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dbg = {'max_feat_points': 1}
+    rgb, depth, acc = run_cuda(ren, dec, scene, debug=dbg, importance_u=u)
+    rgb2, depth2, acc2 = run_cuda(ren, dec, scene, importance_u=u)
+    assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2) and torch.equal(acc, acc2), 'forward must be deterministic'
+    assert float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    assert float(rgb.min()) >= -1 - 1e-5 and float(rgb.max()) <= 1 + 1e-5
+    Pc, Pf = dbg['num_points'], dbg['num_fine_points']
+    print(f'\n[512x512x(64+64)] coarse survivors {Pc} ({Pc / (N * 64):.4f}), fine survivors {Pf} ({Pf / (N * 64):.4f})')
+    assert Pf > Pc                                                             # importance sampling concentrates near the body
+    hit = (dbg['sample_vid'].view(N, 64) >= 0).any(1) | (dbg['fine_sample_vid'] >= 0).any(1)
+    assert torch.all(acc[0, ~hit, 0] == 0) and torch.all(rgb[0, ~hit] == -1.0)
+    # the fine depths of every ray lie inside its mid-point bins
+    t = dbg['fine_depths']
+    nr, fr = scene['near'][0], scene['far'][0]
+    lo = nr + (fr - nr) * (0.5 / 63)
+    hi = fr - (fr - nr) * (0.5 / 63)
+    tol = 1e-5 * (fr - nr).abs() + 1e-6
+    assert torch.all(t >= lo - tol) and torch.all(t <= hi + tol)
+    # shard invariance
+    lo_d, hi_d = depth_range(scene['near'], scene['far'], 64)
+    full = [torch.empty_like(rgb), torch.empty_like(depth), torch.empty_like(acc)]
+    for r in range(2):
+        sh, idx = shard_scene(scene, r, 2)
+        o = run_cuda(ren, dec, sh, depth_clamp=(lo_d, hi_d), importance_u=u[idx.to(dev)].contiguous())
+        for k in range(3):
+            full[k][:, idx] = o[k]
+    assert torch.equal(full[0], rgb) and torch.equal(full[1], depth) and torch.equal(full[2], acc)
