@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--importance', type=int, default=0,
+                    help='fine (importance) samples per ray; 64 = BASELINE configs[4] on one GPU (not the headline workload: the default is configs[1])')
     ap.add_argument('--shard', default='views', choices=['views', 'tiles'], help='N>1: ray-batch sharding granularity')
     return ap.parse_args()
 
@@ -103,27 +105,34 @@ def make_views(n_views, model):
     return base, views
 
 
-def cpu_port_rate(model, n_rays_target, threads):
-    """Times oracle/port.py (CPU restatement of the reference path) on a strided subset of the same 512x512x64 rays."""
+def cpu_port_rate(model, n_rays_target, threads, base=None, n_importance=0):
+    """Times oracle/port.py (CPU restatement of the reference path) on a strided subset of the same 512x512x64 rays.
+    Returns (rate, seconds, description, ray indices, oracle outputs of those rays)."""
     import torch
     from sherf_b200 import synthetic as SY
+    from sherf_b200 import dist as sd
     from sherf_b200.triplane import hot_path_modules
     from oracle import port
     torch.set_num_threads(threads)
-    base = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0), model)
+    if base is None:
+        base = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0), model)
     stride = max(1, int(round((H * W / n_rays_target) ** 0.5)))
     idx = (torch.arange(0, H, stride)[:, None] * W + torch.arange(0, W, stride)[None, :]).reshape(-1)
     sub = dict(base)
     for k in ('ray_origins', 'ray_directions', 'near', 'far'):
         sub[k] = base[k][:, idx].contiguous()
+    sub['rendering_options'] = dict(base['rendering_options'], depth_resolution_importance=n_importance)
+    u = torch.rand(idx.numel(), n_importance, generator=torch.Generator().manual_seed(0)) if n_importance else None
     ren, dec = hot_path_modules(model, seed=0, dense_sigma=True)
     wts = port.hot_path_state_dict(ren, dec)
     mt = SY.smpl_model_to_torch(model)
+    clamp = sd.depth_range(base['near'], base['far'], S)             # ray_marcher.py:57 is global over the full view
     t0 = time.perf_counter()
-    port.render_forward(wts, mt, sub)
+    out = port.render_forward(wts, mt, sub, importance_u=u, depth_clamp=clamp)
     dt = time.perf_counter() - t0
-    n = idx.numel() * S
-    return n / dt, dt, f'{idx.numel()} rays (every {stride}th pixel in x and y of the 512x512 view) x {S} samples = {n} ray-samples'
+    n = idx.numel() * (S + n_importance)
+    desc = f'{idx.numel()} rays (every {stride}th pixel in x and y of the 512x512 view) x {S + n_importance} samples = {n} ray-samples'
+    return n / dt, dt, desc, idx, out, u
 
 
 def run_reference(args):
@@ -140,7 +149,7 @@ def run_reference(args):
     n_rays = int(min(16384, max(256, budget * 9000 / S)))             # ~9e3 ray-samples/s/8 cores measured in the build container
     rates, last = [], None
     for i in range(args.warmup + args.steps):
-        rate, dt, sample = cpu_port_rate(model, n_rays, threads)
+        rate, dt, sample = cpu_port_rate(model, n_rays, threads)[:3]
         if i >= args.warmup:
             rates.append((rate, dt))
         last = sample
@@ -192,6 +201,7 @@ def main():
             return [mv(v) for v in x]
         return x
     scene = {k: mv(v) for k, v in base.items()}
+    scene['rendering_options']['depth_resolution_importance'] = args.importance      # draws: torch.rand on the device inside forward (renderer.py:526)
     N = H * W
     clamp = [sd.depth_range(v['near'], v['far'], S) for v in views]
     # this rank's tiles of every view (device resident for `value`, pinned host copies for `e2e`)
@@ -288,7 +298,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        samples_per_step = world * N * S
+        samples_per_step = world * N * (S + args.importance)
         calls = args.steps * len(my_views)
         mlp_ms = stage_ms[3] / calls
         p_call = points[0] / calls
@@ -325,7 +335,8 @@ def main():
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3 (3xTF32 split products, fp32 accumulate; fp32-grade)',
                                                 'bf16x3': 'bf16x3 decoder (bf16 hi/lo split products, 16 significand bits, fp32 accumulate) + tf32x3 fusion/transformer'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'H': H, 'W': W, 'samples_per_ray': S, 'views_per_step': world,
+            'config': {'workload': WORKLOAD if not args.importance else f'configs[4] shape on this GPU count: 512x512, {S}+{args.importance} coarse+fine importance sampling',
+                       'H': H, 'W': W, 'samples_per_ray': S, 'importance_samples_per_ray': args.importance, 'views_per_step': world,
                        'parallelism': ('single GPU' if world == 1 else (f'256-ray tiles of every view dealt to {world} ranks, one all-gather per view' if by_tiles else
                                         f'ray batch sharded at view granularity over {world} ranks (1 view each), one all-gather of the rendered tiles per step')),
                        'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if by_tiles else p_call,
@@ -346,8 +357,28 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)
-            rate, dt, sample = cpu_port_rate(model, 4096, threads)
+            rate, dt, sample, idx, want, u_sub = cpu_port_rate(model, 4096, threads, base, args.importance)
             line['cpu_baseline'] = {'value': rate, 'unit': 'ray-samples/s', 'cores': threads, 'kind': 'port', 'sample': sample, 'seconds': dt}
+            # BASELINE.json's second metric: PSNR of our image against the oracle's, on the rays the oracle just rendered
+            # (outside the timed region; the full 262 144-ray oracle image would take the CPU ~20 minutes)
+            import math
+            u_full = None
+            if args.importance:
+                u_full = torch.rand(N, args.importance, device=dev)
+                u_full[idx.to(dev)] = u_sub.to(dev)
+            got = ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'], dec,
+                      shard_dev[0]['ray_origins'], shard_dev[0]['ray_directions'], shard_dev[0]['near'], shard_dev[0]['far'],
+                      scene['input_data'], scene['rendering_options'], importance_u=u_full)[0][0].cpu()[idx]
+            ref_img = want[0][0]
+            hit = base['mask_at_box'].reshape(-1)[idx].bool()
+
+            def psnr(a, b):
+                mse = float(((a - b) ** 2).mean()) if a.numel() else 0.0
+                return round(10 * math.log10(4.0 / max(mse, 1e-20)), 2)               # images span (-1, 1)
+            line['psnr_vs_oracle'] = {'all_pixels_db': psnr(got, ref_img), 'mask_at_box_db': psnr(got[hit], ref_img[hit]),
+                                      'pixels': int(idx.numel()), 'mask_at_box_pixels': int(hit.sum()),
+                                      'rgb_linf': float((got - ref_img).abs().max()),
+                                      'note': 'our render vs oracle/port.py on the cpu_baseline ray sample (test_loop.py:36-37,222-223 metric)'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

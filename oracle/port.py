@@ -241,8 +241,10 @@ def fuse_and_decode(w, tri, f2d, f3d, can, cdir):
     return {'tok_pre': pre, 'tok_post': x, 'sigma': sigma[:, 0], 'rgb': rgb}
 
 
-def composite(colors, sigma, depths, rays_d, white_back):
-    """ray_marcher.py:25-64, clamp_mode='relu'.  colors[N,S,3] sigma[N,S] depths[N,S] rays_d[N,3]."""
+def composite(colors, sigma, depths, rays_d, white_back, depth_clamp=None):
+    """ray_marcher.py:25-64, clamp_mode='relu'.  colors[N,S,3] sigma[N,S] depths[N,S] rays_d[N,3].
+    `depth_clamp` = (min, max) of the depths of the FULL view when `depths` holds only a subset of its rays (:57 takes
+    torch.min / torch.max over all rays of the view)."""
     deltas = torch.cat([depths[:, 1:] - depths[:, :-1], torch.full_like(depths[:, :1], 1e10)], 1)
     deltas = deltas * torch.norm(rays_d, dim=-1, keepdim=True)
     alpha = 1 - torch.exp(-(F.relu(sigma) * deltas))
@@ -251,7 +253,8 @@ def composite(colors, sigma, depths, rays_d, white_back):
     rgb = (wts[..., None] * colors).sum(1)
     wsum = wts.sum(1, keepdim=True)
     depth = (wts * depths).sum(1, keepdim=True) / wsum
-    depth = torch.clamp(torch.nan_to_num(depth, float('inf')), depths.min(), depths.max())
+    lo, hi = (depths.min(), depths.max()) if depth_clamp is None else depth_clamp
+    depth = torch.clamp(torch.nan_to_num(depth, float('inf')), lo, hi)
     if white_back:
         rgb = rgb + 1 - wsum
     return rgb * 2 - 1, depth, wts
@@ -320,7 +323,7 @@ def evaluate_samples(weights: dict, smpl: dict, scene: dict, depths=None):
 
 
 @torch.no_grad()
-def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool = False, importance_u=None):
+def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool = False, importance_u=None, depth_clamp=None):
     """The whole hot path.  `weights`: state-dict names prefixed 'renderer.' / 'decoder.' (SURVEY §8b).
     Returns rgb[1,N,3], depth[1,N,1], acc[1,N,1] (+ stages dict).
 
@@ -342,10 +345,10 @@ def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool =
         t_fine, inds = sample_importance(st['depths'], wts_c, n_imp, importance_u)
         colors_f, sigma_f, st_f = evaluate_samples(weights, smpl, scene, t_fine)
         d_all, c_all, s_all = unify_samples(st['depths'], colors, sigma, t_fine, colors_f, sigma_f)
-        rgb, depth, wts = composite(c_all, s_all, d_all, rays_d, opts['white_back'])
+        rgb, depth, wts = composite(c_all, s_all, d_all, rays_d, opts['white_back'], depth_clamp)
         st.update({'coarse_weights': wts_c, 't_fine': t_fine, 'fine_bins': inds, 'fine': st_f})
     else:
-        rgb, depth, wts = composite(colors, sigma, st['depths'], rays_d, opts['white_back'])
+        rgb, depth, wts = composite(colors, sigma, st['depths'], rays_d, opts['white_back'], depth_clamp)
     out = (rgb[None], depth[None], wts.sum(1, keepdim=True)[None])
     if not return_stages:
         return out

@@ -177,7 +177,7 @@ static thread_local StageTimer* g_tm = nullptr;
 // Internal side stream (per host thread): the warp+gather kernel of chunk i+1 runs concurrently with the persistent MLP
 // kernels of chunk i (they leave most issue slots idle and the gather kernel needs no shared memory).
 struct SideStream {
-  cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, gdone[2] = {nullptr, nullptr}, mdone[2] = {nullptr, nullptr}; int dev = -1;
+  cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, ldone = nullptr, gdone[2] = {nullptr, nullptr}, mdone[2] = {nullptr, nullptr}; int dev = -1;
   int ensure() {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) return -1;
@@ -185,6 +185,7 @@ struct SideStream {
     dev = d;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return -1;
     cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ldone, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&gdone[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&mdone[i], cudaEventDisableTiming); }
     return 0;
   }
@@ -264,44 +265,49 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.init(g_profiling != 0, st);
   g_tm = &tm;
 
-  // ---- stage 0: per-frame tables, channels-last feature copies, packed weights ----
+  // ---- stage 0: per-frame tables (SMPL chain, warp tables, grids) on the caller's stream; the channels-last feature copies and the
+  //      weight packing do not depend on them and run on an internal side stream, concurrently with the (latency-bound, tiny-grid)
+  //      SMPL chain and with the cull stage; the point stages wait for both ----
+  const bool side = !getenv("SHERF_NO_PROLOGUE_OVERLAP") && g_side.ensure() == 0;
+  cudaStream_t ls = side ? g_side.s : st;
+  if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); }
   tm.begin(0);
   RC(run_prologue(*smpl, *frame, *rays, *opts, L.ft, st));
-  RC(run_to_channels_last(scene->planes, L.planes_cl, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, st));
+  tm.end();
+  RC(run_to_channels_last(scene->planes, L.planes_cl, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, ls));
   RC(run_to_channels_last(scene->planes + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w,
                           L.planes_cl + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w, scene->plane_ch,
-                          (int64_t)scene->plane_h * scene->plane_w, st));
+                          (int64_t)scene->plane_h * scene->plane_w, ls));
   RC(run_to_channels_last(scene->planes + (size_t)2 * scene->plane_ch * scene->plane_h * scene->plane_w,
                           L.planes_cl + (size_t)2 * scene->plane_ch * scene->plane_h * scene->plane_w, scene->plane_ch,
-                          (int64_t)scene->plane_h * scene->plane_w, st));
-  RC(run_to_channels_last(scene->obs_feat, L.feat_cl, scene->feat_ch, (int64_t)scene->feat_h * scene->feat_w, st));
+                          (int64_t)scene->plane_h * scene->plane_w, ls));
+  RC(run_to_channels_last(scene->obs_feat, L.feat_cl, scene->feat_ch, (int64_t)scene->feat_h * scene->feat_w, ls));
   for (int l = 0; l < 3; ++l)
     RC(run_to_channels_last(scene->vol[l], L.vol_cl[l], scene->vol_ch[l],
-                            (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2], st));
+                            (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2], ls));
   PackedWeights pw;
   CanonWeights cw;
-  if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, st));
-  else RC(run_pack_canonical(*weights, L.canon_w, cw, st));
+  if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, ls));
+  else RC(run_pack_canonical(*weights, L.canon_w, cw, ls));
   FusedPlan fplan;
   PpPlan pplan;
   fplan.pp = nullptr;
   const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
   if (use_fused) {
-    RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, st));
+    RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, ls));
     fplan.xf_blob = nullptr;
     fplan.ff_blob = nullptr;
-    if (!getenv("SHERF_NO_FUSED_FUSION")) { RC(run_pack_fusion(*weights, L.ff_blob, st)); fplan.ff_blob = L.ff_blob; }
-    if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, st)); fplan.xf_blob = L.xf_blob; }
+    if (!getenv("SHERF_NO_FUSED_FUSION")) { RC(run_pack_fusion(*weights, L.ff_blob, ls)); fplan.ff_blob = L.ff_blob; }
+    if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, ls)); fplan.xf_blob = L.xf_blob; }
     if (opts->mlp_precision == SHERF_MLP_BF16X3) {
-      RC(run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, st));
+      RC(run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, ls));
       const int cap = chunk_cap(N, S, SF);
       pplan.xp = L.pp_xv;
       pplan.vp = L.pp_xv + (size_t)((cap + 127) / 128) * 40960;
       fplan.pp = &pplan;
     }
   }
-
-  tm.end();
+  if (side) SHERF_CUDA_OK(cudaEventRecord(g_side.ldone, ls));
 
   // ---- stage 1: cull + ordered compaction ----
   tm.begin(1);
@@ -364,6 +370,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     }
     return SHERF_OK;
   };
+  if (side) SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.ldone, 0));          // layouts + packed weights are ready
   RC(run_points(L.point_sample, L.point_vid, P, S, nullptr, L.sigma, L.rgb, dbg));
   if (dbg && P > 0) {
     const size_t cnt = (size_t)(P < dbg->max_points ? P : dbg->max_points);

@@ -149,16 +149,19 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
         *reinterpret_cast<float4*>(buf + (kg0 + g4) * ff::kLbo + row * 16) = make_float4(h[4 * g4], h[4 * g4 + 1], h[4 * g4 + 2], h[4 * g4 + 3]);
       if (PREC == 3) umma::tmem_st16(tb + lo_col, lo);
     };
-    // stream one 32-column chunk of a row-major global matrix into operand slot (cnt & 1); this thread: 16 columns of its row
-    auto load_chunk = [&](const float* src_row, bool ok) {
-      const int b = cnt & 1;
-      float v[16];
+    // The gathered features are streamed in twelve 32-column chunks per tile (six of f3raw, then tri_t | f2d_t of the three tokens);
+    // this thread handles 16 columns of its row.  The global loads run TWO chunks ahead of the operand-slot hand-off (software
+    // pipeline across chunks and tiles, registers va / vb), so their latency overlaps the slot waits and the MMAs.
+    auto issue_loads = [&](const float* src_row, bool ok, float (&v)[16]) {
       const float4* src = reinterpret_cast<const float4*>(src_row + 16 * hsel);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {                          // issue the loads before waiting for the slot
+      for (int i = 0; i < 4; ++i) {
         const float4 f = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
       }
+    };
+    auto commit_chunk = [&](const float (&v)[16]) {          // registers -> operand slot (cnt & 1)
+      const int b = cnt & 1;
       umma::mbar_wait(&chempty[b], ((cnt >> 1) & 1) ^ 1);
       umma::tc_fence_after_sync();
       split_store(smem + (b ? ff::kCh1 : ff::kCh0), 4 * hsel, (b ? ff::kChLo1 : ff::kChLo0) + (uint32_t)(16 * hsel), v);
@@ -168,31 +171,51 @@ __global__ void __launch_bounds__(320, 1) k_fusion_fused(const FfArgs a) {
       ff_arrive(&chfull[b]);
       ++cnt;
     };
+    auto chunk_src = [&](int m, int k) -> const float* {
+      return k < 6 ? a.f3raw + (size_t)m * 192 + 32 * k : a.comb + (size_t)m * 288 + 96 * ((k - 6) >> 1) + 32 * ((k - 6) & 1);
+    };
+    float va[16], vb[16];
+    {
+      const int m0 = blockIdx.x * 128 + row;
+      const bool ok0 = (int)blockIdx.x < ntiles && m0 < a.np;
+      issue_loads(chunk_src(m0, 0), ok0, va);
+      issue_loads(chunk_src(m0, 1), ok0, vb);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int m = tile * 128 + row;
       const bool row_ok = m < a.np;
-      for (int c = 0; c < 6; ++c) load_chunk(a.f3raw + (size_t)m * 192 + 32 * c, row_ok);
-      // ---- E1: projected 3-D feature = D1 + bias -> operand for the reprojection (48 columns per thread) ----
-      umma::mbar_wait(&acc1, par_t);
-      umma::tc_fence_after_sync();
+      const int mn = (tile + (int)gridDim.x) * 128 + row;                     // this thread's row in the CTA's next tile
+      const bool next_ok = tile + (int)gridDim.x < ntiles && mn < a.np;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c0 = 48 * hsel + 16 * i;
-        uint32_t d[16];
-        umma::tmem_ld16(tb + ff::kD1 + (uint32_t)c0, d);
-        umma::tmem_ld_wait();
-        float v[16];
+      for (int k = 0; k < 12; ++k) {
+        if (k == 6) {
+          // ---- E1: projected 3-D feature = D1 + bias -> operand for the reprojection (48 columns per thread) ----
+          umma::mbar_wait(&acc1, par_t);
+          umma::tc_fence_after_sync();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(d[e]) + s_bp[c0 + e];
-        split_store(smem + ff::kF3d, c0 / 4, ff::kF3dLo + (uint32_t)c0, v);
+          for (int i = 0; i < 3; ++i) {
+            const int c0 = 48 * hsel + 16 * i;
+            uint32_t d[16];
+            umma::tmem_ld16(tb + ff::kD1 + (uint32_t)c0, d);
+            umma::tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(d[e]) + s_bp[c0 + e];
+            split_store(smem + ff::kF3d, c0 / 4, ff::kF3dLo + (uint32_t)c0, v);
+          }
+          if (PREC == 3) umma::tmem_st_wait();
+          umma::fence_proxy_async_smem();
+          umma::tc_fence_before_sync();
+          ff_arrive(&f3d_ready);
+        }
+        if (k & 1) {
+          commit_chunk(vb);
+          if (k + 2 < 12) issue_loads(chunk_src(m, k + 2), row_ok, vb); else issue_loads(chunk_src(mn, k + 2 - 12), next_ok, vb);
+        } else {
+          commit_chunk(va);
+          if (k + 2 < 12) issue_loads(chunk_src(m, k + 2), row_ok, va); else issue_loads(chunk_src(mn, k + 2 - 12), next_ok, va);
+        }
       }
-      if (PREC == 3) umma::tmem_st_wait();
-      umma::fence_proxy_async_smem();
-      umma::tc_fence_before_sync();
-      ff_arrive(&f3d_ready);
-      // ---- stream tri_t / f2d_t of the three tokens ----
-      for (int t = 0; t < 3; ++t)
-        for (int part = 0; part < 2; ++part) load_chunk(a.comb + (size_t)m * 288 + 96 * t + 32 * part, row_ok);
       // ---- E2: tokens = D2 + bias -> global; LayerNorm-1 -> global.  hsel 0: tokens 0 and 2, hsel 1: token 1 ----
       umma::mbar_wait(&acc2, par_t);
       umma::tc_fence_after_sync();

@@ -155,6 +155,16 @@ __global__ void __launch_bounds__(128) k_composite_merged(const float* __restric
   const float nr = nearv[n], fr = farv[n];
   const float dx = dirs[n * 3], dy = dirs[n * 3 + 1], dz = dirs[n * 3 + 2];
   const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  if (start_c[n] == start_c[n + 1] && start_f[n] == start_f[n + 1]) {
+    // no surviving sample in either pass: every alpha is 0 -> exactly what the general path computes (0/0 -> NaN -> +inf -> clamp)
+    if (lane == 0) {
+      const float bg = white_back ? 1.f : -1.f;                                  // (0 + 1 - 0) * 2 - 1  |  0 * 2 - 1
+      out_rgb[(size_t)n * 3] = bg; out_rgb[(size_t)n * 3 + 1] = bg; out_rgb[(size_t)n * 3 + 2] = bg;
+      out_depth[n] = fminf(fmaxf(__int_as_float(0x7f800000), ordered_to_float(fc->dmin_bits)), ordered_to_float(fc->dmax_bits));
+      out_acc[n] = 0.f;
+    }
+    return;
+  }
   // phase 1: depths and compacted point indices (same ballot prefix as k_compact)
   int pos = start_c[n];
   for (int i0 = 0; i0 < S; i0 += 32) {
@@ -179,16 +189,35 @@ __global__ void __launch_bounds__(128) k_composite_merged(const float* __restric
     pos += __popc(m);
   }
   __syncwarp();
-  // phase 2: rank of every entry under (depth, e)
-  for (int e = lane; e < M; e += 32) {
-    const float t = key[e];
-    int r = 0;
-    for (int k = 0; k < M; ++k) {
-      const float tk = key[k];
-      r += (tk < t || (tk == t && k < e)) ? 1 : 0;
+  // phase 2: rank of every entry under (depth, e).  The stratified coarse depths are monotone in i when far >= near, so a coarse
+  // entry's rank among the coarse entries is i and a fine entry's is a binary search; only the fine list needs compare loops.
+  if (fr >= nr) {
+    for (int e = lane; e < M; e += 32) {
+      const float t = key[e];
+      int r;
+      if (e < S) {
+        r = e;
+        for (int k = S; k < M; ++k) r += (key[k] < t) ? 1 : 0;                 // fine entries come after every coarse one in e
+      } else {
+        int lo = 0, hi = S;                                                    // #{i : t_i <= t}
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] <= t) lo = mid + 1; else hi = mid; }
+        r = lo;
+        for (int k = S; k < M; ++k) { const float tk = key[k]; r += (tk < t || (tk == t && k < e)) ? 1 : 0; }
+      }
+      rank[e] = (unsigned short)r;
+      srt[r] = t;
     }
-    rank[e] = (unsigned short)r;
-    srt[r] = t;
+  } else {
+    for (int e = lane; e < M; e += 32) {
+      const float t = key[e];
+      int r = 0;
+      for (int k = 0; k < M; ++k) {
+        const float tk = key[k];
+        r += (tk < t || (tk == t && k < e)) ? 1 : 0;
+      }
+      rank[e] = (unsigned short)r;
+      srt[r] = t;
+    }
   }
   __syncwarp();
   // phase 3: alpha per entry                                                                          ray_marcher.py:27-45

@@ -164,6 +164,17 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
       umma::fence_proxy_async_smem();
       umma::tc_fence_before_sync();
       xf_arrive(&a_bar);
+      // pull what this thread reads later into L2 while the tensor core works: the residual rows of this tile (to_out epilogue),
+      // and the LayerNorm-ed rows / geometry of the CTA's next tile (the fusion kernel's output is larger than L2)
+      {
+        auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        if (row_ok) pf(a.tok + (size_t)(m * 3 + t) * 32);
+        const int mn = m + (int)gridDim.x * 128;
+        if (mn < a.np) {
+          pf(a.ln1 + (size_t)(mn * 3 + t) * 32);
+          if (t == 0) { pf(a.ln1 + (size_t)(mn * 3 + 2) * 32); pf(a.geo + (size_t)mn * 8); }
+        }
+      }
 
       // ---- three heads: attention of query token t over the three tokens ----
       for (int h = 0; h < 3; ++h) {

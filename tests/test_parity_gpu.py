@@ -211,3 +211,55 @@ def test_full_size_precisions_agree(smpl_model):
         print(f'\n[512x512x64 {prec} vs fp32] rgb={e_rgb:.2e} depth={e_depth:.2e} acc={e_acc:.2e} sigma_rel={e_sig:.2e} rgb_pt={e_pt:.2e}')
         assert e_rgb <= 1e-5 and e_acc <= 1e-5 and e_depth <= 1e-5
         assert e_sig <= 1e-4 and e_pt <= 1e-5
+
+
+FULL_SIZE_CONFIGS = {
+    # BASELINE.json configs[1]: 512x512 RenderPeople-shape, 64 samples/ray
+    'c2_512x512x64': (S.SceneSpec(H=512, W=512, samples=64, seed=0), 0),
+    # configs[3] frame shape: 640x360 HuMMan-shape (global rotation R != I), 64 samples/ray
+    'c4_640x360x64_R': (S.SceneSpec(H=360, W=640, samples=64, seed=4, random_global_R=True), 0),
+    # configs[4]: 512x512 ZJU-Mocap-shape, 64 coarse + 64 fine importance samples
+    'c5_512x512x64p64_R': (S.SceneSpec(H=512, W=512, samples=64, seed=6, random_global_R=True, white_back=True), 64),
+}
+
+
+@pytest.mark.parametrize('name', list(FULL_SIZE_CONFIGS))
+def test_full_size_ray_subset_against_port(name, smpl_model, smpl_model_t):
+    """BASELINE.json's full-size configurations against the oracle itself: the CUDA path renders the whole view, oracle/port.py
+    renders every 16th pixel in x and y of the same view (rays are independent; the one global quantity, the depth clamp of
+    ray_marcher.py:57, is handed to the oracle).  Same tolerances as the small fixtures."""
+    from oracle import port
+    from sherf_b200.dist import depth_range
+    from sherf_b200.triplane import hot_path_modules
+    spec, n_imp = FULL_SIZE_CONFIGS[name]
+    dev = torch.device('cuda:0')
+    cpu_scene = S.make_scene(spec, smpl_model)
+    cpu_scene['rendering_options']['depth_resolution_importance'] = n_imp
+    N = spec.H * spec.W
+    idx = (torch.arange(4, spec.H, 16)[:, None] * spec.W + torch.arange(4, spec.W, 16)[None, :]).reshape(-1)
+    u = torch.rand(N, n_imp, generator=torch.Generator().manual_seed(1)) if n_imp else None
+    ren, dec = hot_path_modules(smpl_model, seed=0, dense_sigma=True)
+    w = port.hot_path_state_dict(ren, dec)
+    sub = dict(cpu_scene)
+    for k in ('ray_origins', 'ray_directions', 'near', 'far'):
+        sub[k] = cpu_scene[k][:, idx].contiguous()
+    clamp = depth_range(cpu_scene['near'], cpu_scene['far'], spec.samples)
+    prgb, pdepth, pacc = port.render_forward(w, smpl_model_t, sub, importance_u=None if u is None else u[idx].contiguous(),
+                                             depth_clamp=clamp)
+    ren, dec = ren.to(dev), dec.to(dev)
+    rgb, depth, acc = run_cuda_kw(ren, dec, scene_to(cpu_scene, dev), importance_u=None if u is None else u.to(dev))
+    rgb, depth, acc = rgb.cpu()[:, idx], depth.cpu()[:, idx], acc.cpu()[:, idx]
+    span = (sub['far'] - sub['near'])[0].clamp_min(1e-6)
+    bad = ((rgb[0] - prgb[0]).abs().amax(-1) > 1e-4) | ((acc[0] - pacc[0]).abs()[:, 0] > 1e-4) | (((depth[0] - pdepth[0]).abs() / span)[:, 0] > 1e-3)
+    mse = float(((rgb[0] - prgb[0]) ** 2).mean())
+    psnr = 10 * np.log10(4.0 / max(mse, 1e-20))
+    print(f'\n[{name}] {idx.numel()} oracle rays, hit fraction {float((pacc[0] > 0).float().mean()):.3f}: rgb={linf(rgb, prgb):.2e} acc={linf(acc, pacc):.2e} '
+          f'depth/span={float(((depth[0] - pdepth[0]).abs() / span).max()):.2e} bad rays {float(bad.float().mean()):.4%} PSNR={psnr:.1f} dB')
+    assert float((pacc[0] > 0).float().mean()) > 0.05                  # the subset actually sees the body
+    assert float(bad.float().mean()) <= (0.02 if n_imp else 2e-3)
+
+
+def run_cuda_kw(ren, dec, scene, **kw):
+    return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+               dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'],
+               scene['rendering_options'], **kw)
