@@ -200,6 +200,15 @@ SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* 
 SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */, float* max_out /* host */,
                       void* scratch, size_t scratch_bytes, void* stream);
 
+/* Dataset-side ray setup on the device: get_rays (RenderPeople_dataset.py:14-27) + get_near_far
+ * (:68-101) + the (0,1) near/far fill for rays that miss the box (:129-134) for an H x W pinhole view.
+ * K, R, T, bounds ([2,3] = min xyz, max xyz of the SMPL vertices +-0.05, :284-289) are HOST arrays of doubles (row-major);
+ * outputs are device arrays: origins/dirs [H*W,3] (dirs un-normalised, zeros replaced by 1e-8 as the dataset does in
+ * place), near/far [H*W], mask_at_box [H*W] bytes (optional).  fp64 inside, float32 out, like numpy. */
+SHERF_API int sherf_generate_rays(const double* K, const double* R, const double* T, int32_t H, int32_t W, const double* bounds,
+                                  float* origins, float* dirs, float* near_out, float* far_out, uint8_t* mask_at_box /* may be NULL */,
+                                  void* stream);
+
 /* sample_importance + sample_pdf (renderer.py:483-542) alone, on caller-supplied ray-marcher weights [N*S]
  * and uniform draws u [N*S_f]: writes the fine depths [N*S_f] and (optional) the searchsorted bin indices. */
 SHERF_API int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out,

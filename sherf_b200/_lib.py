@@ -69,7 +69,7 @@ class SherfDebug(C.Structure):
                 ('fine_sigma', c_float_p), ('fine_rgb', c_float_p)]
 
 
-EXPORTS = ['sherf_debug_set_trace', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+EXPORTS = ['sherf_debug_set_trace', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
 
 _lib = None
@@ -107,6 +107,9 @@ def load():
                                        C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sherf_debug_sample_importance.restype = C.c_int
     lib.sherf_debug_sample_importance.argtypes = [C.POINTER(SherfRays), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sherf_generate_rays.restype = C.c_int
+    lib.sherf_generate_rays.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sherf_debug_set_trace.argtypes = [C.c_void_p]
     lib.sherf_last_error.restype = C.c_char_p
     lib.sherf_abi_version.restype = C.c_int

@@ -429,6 +429,17 @@ int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, c
   return SHERF_OK;
 }
 
+int sherf_generate_rays(const double* K, const double* R, const double* T, int32_t H, int32_t W, const double* bounds, float* origins,
+                        float* dirs, float* near_out, float* far_out, uint8_t* mask_at_box, void* stream) {
+  g_err[0] = 0;
+  if (!K || !R || !T || !bounds || !origins || !dirs || !near_out || !far_out) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (H <= 0 || W <= 0 || (int64_t)H * W >= (1LL << 31)) { set_error("bad image size %d x %d", H, W); return SHERF_E_INVALID; }
+  g_launches.n = 0;
+  RC(run_generate_rays(K, R, T, H, W, bounds, origins, dirs, near_out, far_out, mask_at_box, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
 void sherf_debug_set_trace(long long* device_buf) { g_fused_trace = device_buf; }
 
 int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N,

@@ -119,6 +119,10 @@ int run_debug_linear(int prec, const float* A, int lda, const float* W, const fl
 int run_composite(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample,
                   const float* sigma, const float* rgb, const float* noise, int white_back, const SherfOut& out, cudaStream_t st);
 
+// Dataset-side ray setup (rays.cu): get_rays + get_near_far, RenderPeople_dataset.py:14-27,68-101,129-134
+int run_generate_rays(const double* K, const double* R, const double* T, int H, int W, const double* bounds, float* origins, float* dirs,
+                      float* nearv, float* farv, unsigned char* mask_at_box, cudaStream_t st);
+
 // Importance (fine) pass, importance.cu (renderer.py:373-393, 446-456, 483-542)
 int run_importance_sample(const SherfRays& rays, const int* ray_start, const int* point_sample, const float* sigma, const float* noise,
                           const float* w_in, const float* u, float* t_fine, int* bins_out, float* w_out, cudaStream_t st);

@@ -363,4 +363,6 @@ def make_scene(spec: SceneSpec, model: dict | None = None, device='cpu') -> dict
         'ray_origins': input_data['ray_o_all'][:, 0], 'ray_directions': input_data['ray_d_all'][:, 0],
         'near': input_data['near_all'][:, 0], 'far': input_data['far_all'][:, 0],
         'rendering_options': rendering_options, 'mask_at_box': tt(hit), 'spec': spec,
+        # the target camera and body box the rays were made from (numpy float64 / float32, host): input of sherf_b200.rays.generate_rays
+        'camera': {'K': K, 'R': R, 'T': T, 'bounds': wb},
     }
