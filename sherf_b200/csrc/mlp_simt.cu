@@ -557,7 +557,7 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
     // qkv -> attention -> to_out -> LN2 -> FeedForward -> decoder inputs in one persistent tcgen05 kernel (xformer_fused.cu)
     if (span_begin) span_begin(6);
     RC(run_xformer_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->xf_blob, cb.ln, cb.tok, cb.geo, cb.x, cb.fv, np, dbg_tok, p0, dbg_max, st,
-                         pp ? fused->pp->xp : nullptr, pp ? fused->pp->vp : nullptr));
+                         pp ? fused->pp->xp : nullptr, pp ? fused->pp->vp : nullptr, cb.qkv /* unused by the fused path: PE scratch */));
     if (span_end) span_end();
   } else {
     RC(launch_gemm(pw.qkv, cw.qkv, cb.ln, 32, cb.qkv, 144, rows3, ACT_NONE, st));

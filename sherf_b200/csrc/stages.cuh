@@ -104,8 +104,8 @@ int run_fusion_fused(int prec, const SherfWeights& w, const float* blob, const f
 size_t xformer_blob_floats();
 int run_pack_xformer(const SherfWeights& w, float* blob, cudaStream_t st);
 int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const float* ln1, const float* tok, const float* geo, float* x,
-                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp = nullptr,
-                      unsigned char* vp = nullptr);
+                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp,
+                      float* pe_buf /* [np][64] scratch for the positional encodings */);
 
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
 // prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 | SHERF_MLP_BF16X3 (tcgen05 tensor cores)

@@ -262,10 +262,11 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
+// fp32 -> tf32, round to nearest with ties away from zero: bit-identical to `cvt.rna.tf32.f32` on finite inputs.  ptxas expands that
+// cvt into a ~6-instruction sequence (NaN / Inf handling), which made the hi/lo operand splits a third of the fused kernels'
+// instructions (profiles/r1_q); on the sign-magnitude encoding the same rounding is one add and one mask.
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 }  // namespace umma

@@ -35,6 +35,7 @@ constexpr uint32_t kD3 = 0, kD4 = 144, kD5 = 208, kLo1 = 272, kLo2 = 368;     //
 
 struct XfArgs {
   const float *ln1, *tok, *geo;        // [3np][32] LayerNorm-ed tokens, [3np][32] tokens (residual), [np][8] can / cdir
+  const float* pe;                     // [np][64] positional encodings made by k_point_pe: 36 of can (pos_enc) | 24 of cdir (view_enc) | 0 x 4
   const float* wblob;                  // [2][8192] canonical hi | lo
   const float *bo, *ln_w, *ln_b, *b1, *b2;
   float *x, *fv;                       // [np][72], [np][188] (columns 128..187)
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
         if (mn < a.np) {
           pf(a.ln1 + (size_t)(mn * 3 + t) * 32);
           if (t == 0) { pf(a.ln1 + (size_t)(mn * 3 + 2) * 32); pf(a.geo + (size_t)mn * 8); }
+          pf(a.pe + (size_t)mn * 64 + 32 * t);
         }
       }
 
@@ -272,6 +274,14 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
       }
       // ---- ff2 + residual -> decoder inputs ----
       {
+        // positional encodings of this row (renderer.py:432 pos_enc / view_enc), computed by k_point_pe at full occupancy: sixty sinf per
+        // point inside this epilogue were a third of the kernel's instructions on its eight serialised warps (profiles/r1_q)
+        float4 pev[9];
+        {
+          const float4* pr = reinterpret_cast<const float4*>(a.pe + (size_t)m * 64 + (t == 0 ? 0 : 36));
+#pragma unroll
+          for (int i = 0; i < 9; ++i) pev[i] = (row_ok && (t == 0 || i < 6)) ? __ldg(pr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         umma::mbar_wait(&acc_bar, par_acc);
         par_acc ^= 1;
         umma::tc_fence_after_sync();
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
         {
           const float g0 = row_ok ? a.geo[(size_t)m * 8 + 3 * t] : 0.f, g1 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 1] : 0.f,
                       g2 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 2] : 0.f;
-          auto pe = [&](int mm, float gv) -> float { return sinf(__fadd_rn((mm & 1) ? kPi2 : 0.f, __fmul_rn(gv, (float)(1 << (mm >> 1))))); };
+          const float* pef = reinterpret_cast<const float*>(pev);              // pef[3 * mm + c] = sin(phase_mm + g_c * 2^(mm >> 1))
           // packed tile store: 8 consecutive k-columns of this row -> one 16-byte hi and one 16-byte lo chunk (consecutive rows
           // are consecutive chunks, so a warp writes 512 contiguous bytes per core-matrix column)
           auto put8 = [&](unsigned char* tile_base, int kg, uint32_t lo_off, const float* v8) {
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
             float vals[80];
             vals[0] = g0; vals[1] = g1; vals[2] = g2;
 #pragma unroll
-            for (int mm = 0; mm < 12; ++mm) { vals[3 + 3 * mm] = pe(mm, g0); vals[4 + 3 * mm] = pe(mm, g1); vals[5 + 3 * mm] = pe(mm, g2); }
+            for (int o = 0; o < 36; ++o) vals[3 + o] = pef[o];
 #pragma unroll
             for (int o = 0; o < 32; ++o) vals[39 + o] = tok3[o];
 #pragma unroll
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
             float vals[64];
             vals[0] = g0; vals[1] = g1; vals[2] = g2;
 #pragma unroll
-            for (int mm = 0; mm < 8; ++mm) { vals[3 + 3 * mm] = pe(mm, g0); vals[4 + 3 * mm] = pe(mm, g1); vals[5 + 3 * mm] = pe(mm, g2); }
+            for (int o = 0; o < 24; ++o) vals[3 + o] = pef[o];
 #pragma unroll
             for (int o = 0; o < 32; ++o) vals[27 + o] = tok3[o];
 #pragma unroll
@@ -353,6 +363,24 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
   umma::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Positional encodings of the canonical position (pos_enc, 6 octaves) and view direction (view_enc, 4 octaves) of every point
+// (renderer.py:432, PositionalEncoding :900-916): pe[p][3*mm + c] = sin(phase(mm) + x_c * 2^(mm >> 1)), phase = 0 | pi/2 -- the same
+// separately rounded multiply and add as torch.addcmul.  One thread per value: the sixty sinf per point run at full occupancy here.
+__global__ void __launch_bounds__(256) k_point_pe(const float* __restrict__ geo, float* __restrict__ pe, int np) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)np * 64) return;
+  const int p = (int)(idx >> 6), j = (int)(idx & 63);
+  float v = 0.f;
+  if (j < 60) {
+    const int jj = j < 36 ? j : j - 36;
+    const int mm = jj / 3, c = jj - 3 * mm;
+    const float g = geo[(size_t)p * 8 + (j < 36 ? 0 : 3) + c];
+    v = sinf(__fadd_rn((mm & 1) ? kPi2 : 0.f, __fmul_rn(g, (float)(1 << (mm >> 1)))));
+  }
+  pe[idx] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -394,9 +422,13 @@ int run_pack_xformer(const SherfWeights& w, float* blob, cudaStream_t st) {
 }
 
 int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const float* ln1, const float* tok, const float* geo, float* x,
-                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp) {
+                      float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp,
+                      float* pe_buf) {
   if (np <= 0) return SHERF_OK;
+  k_point_pe<<<ceil_div((int64_t)np * 64, 256), 256, 0, st>>>(geo, pe_buf, np);
+  SHERF_LAUNCH_CHECK();
   XfArgs a;
+  a.pe = pe_buf;
   a.ln1 = ln1; a.tok = tok; a.geo = geo; a.wblob = blob; a.bo = w.attn_out_b; a.ln_w = w.ln2_w; a.ln_b = w.ln2_b; a.b1 = w.ff1_b;
   a.b2 = w.ff2_b; a.x = x; a.fv = fv; a.xp = xp; a.vp = vp; a.dbg_tok = dbg_tok; a.p0 = p0; a.dbg_max = dbg_max; a.np = np;
   static bool attr_done = false;
