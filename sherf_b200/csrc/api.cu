@@ -84,6 +84,8 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int SF, int V,
   ft.g1_cell_start = a.take<int>(kMaxCell + 1);
   ft.g3_cell_start = a.take<int>(kMaxCell + 1);
   ft.g_cursor = a.take<int>((size_t)2 * kMaxCell);
+  ft.g_block_sums = a.take<int>((size_t)2 * (kMaxCell / 1024 + 2));
+  ft.g_total = a.take<int64_t>(2);
   ft.g1_verts = a.take<float4>(V);
   ft.g3_verts = a.take<float4>(V);
   ft.g1_occ = a.take<unsigned char>(kMaxCell);
@@ -265,15 +267,18 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.init(g_profiling != 0, st);
   g_tm = &tm;
 
-  // ---- stage 0: per-frame tables (SMPL chain, warp tables, grids) on the caller's stream; the channels-last feature copies and the
-  //      weight packing do not depend on them and run on an internal side stream, concurrently with the (latency-bound, tiny-grid)
-  //      SMPL chain and with the cull stage; the point stages wait for both ----
+  // ---- stage 0: per-frame work, split by consumer.  The caller's stream runs only what the cull needs (posed vertices in SMPL
+  //      space, cull grid, depth range) and goes straight on to the cull; an internal side stream runs, concurrently, what only the
+  //      point stages need: the SMPL chain / offsets / per-vertex warp tables / canonical grid (tiny latency-bound grids), the
+  //      channels-last copies of the feature tensors and the weight packing.  The point stages wait for both. ----
   const bool side = !getenv("SHERF_NO_PROLOGUE_OVERLAP") && g_side.ensure() == 0;
   cudaStream_t ls = side ? g_side.s : st;
-  if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); }
   tm.begin(0);
-  RC(run_prologue(*smpl, *frame, *rays, *opts, L.ft, st));
+  RC(run_prologue_frame(*frame, L.ft, st));
+  if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); }
+  RC(run_prologue_cull(*smpl, *frame, *rays, *opts, L.ft, st));
   tm.end();
+  RC(run_prologue_tables(*smpl, *frame, L.ft, ls));
   RC(run_to_channels_last(scene->planes, L.planes_cl, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, ls));
   RC(run_to_channels_last(scene->planes + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w,
                           L.planes_cl + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w, scene->plane_ch,

@@ -127,16 +127,22 @@ struct FrameTables {           // device pointers carved out of the scratch aren
   VertexWarp* T3;              // [V] canonical -> observation (SMPL space)
   int* g1_cell_start;          // [maxcell+1]
   int* g3_cell_start;
-  int* g_cursor;               // [2][maxcell] scatter cursors
+  int* g_cursor;               // [2][maxcell] per-cell vertex counts (histogram, then scatter cursors)
+  int* g_block_sums;           // [2][maxcell/1024 + 2] scan scratch, one per grid (the grids are built on different streams)
+  int64_t* g_total;            // [2] scan totals (unused)
   float4* g1_verts;            // [V] (x,y,z,id bits) sorted by cell
   float4* g3_verts;
   unsigned char* g1_occ;       // [maxcell] 27-neighbourhood occupancy
   int maxcell;
 };
 
-int run_prologue(const SherfSmplModel& smpl, const SherfFrame& frame, const SherfRays& rays, const SherfOptions& opts,
-                 const FrameTables& ft, cudaStream_t st);
+int run_prologue_frame(const SherfFrame& frame, const FrameTables& ft, cudaStream_t st);
+int run_prologue_cull(const SherfSmplModel& smpl, const SherfFrame& frame, const SherfRays& rays, const SherfOptions& opts,
+                      const FrameTables& ft, cudaStream_t st);
+int run_prologue_tables(const SherfSmplModel& smpl, const SherfFrame& frame, const FrameTables& ft, cudaStream_t st);
 int run_lbs_only(const SherfSmplModel& smpl, const SherfPose& pose, float* A_out, float* joints_tmp, float* pf_tmp, cudaStream_t st);
 int run_depth_range(const SherfRays& rays, FrameConst* fc, cudaStream_t st);
+// exclusive scan of cnt[0..n) -> start[0..n] (start[n] = total, also written to *total_dev); block_sums: n/1024 + 2 ints of scratch
+int run_exclusive_scan(const int* cnt, int n, int* block_sums, int* start, int64_t* total_dev, cudaStream_t st);
 
 }  // namespace sherf

@@ -180,6 +180,17 @@ __global__ void __launch_bounds__(256) k_compact(const int* __restrict__ sample_
   }
 }
 
+int run_exclusive_scan(const int* cnt, int n, int* block_sums, int* start, int64_t* total_dev, cudaStream_t st) {
+  const int nb = ceil_div(n, 1024);
+  k_ray_block_sums<<<nb, 1024, 0, st>>>(cnt, n, block_sums);
+  SHERF_LAUNCH_CHECK();
+  k_scan_rays<<<nb, 1024, 0, st>>>(cnt, block_sums, nb, n, start, total_dev);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+#define RC_SCAN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
 int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
              int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st) {
   const int N = rays.n_rays;
@@ -194,11 +205,7 @@ int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTable
   k_cull_search<<<148 * 8, 256, 0, st>>>(rays.origins, rays.dirs, rays.near_, rays.far_, S, ft.fc, ft.g1_cell_start, ft.g1_verts, thr, depths,
                                          queue, queue_count, sample_vid, ray_count);
   SHERF_LAUNCH_CHECK();
-  const int nb = ceil_div(N, 1024);
-  k_ray_block_sums<<<nb, 1024, 0, st>>>(ray_count, N, block_sums);
-  SHERF_LAUNCH_CHECK();
-  k_scan_rays<<<nb, 1024, 0, st>>>(ray_count, block_sums, nb, N, ray_start, total_dev);
-  SHERF_LAUNCH_CHECK();
+  RC_SCAN(run_exclusive_scan(ray_count, N, block_sums, ray_start, total_dev, st));
   k_compact<<<ceil_div(N, 8), 256, 0, st>>>(sample_vid, ray_start, N, S, point_sample, point_vid);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;

@@ -249,6 +249,20 @@ __global__ void k_vertex_tables(const float* __restrict__ weights, const float* 
     r.pad[0] = r.pad[1] = r.pad[2] = 0.f;
     T3[v] = r;
   }
+  if (verts_smpl) {
+    float p[3], o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = __fsub_rn(vertices[v * 3 + c], fc->Th_tgt[c]);
+    rowvec_mat3(p, fc->R_tgt, o);
+    verts_smpl[v * 3 + 0] = o[0]; verts_smpl[v * 3 + 1] = o[1]; verts_smpl[v * 3 + 2] = o[2];
+  }
+}
+
+// posed vertices in SMPL space, (vertices - Th) @ R (bit-exact, renderer.py:314): all the cull needs from the body
+__global__ void __launch_bounds__(256) k_verts_smpl(const float* __restrict__ vertices, const FrameConst* __restrict__ fc, int V,
+                                                    float* __restrict__ verts_smpl) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
   float p[3], o[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) p[c] = __fsub_rn(vertices[v * 3 + c], fc->Th_tgt[c]);
@@ -257,22 +271,17 @@ __global__ void k_vertex_tables(const float* __restrict__ weights, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// One block per grid: bbox -> cell size -> counting sort of the vertices by cell (+ dilated
-// occupancy for the cull grid).  blockIdx 0: posed vertices (cell >= cull radius), 1: canonical.
-__global__ void __launch_bounds__(1024) k_build_grids(const float* __restrict__ verts_smpl, const float* __restrict__ t_vertices, int V,
-                                                       int maxcell, float min_cell, FrameConst* fc, int* g1_start, int* g3_start,
-                                                       int* cursor, float4* g1_verts, float4* g3_verts, unsigned char* g1_occ) {
-  const int g = blockIdx.x;
+// Uniform grids over the posed (g = 0, cell >= cull radius) and the canonical (g = 1) vertices: bbox -> cell size -> counting sort
+// of the vertices by cell -> 27-neighbourhood occupancy bytes for the cull grid.  Five small kernels instead of one block per
+// grid: the single-block form spent 190 us (profiles/r1_q: 55 % of its stalls on the 27 byte stores per vertex of the dilation,
+// the rest on serial passes over the cells by one SM) on the critical path in front of the cull.
+__global__ void __launch_bounds__(1024) k_grid_setup(const float* __restrict__ verts_smpl, const float* __restrict__ t_vertices, int V,
+                                                      int maxcell, float min_cell, FrameConst* fc, int g0) {
+  const int g = g0 + blockIdx.x;
   const float* P = g == 0 ? verts_smpl : t_vertices;
-  int* start = g == 0 ? g1_start : g3_start;
-  int* cur = cursor + (size_t)g * maxcell;
-  float4* outv = g == 0 ? g1_verts : g3_verts;
   GridDesc* gd = g == 0 ? &fc->g1 : &fc->g3;
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ float smin[3][32], smax[3][32];
-  __shared__ GridDesc sg;
-  __shared__ int spart[1024];
-
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (int v = tid; v < V; v += nt)
 #pragma unroll
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(1024) k_build_grids(const float* __restrict__ 
   }
   __syncthreads();
   if (tid == 0) {
+    GridDesc sg;
     float lo[3], hi[3];
     for (int c = 0; c < 3; ++c) {
       lo[c] = smin[c][0]; hi[c] = smax[c][0];
@@ -306,59 +316,56 @@ __global__ void __launch_bounds__(1024) k_build_grids(const float* __restrict__ 
     sg.ncell = d[0] * d[1] * d[2];
     *gd = sg;
   }
-  __syncthreads();
-  const int ncell = sg.ncell;
-  for (int c = tid; c <= ncell; c += nt) start[c] = 0;
-  if (g == 0) for (int c = tid; c < ncell; c += nt) g1_occ[c] = 0;
-  __syncthreads();
-  // histogram (counts at index cell+1)
-  for (int v = tid; v < V; v += nt) {
-    int cx = min(max(grid_coord(P[v * 3 + 0], sg.origin[0], sg.inv_cell, sg.dim[0]), 0), sg.dim[0] - 1);
-    int cy = min(max(grid_coord(P[v * 3 + 1], sg.origin[1], sg.inv_cell, sg.dim[1]), 0), sg.dim[1] - 1);
-    int cz = min(max(grid_coord(P[v * 3 + 2], sg.origin[2], sg.inv_cell, sg.dim[2]), 0), sg.dim[2] - 1);
-    atomicAdd(&start[(cz * sg.dim[1] + cy) * sg.dim[0] + cx + 1], 1);
-    if (g == 0) {
-      for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-          for (int dx = -1; dx <= 1; ++dx) {
-            int x = cx + dx, y = cy + dy, z = cz + dz;
-            if (x >= 0 && x < sg.dim[0] && y >= 0 && y < sg.dim[1] && z >= 0 && z < sg.dim[2])
-              g1_occ[(z * sg.dim[1] + y) * sg.dim[0] + x] = 1;
-          }
+}
+
+__device__ __forceinline__ int vertex_cell(const GridDesc& sg, float x, float y, float z) {
+  const int cx = min(max(grid_coord(x, sg.origin[0], sg.inv_cell, sg.dim[0]), 0), sg.dim[0] - 1);
+  const int cy = min(max(grid_coord(y, sg.origin[1], sg.inv_cell, sg.dim[1]), 0), sg.dim[1] - 1);
+  const int cz = min(max(grid_coord(z, sg.origin[2], sg.inv_cell, sg.dim[2]), 0), sg.dim[2] - 1);
+  return (cz * sg.dim[1] + cy) * sg.dim[0] + cx;
+}
+
+// histogram of the vertices over the cells; blockIdx.y selects the grid.  counts: [2][maxcell], zeroed by the caller
+__global__ void __launch_bounds__(256) k_grid_count(const float* __restrict__ verts_smpl, const float* __restrict__ t_vertices, int V,
+                                                    const FrameConst* __restrict__ fc, int* __restrict__ counts, int maxcell, int g0) {
+  const int g = g0 + blockIdx.y, v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float* P = g == 0 ? verts_smpl : t_vertices;
+  const GridDesc sg = g == 0 ? fc->g1 : fc->g3;
+  atomicAdd(&counts[(size_t)g * maxcell + vertex_cell(sg, P[v * 3], P[v * 3 + 1], P[v * 3 + 2])], 1);
+}
+
+// counting-sort scatter: the order of the vertices inside a cell is arbitrary, which the searches do not depend on (they take the
+// lexicographic minimum of (d2, id))
+__global__ void __launch_bounds__(256) k_grid_scatter(const float* __restrict__ verts_smpl, const float* __restrict__ t_vertices, int V,
+                                                      const FrameConst* __restrict__ fc, int* __restrict__ counts, int maxcell,
+                                                      const int* __restrict__ g1_start, const int* __restrict__ g3_start,
+                                                      float4* __restrict__ g1_verts, float4* __restrict__ g3_verts, int g0) {
+  const int g = g0 + blockIdx.y, v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float* P = g == 0 ? verts_smpl : t_vertices;
+  const GridDesc sg = g == 0 ? fc->g1 : fc->g3;
+  const float x = P[v * 3], y = P[v * 3 + 1], z = P[v * 3 + 2];
+  const int cell = vertex_cell(sg, x, y, z);
+  const int pos = (g == 0 ? g1_start : g3_start)[cell] + atomicSub(&counts[(size_t)g * maxcell + cell], 1) - 1;
+  (g == 0 ? g1_verts : g3_verts)[pos] = make_float4(x, y, z, __int_as_float(v));
+}
+
+// occupancy byte of a cull-grid cell = "some vertex lies in its 27-neighbourhood" (cells of a row are contiguous in cell_start)
+__global__ void __launch_bounds__(256) k_grid_occupancy(const FrameConst* __restrict__ fc, const int* __restrict__ g1_start,
+                                                        unsigned char* __restrict__ occ) {
+  const GridDesc sg = fc->g1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= sg.ncell) return;
+  const int x = c % sg.dim[0], t = c / sg.dim[0], y = t % sg.dim[1], z = t / sg.dim[1];
+  const int x0 = max(x - 1, 0), x1 = min(x + 1, sg.dim[0] - 1);
+  bool any = false;
+  for (int zz = max(z - 1, 0); zz <= min(z + 1, sg.dim[2] - 1); ++zz)
+    for (int yy = max(y - 1, 0); yy <= min(y + 1, sg.dim[1] - 1); ++yy) {
+      const int row = (zz * sg.dim[1] + yy) * sg.dim[0];
+      any |= g1_start[row + x1 + 1] > g1_start[row + x0];
     }
-  }
-  __syncthreads();
-  // inclusive scan of start[1..ncell] in place (thread-serial spans + block scan of partials)
-  const int span = (ncell + nt - 1) / nt;
-  const int b = 1 + tid * span, e = min(b + span, ncell + 1);
-  int s = 0;
-  for (int c = b; c < e; ++c) s += start[c];
-  spart[tid] = s;
-  __syncthreads();
-  if (tid < 32) {
-    int carry = 0;
-    for (int base = 0; base < nt; base += 32) {
-      int x = spart[base + tid];
-      int y = x;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, y, o); if (tid >= o) y += t; }
-      spart[base + tid] = carry + y - x;      // exclusive prefix of this thread's span
-      carry += __shfl_sync(0xffffffffu, y, 31);
-    }
-  }
-  __syncthreads();
-  int run = spart[tid];
-  for (int c = b; c < e; ++c) { run += start[c]; start[c] = run; }
-  __syncthreads();
-  for (int c = tid; c < ncell; c += nt) cur[c] = start[c];
-  __syncthreads();
-  for (int v = tid; v < V; v += nt) {
-    float x = P[v * 3 + 0], y = P[v * 3 + 1], z = P[v * 3 + 2];
-    int cx = min(max(grid_coord(x, sg.origin[0], sg.inv_cell, sg.dim[0]), 0), sg.dim[0] - 1);
-    int cy = min(max(grid_coord(y, sg.origin[1], sg.inv_cell, sg.dim[1]), 0), sg.dim[1] - 1);
-    int cz = min(max(grid_coord(z, sg.origin[2], sg.inv_cell, sg.dim[2]), 0), sg.dim[2] - 1);
-    int pos = atomicAdd(&cur[(cz * sg.dim[1] + cy) * sg.dim[0] + cx], 1);
-    outv[pos] = make_float4(x, y, z, __int_as_float(v));
-  }
+  occ[c] = any ? 1 : 0;
 }
 
 // global min / max over all sample depths = over rays of {t_0, t_{S-1}} (t is monotone in i)   ray_marcher.py:57
@@ -404,11 +411,58 @@ int run_depth_range(const SherfRays& rays, FrameConst* fc, cudaStream_t st) {
   return SHERF_OK;
 }
 
-int run_prologue(const SherfSmplModel& smpl, const SherfFrame& fr, const SherfRays& rays, const SherfOptions& opts,
-                 const FrameTables& ft, cudaStream_t st) {
-  const int V = smpl.n_verts;
+// counting-sort build of one grid (g = 0: posed vertices / cull grid with occupancy bytes, g = 1: canonical vertices) on `st`
+static int build_grid(int g, const SherfFrame& fr, const FrameTables& ft, int V, cudaStream_t st) {
+  int* counts = ft.g_cursor + (size_t)g * ft.maxcell;
+  int* bsums = ft.g_block_sums + (size_t)g * (ft.maxcell / 1024 + 2);
+  k_grid_setup<<<1, 1024, 0, st>>>(ft.verts_smpl, fr.t_vertices, V, ft.maxcell, 0.0505f, ft.fc, g);
+  SHERF_LAUNCH_CHECK();
+  SHERF_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)ft.maxcell, st));
+  k_grid_count<<<dim3(ceil_div(V, 256), 1), 256, 0, st>>>(ft.verts_smpl, fr.t_vertices, V, ft.fc, ft.g_cursor, ft.maxcell, g);
+  SHERF_LAUNCH_CHECK();
+  // exclusive scan over all maxcell slots (cells beyond ncell hold 0 vertices): cell_start[c], cell_start[maxcell] = V
+  int rc = run_exclusive_scan(counts, ft.maxcell, bsums, g == 0 ? ft.g1_cell_start : ft.g3_cell_start, ft.g_total + g, st);
+  if (rc) return rc;
+  k_grid_scatter<<<dim3(ceil_div(V, 256), 1), 256, 0, st>>>(ft.verts_smpl, fr.t_vertices, V, ft.fc, ft.g_cursor, ft.maxcell, ft.g1_cell_start,
+                                                           ft.g3_cell_start, ft.g1_verts, ft.g3_verts, g);
+  SHERF_LAUNCH_CHECK();
+  if (g == 0) {
+    k_grid_occupancy<<<ceil_div(ft.maxcell, 256), 256, 0, st>>>(ft.fc, ft.g1_cell_start, ft.g1_occ);
+    SHERF_LAUNCH_CHECK();
+  }
+  return SHERF_OK;
+}
+
+// The per-frame work is split by what consumes it, so that the two halves can run on different streams (api.cu):
+//   run_prologue_frame  : FrameConst (everything else reads it)
+//   run_prologue_cull   : what the cull stage needs -- posed vertices in SMPL space, the cull grid, the global depth range
+//   run_prologue_tables : what only the warp + gather stage needs -- SMPL chain of the three pose sets, pose / shape offsets,
+//                         per-vertex warp tables, the canonical-vertex grid
+int run_prologue_frame(const SherfFrame& fr, const FrameTables& ft, cudaStream_t st) {
   k_frame_const<<<1, 32, 0, st>>>(fr, make_float3((float)fr.out_sh[0], (float)fr.out_sh[1], (float)fr.out_sh[2]), ft.fc);
   SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+int run_prologue_cull(const SherfSmplModel& smpl, const SherfFrame& fr, const SherfRays& rays, const SherfOptions& opts,
+                      const FrameTables& ft, cudaStream_t st) {
+  const int V = smpl.n_verts;
+  k_verts_smpl<<<ceil_div(V, 256), 256, 0, st>>>(fr.vertices, ft.fc, V, ft.verts_smpl);
+  SHERF_LAUNCH_CHECK();
+  int rc = build_grid(0, fr, ft, V, st);
+  if (rc) return rc;
+  if (opts.use_external_clamp) {
+    k_set_depth_range<<<1, 1, 0, st>>>(ft.fc, opts.depth_clamp_min, opts.depth_clamp_max);
+    SHERF_LAUNCH_CHECK();
+  } else {
+    rc = run_depth_range(rays, ft.fc, st);
+    if (rc) return rc;
+  }
+  return SHERF_OK;
+}
+
+int run_prologue_tables(const SherfSmplModel& smpl, const SherfFrame& fr, const FrameTables& ft, cudaStream_t st) {
+  const int V = smpl.n_verts;
   k_joints<<<dim3(kJoints, 3), 256, 0, st>>>(smpl.v_template, smpl.shapedirs, smpl.j_regressor, fr.target.shapes,
                                              fr.canonical.shapes, fr.obs.shapes, V, ft.joints);
   SHERF_LAUNCH_CHECK();
@@ -417,20 +471,9 @@ int run_prologue(const SherfSmplModel& smpl, const SherfFrame& fr, const SherfRa
   k_offsets<<<ceil_div(3 * V, 8), 256, 0, st>>>(smpl.posedirs, smpl.shapedirs, ft.posefeat, fr.target.shapes, fr.obs.shapes,
                                                 3 * V, ft.poff, ft.soff);
   SHERF_LAUNCH_CHECK();
-  k_vertex_tables<<<ceil_div(V, 128), 128, 0, st>>>(smpl.weights, ft.A, ft.poff, ft.soff, fr.vertices, ft.fc, V, ft.T1, ft.T3,
-                                                    ft.verts_smpl);
+  k_vertex_tables<<<ceil_div(V, 128), 128, 0, st>>>(smpl.weights, ft.A, ft.poff, ft.soff, fr.vertices, ft.fc, V, ft.T1, ft.T3, nullptr);
   SHERF_LAUNCH_CHECK();
-  k_build_grids<<<2, 1024, 0, st>>>(ft.verts_smpl, fr.t_vertices, V, ft.maxcell, 0.0505f, ft.fc, ft.g1_cell_start,
-                                    ft.g3_cell_start, ft.g_cursor, ft.g1_verts, ft.g3_verts, ft.g1_occ);
-  SHERF_LAUNCH_CHECK();
-  if (opts.use_external_clamp) {
-    k_set_depth_range<<<1, 1, 0, st>>>(ft.fc, opts.depth_clamp_min, opts.depth_clamp_max);
-    SHERF_LAUNCH_CHECK();
-  } else {
-    int rc = run_depth_range(rays, ft.fc, st);
-    if (rc) return rc;
-  }
-  return SHERF_OK;
+  return build_grid(1, fr, ft, V, st);
 }
 
 }  // namespace sherf

@@ -99,3 +99,50 @@ def render_sharded(renderer, decoder, scene: dict, group=None, tile: int = TILE,
         local = scene['ray_origins'].new_zeros(0, 5)
     full = all_gather_tiles(local, n, group, tile)
     return full[None, :, :3], full[None, :, 3:4], full[None, :, 4:5]
+
+
+def _render_frame(renderer, decoder, scene: dict, frame: dict, H: int, W: int):
+    """One frame of a sequence through the CUDA path: rays made on the device (sherf_b200.rays), the frame's target pose
+    swapped into a shallow copy of input_data.  Returns [N,5] = rgb | depth | acc."""
+    from .rays import generate_rays
+    dev = scene['planes'].device
+    cam = frame['camera']
+    rays = generate_rays(H, W, cam['K'], cam['R'], cam['T'], cam['bounds'], dev)
+    idt = dict(scene['input_data'])
+    idt['params'] = {k: torch.as_tensor(v).to(dev) for k, v in frame['params'].items()}
+    idt['vertices'] = torch.as_tensor(frame['vertices']).to(dev)
+    rgb, depth, acc = renderer(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None,
+                               scene['obs_sp_input'], decoder, rays['ray_o_all'][:, 0], rays['ray_d_all'][:, 0], rays['near_all'][:, 0],
+                               rays['far_all'][:, 0], idt, scene['rendering_options'])
+    return torch.cat([rgb[0], depth[0], acc[0]], dim=-1)
+
+
+def render_sequence(renderer, decoder, scene: dict, frames: list, H: int, W: int, group=None, render_fn=None):
+    """BASELINE configs[3]: a streamed novel-pose / novel-view sequence of one observed subject over the ranks of `group`.
+
+    `scene` holds the static observation (planes, 2-D feature map, 3-D volumes, obs_* and t_* entries of input_data, replicated on
+    every rank); `frames[f]` = {'params': {poses, shapes, R, Th}, 'vertices': [1,V,3], 'camera': {K, R, T, bounds}} is all that is
+    uploaded per frame -- the rays are generated on the device (RenderPeople_dataset.py:14-27,68-101 on the GPU).  Frames are dealt
+    round-robin: frame f is rendered by rank f % world; after every round of `world` frames exactly ONE all-gather (20 B per ray)
+    hands the round's images to every rank.  Whole frames have no cross-ray coupling, so no depth-range exchange is needed.
+    Returns a list of [N,5] tensors (rgb | depth | acc), one per frame, on every rank."""
+    use_dist = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if use_dist else 1
+    rank = dist.get_rank(group) if use_dist else 0
+    fn = render_fn or (lambda fr: _render_frame(renderer, decoder, scene, fr, H, W))
+    N = H * W
+    out = []
+    for f0 in range(0, len(frames), world):
+        mine = f0 + rank
+        local = fn(frames[mine]) if mine < len(frames) else None
+        if world == 1:
+            out.append(local)
+            continue
+        if local is None:                                   # last, partial round: ranks without a frame contribute a dummy tile
+            ref = out[-1] if out else None
+            local = torch.zeros(N, 5, device=ref.device if ref is not None else scene['planes'].device)
+        gathered = local.new_empty(world * N, 5)
+        dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+        for r in range(min(world, len(frames) - f0)):
+            out.append(gathered[r * N:(r + 1) * N])
+    return out

@@ -55,3 +55,38 @@ def test_all_gather_tiles_gloo_world2(n):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _seq_worker(rank, world, port, n_frames, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        H, W = 6, 7
+        rendered = []
+
+        def fake_render(frame):                                  # "image" = f(frame id, ray index); records who rendered what
+            rendered.append(frame['id'])
+            return torch.arange(H * W).float()[:, None] * torch.arange(1, 6).float()[None] + 1000.0 * frame['id']
+        frames = [{'id': f} for f in range(n_frames)]
+        scene = {'planes': torch.zeros(1)}
+        outs = sd.render_sequence(None, None, scene, frames, H, W, render_fn=fake_render)
+        ok = len(outs) == n_frames and all(torch.equal(o, fake_render({'id': f})) for f, o in enumerate(outs))
+        q.put((rank, bool(ok), sorted(set(rendered[:len(rendered) - n_frames]))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_frames', [4, 5])
+def test_render_sequence_round_robin_gloo_world2(n_frames):
+    """configs[3] host logic: frame f goes to rank f % world, one all-gather per round, partial last round handled."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + n_frames) % 2000
+    procs = [ctx.Process(target=_seq_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[:2] for r in res] == [(0, True), (1, True)]
+    assert res[0][2] == [f for f in range(n_frames) if f % 2 == 0] and res[1][2] == [f for f in range(n_frames) if f % 2 == 1]

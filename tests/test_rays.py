@@ -95,3 +95,34 @@ def test_render_from_generated_rays(smpl_model):
     assert float((rays['ray_d_all'][:, 0] - scene['ray_directions']).abs().max()) <= 1e-6
     bad = ((a[0] - b[0]).abs().amax(-1) > 1e-4).float().mean()
     assert float(bad) <= 2e-3 and float(a[2].max()) > 0.2
+
+
+@pytest.mark.gpu
+def test_render_sequence_single_gpu(smpl_model):
+    """configs[3] in miniature on one GPU: a 3-frame novel-pose sequence of one observed subject streamed through
+    dist.render_sequence (device-made rays, per-frame pose upload only) == rendering every frame from host-made rays."""
+    from conftest import scene_to
+    from sherf_b200 import dist as sd
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    H, W = 36, 64                                                   # 640x360 / 10
+    static = S.make_scene(S.SceneSpec(H=H, W=W, samples=24, seed=8, random_global_R=True), smpl_model)
+    frames, hosts = [], []
+    for f in range(3):
+        other = S.make_scene(S.SceneSpec(H=H, W=W, samples=24, seed=40 + f, random_global_R=True, cam_azim_deg=10.0 + 50 * f), smpl_model)
+        frames.append({'params': other['input_data']['params'], 'vertices': other['input_data']['vertices'], 'camera': other['camera']})
+        hosts.append(other)
+    scene = scene_to(static, dev)
+    ren, dec = hot_path_modules(smpl_model, seed=0, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    outs = sd.render_sequence(ren, dec, scene, frames, H, W)
+    assert len(outs) == 3
+    for f, o in enumerate(outs):
+        h = scene_to(hosts[f], dev)
+        idt = dict(scene['input_data'])
+        idt['params'], idt['vertices'] = h['input_data']['params'], h['input_data']['vertices']
+        rgb, depth, acc = ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+                              dec, h['ray_origins'], h['ray_directions'], h['near'], h['far'], idt, scene['rendering_options'])
+        bad = ((o[:, :3] - rgb[0]).abs().amax(-1) > 1e-4).float().mean()
+        assert float(bad) <= 2e-3, (f, float(bad))
+        assert float(acc.max()) > 0.2
