@@ -137,6 +137,11 @@ typedef struct SherfOptions {
   const float* importance_u;  /* [N*S_f] uniform draws in [0,1) standing for torch.rand at renderer.py:526; required when
                                  n_importance > 0 (the caller owns the RNG, SURVEY.md 8b "RNG") */
   const float* density_noise_importance; /* optional [N*S_f] additive sigma noise of the fine samples; NULL = none */
+  uint64_t weights_version;   /* 0: the weights are re-packed into the scratch arena on every call.  Non-zero: the caller vouches
+                                 that SherfWeights' contents are unchanged since the previous call THAT USED THE SAME scratch arena,
+                                 mlp_precision and shapes with the same non-zero value; the packed copies made by that call are then
+                                 reused (the reference keeps its nn.Parameters as they are between calls, too).  Change the value
+                                 whenever a parameter is written or the arena is re-allocated. */
 } SherfOptions;
 
 /* Outputs of forward (renderer.py:398): rgb in (-1,1), depth, accumulated weight. */

@@ -11,6 +11,7 @@
 namespace sherf {
 
 thread_local LaunchCounter g_launches;
+thread_local bool g_pack_plan_only = false;
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_last_launches = 0;
 static thread_local int64_t g_last_fine_points = 0;
@@ -176,6 +177,10 @@ struct StageTimer {
 
 static thread_local StageTimer* g_tm = nullptr;
 
+// Packed-weight reuse (SherfOptions.weights_version): identity of the packed blobs currently held by a scratch arena
+struct PackTag { const void* base = nullptr; size_t need = 0; uint64_t version = 0; int precision = -1; int dev = -1; };
+static thread_local PackTag g_pack_tag;
+
 // Internal side stream (per host thread): the warp+gather kernel of chunk i+1 runs concurrently with the persistent MLP
 // kernels of chunk i (they leave most issue slots idle and the gather kernel needs no shared memory).
 struct SideStream {
@@ -267,10 +272,12 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.init(g_profiling != 0, st);
   g_tm = &tm;
 
-  // ---- stage 0: per-frame work, split by consumer.  The caller's stream runs only what the cull needs (posed vertices in SMPL
-  //      space, cull grid, depth range) and goes straight on to the cull; an internal side stream runs, concurrently, what only the
-  //      point stages need: the SMPL chain / offsets / per-vertex warp tables / canonical grid (tiny latency-bound grids), the
-  //      channels-last copies of the feature tensors and the weight packing.  The point stages wait for both. ----
+  // ---- stage 0 + 1.  Per-frame work is split by consumer.  The caller's stream runs only what the cull needs (FrameConst, posed
+  //      vertices in SMPL space, cull grid, depth range) and goes straight on to the cull + ordered compaction; an internal side stream
+  //      runs, concurrently, what only the point stages need: SMPL chain / offsets / per-vertex warp tables / canonical grid (tiny
+  //      latency-bound grids), the channels-last copies of the feature tensors (one launch) and the weight packing.  The host issues
+  //      the cull BEFORE the side-stream work: these ~40 launches are host-issue bound (profiles/r1_t), and the point stages wait
+  //      for both streams anyway. ----
   const bool side = !getenv("SHERF_NO_PROLOGUE_OVERLAP") && g_side.ensure() == 0;
   cudaStream_t ls = side ? g_side.s : st;
   tm.begin(0);
@@ -278,50 +285,61 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); }
   RC(run_prologue_cull(*smpl, *frame, *rays, *opts, L.ft, st));
   tm.end();
+  tm.begin(1);
+  int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
+  RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
+  tm.end();
+  int64_t P = 0;
+  SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+
   RC(run_prologue_tables(*smpl, *frame, L.ft, ls));
-  RC(run_to_channels_last(scene->planes, L.planes_cl, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, ls));
-  RC(run_to_channels_last(scene->planes + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w,
-                          L.planes_cl + (size_t)scene->plane_ch * scene->plane_h * scene->plane_w, scene->plane_ch,
-                          (int64_t)scene->plane_h * scene->plane_w, ls));
-  RC(run_to_channels_last(scene->planes + (size_t)2 * scene->plane_ch * scene->plane_h * scene->plane_w,
-                          L.planes_cl + (size_t)2 * scene->plane_ch * scene->plane_h * scene->plane_w, scene->plane_ch,
-                          (int64_t)scene->plane_h * scene->plane_w, ls));
-  RC(run_to_channels_last(scene->obs_feat, L.feat_cl, scene->feat_ch, (int64_t)scene->feat_h * scene->feat_w, ls));
-  for (int l = 0; l < 3; ++l)
-    RC(run_to_channels_last(scene->vol[l], L.vol_cl[l], scene->vol_ch[l],
-                            (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2], ls));
+  {
+    const size_t plane = (size_t)scene->plane_ch * scene->plane_h * scene->plane_w;
+    const float* in[7] = {scene->planes, scene->planes + plane, scene->planes + 2 * plane, scene->obs_feat, scene->vol[0], scene->vol[1], scene->vol[2]};
+    float* outp[7] = {L.planes_cl, L.planes_cl + plane, L.planes_cl + 2 * plane, L.feat_cl, L.vol_cl[0], L.vol_cl[1], L.vol_cl[2]};
+    int C[7] = {scene->plane_ch, scene->plane_ch, scene->plane_ch, scene->feat_ch, scene->vol_ch[0], scene->vol_ch[1], scene->vol_ch[2]};
+    int64_t M[7] = {(int64_t)scene->plane_h * scene->plane_w, (int64_t)scene->plane_h * scene->plane_w, (int64_t)scene->plane_h * scene->plane_w,
+                    (int64_t)scene->feat_h * scene->feat_w, 0, 0, 0};
+    for (int l = 0; l < 3; ++l) M[4 + l] = (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2];
+    RC(run_to_channels_last_multi(7, in, outp, C, M, ls));
+  }
+  // Weight blobs: packed into the arena on this call unless the caller vouches (SherfOptions.weights_version != 0, unchanged since
+  // the previous call on this arena, same arithmetic) that the parameters have not changed -- then only the host-side plans are rebuilt.
   PackedWeights pw;
   CanonWeights cw;
-  if (opts->mlp_precision == SHERF_MLP_FP32) RC(run_pack_weights(*weights, L.packed_w, pw, ls));
-  else RC(run_pack_canonical(*weights, L.canon_w, cw, ls));
   FusedPlan fplan;
   PpPlan pplan;
-  fplan.pp = nullptr;
+  fplan.pp = nullptr; fplan.xf_blob = nullptr; fplan.ff_blob = nullptr; fplan.blob = nullptr; fplan.bias = nullptr;
   const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
-  if (use_fused) {
-    RC(run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, ls));
-    fplan.xf_blob = nullptr;
-    fplan.ff_blob = nullptr;
-    if (!getenv("SHERF_NO_FUSED_FUSION")) { RC(run_pack_fusion(*weights, L.ff_blob, ls)); fplan.ff_blob = L.ff_blob; }
-    if (!getenv("SHERF_NO_FUSED_XFORMER")) { RC(run_pack_xformer(*weights, L.xf_blob, ls)); fplan.xf_blob = L.xf_blob; }
-    if (opts->mlp_precision == SHERF_MLP_BF16X3) {
-      RC(run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, ls));
+  const bool fuse_ff = use_fused && !getenv("SHERF_NO_FUSED_FUSION"), fuse_xf = use_fused && !getenv("SHERF_NO_FUSED_XFORMER");
+  const bool use_pp = use_fused && opts->mlp_precision == SHERF_MLP_BF16X3;
+  {
+    int devid = 0;
+    SHERF_CUDA_OK(cudaGetDevice(&devid));
+    const bool reuse = opts->weights_version != 0 && g_pack_tag.version == opts->weights_version && g_pack_tag.base == (const void*)a.base &&
+                       g_pack_tag.need == need && g_pack_tag.precision == opts->mlp_precision && g_pack_tag.dev == devid && !getenv("SHERF_NO_PACK_REUSE");
+    g_pack_plan_only = reuse;
+    int rc = SHERF_OK;
+    if (opts->mlp_precision == SHERF_MLP_FP32) rc = run_pack_weights(*weights, L.packed_w, pw, ls);
+    else if (!fuse_ff || !fuse_xf || !use_fused) rc = run_pack_canonical(*weights, L.canon_w, cw, ls);      // per-layer tensor-core kernels
+    if (!rc && use_fused && !use_pp) rc = run_pack_fused_plan(*weights, L.fused_blob, L.fused_bias, fplan, ls);   // tf32 / 3xtf32 fused decoder
+    if (!rc && fuse_ff) { if (!reuse) rc = run_pack_fusion(*weights, L.ff_blob, ls); fplan.ff_blob = L.ff_blob; }
+    if (!rc && fuse_xf) { if (!reuse) rc = run_pack_xformer(*weights, L.xf_blob, ls); fplan.xf_blob = L.xf_blob; }
+    if (!rc && use_pp) {
+      rc = run_pack_pp(*weights, L.pp_blob, L.pp_bias, pplan, ls);
       const int cap = chunk_cap(N, S, SF);
       pplan.xp = L.pp_xv;
       pplan.vp = L.pp_xv + (size_t)((cap + 127) / 128) * 40960;
       fplan.pp = &pplan;
     }
+    g_pack_plan_only = false;
+    if (rc) return rc;
+    g_pack_tag.base = a.base; g_pack_tag.need = need; g_pack_tag.version = opts->weights_version; g_pack_tag.precision = opts->mlp_precision;
+    g_pack_tag.dev = devid;
   }
   if (side) SHERF_CUDA_OK(cudaEventRecord(g_side.ldone, ls));
 
-  // ---- stage 1: cull + ordered compaction ----
-  tm.begin(1);
-  int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
-  RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
-  int64_t P = 0;
-  tm.end();
-  SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  SHERF_CUDA_OK(cudaStreamSynchronize(st));
+  SHERF_CUDA_OK(cudaStreamSynchronize(st));                  // the survivor count P (the cull is done; the side stream may still be running)
   if (n_points_out) *n_points_out = P;
   if (dbg && dbg->point_sample && P > 0)
     SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sample, L.point_sample, sizeof(int) * (size_t)(P < dbg->max_points ? P : dbg->max_points),

@@ -92,6 +92,8 @@ __device__ __forceinline__ void mat3_vec(const float* __restrict__ M, const floa
 struct LaunchCounter { int64_t n = 0; };
 extern thread_local LaunchCounter g_launches;
 void set_error(const char* fmt, ...);
+// true while the host-side weight plans are being rebuilt for blobs that are already packed in the arena (no pack kernel is launched)
+extern thread_local bool g_pack_plan_only;
 
 #define SHERF_CUDA_OK(expr)                                                              \
   do {                                                                                   \

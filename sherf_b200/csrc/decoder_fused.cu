@@ -381,10 +381,12 @@ int run_pack_fused(const SherfWeights& w, unsigned char* blob, float* bias, Fuse
   sch.layer_np[8] = 144;
   sch.layer_np[9] = 64;
   sch.pad[0] = sch.pad[1] = 0;
-  k_pack_fused<<<dim3(8, kFusedChunks), 256, 0, st>>>(jobs, blob);
-  SHERF_LAUNCH_CHECK();
-  k_fused_bias<<<kFusedLayers, 144, 0, st>>>(w, bias);
-  SHERF_LAUNCH_CHECK();
+  if (!g_pack_plan_only) {
+    k_pack_fused<<<dim3(8, kFusedChunks), 256, 0, st>>>(jobs, blob);
+    SHERF_LAUNCH_CHECK();
+    k_fused_bias<<<kFusedLayers, 144, 0, st>>>(w, bias);
+    SHERF_LAUNCH_CHECK();
+  }
   return SHERF_OK;
 }
 

@@ -413,10 +413,12 @@ int run_pack_pp(const SherfWeights& w, unsigned char* blob, float* bias, PpPlan&
     }
   }
   if (c != dpp::kChunks) { set_error("internal: ping-pong decoder schedule has %d chunks", c); return SHERF_E_INVALID; }
-  dpp::k_pack_pp<<<dim3(8, dpp::kChunks), 256, 0, st>>>(jobs, blob);
-  SHERF_LAUNCH_CHECK();
-  dpp::k_pp_bias<<<dpp::kLayers, 128, 0, st>>>(w, bias);
-  SHERF_LAUNCH_CHECK();
+  if (!g_pack_plan_only) {
+    dpp::k_pack_pp<<<dim3(8, dpp::kChunks), 256, 0, st>>>(jobs, blob);
+    SHERF_LAUNCH_CHECK();
+    dpp::k_pp_bias<<<dpp::kLayers, 128, 0, st>>>(w, bias);
+    SHERF_LAUNCH_CHECK();
+  }
   plan.blob = blob;
   plan.bias = bias;
   return SHERF_OK;

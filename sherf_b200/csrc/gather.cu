@@ -8,11 +8,22 @@
 
 namespace sherf {
 
-// [C][M] (channel-major, the reference's NCHW/NCDHW) -> [M][C] channels-last; 32x32 smem tiles.
-__global__ void k_to_channels_last(const float* __restrict__ in, float* __restrict__ out, int C, int64_t M) {
+// [C][M] (channel-major, the reference's NCHW/NCDHW) -> [M][C] channels-last; 32x32 smem tiles.  All the feature tensors of a
+// forward (3 planes, 2-D feature map, 3 volume levels) go through ONE launch: block b belongs to job j with blk0[j] <= b < blk0[j+1].
+struct ClJobs { const float* in[8]; float* out[8]; int C[8]; long long M[8]; int blk0[9]; int n; };
+
+__global__ void __launch_bounds__(256) k_to_channels_last(const ClJobs J) {
   __shared__ float tile[32][33];
-  const int64_t m0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
+  const float* __restrict__ in = J.in[j];
+  float* __restrict__ out = J.out[j];
+  const int C = J.C[j];
+  const int64_t M = J.M[j];
+  const int cblocks = (C + 31) / 32;
+  const int lb = (int)blockIdx.x - J.blk0[j];
+  const int64_t m0 = (int64_t)(lb / cblocks) * 32;
+  const int c0 = (lb % cblocks) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {
@@ -29,6 +40,22 @@ __global__ void k_to_channels_last(const float* __restrict__ in, float* __restri
   }
 }
 
+int run_to_channels_last_multi(int n, const float* const* in, float* const* out, const int* C, const int64_t* M, cudaStream_t st) {
+  if (n <= 0 || n > 8) { set_error("internal: %d channels-last jobs", n); return SHERF_E_INVALID; }
+  ClJobs J;
+  J.n = n;
+  int64_t blocks = 0;
+  for (int j = 0; j < n; ++j) {
+    J.in[j] = in[j]; J.out[j] = out[j]; J.C[j] = C[j]; J.M[j] = M[j];
+    J.blk0[j] = (int)blocks;
+    blocks += ((M[j] + 31) / 32) * ((C[j] + 31) / 32);
+  }
+  J.blk0[n] = (int)blocks;
+  if (blocks >= (1LL << 31)) { set_error("feature tensors too large for one layout launch"); return SHERF_E_INVALID; }
+  k_to_channels_last<<<(unsigned)blocks, 256, 0, st>>>(J);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
 
 __device__ __forceinline__ void warp_lexmin(float& d, int& id) {
 #pragma unroll
@@ -525,12 +552,6 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
   }
 }
 
-int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st) {
-  dim3 grid((unsigned)((M + 31) / 32), (unsigned)((C + 31) / 32));
-  k_to_channels_last<<<grid, 256, 0, st>>>(in, out, C, M);
-  SHERF_LAUNCH_CHECK();
-  return SHERF_OK;
-}
 
 int run_point_gather(const GatherParams& P, cudaStream_t st) {
   if (P.np <= 0) return SHERF_OK;

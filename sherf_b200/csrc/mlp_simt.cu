@@ -52,8 +52,10 @@ int run_pack_weights(const SherfWeights& w, float* base, PackedWeights& pw, cuda
   for (int i = 0; i < 8; ++i) add(pw.pts[i], w.pts_w[i], w.pts_b[i], 128, ptsK[i]);
   add(pw.feature, w.feature_w, w.feature_b, 128, 128);
   add(pw.views, w.views_w, w.views_b, 64, 187);
-  k_pack_weights<<<dim3(8, jobs.n), 256, 0, st>>>(jobs);
-  SHERF_LAUNCH_CHECK();
+  if (!g_pack_plan_only) {
+    k_pack_weights<<<dim3(8, jobs.n), 256, 0, st>>>(jobs);
+    SHERF_LAUNCH_CHECK();
+  }
   return SHERF_OK;
 }
 

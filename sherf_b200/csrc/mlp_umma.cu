@@ -264,8 +264,10 @@ int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cud
   for (int i = 0; i < 8; ++i) add(cw.pts[i], w.pts_w[i], w.pts_b[i], 128, ptsK[i]);
   add(cw.feature, w.feature_w, w.feature_b, 128, 128);
   add(cw.views, w.views_w, w.views_b, 64, 187);
-  k_pack_canonical<<<dim3(16, jobs.n), 256, 0, st>>>(jobs);
-  SHERF_LAUNCH_CHECK();
+  if (!g_pack_plan_only) {
+    k_pack_canonical<<<dim3(16, jobs.n), 256, 0, st>>>(jobs);
+    SHERF_LAUNCH_CHECK();
+  }
   return SHERF_OK;
 }
 

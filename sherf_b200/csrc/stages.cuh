@@ -29,7 +29,7 @@ struct GatherParams {
   int* dbg_vid3; float *dbg_can, *dbg_cdir, *dbg_uv, *dbg_feat; int64_t dbg_max, dbg_feat_max;
 };
 
-int run_to_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
+int run_to_channels_last_multi(int n, const float* const* in, float* const* out, const int* C, const int64_t* M, cudaStream_t st);
 int run_point_gather(const GatherParams& P, cudaStream_t st);
 // S / depths: the sample set to cull -- (rays.n_samples, NULL) for the stratified coarse samples, (rays.n_importance, t_fine) for the fine pass
 int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,

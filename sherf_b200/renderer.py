@@ -19,6 +19,10 @@ import torch.nn as nn
 
 from . import _lib
 
+import itertools
+
+_WEIGHT_EPOCH = itertools.count(1)       # process-wide: a value is never reused, so a stale arena can never look current
+
 PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3, 'bf16x3': _lib.MLP_BF16X3,
               '_tf32x3_tmem_a': 99}      # diagnostic: 3xTF32 with the A_lo operand in tensor memory (sherf_debug_linear only)
 
@@ -165,6 +169,7 @@ class ImportanceRenderer(nn.Module):
         elif os.path.exists(os.path.join('assets', 'SMPL_NEUTRAL.pkl')):
             self.set_smpl_model(read_pickle(os.path.join('assets', 'SMPL_NEUTRAL.pkl')))
         self._scratch = None
+        self._w_epoch = 0
         self._dbg_keep = None
         self.last_num_points = 0
         self.last_num_fine_points = 0
@@ -225,6 +230,7 @@ class ImportanceRenderer(nn.Module):
         w.views_w, w.views_b = P(decoder.views_linear.weight), P(decoder.views_linear.bias)
         w.rgb_w, w.rgb_b = P(decoder.rgb_linear.weight), P(decoder.rgb_linear.bias)
         self._w_cache = (sig, w, keep)
+        self._w_epoch = next(_WEIGHT_EPOCH)          # parameters (re)bound or modified: the packed copies in the arena are stale
         return w
 
     @staticmethod
@@ -334,6 +340,10 @@ class ImportanceRenderer(nn.Module):
             need = lib.sherf_scratch_bytes(C.byref(sc), N, S, SF, smpl.n_verts)
             if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
                 self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+                self._w_epoch = next(_WEIGHT_EPOCH)      # new arena: nothing is packed in it yet
+            # the packed weight blobs of the previous call are reused while no parameter was re-assigned or written in place
+            # (data_ptr / _version signature above); SHERF_NO_PACK_REUSE=1 packs on every call
+            opts.weights_version = self._w_epoch
 
             dbg_p = None
             if debug is not None:

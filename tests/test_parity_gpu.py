@@ -263,3 +263,30 @@ def run_cuda_kw(ren, dec, scene, **kw):
     return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
                dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'],
                scene['rendering_options'], **kw)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'bf16x3'])
+def test_weight_update_invalidates_packed_weights(precision, smpl_model):
+    """The packed weight blobs are reused between calls (SherfOptions.weights_version) only while no parameter changed: an in-place
+    update (optimizer step) or a re-assigned parameter must show up in the very next render, and equal a cold render."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=24, W=24, samples=16, seed=2), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=3, mlp_precision=precision, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    a = run_cuda(ren, dec, scene)
+    b = run_cuda(ren, dec, scene)                                        # second call reuses the packed blobs
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with torch.no_grad():
+        dec.rgb_linear.bias += 0.5                                       # in-place, like an optimizer step
+        ren.conv1d_reprojection.weight.mul_(1.25)
+    c = run_cuda(ren, dec, scene)
+    assert float((c[0] - a[0]).abs().max()) > 1e-3
+    ren2, dec2 = hot_path_modules(smpl_model, seed=3, mlp_precision=precision, dense_sigma=True)
+    ren2.load_state_dict(ren.state_dict())
+    dec2.load_state_dict(dec.state_dict())
+    d = run_cuda(ren2.to(dev), dec2.to(dev), scene)                      # cold render of the updated parameters
+    assert all(torch.equal(x, y) for x, y in zip(c, d))
+    dec.views_linear.weight = torch.nn.Parameter(dec.views_linear.weight.detach() * 0.5)      # re-assigned parameter
+    e = run_cuda(ren, dec, scene)
+    assert float((e[0] - c[0]).abs().max()) > 1e-4
