@@ -186,6 +186,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     lib.sherf_set_profiling(1)
+    lib.sherf_last_stage_ms.restype = __import__('ctypes').c_float
 
     model = SY.make_smpl_model(0)
     base, views = make_views(world, model)
@@ -219,6 +220,7 @@ def main():
                    depth_clamp=clamp[v] if by_tiles else None)
 
     stage_ms = [0.0] * 8
+    host_us = [0.0] * 5             # C-side issue / sync / issue / total, and the Python wrapper around it
     launches = [0]
     points = [0]
 
@@ -231,7 +233,11 @@ def main():
     def step_device():
         outs = []
         for j, v in enumerate(my_views):
+            t_py = time.perf_counter()
             rgb, depth, acc = render(shard_dev[j], v)
+            host_us[4] += (time.perf_counter() - t_py) * 1e6
+            for s_ in range(4):
+                host_us[s_] += lib.sherf_last_host_us(s_)
             for s_ in range(8):
                 stage_ms[s_] += lib.sherf_last_stage_ms(s_)
             launches[0] += ren.last_launches
@@ -276,15 +282,29 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    stage_ms[:] = [0.0] * 8
+    # the timed steps run with the library's per-stage event timers OFF (they cost ~60 host-side event records per forward);
+    # the stage split reported next to `value` comes from the same number of extra, untimed steps with the timers on
+    lib.sherf_set_profiling(0)
+    step_device()
     launches[0] = 0
     points[0] = 0
+    host_us[:] = [0.0] * 5
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     ms = timed(step_device, args.steps)
     barrier()
     clk = clocks.stop()
+    n_launch_timed, n_points_timed = launches[0], points[0]
+    host_timed = [h / (args.steps * len(my_views)) for h in host_us]
+    lib.sherf_set_profiling(1)
+    step_device()
+    stage_ms[:] = [0.0] * 8
+    for _ in range(args.steps):
+        flush.zero_()
+        step_device()
+    launches[0], points[0] = n_launch_timed, n_points_timed
+    lib.sherf_set_profiling(0)
     host_out = [torch.empty(N, 5).pin_memory() for _ in range(world)]
     for _ in range(args.warmup):
         step_e2e(host_out)
@@ -345,6 +365,8 @@ def main():
                     'd2h_bytes_per_step': world * N * 5 * 4, 'ms_per_step': ms_e2e,
                     'note': 'per step: pinned-host rays/near/far/vertices -> device, ImportanceRenderer.forward via the C ABI, rendered rgb+depth+acc -> pinned host'},
             'gpu_launches': launches[0],
+            'host_us_per_view_call': {'c_issue_until_sync': host_timed[0], 'c_blocked_in_sync': host_timed[1], 'c_issue_point_stages': host_timed[2],
+                                      'c_total': host_timed[3], 'python_forward_total': host_timed[4]},
             'clocks': clk,
             'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'warp+gather', 'mlp', 'composite', 'mlp:fused_decoder_kernel', 'mlp:fused_transformer_kernel', 'mlp:fused_fusion_kernel'])},
             'mlp_stage_tflops': p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,

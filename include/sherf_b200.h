@@ -242,6 +242,9 @@ SHERF_API int64_t sherf_last_importance_point_count(void);
  * 7 the fused tcgen05 feature-fusion kernel alone (sub-spans of stage 3; 0 on the fp32 path). */
 SHERF_API void sherf_set_profiling(int enabled);
 SHERF_API float sherf_last_stage_ms(int stage);
+/* Host wall time (microseconds) of the last forward on this thread: 0 launch issue until the survivor-count sync, 1 time blocked in
+ * that sync, 2 launch issue of the point stages and the ray march, 3 whole call. */
+SHERF_API float sherf_last_host_us(int part);
 
 #ifdef __cplusplus
 }

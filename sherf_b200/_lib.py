@@ -70,7 +70,7 @@ class SherfDebug(C.Structure):
 
 
 EXPORTS = ['sherf_debug_set_trace', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
-           'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms']
+           'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms', 'sherf_last_host_us']
 
 _lib = None
 
@@ -118,6 +118,8 @@ def load():
     lib.sherf_set_profiling.argtypes = [C.c_int]
     lib.sherf_last_stage_ms.restype = C.c_float
     lib.sherf_last_stage_ms.argtypes = [C.c_int]
+    lib.sherf_last_host_us.restype = C.c_float
+    lib.sherf_last_host_us.argtypes = [C.c_int]
     if lib.sherf_abi_version() != ABI_VERSION:
         raise RuntimeError('libsherf_b200.so ABI version mismatch')
     _lib = lib

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <chrono>
 
 namespace sherf {
 
@@ -17,6 +18,8 @@ static thread_local int64_t g_last_launches = 0;
 static thread_local int64_t g_last_fine_points = 0;
 static thread_local int g_profiling = 0;
 static thread_local float g_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static thread_local float g_host_us[4] = {0, 0, 0, 0};   // host wall time of the last forward: issue until the P sync, waiting in the sync, issue of the point stages, total
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -181,6 +184,14 @@ static thread_local StageTimer* g_tm = nullptr;
 struct PackTag { const void* base = nullptr; size_t need = 0; uint64_t version = 0; int precision = -1; int dev = -1; };
 static thread_local PackTag g_pack_tag;
 
+// Pinned host words for the survivor counts: a device-to-host cudaMemcpyAsync into PAGEABLE memory blocks the calling thread until the
+// copy has run, i.e. until the whole cull has finished (r1_x: 466 us of "launch issue"), which serialised the side-stream work behind it.
+static int64_t* pinned_counts() {
+  static thread_local int64_t* p = nullptr;
+  if (!p && cudaHostAlloc((void**)&p, 4 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  return p;
+}
+
 // Internal side stream (per host thread): the warp+gather kernel of chunk i+1 runs concurrently with the persistent MLP
 // kernels of chunk i (they leave most issue slots idle and the gather kernel needs no shared memory).
 struct SideStream {
@@ -190,7 +201,11 @@ struct SideStream {
     if (cudaGetDevice(&d) != cudaSuccess) return -1;
     if (s && d == dev) return 0;
     dev = d;
-    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    // highest priority: the side stream carries chains of tiny dependent kernels (SMPL tables, grids) next to the machine-filling cull
+    // kernels of the caller's stream; at default priority each of them queued behind thousands of cull blocks (r1_u: +0.3 ms)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return -1;
     cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ldone, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&gdone[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&mdone[i], cudaEventDisableTiming); }
@@ -213,6 +228,7 @@ int64_t sherf_last_launch_count(void) { return g_last_launches; }
 int64_t sherf_last_importance_point_count(void) { return g_last_fine_points; }
 void sherf_set_profiling(int enabled) { g_profiling = enabled; }
 float sherf_last_stage_ms(int stage) { return (stage >= 0 && stage < 8) ? g_stage_ms[stage] : 0.f; }
+float sherf_last_host_us(int part) { return (part >= 0 && part < 4) ? g_host_us[part] : 0.f; }
 
 size_t sherf_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_importance, int32_t n_verts) {
   if (!scene || n_rays <= 0 || n_samples < 2 || n_importance < 0 || n_verts <= 0) return 0;
@@ -256,6 +272,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
                          const SherfWeights* weights, const SherfRays* rays, const SherfOptions* opts, const SherfOut* out,
                          const SherfDebug* dbg, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {
   g_err[0] = 0;
+  const double t_enter = now_us();
   RC(validate(smpl, frame, scene, weights, rays, opts, out));
   const int N = rays->n_rays, S = rays->n_samples, SF = rays->n_importance, V = smpl->n_verts;
   cudaStream_t st = (cudaStream_t)stream;
@@ -289,8 +306,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
   RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
   tm.end();
-  int64_t P = 0;
-  SHERF_CUDA_OK(cudaMemcpyAsync(&P, L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  int64_t* hcount = pinned_counts();
+  if (!hcount) { set_error("cudaHostAlloc failed for the survivor-count words"); return SHERF_E_CUDA; }
+  SHERF_CUDA_OK(cudaMemcpyAsync(&hcount[0], L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
 
   RC(run_prologue_tables(*smpl, *frame, L.ft, ls));
   {
@@ -339,7 +357,10 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   }
   if (side) SHERF_CUDA_OK(cudaEventRecord(g_side.ldone, ls));
 
+  const double t_sync0 = now_us();
   SHERF_CUDA_OK(cudaStreamSynchronize(st));                  // the survivor count P (the cull is done; the side stream may still be running)
+  const int64_t P = hcount[0];
+  const double t_sync1 = now_us();
   if (n_points_out) *n_points_out = P;
   if (dbg && dbg->point_sample && P > 0)
     SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sample, L.point_sample, sizeof(int) * (size_t)(P < dbg->max_points ? P : dbg->max_points),
@@ -417,9 +438,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     int* vid_f = (dbg && dbg->fine_sample_vid) ? dbg->fine_sample_vid : L.sample_vid_f;
     RC(run_cull(*rays, SF, L.fine_depths, L.ft, vid_f, L.ray_count_f, L.block_sums, L.ray_start_f, L.total_f, L.point_sample_f, L.point_vid_f, st));
     tm.end();
-    int64_t PF = 0;
-    SHERF_CUDA_OK(cudaMemcpyAsync(&PF, L.total_f, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SHERF_CUDA_OK(cudaMemcpyAsync(&hcount[1], L.total_f, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SHERF_CUDA_OK(cudaStreamSynchronize(st));
+    const int64_t PF = hcount[1];
     if (n_points_out) *n_points_out = P + PF;
     g_last_fine_points = PF;
     RC(run_points(L.point_sample_f, L.point_vid_f, PF, SF, L.fine_depths, L.sigma_f, L.rgb_f, nullptr));
@@ -435,6 +456,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.finish();
   g_tm = nullptr;
   g_last_launches = g_launches.n;
+  { const double t_exit = now_us(); g_host_us[0] = (float)(t_sync0 - t_enter); g_host_us[1] = (float)(t_sync1 - t_sync0); g_host_us[2] = (float)(t_exit - t_sync1); g_host_us[3] = (float)(t_exit - t_enter); }
   return SHERF_OK;
 }
 

@@ -10,10 +10,12 @@ namespace sherf {
 
 // [C][M] (channel-major, the reference's NCHW/NCDHW) -> [M][C] channels-last; 32x32 smem tiles.  All the feature tensors of a
 // forward (3 planes, 2-D feature map, 3 volume levels) go through ONE launch: block b belongs to job j with blk0[j] <= b < blk0[j+1].
-struct ClJobs { const float* in[8]; float* out[8]; int C[8]; long long M[8]; int blk0[9]; int n; };
+struct ClJobs { const float* in[8]; float* out[8]; int C[8]; long long M[8]; int blk0[9]; int vec[8]; int n; };
 
+// Tile = 32 channels x 128 positions.  vec jobs (M % 4 == 0, C % 4 == 0, 16-byte aligned bases): 128-bit loads along M and 128-bit
+// stores along C (four times the bytes in flight per thread of the scalar form, which reached 2.7 TB/s); other jobs: scalar accesses.
 __global__ void __launch_bounds__(256) k_to_channels_last(const ClJobs J) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[32][129];
   int j = 0;
   while (j + 1 < J.n && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
   const float* __restrict__ in = J.in[j];
@@ -22,21 +24,47 @@ __global__ void __launch_bounds__(256) k_to_channels_last(const ClJobs J) {
   const int64_t M = J.M[j];
   const int cblocks = (C + 31) / 32;
   const int lb = (int)blockIdx.x - J.blk0[j];
-  const int64_t m0 = (int64_t)(lb / cblocks) * 32;
+  const int64_t m0 = (int64_t)(lb / cblocks) * 128;
   const int c0 = (lb % cblocks) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const int tid = threadIdx.x;
+  if (J.vec[j]) {
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r;
-    const int64_t m = m0 + tx;
-    tile[r][tx] = (c < C && m < M) ? in[(size_t)c * M + m] : 0.f;
-  }
-  __syncthreads();
+    for (int k = 0; k < 4; ++k) {                            // 32 rows (channels) x 32 float4 along M
+      const int idx = tid + 256 * k, r = idx >> 5, q = idx & 31;
+      const int c = c0 + r;
+      const int64_t m = m0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C && m < M) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)c * M + m));
+      tile[r][4 * q] = v.x; tile[r][4 * q + 1] = v.y; tile[r][4 * q + 2] = v.z; tile[r][4 * q + 3] = v.w;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t m = m0 + r;
-    const int c = c0 + tx;
-    if (c < C && m < M) out[(size_t)m * C + c] = tile[tx][r];
+    for (int k = 0; k < 4; ++k) {                            // 128 positions x 8 float4 along C
+      const int idx = tid + 256 * k, mm = idx >> 3, q = idx & 7;
+      const int64_t m = m0 + mm;
+      const int c = c0 + 4 * q;
+      if (c < C && m < M)
+        *reinterpret_cast<float4*>(out + (size_t)m * C + c) = make_float4(tile[4 * q][mm], tile[4 * q + 1][mm], tile[4 * q + 2][mm], tile[4 * q + 3][mm]);
+    }
+  } else {
+    const int tx = tid & 31, ty = tid >> 5;                  // 32 x 8
+    for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll
+      for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const int64_t m = m0 + 32 * sub + tx;
+        tile[r][32 * sub + tx] = (c < C && m < M) ? in[(size_t)c * M + m] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll
+      for (int r = ty; r < 32; r += 8) {
+        const int64_t m = m0 + 32 * sub + r;
+        const int c = c0 + tx;
+        if (c < C && m < M) out[(size_t)m * C + c] = tile[tx][32 * sub + r];
+      }
+    }
   }
 }
 
@@ -47,8 +75,9 @@ int run_to_channels_last_multi(int n, const float* const* in, float* const* out,
   int64_t blocks = 0;
   for (int j = 0; j < n; ++j) {
     J.in[j] = in[j]; J.out[j] = out[j]; J.C[j] = C[j]; J.M[j] = M[j];
+    J.vec[j] = (M[j] % 4 == 0 && C[j] % 4 == 0 && ((uintptr_t)in[j] & 15) == 0 && ((uintptr_t)out[j] & 15) == 0) ? 1 : 0;
     J.blk0[j] = (int)blocks;
-    blocks += ((M[j] + 31) / 32) * ((C[j] + 31) / 32);
+    blocks += ((M[j] + 127) / 128) * ((C[j] + 31) / 32);
   }
   J.blk0[n] = (int)blocks;
   if (blocks >= (1LL << 31)) { set_error("feature tensors too large for one layout launch"); return SHERF_E_INVALID; }

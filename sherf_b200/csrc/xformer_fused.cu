@@ -370,17 +370,21 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
 // (renderer.py:432, PositionalEncoding :900-916): pe[p][3*mm + c] = sin(phase(mm) + x_c * 2^(mm >> 1)), phase = 0 | pi/2 -- the same
 // separately rounded multiply and add as torch.addcmul.  One thread per value: the sixty sinf per point run at full occupancy here.
 __global__ void __launch_bounds__(256) k_point_pe(const float* __restrict__ geo, float* __restrict__ pe, int np) {
+  // thread = (point, slot) with 32 slots per point: slot s < 18 -> position coordinate c = s % 3 at octave k = s / 3 (6 octaves),
+  // 18 <= s < 30 -> direction coordinate at octave (s - 18) / 3 (4 octaves); each thread writes the phase-0 and the phase-pi/2 value
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)np * 64) return;
-  const int p = (int)(idx >> 6), j = (int)(idx & 63);
-  float v = 0.f;
-  if (j < 60) {
-    const int jj = j < 36 ? j : j - 36;
-    const int mm = jj / 3, c = jj - 3 * mm;
-    const float g = geo[(size_t)p * 8 + (j < 36 ? 0 : 3) + c];
-    v = sinf(__fadd_rn((mm & 1) ? kPi2 : 0.f, __fmul_rn(g, (float)(1 << (mm >> 1)))));
-  }
-  pe[idx] = v;
+  if (idx >= (int64_t)np * 32) return;
+  const int p = (int)(idx >> 5), s = (int)(idx & 31);
+  float* row = pe + (size_t)p * 64;
+  if (s >= 30) { row[60 + 2 * (s - 30)] = 0.f; row[61 + 2 * (s - 30)] = 0.f; return; }
+  const bool dir = s >= 18;
+  const int ss = dir ? s - 18 : s;
+  const int k = (ss * 11) >> 5, c = ss - 3 * k;                    // ss / 3 for ss < 18
+  const float g = geo[(size_t)p * 8 + (dir ? 3 : 0) + c];
+  const float y = __fmul_rn(g, (float)(1 << k));
+  float* o = row + (dir ? 36 : 0) + 6 * k + c;                     // pe[3 * mm + c], mm = 2k (phase 0) and 2k + 1 (phase pi/2)
+  o[0] = sinf(__fadd_rn(0.f, y));                                  // torch.addcmul(0, x, f): 0 + y (turns -0 into +0)
+  o[3] = sinf(__fadd_rn(kPi2, y));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -425,7 +429,7 @@ int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const 
                       float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp,
                       float* pe_buf) {
   if (np <= 0) return SHERF_OK;
-  k_point_pe<<<ceil_div((int64_t)np * 64, 256), 256, 0, st>>>(geo, pe_buf, np);
+  k_point_pe<<<ceil_div((int64_t)np * 32, 256), 256, 0, st>>>(geo, pe_buf, np);
   SHERF_LAUNCH_CHECK();
   XfArgs a;
   a.pe = pe_buf;

@@ -135,7 +135,12 @@ class SparseConvNet(nn.Module):
 
 # ---- pointer plumbing -------------------------------------------------------------------------------------------
 def _dev32(t: torch.Tensor, device) -> torch.Tensor:
-    if not torch.is_tensor(t):
+    """fp32, contiguous, on `device`, detached.  The common case (already so) returns the tensor itself: forward() converts ~35
+    tensors per call and the generic path (three dispatcher calls each) was ~0.15 ms of host time per view."""
+    if torch.is_tensor(t):
+        if t.dtype is torch.float32 and t.device == device and t.is_contiguous():
+            return t.detach() if t.requires_grad else t
+    else:
         t = torch.as_tensor(np.asarray(t))
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
@@ -201,35 +206,54 @@ class ImportanceRenderer(nn.Module):
             raise NotImplementedError('sherf_b200 implements the configuration every shipped SHERF script uses: '
                                       'use_1d/2d/3d_feature, use_trans and use_nerf_decoder all True')
 
+    def _weight_slots(self, decoder):
+        """(parameter dict, name) of every tensor SherfWeights points at, in struct order.  Walked on every call (about 15 us) so
+        that a replaced sub-module is seen, not only a replaced or modified parameter."""
+        att, ff = self.transformer.layers[0][0].fn, self.transformer.layers[0][1].fn
+        pts = decoder.pts_linears
+        slots = []
+        for m, has_bias in ((self.conv1d_projection, True), (self.conv1d_reprojection, True), (att.norm, True), (att.fn.to_qkv, False),
+                            (att.fn.to_out[0], True), (ff.norm, True), (ff.fn.net[0], True), (ff.fn.net[3], True),
+                            (pts[0], True), (pts[1], True), (pts[2], True), (pts[3], True), (pts[4], True), (pts[5], True), (pts[6], True),
+                            (pts[7], True), (decoder.alpha_linear, True), (decoder.feature_linear, True), (decoder.views_linear, True),
+                            (decoder.rgb_linear, True)):
+            d = m._parameters
+            slots.append((d, 'weight'))
+            if has_bias:
+                slots.append((d, 'bias'))
+        return slots
+
     def _weights_struct(self, decoder, device, keep):
-        # cache the struct while no parameter has been re-assigned or modified in place (data_ptr / _version signature)
-        params = [p for m in (self.conv1d_projection, self.conv1d_reprojection, self.transformer, decoder) for p in m.parameters()]
-        sig = (str(device), id(decoder)) + tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        # the struct (and the packed copies in the arena) stay valid while no parameter was re-assigned (object identity) or
+        # modified in place (_version, bumped by every in-place op such as an optimizer step)
+        slots = self._weight_slots(decoder)
+        sig = (device,) + tuple((id(d[n]), d[n]._version) for d, n in slots)
         cached = getattr(self, '_w_cache', None)
         if cached is not None and cached[0] == sig:
             return cached[1]
         keep = []
         w = _lib.SherfWeights()
+        it = iter(slots)
 
-        def P(t):
-            t = _dev32(t, device)
+        def P():
+            d, n = next(it)
+            t = _dev32(d[n], device)
             keep.append(t)
             return _ptr(t)
-        w.proj_w, w.proj_b = P(self.conv1d_projection.weight), P(self.conv1d_projection.bias)
-        w.reproj_w, w.reproj_b = P(self.conv1d_reprojection.weight), P(self.conv1d_reprojection.bias)
-        att, ff = self.transformer.layers[0][0].fn, self.transformer.layers[0][1].fn
-        w.ln1_w, w.ln1_b, w.qkv_w = P(att.norm.weight), P(att.norm.bias), P(att.fn.to_qkv.weight)
-        w.attn_out_w, w.attn_out_b = P(att.fn.to_out[0].weight), P(att.fn.to_out[0].bias)
-        w.ln2_w, w.ln2_b = P(ff.norm.weight), P(ff.norm.bias)
-        w.ff1_w, w.ff1_b = P(ff.fn.net[0].weight), P(ff.fn.net[0].bias)
-        w.ff2_w, w.ff2_b = P(ff.fn.net[3].weight), P(ff.fn.net[3].bias)
+        w.proj_w, w.proj_b = P(), P()
+        w.reproj_w, w.reproj_b = P(), P()
+        w.ln1_w, w.ln1_b, w.qkv_w = P(), P(), P()
+        w.attn_out_w, w.attn_out_b = P(), P()
+        w.ln2_w, w.ln2_b = P(), P()
+        w.ff1_w, w.ff1_b = P(), P()
+        w.ff2_w, w.ff2_b = P(), P()
         for i in range(8):
-            w.pts_w[i], w.pts_b[i] = P(decoder.pts_linears[i].weight), P(decoder.pts_linears[i].bias)
-        w.alpha_w, w.alpha_b = P(decoder.alpha_linear.weight), P(decoder.alpha_linear.bias)
-        w.feature_w, w.feature_b = P(decoder.feature_linear.weight), P(decoder.feature_linear.bias)
-        w.views_w, w.views_b = P(decoder.views_linear.weight), P(decoder.views_linear.bias)
-        w.rgb_w, w.rgb_b = P(decoder.rgb_linear.weight), P(decoder.rgb_linear.bias)
-        self._w_cache = (sig, w, keep)
+            w.pts_w[i], w.pts_b[i] = P(), P()
+        w.alpha_w, w.alpha_b = P(), P()
+        w.feature_w, w.feature_b = P(), P()
+        w.views_w, w.views_b = P(), P()
+        w.rgb_w, w.rgb_b = P(), P()
+        self._w_cache = (sig, w, keep, [d[n] for d, n in slots])      # keeps the parameter objects alive, so ids cannot be recycled
         self._w_epoch = next(_WEIGHT_EPOCH)          # parameters (re)bound or modified: the packed copies in the arena are stale
         return w
 
@@ -237,7 +261,7 @@ class ImportanceRenderer(nn.Module):
     def _pose_struct(params, device, keep):
         p = _lib.SherfPose()
         for name in ('poses', 'shapes', 'R', 'Th'):
-            t = _dev32(params[name], device).reshape(-1)
+            t = _dev32(params[name], device)                      # contiguous: the flat layout is the pointer's
             keep.append(t)
             setattr(p, name, _ptr(t))
         return p
@@ -280,10 +304,10 @@ class ImportanceRenderer(nn.Module):
             fr.obs = self._pose_struct(input_data['obs_params'], device, keep)
             for name, key in (('vertices', 'vertices'), ('t_vertices', 't_vertices'), ('t_world_bounds', 't_world_bounds'),
                               ('obs_K', 'obs_K_all'), ('obs_R', 'obs_R_all'), ('obs_T', 'obs_T_all')):
-                t = _dev32(input_data[key], device).reshape(-1)
+                t = _dev32(input_data[key], device)
                 keep.append(t)
                 setattr(fr, name, _ptr(t))
-            t = _dev32(obs_sp_input['bounds'], device).reshape(-1)
+            t = _dev32(obs_sp_input['bounds'], device)
             keep.append(t)
             fr.sp_bounds = _ptr(t)
             for i in range(3):
@@ -305,8 +329,8 @@ class ImportanceRenderer(nn.Module):
 
             w = self._weights_struct(decoder, device, keep)
             rays = _lib.SherfRays()
-            ro, rd = _dev32(ray_origins, device).reshape(-1), _dev32(ray_directions, device).reshape(-1)
-            nr, fa = _dev32(near, device).reshape(-1), _dev32(far, device).reshape(-1)
+            ro, rd = _dev32(ray_origins, device), _dev32(ray_directions, device)
+            nr, fa = _dev32(near, device), _dev32(far, device)
             keep += [ro, rd, nr, fa]
             rays.origins, rays.dirs, rays.near_, rays.far_, rays.n_rays, rays.n_samples = _ptr(ro), _ptr(rd), _ptr(nr), _ptr(fa), N, S
             rays.n_importance = SF
@@ -332,9 +356,8 @@ class ImportanceRenderer(nn.Module):
                 keep.append(uu)
                 opts.importance_u = _ptr(uu)
 
-            rgb = torch.empty(1, N, 3, device=device, dtype=torch.float32)
-            depth = torch.empty(1, N, 1, device=device, dtype=torch.float32)
-            acc = torch.empty(1, N, 1, device=device, dtype=torch.float32)
+            obuf = torch.empty(5 * N, device=device, dtype=torch.float32)          # one allocation: rgb | depth | acc
+            rgb, depth, acc = obuf[:3 * N].view(1, N, 3), obuf[3 * N:4 * N].view(1, N, 1), obuf[4 * N:].view(1, N, 1)
             out = _lib.SherfOut(_ptr(rgb), _ptr(depth), _ptr(acc))
 
             need = lib.sherf_scratch_bytes(C.byref(sc), N, S, SF, smpl.n_verts)
