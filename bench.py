@@ -331,7 +331,7 @@ def main():
             roof_kernel = 'k_decoder_pp (tcgen05 kind::f16 bf16 split products, whole NeRFDecoder, two 128-point tiles in flight per SM; %d launches per view)' % n_launch
             ach_tflops = p_call * FLOP_PER_POINT_FUSED / (fused_ms * 1e-3) / 1e12
             algo = f'{FLOP_PER_POINT_FUSED} FLOP per surviving sample x {p_call:.0f} samples per view, avg launch {1e3 * fused_ms / n_launch:.0f} us'
-            traffic = None
+            traffic = 312.3e6 * (p_call / n_launch) / 524288.0   # profiles/r1_p_ncu_full_k_decoder_pp.csv: dram 302.9 MB read + 9.3 MB written per 524 288-point launch
             peak, issued_per_useful = pk['tensor_tflops'], 3
             peak_src = pk['src'] + ': dense bf16; useful FLOPs counted once although bf16x3 issues 3 MMAs per product (issued_frac counts all three)'
         elif fused_ms > 0:       # 3xTF32 / TF32 path: the dominant kernel is the fused decoder trunk

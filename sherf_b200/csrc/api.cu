@@ -388,6 +388,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
       G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = Sn; G.depths = depths;
       G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np;
       G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
+      G.t_vertices = getenv("SHERF_KNN3_UNSEEDED") ? nullptr : frame->t_vertices;
       G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
       G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
       G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;

@@ -345,6 +345,38 @@ __device__ __forceinline__ void grp_lexmin(float& d, int& id) {      // reduce o
   }
 }
 
+// Exact K=1 search seeded with an upper bound: the canonical position of the point's nearest POSED vertex (knn #1) is almost always
+// within a few centimetres of the canonical point, so d2(q, t_vertices[seed]) bounds the answer and only the cells that intersect the
+// ball of that radius need to be visited (typically 8-18 instead of 27 cells of 5 cm, and never a second, 125-cell round).  Any vertex
+// that beats or ties the seed lies inside the box [q - r, q + r], r = sqrt(d2_seed) (+ guard for the fp32 rounding of d2 and of the
+// cell coordinates), and the vertex cells are clamped exactly like the box, so the lexicographic (d2, id) minimum is unchanged.
+__device__ int nn_seeded8(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
+                          const float* __restrict__ t_vertices, float qx, float qy, float qz, int l8, int seed) {
+  float best = dist2_xyz(qx, qy, qz, t_vertices[seed * 3], t_vertices[seed * 3 + 1], t_vertices[seed * 3 + 2]);
+  int bid = seed;
+  const float rb = sqrtf(best) * 1.0001f + 1.0e-4f * g.cell;
+  const int x0 = min(max(grid_coord(qx - rb, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int x1 = min(max(grid_coord(qx + rb, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int y0 = min(max(grid_coord(qy - rb, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int y1 = min(max(grid_coord(qy + rb, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int z0 = min(max(grid_coord(qz - rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  const int z1 = min(max(grid_coord(qz + rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncells = nx * ny * (z1 - z0 + 1);
+  for (int cc = l8; cc < ncells; cc += 8) {
+    const int xx = x0 + cc % nx, t = cc / nx;
+    const int cell = ((z0 + t / ny) * g.dim[1] + (y0 + t % ny)) * g.dim[0] + xx;
+    const int b = cell_start[cell], e = cell_start[cell + 1];
+    for (int k = b; k < e; ++k) {
+      const float4 v = gv[k];
+      const float d2 = dist2_xyz(qx, qy, qz, v.x, v.y, v.z);
+      const int id = __float_as_int(v.w);
+      if (d2 < best || (d2 == best && id < bid)) { best = d2; bid = id; }
+    }
+  }
+  grp_lexmin(best, bid);
+  return bid;
+}
+
 __device__ int nn_unbounded8(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv, float qx, float qy,
                              float qz, int l8, bool active) {
   const int cx = min(max(grid_coord(qx, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
@@ -412,7 +444,8 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
     rowvec_mat3(dray, fc.R_tgt, vd);
     float can[3] = {q[0], q[1], q[2]}, cdir[3] = {vd[0], vd[1], vd[2]};
     apply_warp(P.T1 + P.point_vid[gp], can, cdir, true);
-    const int vid3 = nn_unbounded8(fc.g3, P.g3_start, P.g3_verts, can[0], can[1], can[2], l8, active);
+    const int vid3 = P.t_vertices ? nn_seeded8(fc.g3, P.g3_start, P.g3_verts, P.t_vertices, can[0], can[1], can[2], l8, P.point_vid[gp])
+                                  : nn_unbounded8(fc.g3, P.g3_start, P.g3_verts, can[0], can[1], can[2], l8, active);
     float ps[3] = {can[0], can[1], can[2]}, dummy[3] = {0.f, 0.f, 0.f};
     apply_warp(P.T3 + vid3, ps, dummy, false);
     float world[3], cam[3], pix[3];
