@@ -214,6 +214,26 @@ SHERF_API int sherf_generate_rays(const double* K, const double* R, const double
                                   float* origins, float* dirs, float* near_out, float* far_out, uint8_t* mask_at_box /* may be NULL */,
                                   void* stream);
 
+/* ---- Sparse 3-D encoder: SparseConvNet.forward's convolutions + .dense() (renderer.py:744-785) ---- */
+#define SHERF_SPARSE_CONVS 13   /* conv0 x2, down0, conv1 x2, down1, conv2 x3, down2, conv3 x3 (renderer.py:728-740; num_layers = 4) */
+typedef struct SherfSparseConv {
+  const float* weight;      /* [c_out,3,3,3,c_in] spconv 2.x layout of (SubM|Sparse)Conv3d.weight, no bias (renderer.py:820,869) */
+  const float *bn_weight, *bn_bias, *bn_mean, *bn_var;   /* BatchNorm1d(eps=1e-3) in evaluation mode: running statistics */
+  int32_t c_in, c_out;
+  int32_t kind;             /* 0 = SubMConv3d k3, 1 = SparseConv3d k3 s2 p1 */
+  int32_t reserved;
+} SherfSparseConv;
+typedef struct SherfSparseEncoder { SherfSparseConv conv[SHERF_SPARSE_CONVS]; } SherfSparseEncoder;
+
+SHERF_API size_t sherf_sparse_encoder_scratch_bytes(int32_t n_voxels, const int32_t* out_sh /* host [3] = D,H,W */);
+/* coord [n,3] int32 (z,y,x; obs_sp_input['coord'][:,1:], triplane.py:193-207) and feat [n,c_in] are the rows of the
+ * SparseConvTensor of triplane.py:137; rows that share a voxel are merged by keeping the smallest row index (spconv leaves this
+ * case unspecified).  vol1/2/3: dense [32,D/2,H/2,W/2], [64,D/4,..], [96,D/8,..] outputs = net1/2/3.dense() (renderer.py:762,771,780),
+ * i.e. the `canonical_sp_conv_volume` list sherf_render_forward's SherfScene.vol takes. */
+SHERF_API int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* coord, const float* feat, int32_t n,
+                                  const int32_t* out_sh /* host [3] */, float* vol1, float* vol2, float* vol3, void* scratch,
+                                  size_t scratch_bytes, void* stream);
+
 /* sample_importance + sample_pdf (renderer.py:483-542) alone, on caller-supplied ray-marcher weights [N*S]
  * and uniform draws u [N*S_f]: writes the fine depths [N*S_f] and (optional) the searchsorted bin indices. */
 SHERF_API int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out,

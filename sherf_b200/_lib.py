@@ -69,7 +69,16 @@ class SherfDebug(C.Structure):
                 ('fine_sigma', c_float_p), ('fine_rgb', c_float_p)]
 
 
-EXPORTS = ['sherf_debug_set_trace', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+class SherfSparseConv(C.Structure):
+    _fields_ = [('weight', c_float_p), ('bn_weight', c_float_p), ('bn_bias', c_float_p), ('bn_mean', c_float_p), ('bn_var', c_float_p),
+                ('c_in', C.c_int32), ('c_out', C.c_int32), ('kind', C.c_int32), ('reserved', C.c_int32)]
+
+
+class SherfSparseEncoder(C.Structure):
+    _fields_ = [('conv', SherfSparseConv * 13)]
+
+
+EXPORTS = ['sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms', 'sherf_last_host_us']
 
 _lib = None
@@ -110,6 +119,11 @@ def load():
     lib.sherf_generate_rays.restype = C.c_int
     lib.sherf_generate_rays.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_int32,
                                         C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sherf_sparse_encoder_scratch_bytes.restype = C.c_size_t
+    lib.sherf_sparse_encoder_scratch_bytes.argtypes = [C.c_int32, C.POINTER(C.c_int32)]
+    lib.sherf_sparse_encode.restype = C.c_int
+    lib.sherf_sparse_encode.argtypes = [C.POINTER(SherfSparseEncoder), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sherf_debug_set_trace.argtypes = [C.c_void_p]
     lib.sherf_last_error.restype = C.c_char_p
     lib.sherf_abi_version.restype = C.c_int

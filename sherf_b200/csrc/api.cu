@@ -486,6 +486,31 @@ int sherf_generate_rays(const double* K, const double* R, const double* T, int32
   return SHERF_OK;
 }
 
+size_t sherf_sparse_encoder_scratch_bytes(int32_t n_voxels, const int32_t* out_sh) {
+  if (n_voxels <= 0 || !out_sh || out_sh[0] <= 0 || out_sh[1] <= 0 || out_sh[2] <= 0) return 0;
+  return sparse_encoder_scratch_bytes(n_voxels, out_sh);
+}
+
+int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* coord, const float* feat, int32_t n, const int32_t* out_sh, float* vol1,
+                        float* vol2, float* vol3, void* scratch, size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!enc || !coord || !feat || !out_sh || !vol1 || !vol2 || !vol3 || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (n <= 0 || out_sh[0] <= 0 || out_sh[1] <= 0 || out_sh[2] <= 0 || (int64_t)out_sh[0] * out_sh[1] * out_sh[2] >= (1LL << 31)) {
+    set_error("bad sparse input: n = %d, out_sh = %d x %d x %d", n, out_sh[0], out_sh[1], out_sh[2]);
+    return SHERF_E_INVALID;
+  }
+  for (int c = 0; c < SHERF_SPARSE_CONVS; ++c)
+    if (!enc->conv[c].weight || !enc->conv[c].bn_weight || !enc->conv[c].bn_bias || !enc->conv[c].bn_mean || !enc->conv[c].bn_var) {
+      set_error("sparse conv %d: null parameter pointer", c);
+      return SHERF_E_INVALID;
+    }
+  float* vols[3] = {vol1, vol2, vol3};
+  g_launches.n = 0;
+  RC(run_sparse_encode(*enc, coord, feat, n, out_sh, vols, scratch, scratch_bytes, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
 void sherf_debug_set_trace(long long* device_buf) { g_fused_trace = device_buf; }
 
 int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N,

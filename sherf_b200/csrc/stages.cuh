@@ -124,6 +124,11 @@ int run_composite(const SherfRays& rays, const FrameConst* fc, const int* ray_st
 int run_generate_rays(const double* K, const double* R, const double* T, int H, int W, const double* bounds, float* origins, float* dirs,
                       float* nearv, float* farv, unsigned char* mask_at_box, cudaStream_t st);
 
+// Sparse 3-D encoder (sparse_encoder.cu): renderer.py:744-785
+size_t sparse_encoder_scratch_bytes(int n, const int32_t* out_sh);
+int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
+                      void* scratch, size_t scratch_bytes, cudaStream_t st);
+
 // Importance (fine) pass, importance.cu (renderer.py:373-393, 446-456, 483-542)
 int run_importance_sample(const SherfRays& rays, const int* ray_start, const int* point_sample, const float* sigma, const float* noise,
                           const float* w_in, const float* u, float* t_fine, int* bins_out, float* w_out, cudaStream_t st);

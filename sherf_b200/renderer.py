@@ -119,9 +119,19 @@ def _sp_block(cin, cout, n):
     return nn.Sequential(*mods)
 
 
+class SparseConvTensor:
+    """Minimal stand-in for spconv.core.SparseConvTensor as triplane.py:137 builds it: features [n,C], indices [n,4] int32
+    (batch, z, y, x), spatial_shape (D,H,W), batch_size.  A real spconv tensor is accepted wherever this one is (same attributes)."""
+
+    def __init__(self, features, indices, spatial_shape, batch_size=1):
+        self.features, self.indices, self.spatial_shape, self.batch_size = features, indices, list(spatial_shape), batch_size
+
+
 class SparseConvNet(nn.Module):
-    """Parameter names of renderer.py:708-742.  The sparse 3-D encoder itself is SURVEY.md 8(f) rank 1 ("next"); this
-    round the renderer consumes the three densified pyramid levels directly."""
+    """The sparse 3-D encoder of renderer.py:708-742 (parameter names included).  forward() evaluates the convolutions of
+    SparseConvNet.forward (renderer.py:756-782) and returns the three densified levels [net1.dense(), net2.dense(), net3.dense()]
+    -- the grid_sample calls of :764,773,782 happen inside the render kernels.  The arithmetic runs in libsherf_b200.so
+    (csrc/sparse_encoder.cu); semantics of the spconv ops: oracle/sparse_encoder.py.  Evaluation-mode BatchNorm only."""
 
     def __init__(self, num_layers=4):
         super().__init__()
@@ -131,6 +141,56 @@ class SparseConvNet(nn.Module):
         self.conv2, self.down2 = _sp_block(64, 64, 3), _sp_block(64, 96, 1)
         self.conv3, self.down3 = _sp_block(96, 96, 3), _sp_block(96, 96, 1)
         self.conv4 = _sp_block(96, 96, 3)
+        self._scratch = None
+
+    def _convs(self):
+        """(conv container, BatchNorm1d, kind) x 13 in execution order for num_layers = 4 (down3 / conv4 outputs are never used)."""
+        out = []
+        for block, kind in ((self.conv0, 0), (self.down0, 1), (self.conv1, 0), (self.down1, 1), (self.conv2, 0), (self.down2, 1), (self.conv3, 0)):
+            for i in range(0, len(block), 3):
+                out.append((block[i], block[i + 1], kind))
+        return out
+
+    def forward(self, x, point_normalied_coords=None):
+        if self.num_layers != 4:
+            raise NotImplementedError('the CUDA encoder implements num_layers = 4 (renderer.py:270)')
+        if self.training:
+            raise NotImplementedError('sherf_b200 SparseConvNet: evaluation-mode BatchNorm only (training needs batch statistics + backward)')
+        feats, idx, out_sh = x.features, x.indices, [int(v) for v in x.spatial_shape]
+        device = feats.device
+        if device.type != 'cuda':
+            raise RuntimeError('sherf_b200.SparseConvNet runs on CUDA tensors only (no CPU fallback)')
+        if int(getattr(x, 'batch_size', 1)) != 1:
+            raise NotImplementedError('per-GPU batch must be 1, as in the renderer (renderer.py:320-321)')
+        lib = _lib.load()
+        keep = []
+        enc = _lib.SherfSparseEncoder()
+        for c, (conv, bn, kind) in enumerate(self._convs()):
+            w = _dev32(conv.weight, device)
+            ts = [w, _dev32(bn.weight, device), _dev32(bn.bias, device), _dev32(bn.running_mean, device), _dev32(bn.running_var, device)]
+            keep += ts
+            e = enc.conv[c]
+            e.weight, e.bn_weight, e.bn_bias, e.bn_mean, e.bn_var = (_ptr(t) for t in ts)
+            e.c_out, e.c_in, e.kind = w.shape[0], w.shape[-1], kind
+        coord = idx[:, 1:].to(device=device, dtype=torch.int32).contiguous()
+        feats = _dev32(feats, device)
+        n = coord.shape[0]
+        sh = (C.c_int32 * 3)(*out_sh)
+        with torch.cuda.device(device):
+            vols = []
+            for lvl, ch in ((1, 32), (2, 64), (3, 96)):
+                dims = list(out_sh)
+                for _ in range(lvl):
+                    dims = [(d + 2 - 3) // 2 + 1 for d in dims]
+                vols.append(torch.empty(1, ch, *dims, device=device, dtype=torch.float32))
+            need = lib.sherf_sparse_encoder_scratch_bytes(n, sh)
+            if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
+                self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+            _lib.check(lib.sherf_sparse_encode(C.byref(enc), coord.data_ptr(), feats.data_ptr(), n, sh, vols[0].data_ptr(), vols[1].data_ptr(),
+                                               vols[2].data_ptr(), self._scratch.data_ptr(), self._scratch.numel(),
+                                               torch.cuda.current_stream(device).cuda_stream))
+        del keep
+        return vols
 
 
 # ---- pointer plumbing -------------------------------------------------------------------------------------------
@@ -272,7 +332,9 @@ class ImportanceRenderer(nn.Module):
                 depth_clamp: tuple | None = None, importance_u: torch.Tensor | None = None):
         """Same positional signature and return value as renderer.py:286,398:
         (rgb[B,N,3] in (-1,1), depth[B,N,1], acc[B,N,1]).  `canonical_sp_conv_volume` is the list of the three densified
-        pyramid levels [1,32,D/2..], [1,64,D/4..], [1,96,D/8..] (what SparseConvNet.forward densifies at renderer.py:762-782).
+        pyramid levels [1,32,D/2..], [1,64,D/4..], [1,96,D/8..] (what SparseConvNet.forward densifies at renderer.py:762-782), or
+        the reference's own argument, the SparseConvTensor of triplane.py:137 (spconv's, or sherf_b200.renderer.SparseConvTensor),
+        which is first run through self.encoder_3d (csrc/sparse_encoder.cu).
         Extra keyword-only hooks: `debug` (dict filled with stage-wise tensors), `depth_clamp` ((min,max) of the full
         view's depths when this call renders a shard of its rays, ray_marcher.py:57) and `importance_u` ([N,S_f] uniform
         draws replacing the torch.rand of renderer.py:526; drawn here with torch.rand when omitted).
@@ -290,8 +352,12 @@ class ImportanceRenderer(nn.Module):
             raise NotImplementedError("only clamp_mode='relu' (train.py:332)")
         if rendering_options.get('disparity_space_sampling', False):
             raise NotImplementedError('disparity_space_sampling')
+        if hasattr(canonical_sp_conv_volume, 'features') and hasattr(canonical_sp_conv_volume, 'indices'):
+            # the reference's own argument: the SparseConvTensor of triplane.py:137 -> run the sparse 3-D encoder (renderer.py:349)
+            canonical_sp_conv_volume = self.encoder_3d(canonical_sp_conv_volume)
         if not isinstance(canonical_sp_conv_volume, (list, tuple)) or len(canonical_sp_conv_volume) != 3:
-            raise NotImplementedError('pass the three densified pyramid levels; the sparse 3-D encoder is a "next" row (SURVEY 8f)')
+            raise NotImplementedError('canonical_sp_conv_volume must be a SparseConvTensor (features / indices / spatial_shape) or the '
+                                      'list of the three densified pyramid levels')
         keep = []
         N = ray_origins.shape[1]
         S = int(rendering_options['depth_resolution'])

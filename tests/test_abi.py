@@ -37,7 +37,7 @@ def test_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header(tmp_path):
     structs = ['SherfSmplModel', 'SherfPose', 'SherfFrame', 'SherfScene', 'SherfWeights', 'SherfRays', 'SherfOptions', 'SherfOut',
-               'SherfDebug']
+               'SherfDebug', 'SherfSparseConv', 'SherfSparseEncoder']
     prog = '#include <stdio.h>\n#include "sherf_b200.h"\nint main(){' + ''.join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + 'return 0;}'
     c = tmp_path / 'sz.c'

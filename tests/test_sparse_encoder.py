@@ -1,0 +1,102 @@
+"""Sparse 3-D encoder.  "Parity unpinned": spconv 2.3.3 is absent, so the oracle states its semantics
+(oracle/sparse_encoder.py header).  CPU: the gather-form oracle == the dense conv3d + activity-mask formulation of the same network.
+GPU: sherf_sparse_encode (through SparseConvNet.forward) == the oracle; then the render path fed with a SparseConvTensor == the
+render path fed with the oracle's dense volumes.  Tolerance: 2e-4 relative to each level's maximum (fp32, different summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from sherf_b200 import synthetic as S
+from oracle import sparse_encoder as SE
+
+
+def _shell(n, shape, seed, dup=20):
+    """Voxel coordinates on an ellipsoid shell (like SMPL vertices at 5 mm) with `dup` duplicated rows."""
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(n, 3, generator=g)
+    p = p / p.norm(dim=1, keepdim=True)
+    half = torch.tensor([(s - 1) / 2.0 for s in shape])
+    coord = torch.round(p * (half * 0.8) + half).int()
+    coord = torch.cat([coord, coord[:dup]])
+    feat = torch.randn(coord.shape[0], 32, generator=g)
+    return coord, feat
+
+
+def test_oracle_sparse_equals_dense_formulation():
+    from sherf_b200.renderer import SparseConvNet
+    torch.manual_seed(0)
+    sd = SE.random_state_dict(SparseConvNet(4), 1)
+    coord, feat = _shell(200, (32, 64, 64), 2)
+    a = SE.encode_sparse(sd, coord, feat, (32, 64, 64))
+    b = SE.encode_dense(sd, coord, feat, (32, 64, 64))
+    assert [tuple(v.shape) for v in a] == [(1, 32, 16, 32, 32), (1, 64, 8, 16, 16), (1, 96, 4, 8, 8)]
+    for x, y in zip(a, b):
+        assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max())
+        assert int((x != 0).any(1).sum()) > 20
+    assert len(SE.conv_list()) == 13 and SE.conv_list()[2][2] == 'down'
+
+
+def test_duplicate_voxels_first_row_wins():
+    coord = torch.tensor([[1, 2, 3], [4, 4, 4], [1, 2, 3]], dtype=torch.int32)
+    feat = torch.arange(3 * 32, dtype=torch.float32).reshape(3, 32)
+    c, f = SE.unique_voxels(coord, feat)
+    assert c.tolist() == [[1, 2, 3], [4, 4, 4]] and torch.equal(f, feat[:2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape,n', [((32, 64, 64), 300), ((32, 32, 96), 40)])
+def test_cuda_encoder_against_oracle(shape, n):
+    from sherf_b200.renderer import SparseConvNet, SparseConvTensor
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    enc = SparseConvNet(4)
+    sd = SE.random_state_dict(enc, 3)
+    enc.load_state_dict(sd)
+    coord, feat = _shell(n, shape, 5)
+    want = SE.encode_sparse(sd, coord, feat, shape)
+    idx = torch.cat([torch.zeros(coord.shape[0], 1, dtype=torch.int32), coord], 1)
+    got = enc.to(dev).eval()(SparseConvTensor(feat.to(dev), idx.to(dev), list(shape), 1))
+    torch.cuda.synchronize()
+    for lvl, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape
+        err = float((g.cpu() - w).abs().max()) / float(w.abs().max())
+        same_sites = bool(torch.equal((g.cpu() != 0).any(1), (w != 0).any(1)))
+        print(f'\\n[sparse encoder {shape} level {lvl + 1}] active sites {int((w != 0).any(1).sum())}, max err / max = {err:.2e}, same sites {same_sites}')
+        assert err <= 2e-4
+    again = enc(SparseConvTensor(feat.to(dev), idx.to(dev), list(shape), 1))
+    assert all(torch.equal(a, b) for a, b in zip(got, again)), 'the encoder must be deterministic'
+
+
+@pytest.mark.gpu
+def test_render_from_sparse_tensor(smpl_model):
+    """The reference's own call: ImportanceRenderer.forward(..., canonical_sp_conv_volume = SparseConvTensor, ...) (triplane.py:137,156).
+    The sparse tensor is made like prepare_sp_input does (triplane.py:174-217) from the canonical vertices."""
+    from conftest import scene_to
+    from sherf_b200.renderer import SparseConvTensor
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    cpu_scene = S.make_scene(S.SceneSpec(H=32, W=32, samples=24, seed=3), smpl_model)
+    scene = scene_to(cpu_scene, dev)
+    ren, dec = hot_path_modules(smpl_model, seed=0, dense_sigma=True)
+    sd = SE.random_state_dict(ren.encoder_3d, 7)
+    ren.encoder_3d.load_state_dict(sd)
+    tv = cpu_scene['input_data']['t_vertices'][0]
+    bounds = cpu_scene['obs_sp_input']['bounds'][0]
+    out_sh = cpu_scene['obs_sp_input']['out_sh']
+    coord = torch.round((tv[:, [2, 1, 0]] - bounds[0][[2, 1, 0]]) / 0.005).to(torch.int32)          # triplane.py:193
+    feat = torch.randn(coord.shape[0], 32, generator=torch.Generator().manual_seed(1))
+    idx = torch.cat([torch.zeros(coord.shape[0], 1, dtype=torch.int32), coord], 1)
+    ren, dec = ren.to(dev).eval(), dec.to(dev)
+    sp = SparseConvTensor(feat.to(dev), idx.to(dev), out_sh, 1)
+
+    def render(vol):
+        return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], vol, None, scene['obs_sp_input'], dec,
+                   scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'], scene['rendering_options'])
+    a = render(sp)
+    vols = ren.encoder_3d(sp)
+    assert [tuple(v.shape[1:]) for v in vols] == [(32, out_sh[0] // 2, out_sh[1] // 2, out_sh[2] // 2),
+                                                 (64, out_sh[0] // 4, out_sh[1] // 4, out_sh[2] // 4), (96, out_sh[0] // 8, out_sh[1] // 8, out_sh[2] // 8)]
+    b = render(vols)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert float(a[2].max()) > 0.2 and float(vols[0].abs().max()) > 0
+    print(f'\\n[render from SparseConvTensor] {coord.shape[0]} vertices -> active level-1 sites {int((vols[0][0] != 0).any(0).sum())}')
