@@ -98,3 +98,57 @@ def test_checkpoint_names_match_reference_contract(smpl_model):
     n_hot = sum(v.numel() for k, v in ren.state_dict().items() if k.startswith(('conv1d', 'transformer'))) + sum(
         p.numel() for p in dec.parameters())
     assert n_hot == 192804                                                       # SURVEY.md section 7 "hard parts"
+
+
+def test_importance_and_sparse_argument_validation(lib):
+    """Argument checks run before any CUDA call, so they can be exercised without a GPU: the importance pass needs S >= 3 and the
+    uniform draws; the sparse encoder and the ray generator reject null / degenerate arguments with SHERF_E_INVALID."""
+    sc = _lib.SherfScene()
+    sc.plane_ch, sc.plane_h, sc.plane_w = 32, 8, 8
+    sc.img_h = sc.img_w = 8
+    sc.feat_ch, sc.feat_h, sc.feat_w = 64, 4, 4
+    for l, c in enumerate((32, 64, 96)):
+        sc.vol_ch[l] = c
+        for a in range(3):
+            sc.vol_dim[l][a] = 4
+    with_f = lib.sherf_scratch_bytes(ctypes.byref(sc), 1024, 16, 16, 6890)
+    without = lib.sherf_scratch_bytes(ctypes.byref(sc), 1024, 16, 0, 6890)
+    assert with_f > without > 0                                    # the fine pass carries its own per-sample bookkeeping
+    assert lib.sherf_scratch_bytes(ctypes.byref(sc), 1024, 16, -1, 6890) == 0
+    one = ctypes.c_float(0)
+    p = ctypes.addressof(one)                                       # any non-null address: validation never dereferences it
+    smpl, fr, w, rays, opts, out = _lib.SherfSmplModel(), _lib.SherfFrame(), _lib.SherfWeights(), _lib.SherfRays(), _lib.SherfOptions(), _lib.SherfOut()
+    smpl.weights = smpl.posedirs = p
+    smpl.n_verts = 6890
+    sc.planes = sc.obs_img = sc.obs_feat = p
+    for l in range(3):
+        sc.vol[l] = p
+    rays.origins = rays.dirs = rays.near_ = rays.far_ = p
+    out.rgb = out.depth = out.acc = p
+    rays.n_rays, rays.n_samples, rays.n_importance = 16, 2, 4
+    args = [ctypes.byref(x) for x in (smpl, fr, sc, w, rays, opts, out)] + [None, None, 0, None, None]
+    assert lib.sherf_render_forward(*args) == -1 and b'n_samples >= 3' in lib.sherf_last_error()
+    rays.n_samples = 8
+    assert lib.sherf_render_forward(*args) == -1 and b'importance_u' in lib.sherf_last_error()
+    rays.n_importance = 300
+    assert lib.sherf_render_forward(*args) == -1 and b'n_importance' in lib.sherf_last_error()
+    sh = (ctypes.c_int32 * 3)(32, 64, 64)
+    assert lib.sherf_sparse_encoder_scratch_bytes(100, sh) > 4 * 32 * 64 * 64
+    assert lib.sherf_sparse_encoder_scratch_bytes(0, sh) == 0
+    assert lib.sherf_sparse_encode(None, None, None, 0, None, None, None, None, None, 0, None) == -1
+    assert lib.sherf_generate_rays(None, None, None, 4, 4, None, None, None, None, None, None, None) == -1
+    assert lib.sherf_debug_sample_importance(None, None, None, None, None, None) == -1
+
+
+def test_cuda_only_entry_points_refuse_cpu():
+    from sherf_b200.rays import generate_rays
+    from sherf_b200.renderer import SparseConvNet, SparseConvTensor
+    import numpy as np
+    with pytest.raises(RuntimeError, match='CUDA'):
+        generate_rays(4, 4, np.eye(3), np.eye(3), np.zeros(3), np.array([[0, 0, 0], [1, 1, 1.0]]), 'cpu')
+    enc = SparseConvNet(4).eval()
+    sp = SparseConvTensor(torch.zeros(3, 32), torch.zeros(3, 4, dtype=torch.int32), [32, 32, 32], 1)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        enc(sp)
+    with pytest.raises(NotImplementedError, match='BatchNorm'):
+        SparseConvNet(4).train()(sp)
