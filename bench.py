@@ -100,7 +100,7 @@ def make_views(n_views, model):
     base = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0, cam_azim_deg=25.0), model)
     views = [{k: base[k] for k in ('ray_origins', 'ray_directions', 'near', 'far')}]
     for v in range(1, n_views):
-        sc = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0, cam_azim_deg=25.0 + 360.0 * v / n_views), model)
+        sc = SY.make_scene(SY.SceneSpec(H=H, W=W, samples=S, seed=0, cam_azim_deg=25.0 + 360.0 * v / n_views), model, rays_only=True)
         views.append({k: sc[k] for k in ('ray_origins', 'ray_directions', 'near', 'far')})
     return base, views
 

@@ -259,12 +259,13 @@ class SceneSpec:
     obs_azim_deg: float = -40.0
 
 
-def make_scene(spec: SceneSpec, model: dict | None = None, device='cpu') -> dict:
+def make_scene(spec: SceneSpec, model: dict | None = None, device='cpu', rays_only: bool = False) -> dict:
     """Everything ImportanceRenderer.forward consumes, as torch tensors on `device`.
 
     Returns dict with: input_data (the reference's dict), planes, obs_input_img, obs_input_feature,
     volumes (3 dense [1,C,D,H,W]), obs_sp_input {'bounds','out_sh'}, ray_origins, ray_directions, near, far,
-    rendering_options, mask_at_box.
+    rendering_options, mask_at_box.  `rays_only`: stop after the target camera's rays (same values as the full scene's; skips the
+    ~600 MB of random feature tensors) and return only ray_origins / ray_directions / near / far / mask_at_box / camera.
     """
     model = model or make_smpl_model(0)
     rng = np.random.default_rng(1000 + spec.seed)
@@ -310,6 +311,10 @@ def make_scene(spec: SceneSpec, model: dict | None = None, device='cpu') -> dict
     ray_d = ray_d.reshape(-1, 3).astype(np.float32)
     wb = np.stack([vertices.min(0) - 0.05, vertices.max(0) + 0.05], 0)
     near, far, hit = near_far_np(wb, ray_o, ray_d)
+    if rays_only:
+        t_ = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(device)
+        return {'ray_origins': t_(ray_o[None]), 'ray_directions': t_(ray_d[None]), 'near': t_(near[None, :, None]), 'far': t_(far[None, :, None]),
+                'mask_at_box': t_(hit), 'camera': {'K': K, 'R': R, 'T': T, 'bounds': wb}, 'spec': spec}
 
     out_sh, lv_shapes, sp_bounds = volume_shapes(t_vertices)
     chans = (32, 64, 96)
