@@ -126,3 +126,25 @@ def test_render_sequence_single_gpu(smpl_model):
         bad = ((o[:, :3] - rgb[0]).abs().amax(-1) > 1e-4).float().mean()
         assert float(bad) <= 2e-3, (f, float(bad))
         assert float(acc.max()) > 0.2
+
+
+@pytest.mark.gpu
+def test_sampler_writes_test_loop_style_outputs(smpl_model, tmp_path):
+    """sherf_b200.sample.render_orbit: novel views through the public API, files named and encoded like
+    test_loop.py:197,218-222 writes its predictions."""
+    from PIL import Image
+    from conftest import scene_to
+    from sherf_b200.sample import render_orbit, to8b
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    H = W = 32
+    scene = scene_to(S.make_scene(S.SceneSpec(H=H, W=W, samples=16, seed=8), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=0, dense_sigma=True)
+    outs = render_orbit(ren.to(dev), dec.to(dev), scene, 3, H, W, str(tmp_path), pose_index=7)
+    assert len(outs) == 3 and all(o.shape == (H * W, 5) for o in outs)
+    for v, o in enumerate(outs):
+        png = np.asarray(Image.open(tmp_path / f'frame0007_view{v:04d}.png'))
+        assert png.shape == (H, W, 3) and png.dtype == np.uint8
+        assert np.array_equal(png, to8b((o[:, :3].reshape(H, W, 3) / 2 + 0.5).cpu().numpy()))
+        assert np.array_equal(np.load(tmp_path / f'frame0007_view{v:04d}_acc.npy'), o[:, 4].reshape(H, W).cpu().numpy())
+    assert float(torch.stack([o[:, 4].max() for o in outs]).max()) > 0.2          # the body is visible from the orbit
