@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gpu-eager-baseline', action='store_true',
+                    help='also time oracle/port.py (the reference path written as eager PyTorch) on this GPU for one full view (BASELINE.md 3.4)')
     ap.add_argument('--importance', type=int, default=0,
                     help='fine (importance) samples per ray; 64 = BASELINE configs[4] on one GPU (not the headline workload: the default is configs[1])')
     ap.add_argument('--shard', default='views', choices=['views', 'tiles'], help='N>1: ray-batch sharding granularity')
@@ -401,6 +403,33 @@ def main():
                                       'pixels': int(idx.numel()), 'mask_at_box_pixels': int(hit.sum()),
                                       'rgb_linf': float((got - ref_img).abs().max()),
                                       'note': 'our render vs oracle/port.py on the cpu_baseline ray sample (test_loop.py:36-37,222-223 metric)'}
+        if world == 1 and args.gpu_eager_baseline:
+            # "the reference on the same box in GPU-eager mode".  The reference itself cannot travel (pytorch3d, spconv,
+            # /root/reference absent on the GPU box), so this is its restatement oracle/port.py run on CUDA tensors: brute-force KNN in
+            # 8192-query chunks, torch.inverse per point, F.grid_sample gathers, ~25 small GEMMs -- reported, not optimised against.
+            from oracle import port
+            wts = {k: v.to(dev) for k, v in port.hot_path_state_dict(ren, dec).items()}
+            mt = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in SY.smpl_model_to_torch(model).items()}
+            sc_full = dict(scene)
+            for k in ('ray_origins', 'ray_directions', 'near', 'far'):
+                sc_full[k] = shard_dev[0][k]
+            sc_full['rendering_options'] = dict(scene['rendering_options'], depth_resolution_importance=0)
+            port.render_forward(wts, mt, sc_full)                                   # warm-up (cuBLAS / cuSOLVER handles, allocator)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ref_out = port.render_forward(wts, mt, sc_full)
+            e1.record()
+            e1.synchronize()
+            secs = e0.elapsed_time(e1) * 1e-3
+            ours = ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'], dec,
+                       shard_dev[0]['ray_origins'], shard_dev[0]['ray_directions'], shard_dev[0]['near'], shard_dev[0]['far'],
+                       scene['input_data'], sc_full['rendering_options'])
+            line['gpu_eager_baseline'] = {'value': N * S / secs, 'unit': 'ray-samples/s', 'seconds_per_view': secs, 'kind': 'port',
+                                          'what': 'oracle/port.py (restatement of the reference path) as eager PyTorch on this GPU, one full 512x512x64 view',
+                                          'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9,
+                                          'rgb_linf_vs_cuda_path_full_view': float((ours[0] - ref_out[0]).abs().max()),
+                                          'acc_linf_vs_cuda_path_full_view': float((ours[2] - ref_out[2]).abs().max())}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

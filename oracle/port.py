@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE -- not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs may import this.
+cpu_baseline / --impl reference legs may import this.  (Device-agnostic: on CUDA tensors it is "the reference written as eager
+PyTorch on the same GPU", the bar BASELINE.md 3.4 asks to report next to the CUDA path -- bench.py --gpu-eager-baseline.)
 
 CPU restatement (torch, fp32) of the reference's hot path -- ImportanceRenderer.forward
 (renderer.py:286-398) + NeRFDecoder.forward (triplane.py:285-316) -- for per-GPU batch 1.  It exists
@@ -48,8 +49,8 @@ def matvec3_rows(p, M):
 
 def knn1(q, v, chunk=8192):
     """K=1 nearest neighbour, squared L2 in x,y,z order, smallest index on ties.  q[P,3], v[V,3]."""
-    d2_out = torch.empty(q.shape[0], dtype=torch.float32)
-    id_out = torch.empty(q.shape[0], dtype=torch.long)
+    d2_out = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+    id_out = torch.empty(q.shape[0], dtype=torch.long, device=q.device)
     vx, vy, vz = v[:, 0][None], v[:, 1][None], v[:, 2][None]
     for s in range(0, q.shape[0], chunk):
         c = q[s:s + chunk]
@@ -68,7 +69,7 @@ def rodrigues(rvec):
     c, s = torch.cos(angle)[:, None], torch.sin(angle)[:, None]
     z = torch.zeros_like(k[:, :1])
     K = torch.cat([z, -k[:, 2:3], k[:, 1:2], k[:, 2:3], z, -k[:, 0:1], -k[:, 1:2], k[:, 0:1], z], 1).reshape(-1, 3, 3)
-    return torch.eye(3)[None] + s * K + (1 - c) * torch.matmul(K, K)
+    return torch.eye(3, device=rvec.device)[None] + s * K + (1 - c) * torch.matmul(K, K)
 
 
 def lbs_transforms(smpl, poses, shapes):
@@ -79,7 +80,7 @@ def lbs_transforms(smpl, poses, shapes):
     parents = smpl['kintree_table'][0]
     rel = joints.clone()
     rel[1:] -= joints[parents[1:]]
-    local = torch.zeros(24, 4, 4)
+    local = torch.zeros(24, 4, 4, device=joints.device)
     local[:, :3, :3] = rot
     local[:, :3, 3] = rel
     local[:, 3, 3] = 1
@@ -87,7 +88,7 @@ def lbs_transforms(smpl, poses, shapes):
     for i in range(1, 24):
         chain.append(chain[int(parents[i])] @ local[i])
     A = torch.stack(chain, 0)
-    jh = torch.cat([joints, torch.zeros(24, 1)], 1)
+    jh = torch.cat([joints, torch.zeros(24, 1, device=joints.device)], 1)
     A[..., 3] = A[..., 3] - (A * jh[:, None, :]).sum(-1)
     return A
 
@@ -95,7 +96,7 @@ def lbs_transforms(smpl, poses, shapes):
 def pose_offsets(smpl, poses):
     """renderer.py:578-584: posedirs @ (R(theta)[1:] - I)."""
     rot = rodrigues(poses.reshape(-1, 3))
-    feat = (rot[1:] - torch.eye(3)).reshape(1, -1)
+    feat = (rot[1:] - torch.eye(3, device=rot.device)).reshape(1, -1)
     return (feat @ smpl['posedirs'].reshape(6890 * 3, -1).t()).reshape(-1, 3)
 
 
@@ -107,8 +108,8 @@ def shape_offsets(smpl, shapes):
 def positional_encoding(x, num_freqs):
     """renderer.py:875-916: [x, sin(x f0), sin(x f0 + pi/2), sin(x f1), ...] with the reference's interleave:
     embed[:, 2k+b, c] = sin(phase_b + x_c * 2^k) flattened as (freq-pair major, coordinate minor)."""
-    freqs = torch.repeat_interleave(2. ** torch.linspace(0., num_freqs - 1, steps=num_freqs), 2).view(1, -1, 1)
-    phases = torch.zeros(2 * num_freqs)
+    freqs = torch.repeat_interleave(2. ** torch.linspace(0., num_freqs - 1, steps=num_freqs), 2).view(1, -1, 1).to(x.device)
+    phases = torch.zeros(2 * num_freqs, device=x.device)
     phases[1::2] = torch.pi * 0.5
     phases = phases.view(1, -1, 1)
     e = x.unsqueeze(1).repeat(1, num_freqs * 2, 1)
@@ -120,7 +121,7 @@ def positional_encoding(x, num_freqs):
 
 def sample_depths(near, far, S):
     """renderer.py:458-481 (tensor branch, jitter commented out) -> [N,S]."""
-    steps = torch.arange(S, dtype=torch.float32) / (S - 1)
+    steps = torch.arange(S, dtype=torch.float32, device=near.device) / (S - 1)
     return near.reshape(-1, 1) + steps[None] * (far - near).reshape(-1, 1)
 
 
@@ -184,7 +185,7 @@ def project(world, Rc, Tc, Kc):
 
 def gather_2d(obs_img, obs_feat, uv):
     """renderer.py:331-340: uv normalised by the IMAGE size, sampled (align_corners=True) from both maps."""
-    g = 2.0 * uv[None, :, None, :] / torch.tensor([obs_img.shape[-1], obs_img.shape[-2]], dtype=torch.float32) - 1.0
+    g = 2.0 * uv[None, :, None, :] / torch.tensor([obs_img.shape[-1], obs_img.shape[-2]], dtype=torch.float32, device=uv.device) - 1.0
     feat = F.grid_sample(obs_feat, g, align_corners=True)[0, :, :, 0].t()
     rgb = F.grid_sample(obs_img, g, align_corners=True)[0, :, :, 0].t()
     return torch.cat([feat, positional_encoding(rgb, 5)[:, :32]], -1)
@@ -192,8 +193,8 @@ def gather_2d(obs_img, obs_feat, uv):
 
 def gather_3d(volumes, sp_bounds, out_sh, can):
     """renderer.py:544-556 + :762-797: voxel coords (0.005 m), 3 trilinear gathers, concat 192."""
-    dhw = (can[:, [2, 1, 0]] - sp_bounds[0][[2, 1, 0]]) / torch.tensor([0.005, 0.005, 0.005])
-    dhw = dhw / torch.tensor(out_sh, dtype=torch.float32) * 2 - 1
+    dhw = (can[:, [2, 1, 0]] - sp_bounds[0][[2, 1, 0]]) / torch.tensor([0.005, 0.005, 0.005], device=can.device)
+    dhw = dhw / torch.tensor(out_sh, dtype=torch.float32, device=can.device) * 2 - 1
     g = dhw[:, [2, 1, 0]][None, None, None]
     fs = [F.grid_sample(v, g, padding_mode='zeros', align_corners=True) for v in volumes]
     fs = torch.cat(fs, 1)
@@ -303,8 +304,8 @@ def evaluate_samples(weights: dict, smpl: dict, scene: dict, depths=None):
     N, S = st['depths'].shape
     sel = st['mask'].nonzero()[:, 0]                                              # row-major [N,S] order
     st['sel'] = sel
-    colors = torch.zeros(N * S, 3)
-    sigma = torch.full((N * S,), -80.0)
+    colors = torch.zeros(N * S, 3, device=sel.device)
+    sigma = torch.full((N * S,), -80.0, device=sel.device)
     if sel.numel() > 0:                                                           # else every sample keeps sigma = -80
         q, vdir, vid = st['q'][sel], st['vdir'][sel], st['id1'][sel]
         can, cdir = warp_to_canonical(smpl, idt['params'], idt['t_params'], q, vdir, vid)
