@@ -429,7 +429,8 @@ def main():
                                           'what': 'oracle/port.py (restatement of the reference path) as eager PyTorch on this GPU, one full 512x512x64 view',
                                           'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9,
                                           'rgb_linf_vs_cuda_path_full_view': float((ours[0] - ref_out[0]).abs().max()),
-                                          'acc_linf_vs_cuda_path_full_view': float((ours[2] - ref_out[2]).abs().max())}
+                                          'acc_linf_vs_cuda_path_full_view': float((ours[2] - ref_out[2]).abs().max()),
+                                          'rays_beyond_1e-4': float(((ours[0] - ref_out[0]).abs().amax(-1) > 1e-4).float().mean())}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
