@@ -90,3 +90,43 @@ def test_render_sequence_round_robin_gloo_world2(n_frames):
         p.join(timeout=60)
     assert [r[:2] for r in res] == [(0, True), (1, True)]
     assert res[0][2] == [f for f in range(n_frames) if f % 2 == 0] and res[1][2] == [f for f in range(n_frames) if f % 2 == 1]
+
+
+def _sharded_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        scene = {'ray_origins': torch.randn(1, n, 3), 'ray_directions': torch.randn(1, n, 3), 'near': torch.rand(1, n, 1),
+                 'far': torch.rand(1, n, 1) + 2, 'planes': None, 'obs_input_img': None, 'obs_input_feature': None, 'volumes': None,
+                 'obs_sp_input': None, 'input_data': None, 'rendering_options': {'depth_resolution': 8, 'depth_resolution_importance': 4}}
+        u = torch.rand(n, 4)
+        seen = {}
+
+        def fake_renderer(planes, img, feat, vol, mask, sp, decoder, o, d, near, far, idt, opts, depth_clamp=None, importance_u=None):
+            # a "render" that depends on the ray, on ITS row of the importance draws and on the global depth range
+            seen['clamp'] = depth_clamp
+            val = o.sum(-1, keepdim=True) + importance_u.sum(-1)[None, :, None] + depth_clamp[1]
+            return val.expand(-1, -1, 3).contiguous(), near + val, far + val
+        rgb, depth, acc = sd.render_sharded(fake_renderer, None, scene, importance_u=u)
+        clamp = sd.depth_range(scene['near'], scene['far'], 8)
+        val = scene['ray_origins'].sum(-1, keepdim=True) + u.sum(-1)[None, :, None] + clamp[1]
+        ok = torch.equal(rgb, val.expand(-1, -1, 3)) and torch.equal(depth, scene['near'] + val) and torch.equal(acc, scene['far'] + val)
+        q.put((rank, bool(ok), seen['clamp'] == clamp))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_sharded_passes_each_rank_its_rows_of_the_importance_draws():
+    """dist.render_sharded on CPU tensors with a stand-in renderer: every rank gets its rays, ITS rows of the full view's draws and the
+    full view's depth range; the reassembled image equals the unsharded one."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, 1000, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, True), (1, True, True)]
