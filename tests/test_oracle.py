@@ -126,3 +126,28 @@ def test_composite_background_and_clamp():
     assert torch.all(rgb[0] == -1) and float(depth[0]) == 3.0           # empty ray: nan -> inf -> clamp to max(depths)
     assert float(w[1].sum()) == pytest.approx(1.0, abs=1e-6)
     assert torch.allclose(rgb[1], torch.tensor([0.2, 0.4, 0.6]) * 2 - 1, atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree is only mounted in the build container')
+@pytest.mark.parametrize('S_,SF', [(16, 12), (64, 64), (5, 9)])
+def test_sample_importance_matches_reference_function(S_, SF, smpl_model_t):
+    """port.sample_importance against the reference's OWN sample_importance / sample_pdf (renderer.py:483-542) on random ray-marcher
+    weights, with torch.rand (:526) returning the same draws: identical bins, depths to the last few ulp."""
+    ren, _ = ref_shim.build_reference(smpl_model_t, seed=0)
+    g = torch.Generator().manual_seed(S_ * 100 + SF)
+    n = 300
+    near = torch.rand(n, generator=g) + 0.5
+    far = near + torch.rand(n, generator=g) * 2 + 0.1
+    depths = port.sample_depths(near, far, S_)
+    w = torch.rand(n, S_, generator=g) ** 6
+    w[::4] = 0
+    u = torch.rand(n, SF, generator=g)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: u
+    try:
+        want = ren.sample_importance(depths.view(1, n, S_, 1), w.view(1, n, S_, 1), SF)[0, :, :, 0]
+    finally:
+        torch.rand = orig
+    got, bins = port.sample_importance(depths, w, SF, u)
+    assert float((got - want).abs().max()) <= 1e-6 * float((far - near).max())
+    assert int(bins.min()) >= 1 and int(bins.max()) <= S_ - 2
