@@ -151,3 +151,32 @@ def test_sample_importance_matches_reference_function(S_, SF, smpl_model_t):
     got, bins = port.sample_importance(depths, w, SF, u)
     assert float((got - want).abs().max()) <= 1e-6 * float((far - near).max())
     assert int(bins.min()) >= 1 and int(bins.max()) <= S_ - 2
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree is only mounted in the build container')
+@pytest.mark.parametrize('white', [False, True])
+def test_composite_and_unify_match_reference_functions(white, smpl_model_t):
+    """port.composite == the reference's MipRayMarcher2 (ray_marcher.py:25-64) and port.unify_samples == ImportanceRenderer.unify_samples
+    (renderer.py:446-456) on random colours / densities / depths (incl. sigma = -80 "culled" samples and empty rays)."""
+    ren, _ = ref_shim.build_reference(smpl_model_t, seed=0)
+    g = torch.Generator().manual_seed(11)
+    n, S1, S2 = 200, 16, 12
+    d1 = port.sample_depths(torch.rand(n, generator=g) + 0.5, torch.rand(n, generator=g) + 2.0, S1)
+    d2 = d1[:, :1] + torch.rand(n, S2, generator=g) * (d1[:, -1:] - d1[:, :1])
+    c1, c2 = torch.rand(n, S1, 3, generator=g), torch.rand(n, S2, 3, generator=g)
+    s1, s2 = torch.randn(n, S1, generator=g) * 20, torch.randn(n, S2, generator=g) * 20
+    s1[torch.rand(n, S1, generator=g) < 0.5] = -80.0
+    s1[::7] = -80.0
+    s2[::7] = -80.0
+    rays_d = torch.randn(n, 3, generator=g)
+    opts = {'clamp_mode': 'relu', 'white_back': white}
+    ref_rgb, ref_depth, ref_w = ren.ray_marcher(c1[None], s1[None, :, :, None], d1[None, :, :, None], rays_d[None], opts)
+    rgb, depth, w = port.composite(c1, s1, d1, rays_d, white)
+    assert float((rgb - ref_rgb[0]).abs().max()) <= 1e-6 and float((w - ref_w[0, :, :, 0]).abs().max()) <= 1e-6
+    assert torch.equal(depth, ref_depth[0])
+    ad, ac, as_ = ren.unify_samples(d1[None, :, :, None], c1[None], s1[None, :, :, None], d2[None, :, :, None], c2[None], s2[None, :, :, None])
+    pd, pc, ps = port.unify_samples(d1, c1, s1, d2, c2, s2)
+    assert torch.equal(pd, ad[0, :, :, 0]) and torch.equal(pc, ac[0]) and torch.equal(ps, as_[0, :, :, 0])
+    ref2 = ren.ray_marcher(ac, as_, ad, rays_d[None], opts)
+    got2 = port.composite(pc, ps, pd, rays_d, white)
+    assert float((got2[0] - ref2[0][0]).abs().max()) <= 1e-6
