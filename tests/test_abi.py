@@ -152,3 +152,14 @@ def test_cuda_only_entry_points_refuse_cpu():
         enc(sp)
     with pytest.raises(NotImplementedError, match='BatchNorm'):
         SparseConvNet(4).train()(sp)
+
+
+def test_plain_c_client_binds_the_library(tmp_path, lib):
+    """include/sherf_b200.h compiles as C99 and a dlopen()ing C program resolves and calls the entry points (tests/c/cabi_client.c)."""
+    exe = tmp_path / 'cabi_client'
+    src = os.path.join(ROOT, 'tests', 'c', 'cabi_client.c')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.dirname(HEADER), src, '-o', str(exe), '-ldl'], check=True)
+    r = subprocess.run([str(exe), _lib.lib_path()], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith('ok abi=2')
+    print(r.stdout.strip())
