@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SHERF_ABI_VERSION 2
+#define SHERF_ABI_VERSION 3
 #if defined(__GNUC__)
 #define SHERF_API __attribute__((visibility("default")))
 #else
@@ -234,6 +234,38 @@ SHERF_API int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* 
                                   const int32_t* out_sh /* host [3] */, float* vol1, float* vol2, float* vol3, void* scratch,
                                   size_t scratch_bytes, void* stream);
 
+/* ---- Observation preparation ("vertex-feature splat"): what TriPlaneGenerator.synthesis computes once per
+ * observation image before calling the renderer (triplane.py:105-137) -- the rows of the SparseConvTensor of triplane.py:137. ---- */
+typedef struct SherfObservation {
+  SherfPose obs;               /* input_data['obs_params'] */
+  SherfPose canonical;         /* input_data['t_params'] */
+  const float* obs_vertices;   /* [V,3] input_data['obs_vertices'], world space */
+  const float* t_vertices;     /* [V,3] input_data['t_vertices'] */
+  const float* obs_K;          /* [3,3] */
+  const float* obs_R;          /* [3,3] */
+  const float* obs_T;          /* [3] */
+  const int32_t* faces;        /* [F,3] SMPL_NEUTRAL['f'] as int32 (renderer.projection's `face`, renderer.py:692-695) */
+  const int32_t* last_face;    /* [3,V]: for corner slot k, the LAST face f with faces[f][k] == v, or -1 (compute_normal's
+                                  `norm[:, faces[:, k]] += n` is an index_put WITHOUT accumulation, renderer.py:58-60) */
+  int32_t n_faces;
+  int32_t reserved;
+  const float* obs_img;        /* [3,img_h,img_w] input_data['obs_img_all'][:,0] */
+  int32_t img_h, img_w;
+  const float* obs_feat;       /* [feat_ch,feat_h,feat_w] encoder_2d_feature(obs_img, extract_feature=True) (triplane.py:108) */
+  int32_t feat_ch, feat_h, feat_w;
+  int32_t reserved2;
+  const float *proj_w, *proj_b; /* TriPlaneGenerator.conv1d_projection [32,96(,1)], [32] (triplane.py:57,124) */
+} SherfObservation;
+
+SHERF_API size_t sherf_observation_scratch_bytes(int32_t n_verts);
+/* Outputs (device unless noted): vert_feat [V,32] = obs_vertex_3d_feature (zero where the vertex faces away, triplane.py:126);
+ * coord [V,4] int32 = obs_sp_input['coord'] (batch, z, y, x; triplane.py:193-207); vertex_mask [V] bytes = obs_smpl_vertex_mask (may be
+ * NULL); bounds [2,3] = obs_sp_input['bounds'][0]; out_sh_host [3] (HOST) = obs_sp_input['out_sh']; canonical_out [V,3] (may be NULL)
+ * = coarse_obs_vertex_canonical_pts.  Synchronises the stream once (out_sh sizes the caller's volumes). */
+SHERF_API int sherf_prepare_observation(const SherfSmplModel* smpl, const SherfObservation* obs, float* vert_feat, int32_t* coord,
+                                        uint8_t* vertex_mask, float* bounds, int32_t* out_sh_host, float* canonical_out, void* scratch,
+                                        size_t scratch_bytes, void* stream);
+
 /* sample_importance + sample_pdf (renderer.py:483-542) alone, on caller-supplied ray-marcher weights [N*S]
  * and uniform draws u [N*S_f]: writes the fine depths [N*S_f] and (optional) the searchsorted bin indices. */
 SHERF_API int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out,
@@ -250,7 +282,7 @@ SHERF_API int sherf_debug_linear(int precision, const float* A, int lda, const f
 SHERF_API void sherf_debug_set_trace(long long* device_buf);
 
 SHERF_API const char* sherf_last_error(void);
-SHERF_API int sherf_abi_version(void);
+SHERF_API int sherf_abi_version(void);   /* == SHERF_ABI_VERSION (3) */
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */
 SHERF_API int64_t sherf_last_launch_count(void);
 /* Number of FINE (importance) samples that survived the cull in the last sherf_render_forward on this thread

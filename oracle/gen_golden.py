@@ -78,12 +78,18 @@ def run_case(name, cfg, model, model_t):
     def run_model(planes, f2d, f3d, *a, **k):
         cap['f2d'], cap['f3d'] = f2d[0], f3d[0]; return o_run(planes, f2d, f3d, *a, **k)
     ren.coarse_deform_target2c, ren.coarse_deform_c2source, ren.projection, ren.run_model = t2c, c2s, proj, run_model
+    orig_sfp = ref_renderer.sample_from_planes
+
+    def sfp_tap(*a, **k):
+        r = orig_sfp(*a, **k); cap['tri'] = r[0]; return r          # [3, P, 32]  (renderer.py:234-243, called at :402)
+    ref_renderer.sample_from_planes = sfp_tap
     hk = dec.register_forward_hook(lambda m, i, o: cap.update(sigma=o['sigma'][0, :, 0], rgbp=o['rgb'][0], tok=i[1]))
     h3 = ren.encoder_3d.register_forward_hook(lambda m, i, o: cap.update(f3raw=o[0]))
     try:
         rgb, depth, acc = ref_shim.render(ren, dec, scene)
     finally:
         ref_renderer.knn_points = orig_knn
+        ref_renderer.sample_from_planes = orig_sfp
         hk.remove(); h3.remove()
     d2_1, id_1 = cap['knn'][0]
     mask = d2_1 < (0.05 ** 2)
@@ -102,6 +108,7 @@ def run_case(name, cfg, model, model_t):
         'sigma': cap['sigma'].numpy(), 'rgb_pts': cap['rgbp'].numpy(),
         'tok01_head': cap['tok'][:2, :k].permute(1, 0, 2).reshape(k, 64).numpy(),
         'f2d_head': cap['f2d'][:k].numpy(), 'f3raw_head': cap['f3raw'][:k].numpy(),
+        'tri_head': cap['tri'][:, :k].permute(1, 0, 2).reshape(k, 96).numpy(),
     }
     for name_w, t in w.items():
         out['w/' + name_w] = t.numpy()

@@ -511,6 +511,29 @@ int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* coord, con
   return SHERF_OK;
 }
 
+size_t sherf_observation_scratch_bytes(int32_t n_verts) { return n_verts > 0 ? observation_scratch_bytes(n_verts, kMaxCell) + 512 : 0; }
+
+int sherf_prepare_observation(const SherfSmplModel* smpl, const SherfObservation* obs, float* vert_feat, int32_t* coord, uint8_t* vertex_mask,
+                              float* bounds, int32_t* out_sh_host, float* canonical_out, void* scratch, size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!smpl || !obs || !vert_feat || !coord || !bounds || !out_sh_host || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (smpl->n_verts <= 0 || !smpl->weights || !smpl->posedirs || !obs->obs_vertices || !obs->t_vertices || !obs->faces || !obs->last_face ||
+      !obs->obs_img || !obs->obs_feat || !obs->proj_w || !obs->proj_b || !obs->obs_K || !obs->obs_R || !obs->obs_T || !obs->obs.poses ||
+      !obs->canonical.poses) {
+    set_error("null device pointer in SherfObservation / SherfSmplModel");
+    return SHERF_E_INVALID;
+  }
+  if (obs->feat_ch != 64 || obs->img_h <= 0 || obs->img_w <= 0 || obs->feat_h <= 0 || obs->feat_w <= 0) {
+    set_error("unsupported observation shapes (feature channels %d, expected 64)", obs->feat_ch);
+    return SHERF_E_UNSUPPORTED;
+  }
+  g_launches.n = 0;
+  RC(run_prepare_observation(*smpl, *obs, vert_feat, coord, vertex_mask, bounds, out_sh_host, canonical_out, scratch, scratch_bytes,
+                             (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
 void sherf_debug_set_trace(long long* device_buf) { g_fused_trace = device_buf; }
 
 int sherf_debug_linear(int precision, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N,

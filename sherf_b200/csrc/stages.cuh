@@ -129,6 +129,11 @@ size_t sparse_encoder_scratch_bytes(int n, const int32_t* out_sh);
 int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
                       void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+// Observation preparation (observation.cu): triplane.py:105-137
+size_t observation_scratch_bytes(int V, int maxcell);
+int run_prepare_observation(const SherfSmplModel& smpl, const SherfObservation& ob, float* vert_feat, int32_t* coord, uint8_t* vmask_out,
+                            float* bounds_out, int32_t* out_sh_host, float* can_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
 // Importance (fine) pass, importance.cu (renderer.py:373-393, 446-456, 483-542)
 int run_importance_sample(const SherfRays& rays, const int* ray_start, const int* point_sample, const float* sigma, const float* noise,
                           const float* w_in, const float* u, float* t_fine, int* bins_out, float* w_out, cudaStream_t st);

@@ -1,4 +1,5 @@
-"""Thin diagnostics over single kernels of the hot path (used by tests; not a user-facing op library)."""
+"""Functional access to the auxiliary C-ABI entry points: the per-pose SMPL transforms (`sherf_lbs_transforms`), the global depth
+range of a view (`sherf_depth_range`, what ray shards need) and the single-layer diagnostic (`sherf_debug_linear`)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -32,3 +33,41 @@ def linear(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, a
                                 torch.cuda.current_stream(A.device).cuda_stream)
     _lib.check(rc)
     return Y
+
+
+def lbs_transforms(renderer, params: dict) -> torch.Tensor:
+    """The 24 rigid joint transforms A[24,4,4] of one pose through `sherf_lbs_transforms` (replaces get_transform_params_torch,
+    renderer.py:129-157).  `renderer` supplies the SMPL model (ImportanceRenderer.set_smpl_model / assets/SMPL_NEUTRAL.pkl);
+    `params` is an `input_data['params']`-style dict of CUDA tensors (poses [..,72], shapes [..,10], R, Th)."""
+    lib = _lib.load()
+    device = params['poses'].device
+    if device.type != 'cuda':
+        raise RuntimeError('sherf_b200.ops.lbs_transforms runs on CUDA tensors only (no CPU fallback)')
+    with torch.cuda.device(device):
+        keep = []
+        smpl = renderer._smpl_struct(device)
+        pose = renderer._pose_struct(params, device, keep)
+        A = torch.empty(24, 4, 4, device=device, dtype=torch.float32)
+        scratch = torch.empty(4096, dtype=torch.uint8, device=device)
+        _lib.check(lib.sherf_lbs_transforms(C.byref(smpl), C.byref(pose), A.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                            torch.cuda.current_stream(device).cuda_stream))
+        del keep
+    return A
+
+
+def depth_range(near: torch.Tensor, far: torch.Tensor, n_samples: int):
+    """(min, max) of all stratified sample depths of a view through `sherf_depth_range` (torch.min / torch.max(depths),
+    ray_marcher.py:57); near / far: CUDA tensors with one value per ray."""
+    lib = _lib.load()
+    device = near.device
+    if device.type != 'cuda':
+        raise RuntimeError('sherf_b200.ops.depth_range runs on CUDA tensors only (no CPU fallback)')
+    nr, fa = near.detach().float().contiguous(), far.detach().float().contiguous()
+    rays = _lib.SherfRays()
+    rays.near_, rays.far_, rays.n_rays, rays.n_samples = nr.data_ptr(), fa.data_ptr(), nr.numel(), int(n_samples)
+    lo, hi = C.c_float(0), C.c_float(0)
+    with torch.cuda.device(device):
+        scratch = torch.empty(4096, dtype=torch.uint8, device=device)
+        _lib.check(lib.sherf_depth_range(C.byref(rays), C.byref(lo), C.byref(hi), scratch.data_ptr(), scratch.numel(),
+                                         torch.cuda.current_stream(device).cuda_stream))
+    return float(lo.value), float(hi.value)

@@ -20,8 +20,37 @@ import torch.nn as nn
 from . import _lib
 
 import itertools
+import warnings
+import weakref
 
 _WEIGHT_EPOCH = itertools.count(1)       # process-wide: a value is never reused, so a stale arena can never look current
+
+
+class _Runtime:
+    """Per-module, per-process device state: ctypes structs holding raw pointers, the scratch arena, keep-alive lists.  It lives in a
+    module-level WeakKeyDictionary, NOT in the nn.Module's __dict__: the reference deep-copies and pickles the generator every tick
+    (training_loop.py:196,572-579), and ctypes structures with pointers cannot be pickled (and a copied arena would double HBM).
+    A copy / unpickled module simply starts with an empty runtime and rebuilds it lazily on its first forward."""
+    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', '__weakref__')
+
+    def __init__(self):
+        self.smpl_dev = None
+        self.scratch = None
+        self.w_cache = None
+        self.w_epoch = 0
+        self.dbg_keep = None
+        self.faces_dev = None
+        self.obs_scratch = None
+
+
+_RUNTIME = weakref.WeakKeyDictionary()
+
+
+def _runtime(module) -> _Runtime:
+    rt = _RUNTIME.get(module)
+    if rt is None:
+        rt = _RUNTIME[module] = _Runtime()
+    return rt
 
 PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3, 'bf16x3': _lib.MLP_BF16X3,
               '_tf32x3_tmem_a': 99}      # diagnostic: 3xTF32 with the A_lo operand in tensor memory (sherf_debug_linear only)
@@ -141,7 +170,6 @@ class SparseConvNet(nn.Module):
         self.conv2, self.down2 = _sp_block(64, 64, 3), _sp_block(64, 96, 1)
         self.conv3, self.down3 = _sp_block(96, 96, 3), _sp_block(96, 96, 1)
         self.conv4 = _sp_block(96, 96, 3)
-        self._scratch = None
 
     def _convs(self):
         """(conv container, BatchNorm1d, kind) x 13 in execution order for num_layers = 4 (down3 / conv4 outputs are never used)."""
@@ -184,10 +212,11 @@ class SparseConvNet(nn.Module):
                     dims = [(d + 2 - 3) // 2 + 1 for d in dims]
                 vols.append(torch.empty(1, ch, *dims, device=device, dtype=torch.float32))
             need = lib.sherf_sparse_encoder_scratch_bytes(n, sh)
-            if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
-                self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+            rt = _runtime(self)
+            if rt.scratch is None or rt.scratch.numel() < need or rt.scratch.device != device:
+                rt.scratch = torch.empty(need, dtype=torch.uint8, device=device)
             _lib.check(lib.sherf_sparse_encode(C.byref(enc), coord.data_ptr(), feats.data_ptr(), n, sh, vols[0].data_ptr(), vols[1].data_ptr(),
-                                               vols[2].data_ptr(), self._scratch.data_ptr(), self._scratch.numel(),
+                                               vols[2].data_ptr(), rt.scratch.data_ptr(), rt.scratch.numel(),
                                                torch.cuda.current_stream(device).cuda_stream))
         del keep
         return vols
@@ -228,14 +257,10 @@ class ImportanceRenderer(nn.Module):
         self.view_enc = PositionalEncoding(num_freqs=4)
         # SMPL model: same default location as renderer.py:283; tests and the bench inject a synthetic body.
         self.SMPL_NEUTRAL = None
-        self._smpl_dev = None
         if smpl_model is not None:
             self.set_smpl_model(smpl_model)
         elif os.path.exists(os.path.join('assets', 'SMPL_NEUTRAL.pkl')):
             self.set_smpl_model(read_pickle(os.path.join('assets', 'SMPL_NEUTRAL.pkl')))
-        self._scratch = None
-        self._w_epoch = 0
-        self._dbg_keep = None
         self.last_num_points = 0
         self.last_num_fine_points = 0
         self.last_launches = 0
@@ -243,12 +268,23 @@ class ImportanceRenderer(nn.Module):
     # -- configuration ------------------------------------------------------------------------------------------
     def set_smpl_model(self, model: dict):
         self.SMPL_NEUTRAL = SMPL_to_tensor(model, device='cpu')
-        self._smpl_dev = None
+        _runtime(self).smpl_dev = None
+
+    def invalidate_weights(self):
+        """Forget the cached SherfWeights struct and the packed weight blobs in the arena: the next forward re-reads every parameter
+        and re-packs.  Needed only after a write the signature below cannot see (it covers object identity, `_version`, `data_ptr`,
+        dtype and device, i.e. optimizer steps, `.data = ...`, `.to()`, `load_state_dict`, `copy_params_and_buffers`); an in-place
+        write through `.data` (`p.data.add_(...)`) bumps neither, so forward() re-packs on every call while the module is in
+        training mode or any hot-path parameter requires grad, and this method is the explicit hook for the rest."""
+        rt = _runtime(self)
+        rt.w_cache = None
+        rt.w_epoch = next(_WEIGHT_EPOCH)
 
     def _smpl_struct(self, device):
         if self.SMPL_NEUTRAL is None:
             raise RuntimeError('no SMPL model: put assets/SMPL_NEUTRAL.pkl in the cwd or call set_smpl_model()')
-        if self._smpl_dev is None or self._smpl_dev[0] != device:
+        rt = _runtime(self)
+        if rt.smpl_dev is None or rt.smpl_dev[0] != device:
             m = self.SMPL_NEUTRAL
             keep = {k: _dev32(m[k], device) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights')}
             st = _lib.SherfSmplModel()
@@ -258,8 +294,8 @@ class ImportanceRenderer(nn.Module):
             for j in range(24):
                 st.parents[j] = 0 if j == 0 else int(par[j])
             st.n_verts = keep['v_template'].shape[0]
-            self._smpl_dev = (device, keep, st)
-        return self._smpl_dev[2]
+            rt.smpl_dev = (device, keep, st)
+        return rt.smpl_dev[2]
 
     def _check_supported(self):
         if not (self.use_1d_feature and self.use_2d_feature and self.use_3d_feature and self.use_trans and self.use_NeRF_decoder):
@@ -284,11 +320,13 @@ class ImportanceRenderer(nn.Module):
         return slots
 
     def _weights_struct(self, decoder, device, keep):
-        # the struct (and the packed copies in the arena) stay valid while no parameter was re-assigned (object identity) or
-        # modified in place (_version, bumped by every in-place op such as an optimizer step)
+        # the struct (and the packed copies in the arena) stay valid while no parameter was re-assigned (object identity), modified
+        # in place (_version, bumped by every in-place op such as an optimizer step) or re-bound to other storage (`p.data = t`,
+        # module.to()/.float(): data_ptr / dtype / device).  In-place writes THROUGH `.data` bump nothing: see invalidate_weights().
         slots = self._weight_slots(decoder)
-        sig = (device,) + tuple((id(d[n]), d[n]._version) for d, n in slots)
-        cached = getattr(self, '_w_cache', None)
+        sig = (device,) + tuple((id(d[n]), d[n]._version, d[n].data_ptr(), d[n].dtype, d[n].device) for d, n in slots)
+        rt = _runtime(self)
+        cached = rt.w_cache
         if cached is not None and cached[0] == sig:
             return cached[1]
         keep = []
@@ -313,8 +351,8 @@ class ImportanceRenderer(nn.Module):
         w.feature_w, w.feature_b = P(), P()
         w.views_w, w.views_b = P(), P()
         w.rgb_w, w.rgb_b = P(), P()
-        self._w_cache = (sig, w, keep, [d[n] for d, n in slots])      # keeps the parameter objects alive, so ids cannot be recycled
-        self._w_epoch = next(_WEIGHT_EPOCH)          # parameters (re)bound or modified: the packed copies in the arena are stale
+        rt.w_cache = (sig, w, keep, [d[n] for d, n in slots])      # keeps the parameter objects alive, so ids cannot be recycled
+        rt.w_epoch = next(_WEIGHT_EPOCH)          # parameters (re)bound or modified: the packed copies in the arena are stale
         return w
 
     @staticmethod
@@ -325,6 +363,72 @@ class ImportanceRenderer(nn.Module):
             keep.append(t)
             setattr(p, name, _ptr(t))
         return p
+
+    # -- once per observation image (triplane.py:105-137) ----------------------------------------------------------------
+    def _faces_struct(self, device):
+        """SMPL faces as int32 and, per corner slot, the last face listing each vertex (see SherfObservation.last_face)."""
+        rt = _runtime(self)
+        if rt.faces_dev is None or rt.faces_dev[0] != device:
+            f = self.SMPL_NEUTRAL['f'].cpu().numpy().astype(np.int64)
+            V = int(self.SMPL_NEUTRAL['v_template'].shape[0])
+            last = np.full((3, V), -1, np.int32)
+            for k in range(3):
+                last[k, f[:, k]] = np.arange(f.shape[0], dtype=np.int32)           # numpy fancy assignment: last occurrence wins
+            rt.faces_dev = (device, torch.from_numpy(f.astype(np.int32)).to(device).contiguous(), torch.from_numpy(last).to(device).contiguous())
+        return rt.faces_dev[1], rt.faces_dev[2]
+
+    def prepare_observation(self, input_data, obs_input_img, obs_input_feature, projection_conv, return_canonical: bool = False):
+        """Everything TriPlaneGenerator.synthesis derives from the observation before the render call (triplane.py:105-137), on the
+        device through `sherf_prepare_observation`: per-vertex pixel-aligned features -> Conv1d(96,32,1) (`projection_conv`, the
+        generator's own conv1d_projection) masked by visibility, canonical-pose vertices, 5 mm voxel coordinates and the box.
+        Returns (SparseConvTensor, obs_sp_input dict, obs_smpl_vertex_mask [1,V] bool) -- the three arguments `forward` takes as
+        canonical_sp_conv_volume / obs_sp_input / obs_smpl_vertex_mask."""
+        lib = _lib.load()
+        device = obs_input_img.device
+        if device.type != 'cuda':
+            raise RuntimeError('sherf_b200.ImportanceRenderer.prepare_observation runs on CUDA tensors only (no CPU fallback)')
+        if obs_input_img.shape[0] != 1:
+            raise NotImplementedError('per-GPU batch must be 1, as in the renderer (renderer.py:320-321)')
+        keep = []
+        with torch.cuda.device(device):
+            smpl = self._smpl_struct(device)
+            V = smpl.n_verts
+            ob = _lib.SherfObservation()
+            ob.obs = self._pose_struct(input_data['obs_params'], device, keep)
+            ob.canonical = self._pose_struct(input_data['t_params'], device, keep)
+            for name, key in (('obs_vertices', 'obs_vertices'), ('t_vertices', 't_vertices'), ('obs_K', 'obs_K_all'), ('obs_R', 'obs_R_all'),
+                              ('obs_T', 'obs_T_all')):
+                t = _dev32(input_data[key], device); keep.append(t)
+                setattr(ob, name, _ptr(t))
+            faces, last = self._faces_struct(device)
+            ob.faces, ob.last_face, ob.n_faces = _ptr(faces), _ptr(last), faces.shape[0]
+            im = _dev32(obs_input_img, device); keep.append(im)
+            ob.obs_img, ob.img_h, ob.img_w = _ptr(im), im.shape[-2], im.shape[-1]
+            ft = _dev32(obs_input_feature, device); keep.append(ft)
+            ob.obs_feat, ob.feat_ch, ob.feat_h, ob.feat_w = _ptr(ft), ft.shape[-3], ft.shape[-2], ft.shape[-1]
+            pw, pb = _dev32(projection_conv.weight, device), _dev32(projection_conv.bias, device)
+            keep += [pw, pb]
+            ob.proj_w, ob.proj_b = _ptr(pw), _ptr(pb)
+            feat = torch.empty(V, 32, device=device, dtype=torch.float32)
+            coord = torch.empty(V, 4, device=device, dtype=torch.int32)
+            vmask = torch.empty(V, device=device, dtype=torch.uint8)
+            bounds = torch.empty(1, 2, 3, device=device, dtype=torch.float32)
+            can = torch.empty(1, V, 3, device=device, dtype=torch.float32) if return_canonical else None
+            out_sh = (C.c_int32 * 3)()
+            rt = _runtime(self)
+            need = lib.sherf_observation_scratch_bytes(V)
+            if rt.obs_scratch is None or rt.obs_scratch.numel() < need or rt.obs_scratch.device != device:
+                rt.obs_scratch = torch.empty(need, dtype=torch.uint8, device=device)
+            _lib.check(lib.sherf_prepare_observation(C.byref(smpl), C.byref(ob), feat.data_ptr(), coord.data_ptr(), vmask.data_ptr(),
+                                                     bounds.data_ptr(), out_sh, can.data_ptr() if can is not None else None,
+                                                     rt.obs_scratch.data_ptr(), rt.obs_scratch.numel(),
+                                                     torch.cuda.current_stream(device).cuda_stream))
+            del keep
+        sp_input = {'coord': coord, 'out_sh': [int(out_sh[0]), int(out_sh[1]), int(out_sh[2])], 'batch_size': 1, 'bounds': bounds}
+        vol = SparseConvTensor(feat, coord, sp_input['out_sh'], 1)
+        if return_canonical:
+            return vol, sp_input, vmask.bool().view(1, V), can
+        return vol, sp_input, vmask.bool().view(1, V)
 
     # -- the hot path ----------------------------------------------------------------------------------------------
     def forward(self, planes, obs_input_img, obs_input_feature, canonical_sp_conv_volume, obs_smpl_vertex_mask, obs_sp_input,
@@ -394,6 +498,14 @@ class ImportanceRenderer(nn.Module):
                     sc.vol_dim[l][a] = v.shape[2 + a]
 
             w = self._weights_struct(decoder, device, keep)
+            hot_params = _runtime(self).w_cache[3]
+            wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in hot_params)
+            volatile_weights = self.training or decoder.training or wants_grad
+            if wants_grad and not getattr(self, '_warned_no_grad', False):
+                warnings.warn('sherf_b200.ImportanceRenderer.forward is the inference kernel: its outputs carry no autograd graph. '
+                              'Use sherf_b200.autograd.render_with_grad (or wrap the call in torch.no_grad()) when gradients are needed.',
+                              stacklevel=2)
+                self._warned_no_grad = True
             rays = _lib.SherfRays()
             ro, rd = _dev32(ray_origins, device), _dev32(ray_directions, device)
             nr, fa = _dev32(near, device), _dev32(far, device)
@@ -427,12 +539,15 @@ class ImportanceRenderer(nn.Module):
             out = _lib.SherfOut(_ptr(rgb), _ptr(depth), _ptr(acc))
 
             need = lib.sherf_scratch_bytes(C.byref(sc), N, S, SF, smpl.n_verts)
-            if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
-                self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
-                self._w_epoch = next(_WEIGHT_EPOCH)      # new arena: nothing is packed in it yet
+            rt = _runtime(self)
+            if rt.scratch is None or rt.scratch.numel() < need or rt.scratch.device != device:
+                rt.scratch = torch.empty(need, dtype=torch.uint8, device=device)
+                rt.w_epoch = next(_WEIGHT_EPOCH)      # new arena: nothing is packed in it yet
             # the packed weight blobs of the previous call are reused while no parameter was re-assigned or written in place
-            # (data_ptr / _version signature above); SHERF_NO_PACK_REUSE=1 packs on every call
-            opts.weights_version = self._w_epoch
+            # (identity / _version / data_ptr signature above); SHERF_NO_PACK_REUSE=1 packs on every call.  While training (module
+            # in training mode, or a hot-path parameter requires grad) reuse is off: EMA / clamp / init code writes through `.data`,
+            # which no signature can see (weights_version 0 = "pack on this call").
+            opts.weights_version = 0 if volatile_weights else rt.w_epoch
 
             dbg_p = None
             if debug is not None:
@@ -458,12 +573,12 @@ class ImportanceRenderer(nn.Module):
                 d.max_points = NS
                 d.max_feat_points = cap_feat
                 dbg_p = C.byref(d)
-                self._dbg_keep = (d, bufs)
+                rt.dbg_keep = (d, bufs)
 
             npts = C.c_int64(0)
             stream = torch.cuda.current_stream(device).cuda_stream
             rc = lib.sherf_render_forward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(opts),
-                                          C.byref(out), dbg_p, self._scratch.data_ptr(), self._scratch.numel(), stream,
+                                          C.byref(out), dbg_p, rt.scratch.data_ptr(), rt.scratch.numel(), stream,
                                           C.byref(npts))
             _lib.check(rc)
             self.last_num_points = int(npts.value)                               # coarse + fine survivors
@@ -471,7 +586,7 @@ class ImportanceRenderer(nn.Module):
             self.last_launches = int(lib.sherf_last_launch_count())
             if debug is not None:
                 Pn = self.last_num_points - self.last_num_fine_points          # point-indexed taps describe the coarse pass
-                for k, v in self._dbg_keep[1].items():
+                for k, v in rt.dbg_keep[1].items():
                     debug[k] = v if (k == 'sample_vid' or k.startswith('fine_') or k == 'coarse_weights') else v[:min(Pn, v.shape[0])]
                 debug['num_points'] = Pn
                 debug['num_fine_points'] = self.last_num_fine_points

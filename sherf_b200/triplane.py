@@ -48,4 +48,4 @@ def hot_path_modules(smpl_model: dict | None = None, seed: int = 0, mlp_precisio
         with torch.no_grad():
             dec.alpha_linear.weight *= 30
             dec.alpha_linear.bias += 2.0
-    return ren.eval(), dec.eval()
+    return ren.eval().requires_grad_(False), dec.eval().requires_grad_(False)

@@ -32,12 +32,12 @@ def test_exports_every_declared_symbol(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f'{n} declared in the header but not exported'
-    assert lib.sherf_abi_version() == 2
+    assert lib.sherf_abi_version() == 3
 
 
 def test_struct_layouts_match_header(tmp_path):
     structs = ['SherfSmplModel', 'SherfPose', 'SherfFrame', 'SherfScene', 'SherfWeights', 'SherfRays', 'SherfOptions', 'SherfOut',
-               'SherfDebug', 'SherfSparseConv', 'SherfSparseEncoder']
+               'SherfDebug', 'SherfSparseConv', 'SherfSparseEncoder', 'SherfObservation']
     prog = '#include <stdio.h>\n#include "sherf_b200.h"\nint main(){' + ''.join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + 'return 0;}'
     c = tmp_path / 'sz.c'
@@ -161,5 +161,30 @@ def test_plain_c_client_binds_the_library(tmp_path, lib):
     subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.dirname(HEADER), src, '-o', str(exe), '-ldl'], check=True)
     r = subprocess.run([str(exe), _lib.lib_path()], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert r.stdout.startswith('ok abi=2')
+    assert r.stdout.startswith('ok abi=3')
     print(r.stdout.strip())
+
+
+def test_modules_deepcopy_and_pickle_without_runtime_state(smpl_model):
+    """training_loop.py:196,572-579: the generator is deep-copied and pickled every tick.  Device-side state (ctypes structs with raw
+    pointers, the scratch arena) lives outside the modules' __dict__ (renderer._RUNTIME), so it can never leak into a copy."""
+    import copy
+    import pickle
+    from sherf_b200 import renderer as R
+    from sherf_b200.triplane import hot_path_modules
+    ren, dec = hot_path_modules(smpl_model)
+    rt = R._runtime(ren)
+    rt.smpl_dev = ('cuda:0', [], _lib.SherfSmplModel())                      # what a forward leaves behind
+    rt.w_cache = ((), _lib.SherfWeights(), [], [])
+    rt.scratch = torch.empty(16, dtype=torch.uint8)
+    with pytest.raises(ValueError):
+        pickle.dumps(rt.w_cache[1])                                          # the reason they must stay out of the module
+    ren2 = copy.deepcopy(ren)
+    ren3 = pickle.loads(pickle.dumps(ren))
+    for r in (ren2, ren3):
+        assert R._runtime(r).scratch is None and R._runtime(r).w_cache is None and R._runtime(r).smpl_dev is None
+        assert set(r.state_dict()) == set(ren.state_dict())
+        assert all(torch.equal(v, r.state_dict()[k]) for k, v in ren.state_dict().items())
+    assert not any(isinstance(v, ctypes.Structure) for v in vars(ren).values())
+    ren.invalidate_weights()
+    assert R._runtime(ren).w_cache is None

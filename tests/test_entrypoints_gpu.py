@@ -1,0 +1,134 @@
+"""GPU tests of the auxiliary C-ABI entry points and of the module-level contract of the boundary:
+ * sherf_lbs_transforms  vs  the oracle's restatement of get_transform_params_torch (renderer.py:129-157),
+ * sherf_depth_range     vs  torch.min / torch.max over the materialised depths (ray_marcher.py:57),
+ * copy.deepcopy / pickle of the modules AFTER a forward (training_loop.py:196,572-579) render identically,
+ * parity with the oracle under weights far from PyTorch's default init (scaled / heavy-tailed), all precisions."""
+import copy
+import io
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import scene_to
+from sherf_b200 import ops, synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(ren, dec, scene, **kw):
+    return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+               dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'],
+               scene['rendering_options'], **kw)
+
+
+@pytest.mark.parametrize('seed', [0, 3])
+def test_lbs_transforms_against_port(seed, smpl_model, smpl_model_t):
+    from oracle import port
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    ren, _ = hot_path_modules(smpl_model)
+    scene = S.make_scene(S.SceneSpec(H=4, W=4, samples=4, seed=seed, random_global_R=bool(seed)), smpl_model)
+    for key in ('params', 't_params', 'obs_params'):
+        p = scene['input_data'][key]
+        want = port.lbs_transforms(smpl_model_t, p['poses'].reshape(-1), p['shapes'].reshape(-1))
+        got = ops.lbs_transforms(ren, {k: v.to(dev) for k, v in p.items()}).cpu()
+        err = float((got - want).abs().max())
+        print(f'\n[lbs {key} seed {seed}] max |A - oracle| = {err:.2e}')
+        assert got.shape == (24, 4, 4)
+        assert err <= 2e-6                                          # fp32, 24-joint chain of 4x4 products
+        assert torch.equal(got[:, 3], torch.tensor([0., 0., 0., 1.]).expand(24, 4))
+
+
+@pytest.mark.parametrize('shape', [(64, 64, 16), (45, 38, 24), (512, 512, 64)])
+def test_depth_range_against_torch(shape, smpl_model):
+    from sherf_b200.dist import depth_range as host_range
+    H, W, S_ = shape
+    dev = torch.device('cuda:0')
+    scene = S.make_scene(S.SceneSpec(H=H, W=W, samples=S_, seed=1), smpl_model)
+    near, far = scene['near'], scene['far']
+    # the reference's own arithmetic (math_utils.py:101-118 via renderer.py:458-481), materialised
+    steps = torch.arange(S_, dtype=torch.float32) / (S_ - 1)
+    depths = near[0] + steps[None, :] * (far[0] - near[0])
+    want = (float(depths.min()), float(depths.max()))
+    got = ops.depth_range(near.to(dev), far.to(dev), S_)
+    assert got == want, (got, want)
+    assert host_range(near, far, S_) == want
+
+
+def test_module_survives_deepcopy_and_pickle_after_forward(smpl_model):
+    """training_loop.py:196 deep-copies the generator, :572-579 pickles it every tick: the module must not carry ctypes structs
+    or the scratch arena in its state, and a copy must render bit-identically (lazily rebuilding its own runtime)."""
+    from sherf_b200 import renderer as R
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=24, W=24, samples=16, seed=2), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=3, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    a = run_cuda(ren, dec, scene, debug={})
+    assert R._runtime(ren).scratch is not None and R._runtime(ren).w_cache is not None
+    ren2, dec2 = copy.deepcopy(ren), copy.deepcopy(dec)
+    assert R._runtime(ren2).scratch is None, 'a copy must not inherit (or duplicate) the arena'
+    buf = io.BytesIO()
+    pickle.dump({'ren': ren, 'dec': dec}, buf)
+    buf.seek(0)
+    back = pickle.load(buf)
+    for r_, d_ in ((ren2, dec2), (back['ren'], back['dec'])):
+        b = run_cuda(r_, d_, scene)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # .data rebinding / module.float() do not bump _version: the data_ptr part of the signature must catch them
+    with torch.no_grad():
+        dec.rgb_linear.bias.data = dec.rgb_linear.bias.data + 0.5
+    c = run_cuda(ren, dec, scene)
+    assert float((c[0] - a[0]).abs().max()) > 1e-3
+    with torch.no_grad():
+        dec.rgb_linear.bias.data.sub_(0.5)                           # in-place through .data: invisible -> explicit hook
+    ren.invalidate_weights()
+    d = run_cuda(ren, dec, scene)
+    assert all(torch.allclose(x, y, atol=1e-6) for x, y in zip(a, d))
+
+
+def _heavy_tailed(ren, dec, seed):
+    """Hot-path weights far from default init: every weight matrix scaled by 3 and multiplied elementwise by a log-normal factor
+    (heavy right tail), biases tripled; the density head is rescaled so that the body stays semi-opaque."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in (ren.conv1d_projection, ren.conv1d_reprojection, ren.transformer, dec):
+            for n, p in mod.named_parameters():
+                if p.dim() >= 2:
+                    p.mul_(torch.exp(0.7 * torch.randn(p.shape, generator=g)) * (3.0 if 'pts_linears' not in n else 1.6))
+                elif 'norm' not in n:
+                    p.mul_(3.0)
+        dec.alpha_linear.weight.mul_(0.01)
+        dec.alpha_linear.bias.mul_(0.1)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'bf16x3'])
+def test_heavy_tailed_weights_against_port(precision, smpl_model, smpl_model_t):
+    from oracle import port
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    ren, dec = hot_path_modules(smpl_model, seed=11, mlp_precision=precision, dense_sigma=True)
+    _heavy_tailed(ren, dec, 5)
+    w = port.hot_path_state_dict(ren, dec)
+    cpu_scene = S.make_scene(S.SceneSpec(H=40, W=40, samples=24, seed=8), smpl_model)
+    prgb, pdepth, pacc, st = port.render_forward(w, smpl_model_t, cpu_scene, return_stages=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dbg = {}
+    rgb, depth, acc = run_cuda(ren, dec, scene_to(cpu_scene, dev), debug=dbg)
+    sig_o = st['sigma'] if 'sigma' in st else None
+    e_rgb = float((rgb.cpu() - prgb).abs().max())
+    e_acc = float((acc.cpu() - pacc).abs().max())
+    span = float((cpu_scene['far'] - cpu_scene['near']).abs().max())
+    e_depth = float((depth.cpu() - pdepth).abs().max()) / span
+    msg = f'\n[heavy-tailed {precision}] P={dbg["num_points"]} rgb={e_rgb:.2e} acc={e_acc:.2e} depth/span={e_depth:.2e}'
+    if sig_o is not None:
+        sig_o = sig_o.reshape(-1)
+        e_sig = float(((dbg['point_sigma'].cpu() - sig_o).abs() / (sig_o.abs() + 1)).max())
+        msg += f' sigma_rel={e_sig:.2e} |sigma|max={float(sig_o.abs().max()):.1f}'
+        assert e_sig <= 2e-3
+    print(msg)
+    bad = ((rgb.cpu() - prgb).abs().amax(-1) > 1e-4).float().mean()
+    assert float(bad) <= 2e-3, f'{float(bad):.4%} of rays exceed 1e-4'
+    assert e_depth <= 1e-3

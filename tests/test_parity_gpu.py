@@ -62,6 +62,7 @@ def test_against_reference_golden(case, precision, smpl_model):
     k = g['f2d_head'].shape[0]
     okk = ok[:k]
     feat = dbg['point_feat'].cpu()[:k]
+    e_tri = linf(feat[:, 0:96], torch.from_numpy(g['tri_head']))            # tri-plane taps depend on the canonical point only (a11)
     e_f2d = linf(feat[:, 96:192][okk], torch.from_numpy(g['f2d_head'])[okk])
     e_f3 = linf(feat[:, 192:384], torch.from_numpy(g['f3raw_head']))
     e_tok = linf(dbg['point_tok'].cpu()[:k][okk], torch.from_numpy(g['tok01_head'])[okk])
@@ -73,17 +74,21 @@ def test_against_reference_golden(case, precision, smpl_model):
     e_acc = linf(acc.cpu()[0], torch.from_numpy(g['acc']))
     span = float((scene['far'] - scene['near']).abs().max())
     e_depth = linf(depth.cpu()[0], torch.from_numpy(g['depth'])) / span
-    print(f'\n[{case} {precision}] P={dbg["num_points"]} id3-match={rate3:.5f} can={e_can:.2e} dir={e_dir:.2e} uv={e_uv:.2e} f2d={e_f2d:.2e} '
+    print(f'\n[{case} {precision}] P={dbg["num_points"]} id3-match={rate3:.5f} can={e_can:.2e} dir={e_dir:.2e} uv={e_uv:.2e} tri={e_tri:.2e} f2d={e_f2d:.2e} '
           f'f3d={e_f3:.2e} tok={e_tok:.2e} sigma={e_sig:.2e} rgb_pt={e_rgbp:.2e} | rgb={e_rgb:.2e} acc={e_acc:.2e} depth/span={e_depth:.2e}')
     assert rate3 >= 0.999
     assert e_can <= 5e-6 and e_dir <= 5e-6
     assert e_uv <= 2e-3
-    assert e_f2d <= 1e-3 and e_f3 <= 5e-4 and e_tok <= 1e-3
+    assert e_tri <= 5e-4 and e_f2d <= 1e-3 and e_f3 <= 5e-4 and e_tok <= 1e-3
     assert e_sig <= 2e-3 and e_rgbp <= 2e-5
     # final image: a flipped knn-#3 tie changes one point's 2-D feature; allow it to show on < 0.1 % of the rays
     bad = ((rgb.cpu()[0] - torch.from_numpy(g['rgb'])).abs().amax(-1) > 1e-4).float().mean()
     assert float(bad) <= 1e-3, f'{float(bad):.4%} of rays exceed 1e-4 (max {e_rgb:.2e})'
-    assert e_acc <= 1e-4 or float(bad) > 0
+    # acc depends on the densities only; a flipped knn-#3 tie reaches sigma through tok0, so the same < 0.1 % ray allowance applies
+    bad_acc = ((acc.cpu()[0] - torch.from_numpy(g['acc'])).abs()[:, 0] > 1e-4).float().mean()
+    assert float(bad_acc) <= 1e-3, f'{float(bad_acc):.4%} of rays exceed 1e-4 on acc (max {e_acc:.2e})'
+    if rate3 == 1.0:
+        assert e_rgb <= 1e-4 and e_acc <= 1e-4                        # no flipped tie: every ray is within tolerance
     assert e_depth <= 1e-3
 
 
@@ -256,7 +261,7 @@ def test_full_size_ray_subset_against_port(name, smpl_model, smpl_model_t):
     print(f'\n[{name}] {idx.numel()} oracle rays, hit fraction {float((pacc[0] > 0).float().mean()):.3f}: rgb={linf(rgb, prgb):.2e} acc={linf(acc, pacc):.2e} '
           f'depth/span={float(((depth[0] - pdepth[0]).abs() / span).max()):.2e} bad rays {float(bad.float().mean()):.4%} PSNR={psnr:.1f} dB')
     assert float((pacc[0] > 0).float().mean()) > 0.05                  # the subset actually sees the body
-    assert float(bad.float().mean()) <= (0.02 if n_imp else 2e-3)
+    assert float(bad.float().mean()) <= 2e-3                          # 0.2 % of the oracle rays, with or without the importance pass
 
 
 def run_cuda_kw(ren, dec, scene, **kw):
