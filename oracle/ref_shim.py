@@ -29,11 +29,20 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = '/root/reference/sherf'
+# the mounted reference where it exists (build container); else the byte-identical copies oracle/make_ref.py left in oracle/_ref/
+# (git-ignored, shipped to the GPU box with the snapshot)
+_MOUNTED = '/root/reference/sherf'
+_COPIED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'sherf')
+REF_ROOT = _MOUNTED if os.path.isdir(os.path.join(_MOUNTED, 'training', 'volumetric_rendering')) else _COPIED
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, 'training', 'volumetric_rendering'))
+
+
+def mounted() -> bool:
+    """True where the full reference tree is mounted (tests that need more than the hot-path closure skip otherwise)."""
+    return REF_ROOT == _MOUNTED
 
 
 def knn_points_bruteforce(p1, p2, K=1, chunk=4096, **_):
@@ -108,7 +117,9 @@ def load(smpl_model_torch: dict):
     sys.modules.update({'spconv': spr, 'spconv.pytorch': sp, 'spconv.core': core})
     sys.modules.setdefault('imageio', types.ModuleType('imageio'))
 
-    if not torch.cuda.is_available():
+    if not torch.cuda.is_available() or os.environ.get('SHERF_REF_FORCE_CPU') == '1':
+        # shim 3: the reference hard-codes .cuda(); on a CPU-only box, or when its CPU path is being timed on a GPU box
+        # (SHERF_REF_FORCE_CPU=1: bench.py --impl reference, always in its own process), .cuda() is the identity
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.cuda.current_device = lambda: 0
 

@@ -13,7 +13,7 @@ from conftest import ROOT
 from oracle import ref_shim
 
 
-@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present')
+@pytest.mark.skipif(not ref_shim.mounted(), reason='the full reference tree (backbone, super-resolution, dnnlib) is not mounted here')
 def test_overlay_generator_matches_reference_names_and_resumes():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'helpers', 'overlay_vs_reference.py')], capture_output=True, text=True,
                        timeout=1200, cwd=ROOT)
