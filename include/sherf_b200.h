@@ -142,6 +142,10 @@ typedef struct SherfOptions {
                                  mlp_precision and shapes with the same non-zero value; the packed copies made by that call are then
                                  reused (the reference keeps its nn.Parameters as they are between calls, too).  Change the value
                                  whenever a parameter is written or the arena is re-allocated. */
+  uint64_t scene_version;     /* same contract for SherfScene: non-zero and unchanged since the previous call on this arena = the feature
+                                 tensors (planes, 2-D map, volumes) are unchanged, so the channels-last copies the arena holds (312 MB at
+                                 512x512) are reused instead of re-made -- the "prepare once per observation, render many views" split of
+                                 SURVEY.md 8b (orbit views, ray shards, streamed poses).  0 = copy on every call. */
 } SherfOptions;
 
 /* Outputs of forward (renderer.py:398): rgb in (-1,1), depth, accumulated weight. */

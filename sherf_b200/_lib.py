@@ -54,7 +54,7 @@ class SherfRays(C.Structure):
 class SherfOptions(C.Structure):
     _fields_ = [('white_back', C.c_int32), ('mlp_precision', C.c_int32), ('depth_clamp_min', C.c_float),
                 ('depth_clamp_max', C.c_float), ('use_external_clamp', C.c_int32), ('density_noise', c_float_p),
-                ('importance_u', c_float_p), ('density_noise_importance', c_float_p), ('weights_version', C.c_uint64)]
+                ('importance_u', c_float_p), ('density_noise_importance', c_float_p), ('weights_version', C.c_uint64), ('scene_version', C.c_uint64)]
 
 
 class SherfOut(C.Structure):

@@ -63,6 +63,7 @@ struct Layout {
   float* canon_w;
   unsigned char* fused_blob; float* fused_bias; float* xf_blob; float* ff_blob;
   unsigned char* pp_blob; float* pp_bias; unsigned char* pp_xv;
+  unsigned char* xb_blob; unsigned char* fr_blob;
   float* chunk;
   float* gather2;        // second set of gather outputs (comb | f3raw | geo) for the gather / MLP overlap
   float* lbs_joints; float* lbs_pf;
@@ -134,6 +135,8 @@ static size_t carve(Arena& a, const SherfScene& sc, int N, int S, int SF, int V,
   L.pp_bias = a.take<float>(10 * 128);
   L.pp_xv = a.take<unsigned char>(pp_xv_bytes(cap));
   L.gather2 = a.take<float>((size_t)cap * (288 + 192 + 8));
+  L.xb_blob = a.take<unsigned char>(xformer_bf16_blob_bytes());
+  L.fr_blob = a.take<unsigned char>(front_blob_bytes());
   return a.off;
 }
 
@@ -181,7 +184,7 @@ struct StageTimer {
 static thread_local StageTimer* g_tm = nullptr;
 
 // Packed-weight reuse (SherfOptions.weights_version): identity of the packed blobs currently held by a scratch arena
-struct PackTag { const void* base = nullptr; size_t need = 0; uint64_t version = 0; int precision = -1; int dev = -1; };
+struct PackTag { const void* base = nullptr; size_t need = 0; uint64_t version = 0; int precision = -1; int dev = -1; uint64_t scene = 0; };
 static thread_local PackTag g_pack_tag;
 
 // Pinned host words for the survivor counts: a device-to-host cudaMemcpyAsync into PAGEABLE memory blocks the calling thread until the
@@ -190,6 +193,18 @@ static int64_t* pinned_counts() {
   static thread_local int64_t* p = nullptr;
   if (!p && cudaHostAlloc((void**)&p, 4 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
   return p;
+}
+
+// Events recorded right after the survivor-count copies: the host waits on THEM, not on the stream, so the first chunk of the point stages
+// (issued earlier with a device-side count) keeps the GPU busy while the host learns P.
+static cudaEvent_t count_event(int which) {
+  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+  static thread_local int dev = -1;
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) return nullptr;
+  if (d != dev) { ev[0] = ev[1] = nullptr; dev = d; }
+  if (!ev[which] && cudaEventCreateWithFlags(&ev[which], cudaEventDisableTiming) != cudaSuccess) ev[which] = nullptr;
+  return ev[which];
 }
 
 // Internal side stream (per host thread): the warp+gather kernel of chunk i+1 runs concurrently with the persistent MLP
@@ -309,9 +324,16 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   int64_t* hcount = pinned_counts();
   if (!hcount) { set_error("cudaHostAlloc failed for the survivor-count words"); return SHERF_E_CUDA; }
   SHERF_CUDA_OK(cudaMemcpyAsync(&hcount[0], L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  cudaEvent_t ev_cnt0 = count_event(0), ev_cnt1 = count_event(1);
+  if (!ev_cnt0 || !ev_cnt1) { set_error("cudaEventCreate failed"); return SHERF_E_CUDA; }
+  SHERF_CUDA_OK(cudaEventRecord(ev_cnt0, st));
 
   RC(run_prologue_tables(*smpl, *frame, L.ft, ls));
-  {
+  int devid0 = 0;
+  SHERF_CUDA_OK(cudaGetDevice(&devid0));
+  const bool scene_cached = opts->scene_version != 0 && g_pack_tag.scene == opts->scene_version && g_pack_tag.base == (const void*)a.base &&
+                            g_pack_tag.need == need && g_pack_tag.dev == devid0 && !getenv("SHERF_NO_SCENE_REUSE");
+  if (!scene_cached) {
     const size_t plane = (size_t)scene->plane_ch * scene->plane_h * scene->plane_w;
     const float* in[7] = {scene->planes, scene->planes + plane, scene->planes + 2 * plane, scene->obs_feat, scene->vol[0], scene->vol[1], scene->vol[2]};
     float* outp[7] = {L.planes_cl, L.planes_cl + plane, L.planes_cl + 2 * plane, L.feat_cl, L.vol_cl[0], L.vol_cl[1], L.vol_cl[2]};
@@ -320,6 +342,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
                     (int64_t)scene->feat_h * scene->feat_w, 0, 0, 0};
     for (int l = 0; l < 3; ++l) M[4 + l] = (int64_t)scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2];
     RC(run_to_channels_last_multi(7, in, outp, C, M, ls));
+    g_pack_tag.scene = 0;                       // (set below, once the arena identity of this call is recorded)
   }
   // Weight blobs: packed into the arena on this call unless the caller vouches (SherfOptions.weights_version != 0, unchanged since
   // the previous call on this arena, same arithmetic) that the parameters have not changed -- then only the host-side plans are rebuilt.
@@ -327,7 +350,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   CanonWeights cw;
   FusedPlan fplan;
   PpPlan pplan;
-  fplan.pp = nullptr; fplan.xf_blob = nullptr; fplan.ff_blob = nullptr; fplan.blob = nullptr; fplan.bias = nullptr;
+  fplan.pp = nullptr; fplan.xf_blob = nullptr; fplan.ff_blob = nullptr; fplan.blob = nullptr; fplan.bias = nullptr; fplan.xb_blob = nullptr; fplan.fr_blob = nullptr;
   const bool use_fused = opts->mlp_precision != SHERF_MLP_FP32 && !getenv("SHERF_NO_FUSED_DECODER");
   const bool fuse_ff = use_fused && !getenv("SHERF_NO_FUSED_FUSION"), fuse_xf = use_fused && !getenv("SHERF_NO_FUSED_XFORMER");
   const bool use_pp = use_fused && opts->mlp_precision == SHERF_MLP_BF16X3;
@@ -349,74 +372,96 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
       pplan.xp = L.pp_xv;
       pplan.vp = L.pp_xv + (size_t)((cap + 127) / 128) * 40960;
       fplan.pp = &pplan;
+      if (!rc && fuse_xf && !getenv("SHERF_LEGACY_XFORMER")) {              // bf16 split-product transformer, two CTAs per SM
+        if (!reuse) rc = run_pack_xformer_bf16(*weights, L.xb_blob, ls);
+        fplan.xb_blob = L.xb_blob;
+        if (!rc && fuse_ff && !getenv("SHERF_LEGACY_FRONT") && !getenv("SHERF_KNN3_UNSEEDED") && !getenv("SHERF_GATHER_V1")) {
+          if (!reuse) rc = run_pack_front(*weights, L.fr_blob, ls);       // warp + gather + fusion in one kernel (front_fused.cu)
+          fplan.fr_blob = L.fr_blob;
+        }
+      }
     }
     g_pack_plan_only = false;
     if (rc) return rc;
     g_pack_tag.base = a.base; g_pack_tag.need = need; g_pack_tag.version = opts->weights_version; g_pack_tag.precision = opts->mlp_precision;
     g_pack_tag.dev = devid;
+    g_pack_tag.scene = opts->scene_version;
   }
   if (side) SHERF_CUDA_OK(cudaEventRecord(g_side.ldone, ls));
 
+  // ---- stages 2+3 per chunk of surviving points: warp + gather (+ fusion), then transformer / decoder ----
+  ChunkBuffers cb;
+  carve_chunk_buffers(L.chunk, chunk_cap(N, S, SF), cb);
+  ChunkBuffers cbs[2] = {cb, cb};                                   // two sets of gather outputs, everything else shared
+  cbs[1].comb = L.gather2; cbs[1].f3raw = L.gather2 + (size_t)cb.cap * 288; cbs[1].geo = L.gather2 + (size_t)cb.cap * (288 + 192);
+  // one chunk of a compacted point list (coarse: stratified depths; fine: importance-sampled depths): renderer.py:323-362.
+  // dc.total != NULL: the chunk's point count is resolved on the device (np is then the upper bound that sizes the grids)
+  auto issue_chunk = [&](const int* point_sample, const int* point_vid, int64_t p0, int np, int Sn, const float* depths, float* sigma_out,
+                         float* rgb_out, const SherfDebug* d, DevCount dc, int ci, bool overlap, cudaStream_t gs) -> int {
+    const int bsel = overlap ? (ci & 1) : 0;
+    const ChunkBuffers& cbi = cbs[bsel];
+    GatherParams G;
+    G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = Sn; G.depths = depths;
+    G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np; G.dc = dc;
+    G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
+    G.t_vertices = getenv("SHERF_KNN3_UNSEEDED") ? nullptr : frame->t_vertices;
+    G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
+    G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
+    G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;
+    for (int l = 0; l < 3; ++l) {
+      G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
+      G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
+    }
+    G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
+    G.dbg_vid3 = d ? d->point_vid3 : nullptr; G.dbg_can = d ? d->point_can : nullptr;
+    G.dbg_cdir = d ? d->point_cdir : nullptr; G.dbg_uv = d ? d->point_uv : nullptr;
+    G.dbg_feat = d ? d->point_feat : nullptr; G.dbg_max = d ? d->max_points : 0;
+    G.dbg_feat_max = d ? d->max_feat_points : 0;
+    // gather of chunk ci (side stream): its output buffers must have been released by the MLP of chunk ci-2
+    if (overlap && ci >= 2) SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.mdone[bsel], 0));
+    tm.begin(2, gs);
+    if (fplan.fr_blob) RC(run_front_fused(G, *weights, fplan.fr_blob, cbi.tok, gs));     // tokens straight from the gather lanes (no comb / f3raw)
+    else RC(run_point_gather(G, gs));
+    tm.end();
+    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.gdone[bsel], gs)); SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.gdone[bsel], 0)); }
+    tm.begin(3);
+    RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cbi, np, p0, sigma_out, rgb_out, d ? d->point_tok : nullptr,
+               d ? d->max_points : 0, st, nested_begin, nested_end, dc));
+    tm.end();
+    if (overlap) SHERF_CUDA_OK(cudaEventRecord(g_side.mdone[bsel], st));
+    return SHERF_OK;
+  };
+  // chunks [first_p0, Pn) of a pass with the host-side count
+  auto run_points = [&](const int* point_sample, const int* point_vid, int64_t Pn, int64_t first_p0, int Sn, const float* depths, float* sigma_out,
+                        float* rgb_out, const SherfDebug* d) -> int {
+    // measured on B200 (r1): the overlap is neutral (6.98 vs 7.00 ms) -- the gather blocks delay the start of the persistent MLP CTAs
+    // by as much as they hide -- so it is opt-in (SHERF_OVERLAP=1)
+    const bool overlap = first_p0 == 0 && Pn > cb.cap && getenv("SHERF_OVERLAP") && g_side.ensure() == 0;
+    cudaStream_t gs = overlap ? g_side.s : st;
+    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.fork, 0)); }
+    int ci = (int)(first_p0 / cb.cap);
+    for (int64_t p0 = first_p0; p0 < Pn; p0 += cb.cap, ++ci) {
+      const int np = (int)((Pn - p0 < cb.cap) ? (Pn - p0) : cb.cap);
+      RC(issue_chunk(point_sample, point_vid, p0, np, Sn, depths, sigma_out, rgb_out, d, DevCount{nullptr, 0, 0}, ci, overlap, gs));
+    }
+    return SHERF_OK;
+  };
+  // The FIRST chunk of a pass is enqueued before the host knows the survivor count: its kernels resolve min(P, cap) from device memory
+  // (front_fused / xformer_bf16 / decoder_pp, i.e. the default bf16x3 path without debug taps).  The host then waits for the COUNT EVENT
+  // only -- the GPU is already working on chunk 0 -- and enqueues the remaining chunks with exact counts.
+  const bool async_first = fplan.fr_blob && fplan.xb_blob && use_pp && !dbg && !getenv("SHERF_SYNC_FIRST_CHUNK");
+  if (side) SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.ldone, 0));          // layouts + packed weights are ready
+  if (async_first)
+    RC(issue_chunk(L.point_sample, L.point_vid, 0, cb.cap, S, nullptr, L.sigma, L.rgb, nullptr, DevCount{L.total, 0, cb.cap}, 0, false, st));
   const double t_sync0 = now_us();
-  SHERF_CUDA_OK(cudaStreamSynchronize(st));                  // the survivor count P (the cull is done; the side stream may still be running)
+  SHERF_CUDA_OK(cudaEventSynchronize(ev_cnt0));              // the survivor count P (the cull is done; everything enqueued after it may still run)
   const int64_t P = hcount[0];
   const double t_sync1 = now_us();
   if (n_points_out) *n_points_out = P;
   if (dbg && dbg->point_sample && P > 0)
     SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sample, L.point_sample, sizeof(int) * (size_t)(P < dbg->max_points ? P : dbg->max_points),
                                   cudaMemcpyDeviceToDevice, st));
-
-  // ---- stages 2+3 per chunk of surviving points: warp + gather, then fusion / transformer / decoder ----
-  ChunkBuffers cb;
-  carve_chunk_buffers(L.chunk, chunk_cap(N, S, SF), cb);
-  ChunkBuffers cbs[2] = {cb, cb};                                   // two sets of gather outputs, everything else shared
-  cbs[1].comb = L.gather2; cbs[1].f3raw = L.gather2 + (size_t)cb.cap * 288; cbs[1].geo = L.gather2 + (size_t)cb.cap * (288 + 192);
-  // One pass over a compacted point list (coarse: stratified depths; fine: importance-sampled depths): renderer.py:323-362
-  auto run_points = [&](const int* point_sample, const int* point_vid, int64_t Pn, int Sn, const float* depths, float* sigma_out, float* rgb_out,
-                        const SherfDebug* d) -> int {
-    // measured on B200 (r1): the overlap is neutral (6.98 vs 7.00 ms) -- the gather blocks delay the start of the persistent MLP CTAs
-    // by as much as they hide -- so it is opt-in (SHERF_OVERLAP=1)
-    const bool overlap = Pn > cb.cap && getenv("SHERF_OVERLAP") && g_side.ensure() == 0;
-    cudaStream_t gs = overlap ? g_side.s : st;
-    if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.fork, 0)); }
-    int ci = 0;
-    for (int64_t p0 = 0; p0 < Pn; p0 += cb.cap, ++ci) {
-      const int np = (int)((Pn - p0 < cb.cap) ? (Pn - p0) : cb.cap);
-      const int bsel = overlap ? (ci & 1) : 0;
-      const ChunkBuffers& cbi = cbs[bsel];
-      GatherParams G;
-      G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = Sn; G.depths = depths;
-      G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np;
-      G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
-      G.t_vertices = getenv("SHERF_KNN3_UNSEEDED") ? nullptr : frame->t_vertices;
-      G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
-      G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
-      G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;
-      for (int l = 0; l < 3; ++l) {
-        G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
-        G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
-      }
-      G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
-      G.dbg_vid3 = d ? d->point_vid3 : nullptr; G.dbg_can = d ? d->point_can : nullptr;
-      G.dbg_cdir = d ? d->point_cdir : nullptr; G.dbg_uv = d ? d->point_uv : nullptr;
-      G.dbg_feat = d ? d->point_feat : nullptr; G.dbg_max = d ? d->max_points : 0;
-      G.dbg_feat_max = d ? d->max_feat_points : 0;
-      // gather of chunk ci (side stream): its output buffers must have been released by the MLP of chunk ci-2
-      if (overlap && ci >= 2) SHERF_CUDA_OK(cudaStreamWaitEvent(gs, g_side.mdone[bsel], 0));
-      tm.begin(2, gs);
-      RC(run_point_gather(G, gs));
-      tm.end();
-      if (overlap) { SHERF_CUDA_OK(cudaEventRecord(g_side.gdone[bsel], gs)); SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.gdone[bsel], 0)); }
-      tm.begin(3);
-      RC(run_mlp(opts->mlp_precision, *weights, pw, cw, use_fused ? &fplan : nullptr, cbi, np, p0, sigma_out, rgb_out, d ? d->point_tok : nullptr,
-                 d ? d->max_points : 0, st, nested_begin, nested_end));
-      tm.end();
-      if (overlap) SHERF_CUDA_OK(cudaEventRecord(g_side.mdone[bsel], st));
-    }
-    return SHERF_OK;
-  };
-  if (side) SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.ldone, 0));          // layouts + packed weights are ready
-  RC(run_points(L.point_sample, L.point_vid, P, S, nullptr, L.sigma, L.rgb, dbg));
+  RC(run_points(L.point_sample, L.point_vid, P, async_first ? cb.cap : 0, S, nullptr, L.sigma, L.rgb, dbg));
   if (dbg && P > 0) {
     const size_t cnt = (size_t)(P < dbg->max_points ? P : dbg->max_points);
     if (dbg->point_sigma) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->point_sigma, L.sigma, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, st));
@@ -440,11 +485,14 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     RC(run_cull(*rays, SF, L.fine_depths, L.ft, vid_f, L.ray_count_f, L.block_sums, L.ray_start_f, L.total_f, L.point_sample_f, L.point_vid_f, st));
     tm.end();
     SHERF_CUDA_OK(cudaMemcpyAsync(&hcount[1], L.total_f, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    SHERF_CUDA_OK(cudaStreamSynchronize(st));
+    SHERF_CUDA_OK(cudaEventRecord(ev_cnt1, st));
+    if (async_first)
+      RC(issue_chunk(L.point_sample_f, L.point_vid_f, 0, cb.cap, SF, L.fine_depths, L.sigma_f, L.rgb_f, nullptr, DevCount{L.total_f, 0, cb.cap}, 0, false, st));
+    SHERF_CUDA_OK(cudaEventSynchronize(ev_cnt1));
     const int64_t PF = hcount[1];
     if (n_points_out) *n_points_out = P + PF;
     g_last_fine_points = PF;
-    RC(run_points(L.point_sample_f, L.point_vid_f, PF, SF, L.fine_depths, L.sigma_f, L.rgb_f, nullptr));
+    RC(run_points(L.point_sample_f, L.point_vid_f, PF, async_first ? cb.cap : 0, SF, L.fine_depths, L.sigma_f, L.rgb_f, nullptr));
     if (dbg) {
       if (dbg->fine_depths) SHERF_CUDA_OK(cudaMemcpyAsync(dbg->fine_depths, L.fine_depths, sizeof(float) * (size_t)N * SF, cudaMemcpyDeviceToDevice, st));
       RC(run_dense_taps(L.point_sample_f, L.sigma_f, L.rgb_f, PF, (int64_t)N * SF, dbg->fine_sigma, dbg->fine_rgb, st));

@@ -54,6 +54,7 @@ struct Args {
   float* sigma;                // [np]
   float* rgb;                  // [np][3]
   int np;
+  DevCount dc;
   long long* trace;            // optional [gridDim][16] cycle counters (diagnostics)
 };
 
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(352, 1) k_decoder_pp(const Args a) {
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const int ntiles = (a.np + 127) / 128;
+  const int np = resolve_np(a.np, a.dc);
+  const int ntiles = (np + 127) / 128;
   const int G = gridDim.x;
   // tile pair p of this CTA: slot 0 <- tile (2p)G + b, slot 1 <- tile (2p+1)G + b
 
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(352, 1) k_decoder_pp(const Args a) {
     long long t_acc = 0, t0c = TRACE_CLK();
     for (int tile = blockIdx.x + s * G; tile < ntiles; tile += 2 * G) {
       const int m = tile * 128 + row;
-      const bool row_ok = m < a.np;
+      const bool row_ok = m < np;
       for (int l = 0; l < kLayers; ++l) {
         const long long w0 = TRACE_CLK();
         umma::mbar_wait(&acc_bar[s], par_acc);
@@ -432,13 +434,13 @@ int run_pack_xv(const float* x, int ldx, const float* fv, int ldfv, int np, unsi
 }
 
 int run_decoder_pp(const PpPlan& plan, const SherfWeights& w, const unsigned char* xp, const unsigned char* vp, float* sigma, float* rgb, int np,
-                   cudaStream_t st) {
+                   cudaStream_t st, DevCount dc) {
   if (np <= 0) return SHERF_OK;
   dpp::Args a;
   a.xp = xp; a.vp = vp; a.wblob = plan.blob; a.bias = plan.bias;
   for (int c = 0; c < dpp::kChunks; ++c) a.w_off[c] = plan.w_off[c];
   a.alpha_w = w.alpha_w; a.alpha_b = w.alpha_b; a.rgb_w = w.rgb_w; a.rgb_b = w.rgb_b;
-  a.sigma = sigma; a.rgb = rgb; a.np = np;
+  a.sigma = sigma; a.rgb = rgb; a.np = np; a.dc = dc;
   a.trace = g_fused_trace;
   const size_t smem = 2 * dpp::kXTile + dpp::kStages * dpp::kStageBytes + (dpp::kLayers * 128 + 132 + 196) * sizeof(float);
   static bool attr_done = false;

@@ -1,0 +1,551 @@
+// The "front" kernel of the point stages: warp + gather + feature fusion in ONE kernel, nothing in between touches HBM.
+//   renderer.py:323-350  inverse-LBS warp to canonical space, canonical -> observation warp, projection, pixel-aligned 2-D gather,
+//                        3-D pyramid gather, conv1d_projection 192 -> 96
+//   renderer.py:402,423-424  tri-plane gather, conv1d_reprojection 96 -> 32 over [tri_k | f2d_k | f3d_k], k = 0..2
+// Output: the three 32-channel tokens of every surviving point (384 B) + its canonical position / direction (32 B).  The gathered
+// features (1.5 KB per point through HBM in round 1: 770 MB written by the gather + 810 MB read back by the fusion kernel per 524 288
+// points, profiles/r1_ab) now go from the gather lanes' registers straight into the tensor-core operand slots in shared memory.
+//
+// One CTA = one 128-point tile at a time, 16 warps, TWO CTAs per SM (one CTA's gather overlaps the other's MMA / epilogue phases).
+//   gather : as in gather.cu, 8 lanes per point (lane l8 owns channels 4*l8..4*l8+3 of every 32-channel group, one 16-byte load per
+//            tap); each lane group owns rows g and g + 64 of the tile.  The tile is produced in twelve 32-channel CHUNKS
+//            (six of the 3-D pyramid, three tri-planes, two feature-map halves, the rgb encoding); a chunk's values are split into
+//            bf16 hi / lo and stored as the K-major no-swizzle UMMA operand (8 B per lane: conflict-free with LBO = 2080).
+//   MMA    : bf16 split products a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05 kind::f16, fp32 accumulators in TMEM; chunk c's MMAs
+//            run while chunk c+1 is gathered (two operand slots; projection weights stream through a two-stage TMA ring, 12 KB per
+//            chunk from L2; reprojection weights resident).  Warp 0 issues (after producing its own part of the chunk).
+//   E1     : projected 3-D feature = D1 + bias -> bf16 hi (shared memory) / lo (TMEM) operand of the reprojection; never leaves the SM.
+//   E2     : tokens = D2 + bias -> global.
+#include "common.cuh"
+#include "stages.cuh"
+#include "umma.cuh"
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+namespace sherf {
+
+namespace fr {
+constexpr uint32_t kLboA = 2080;                          // streamed operand chunks: 8-byte stores from the gather lanes are conflict-free
+constexpr uint32_t kChunkHalf = 4 * kLboA;                // hi (or lo) part of one 32-channel chunk: 4 core-matrix columns
+constexpr uint32_t kChunk = 2 * kChunkHalf;
+constexpr uint32_t kA0 = 0, kA1 = kChunk;
+constexpr uint32_t kLboF = 2064;                          // projected 3-D feature (16-byte stores, thread = row)
+constexpr uint32_t kF3d = 2 * kChunk;                     // 12 core-matrix columns (96 channels), hi part
+constexpr uint32_t kWr = kF3d + 12 * kLboF;               // reprojection weights: 3 source blocks x (hi 2048 B | lo 2048 B)
+constexpr uint32_t kWrBlock = 4096;
+constexpr uint32_t kWp = kWr + 3 * kWrBlock;              // projection weight ring: 2 stages x (hi 6144 B | lo 6144 B)
+constexpr uint32_t kWpStage = 12288;
+constexpr uint32_t kSmemBytes = kWp + 2 * kWpStage;
+constexpr uint32_t kD1 = 0, kD2 = 96, kF3dLo = 192;       // tensor-memory columns (256 allocated)
+constexpr int kThreads = 512;
+}  // namespace fr
+
+struct FrontArgs {
+  GatherParams G;
+  const unsigned char* wblob;          // 6 projection chunks (hi | lo), then 3 reprojection blocks (hi | lo)
+  const float *bp, *br;                // conv1d_projection bias [96], conv1d_reprojection bias [32]
+  float* tok;                          // [np][3][32]
+};
+
+__device__ __forceinline__ void fr_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void fr_apply_warp(const VertexWarp* __restrict__ Tp, float p[3], float d[3], bool with_dir) {
+  const float4* r4 = reinterpret_cast<const float4*>(Tp);
+  float w[36];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { float4 v = r4[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+  float a[3] = {p[0] - w[9], p[1] - w[10], p[2] - w[11]};
+  float c[3];
+  mat3_vec(w, a, c);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { c[k] = c[k] + w[12 + k]; c[k] = c[k] + w[15 + k]; c[k] = c[k] + w[18 + k]; }
+  const float* Af = w + 21;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = (Af[4 * k] * c[0] + Af[4 * k + 1] * c[1] + Af[4 * k + 2] * c[2]) + Af[4 * k + 3];
+  if (with_dir) {
+    float e[3];
+    mat3_vec(w, d, e);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = Af[4 * k] * e[0] + Af[4 * k + 1] * e[1] + Af[4 * k + 2] * e[2];
+  }
+}
+
+__device__ __forceinline__ void fr_grp_lexmin(float& d, int& id) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+    if (od < d || (od == d && oi < id)) { d = od; id = oi; }
+  }
+}
+
+// exact K=1 search over the canonical vertices seeded by the nearest posed vertex (gather.cu: nn_seeded8), 8 lanes per point
+__device__ __forceinline__ int fr_nn_seeded8(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
+                                             const float* __restrict__ t_vertices, float qx, float qy, float qz, int l8, int seed) {
+  float best = dist2_xyz(qx, qy, qz, t_vertices[seed * 3], t_vertices[seed * 3 + 1], t_vertices[seed * 3 + 2]);
+  int bid = seed;
+  const float rb = sqrtf(best) * 1.0001f + 1.0e-4f * g.cell;
+  const int x0 = min(max(grid_coord(qx - rb, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int x1 = min(max(grid_coord(qx + rb, g.origin[0], g.inv_cell, g.dim[0]), 0), g.dim[0] - 1);
+  const int y0 = min(max(grid_coord(qy - rb, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int y1 = min(max(grid_coord(qy + rb, g.origin[1], g.inv_cell, g.dim[1]), 0), g.dim[1] - 1);
+  const int z0 = min(max(grid_coord(qz - rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  const int z1 = min(max(grid_coord(qz + rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
+  const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncells = nx * ny * (z1 - z0 + 1);
+  for (int cc = l8; cc < ncells; cc += 8) {
+    const int xx = x0 + cc % nx, t = cc / nx;
+    const int cell = ((z0 + t / ny) * g.dim[1] + (y0 + t % ny)) * g.dim[0] + xx;
+    const int b = cell_start[cell], e = cell_start[cell + 1];
+    for (int k = b; k < e; ++k) {
+      const float4 v = gv[k];
+      const float d2 = dist2_xyz(qx, qy, qz, v.x, v.y, v.z);
+      const int id = __float_as_int(v.w);
+      if (d2 < best || (d2 == best && id < bid)) { best = d2; bid = id; }
+    }
+  }
+  fr_grp_lexmin(best, bid);
+  return bid;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ FrameConst fc;
+  __shared__ __align__(8) uint64_t a_full[2], a_free[2], w_full[2], acc1, acc2, f3d_ready;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bp[96], s_br[32];
+  const GatherParams& P = a.G;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l8 = lane & 7, gbase = lane & 24;
+  const int c4 = 4 * l8;
+
+  for (int i = tid; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(&a_full[b], fr::kThreads); umma::mbar_init(&a_free[b], 1); umma::mbar_init(&w_full[b], 1); }
+    umma::mbar_init(&acc1, 1); umma::mbar_init(&acc2, 1); umma::mbar_init(&f3d_ready, fr::kThreads);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  for (int i = tid; i < (int)(3 * fr::kWrBlock / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + fr::kWr)[i] = __ldg(reinterpret_cast<const uint4*>(a.wblob + 6 * fr::kWpStage) + i);
+  if (tid < 96) s_bp[tid] = a.bp[tid];
+  if (tid < 32) s_br[tid] = a.br[tid];
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t sbase = umma::smem_u32(smem);
+  const int np = resolve_np(P.np, P.dc);
+  const int ntiles = (np + 127) / 128;
+  const uint32_t el = umma::elect_one();                   // warp 0 stays converged in the issue code; one lane issues
+  const int gi = warp * 4 + (lane >> 3);                   // lane group 0..63: rows gi and gi + 64 of the tile
+  // E1 / E2 role of this thread: TMEM lane quarter = warp & 3, 24-column group = warp >> 2
+  const int erow = 32 * (warp & 3) + lane, ecg = warp >> 2;
+  const uint32_t etb = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+
+  if (warp == 0 && lane == 0 && (int)blockIdx.x < ntiles) {          // projection weight chunks 0, 1 of the first tile
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_arrive_expect_tx(&w_full[s], fr::kWpStage);
+      umma::bulk_g2s(smem + fr::kWp + s * fr::kWpStage, a.wblob + (size_t)s * fr::kWpStage, fr::kWpStage, &w_full[s]);
+    }
+  }
+
+  // split products of one 32-channel block: D[:, dcol:+N] (+)= A * W^T, A hi from shared memory, A lo from shared or tensor memory
+  auto gemm32 = [&](uint32_t a_hi_addr, uint32_t a_lbo, bool lo_in_tmem, uint32_t a_lo, uint32_t w_hi_addr, uint32_t w_lo_addr, int N, uint32_t dcol,
+                    uint32_t acc0) {
+    const uint32_t idesc = umma::make_idesc_bf16(128, N);
+    const uint32_t w_lbo = (uint32_t)N * 16u;
+    const uint64_t ah0 = umma::make_smem_desc(a_hi_addr, a_lbo, 128u);
+    const uint64_t al0 = umma::make_smem_desc(a_lo, a_lbo, 128u);
+    const uint64_t wh0 = umma::make_smem_desc(w_hi_addr, w_lbo, 128u);
+    const uint64_t wl0 = umma::make_smem_desc(w_lo_addr, w_lbo, 128u);
+    const uint64_t da = (uint64_t)((2u * a_lbo) >> 4), dw = (uint64_t)((2u * w_lbo) >> 4);
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+      const uint32_t acc = st == 0 ? acc0 : 1u;
+      if (lo_in_tmem) umma::mma_bf16_ts_e(tmem_base + dcol, tmem_base + a_lo + (uint32_t)st * 8u, wh0 + (uint64_t)st * dw, idesc, acc, el);
+      else umma::mma_bf16_ss_e(tmem_base + dcol, al0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, acc, el);
+      umma::mma_bf16_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wl0 + (uint64_t)st * dw, idesc, 1u, el);
+      umma::mma_bf16_ss_e(tmem_base + dcol, ah0 + (uint64_t)st * da, wh0 + (uint64_t)st * dw, idesc, 1u, el);
+    }
+  };
+
+  uint32_t ti = 0;                                          // tile iteration of this CTA (barrier phase bookkeeping)
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    const bool has_next = tile + (int)gridDim.x < ntiles;
+    // =========================== phase A: geometry of this lane group's two points ===========================
+    float can[2][3], uvp[2][2];
+    int64_t gpt[2];
+    bool act[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int lp_raw = tile * 128 + gi + 64 * p;
+      act[p] = lp_raw < np;
+      const int lp = act[p] ? lp_raw : np - 1;             // rows beyond the list shadow the last point; nothing of them is stored
+      const int64_t gp = P.p0 + lp;
+      gpt[p] = gp;
+      const int s = P.point_sample[gp];
+      const int n = s / P.S, i = s - n * P.S;
+      const float t = P.depths ? P.depths[s] : sample_depth(P.nearv[n], P.farv[n], i, P.S);
+      float dray[3] = {P.dirs[n * 3], P.dirs[n * 3 + 1], P.dirs[n * 3 + 2]};
+      float pw[3], q[3], vd[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pw[k] = __fsub_rn(mul_add_sep(t, dray[k], P.origins[n * 3 + k]), fc.Th_tgt[k]);
+      rowvec_mat3(pw, fc.R_tgt, q);
+      rowvec_mat3(dray, fc.R_tgt, vd);
+      float cn[3] = {q[0], q[1], q[2]}, cdir[3] = {vd[0], vd[1], vd[2]};
+      const int vid1 = P.point_vid[gp];
+      fr_apply_warp(P.T1 + vid1, cn, cdir, true);                                      // target -> canonical   renderer.py:558-621
+      const int vid3 = fr_nn_seeded8(fc.g3, P.g3_start, P.g3_verts, P.t_vertices, cn[0], cn[1], cn[2], l8, vid1);
+      float ps[3] = {cn[0], cn[1], cn[2]}, dummy[3] = {0.f, 0.f, 0.f};
+      fr_apply_warp(P.T3 + vid3, ps, dummy, false);                                    // canonical -> observation   renderer.py:623-684
+      float world[3], cam[3], pix[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) world[k] = (ps[0] * fc.Rinv_obs[k] + ps[1] * fc.Rinv_obs[3 + k] + ps[2] * fc.Rinv_obs[6 + k]) + fc.Th_obs[k];
+      mat3_vec(fc.camR, world, cam);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cam[k] += fc.camT[k];
+      mat3_vec(fc.camK, cam, pix);                                                     // renderer.py:686-704
+      const float zz = pix[2] + 1e-5f;
+      uvp[p][0] = pix[0] / zz; uvp[p][1] = pix[1] / zz;
+      can[p][0] = cn[0]; can[p][1] = cn[1]; can[p][2] = cn[2];
+      if (act[p]) {
+        float gval = 0.f;
+        if (l8 == 0) gval = cn[0]; else if (l8 == 1) gval = cn[1]; else if (l8 == 2) gval = cn[2];
+        else if (l8 == 3) gval = cdir[0]; else if (l8 == 4) gval = cdir[1]; else if (l8 == 5) gval = cdir[2];
+        P.geo[(size_t)lp * 8 + l8] = gval;
+        if (DBG && l8 == 0 && gp < P.dbg_max) {
+          if (P.dbg_vid3) P.dbg_vid3[gp] = vid3;
+          if (P.dbg_can) { P.dbg_can[gp * 3] = cn[0]; P.dbg_can[gp * 3 + 1] = cn[1]; P.dbg_can[gp * 3 + 2] = cn[2]; }
+          if (P.dbg_cdir) { P.dbg_cdir[gp * 3] = cdir[0]; P.dbg_cdir[gp * 3 + 1] = cdir[1]; P.dbg_cdir[gp * 3 + 2] = cdir[2]; }
+          if (P.dbg_uv) { P.dbg_uv[gp * 2] = uvp[p][0]; P.dbg_uv[gp * 2 + 1] = uvp[p][1]; }
+        }
+      }
+    }
+
+    // =========================== chunk plumbing ===========================
+    // chunk c (0..11) of this tile uses operand slot b = c & 1 for the (ti * 6 + c / 2)-th time
+    auto begin_chunk = [&](int c) -> unsigned char* {
+      const int b = c & 1;
+      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
+      umma::mbar_wait(&a_free[b], (u & 1u) ^ 1u);            // the MMAs that read this slot two chunks ago have completed
+      if (warp == 0 && lane == 0 && c >= 2 && c <= 7) {      // ... and so have the reads of weight stage b: refill it
+        const int wc = c <= 5 ? c : c - 6;                   // this tile's chunk c, or the next tile's chunk 0 / 1
+        if (c <= 5 || has_next) {
+          umma::mbar_arrive_expect_tx(&w_full[b], fr::kWpStage);
+          umma::bulk_g2s(smem + fr::kWp + b * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[b]);
+        }
+      }
+      return smem + (b ? fr::kA1 : fr::kA0);
+    };
+    auto store4 = [&](unsigned char* buf, int p, const float4& v) {   // 4 channels of row gi + 64p -> bf16 hi | lo halves of a 16-byte core-matrix row
+      uint2 h, l;
+      umma::split_bf16x2(v.x, v.y, h.x, l.x);
+      umma::split_bf16x2(v.z, v.w, h.y, l.y);
+      unsigned char* dst = buf + (size_t)(l8 >> 1) * fr::kLboA + (size_t)(gi + 64 * p) * 16 + (l8 & 1) * 8;
+      *reinterpret_cast<uint2*>(dst) = h;
+      *reinterpret_cast<uint2*>(dst + fr::kChunkHalf) = l;
+    };
+    auto issue_chunk = [&](int c) {                           // warp 0 only, converged
+      const int b = c & 1;
+      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
+      umma::mbar_wait(&a_full[b], u & 1u);
+      const uint32_t a_hi = sbase + (b ? fr::kA1 : fr::kA0), a_lo = a_hi + fr::kChunkHalf;
+      if (c < 6) {
+        umma::mbar_wait(&w_full[b], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
+        umma::tc_fence_after_sync();
+        const uint32_t w_hi = sbase + fr::kWp + (uint32_t)b * fr::kWpStage;
+        gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
+        umma::mma_commit_e(&a_free[b], el);
+        if (c == 5) umma::mma_commit_e(&acc1, el);
+      } else {
+        umma::tc_fence_after_sync();
+        const int tt = (c - 6) % 3, sblk = c < 9 ? 0 : 1;     // tri_t -> source block 0 (first MMA of token t), f2d_t -> block 1
+        if (c == 9) {                                         // all three tokens are initialised: add the projected 3-D feature (source block 2)
+          umma::mbar_wait(&f3d_ready, ti & 1u);
+          umma::tc_fence_after_sync();
+          const uint32_t w2 = sbase + fr::kWr + 2u * fr::kWrBlock;
+          for (int t3 = 0; t3 < 3; ++t3)
+            gemm32(sbase + fr::kF3d + (uint32_t)(4 * t3) * fr::kLboF, fr::kLboF, true, fr::kF3dLo + (uint32_t)(16 * t3), w2, w2 + fr::kWrBlock / 2, 32,
+                   fr::kD2 + (uint32_t)(32 * t3), 1u);
+        }
+        const uint32_t wb = sbase + fr::kWr + (uint32_t)sblk * fr::kWrBlock;
+        gemm32(a_hi, fr::kLboA, false, a_lo, wb, wb + fr::kWrBlock / 2, 32, fr::kD2 + (uint32_t)(32 * tt), c < 9 ? 0u : 1u);
+        umma::mma_commit_e(&a_free[b], el);
+        if (c == 11) umma::mma_commit_e(&acc2, el);
+      }
+    };
+    auto end_chunk = [&](int c) {
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before_sync();
+      fr_arrive(&a_full[c & 1]);
+      if (warp == 0) { issue_chunk(c); __syncwarp(); }
+    };
+
+    // =========================== phase B: the 3-D pyramid, chunks 0..5 (renderer.py:544-556,762-797) ===========================
+    {
+      int c = 0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        int offB[2]; float wB[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {                          // lane l8 prepares corner l8 (bit0 x, bit1 y, bit2 z) of level l
+          const int D = P.vol_d[l], Hh = P.vol_h[l], Ww = P.vol_w[l], C = P.vol_ch[l];
+          float gn[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) gn[k] = ((can[p][k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
+          const float ix = (gn[0] + 1.f) * 0.5f * (float)(Ww - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(Hh - 1), iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
+          const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+          const int bx = l8 & 1, by = (l8 >> 1) & 1, bz = (l8 >> 2) & 1;
+          const int xx = (int)fx + bx, yy = (int)fy + by, zz2 = (int)fz + bz;
+          const float wx = bx ? ix - fx : (fx + 1.f) - ix, wy = by ? iy - fy : (fy + 1.f) - iy, wz = bz ? iz - fz : (fz + 1.f) - iz;
+          wB[p] = wx * wy * wz;
+          offB[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh && zz2 >= 0 && zz2 < D) ? ((zz2 * Hh + yy) * Ww + xx) * C : -1;
+        }
+#pragma unroll
+        for (int gsel = 0; gsel < 3; ++gsel) {
+          if (gsel <= l) {                                     // level l has 32 * (l + 1) channels
+            unsigned char* buf = begin_chunk(c);
+            const float* vol = P.vol_cl[l] + c4 + 32 * gsel;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int tp = 0; tp < 8; ++tp) {
+                const int off = __shfl_sync(0xffffffffu, offB[p], gbase + tp);
+                const float w = __shfl_sync(0xffffffffu, wB[p], gbase + tp);
+                const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w;
+              }
+              store4(buf, p, acc);
+              if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 192 + 32 * c + c4) = acc;
+            }
+            end_chunk(c);
+            ++c;
+          }
+        }
+      }
+    }
+    // =========================== chunks 6..8: tri-planes (renderer.py:234-243, align_corners=False) ===========================
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int offA[2]; float wA[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {                            // lanes 0-3 of the group prepare the four corners (nw, ne, sw, se)
+        float cn[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) cn[e] = 2.f * (can[p][e] - fc.twb_min[e]) / (fc.twb_max[e] - fc.twb_min[e]) - 1.f;
+        const float px = k == 2 ? cn[2] : cn[0], py = k == 1 ? cn[2] : cn[1];
+        const int Ww = P.plane_w, Hh = P.plane_h;
+        const float ix = ((px + 1.f) * (float)Ww - 1.f) * 0.5f, iy = ((py + 1.f) * (float)Hh - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
+        const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+        const float wx = cxb ? ix - fx : (fx + 1.f) - ix, wy = cyb ? iy - fy : (fy + 1.f) - iy;
+        wA[p] = wx * wy;
+        offA[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
+      }
+      unsigned char* buf = begin_chunk(6 + k);
+      const float* base = P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + c4;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          const int off = __shfl_sync(0xffffffffu, offA[p], gbase + tp);
+          const float w = __shfl_sync(0xffffffffu, wA[p], gbase + tp);
+          const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tp == 0) { acc.x = val.x * w; acc.y = val.y * w; acc.z = val.z * w; acc.w = val.w * w; }
+          else { acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w; }
+        }
+        store4(buf, p, acc);
+        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 32 * k + c4) = acc;
+      }
+      end_chunk(6 + k);
+      if (k == 0) {
+        // =========================== E1: projected 3-D feature -> reprojection operand (on-chip only) ===========================
+        umma::mbar_wait(&acc1, ti & 1u);
+        umma::tc_fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int c0 = 24 * ecg + 8 * i;
+          uint32_t d[8];
+          umma::tmem_ld8(etb + fr::kD1 + (uint32_t)c0, d);
+          umma::tmem_ld_wait();
+          uint4 h; uint32_t lo[4];
+          umma::split_bf16x2(__uint_as_float(d[0]) + s_bp[c0], __uint_as_float(d[1]) + s_bp[c0 + 1], h.x, lo[0]);
+          umma::split_bf16x2(__uint_as_float(d[2]) + s_bp[c0 + 2], __uint_as_float(d[3]) + s_bp[c0 + 3], h.y, lo[1]);
+          umma::split_bf16x2(__uint_as_float(d[4]) + s_bp[c0 + 4], __uint_as_float(d[5]) + s_bp[c0 + 5], h.z, lo[2]);
+          umma::split_bf16x2(__uint_as_float(d[6]) + s_bp[c0 + 6], __uint_as_float(d[7]) + s_bp[c0 + 7], h.w, lo[3]);
+          *reinterpret_cast<uint4*>(smem + fr::kF3d + (size_t)(c0 >> 3) * fr::kLboF + erow * 16) = h;
+          umma::tmem_st4(etb + fr::kF3dLo + (uint32_t)(c0 >> 1), lo);
+        }
+        umma::tmem_st_wait();
+        umma::fence_proxy_async_smem();
+        umma::tc_fence_before_sync();
+        fr_arrive(&f3d_ready);
+      }
+    }
+    // =========================== chunks 9..11: pixel-aligned 2-D features + rgb encoding (renderer.py:331-340) ===========================
+    {
+      int offF[2], offI[2]; float wF[2], wI[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {                            // align_corners=True, uv normalised by the IMAGE size for both maps
+        const float gx = 2.0f * uvp[p][0] / (float)P.img_w - 1.0f, gy = 2.0f * uvp[p][1] / (float)P.img_h - 1.0f;
+        const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
+        {
+          const int Ww = P.feat_w, Hh = P.feat_h;
+          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+          wF[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+          offF[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * P.feat_ch : -1;
+        }
+        {
+          const int Ww = P.img_w, Hh = P.img_h;
+          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+          wI[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+          offI[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
+        }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        unsigned char* buf = begin_chunk(9 + half);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {
+            const int off = __shfl_sync(0xffffffffu, offF[p], gbase + tp);
+            const float w = __shfl_sync(0xffffffffu, wF[p], gbase + tp);
+            const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(P.feat_cl + off + 32 * half + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp == 0) { acc.x = val.x * w; acc.y = val.y * w; acc.z = val.z * w; acc.w = val.w * w; }
+            else { acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w; }
+          }
+          store4(buf, p, acc);
+          if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 96 + 32 * half + c4) = acc;
+        }
+        end_chunk(9 + half);
+      }
+      unsigned char* buf = begin_chunk(11);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float rgbc = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          const int offi = __shfl_sync(0xffffffffu, offI[p], gbase + tp);
+          const float wi = __shfl_sync(0xffffffffu, wI[p], gbase + tp);
+          const float vi = (l8 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l8 * P.img_h * P.img_w + offi) : 0.f;
+          rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
+        }
+        // rgb_enc outputs 4*l8 .. 4*l8+3 of the 32 kept ones: [r, g, b, sin(..) ...]                        renderer.py:339,900-916
+        const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
+                    r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
+        float enc[4];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const int o = c4 + e4;
+          if (o < 3) enc[e4] = o == 0 ? r0 : (o == 1 ? r1 : r2);
+          else {
+            const int e = o - 3, m = e / 3, cc = e - 3 * m;
+            const float xc = cc == 0 ? r0 : (cc == 1 ? r1 : r2);
+            enc[e4] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+          }
+        }
+        const float4 ev = make_float4(enc[0], enc[1], enc[2], enc[3]);
+        store4(buf, p, ev);
+        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 160 + c4) = ev;
+      }
+      end_chunk(11);
+    }
+    // =========================== E2: tokens = D2 + bias -> global ===========================
+    {
+      umma::mbar_wait(&acc2, ti & 1u);
+      umma::tc_fence_after_sync();
+      const int m = tile * 128 + erow;
+      uint32_t d[3][8];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) umma::tmem_ld8(etb + fr::kD2 + (uint32_t)(24 * ecg + 8 * i), d[i]);
+      umma::tmem_ld_wait();
+      umma::tc_fence_before_sync();
+      if (m < np) {
+        float4* dst = reinterpret_cast<float4*>(a.tok + (size_t)m * 96 + 24 * ecg);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int c0 = (24 * ecg + 8 * i) & 31;               // bias index: column within the 32-channel token
+          dst[2 * i] = make_float4(__uint_as_float(d[i][0]) + s_br[c0], __uint_as_float(d[i][1]) + s_br[c0 + 1], __uint_as_float(d[i][2]) + s_br[c0 + 2],
+                                   __uint_as_float(d[i][3]) + s_br[c0 + 3]);
+          dst[2 * i + 1] = make_float4(__uint_as_float(d[i][4]) + s_br[c0 + 4], __uint_as_float(d[i][5]) + s_br[c0 + 5], __uint_as_float(d[i][6]) + s_br[c0 + 6],
+                                       __uint_as_float(d[i][7]) + s_br[c0 + 7]);
+        }
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// blob: 6 x [hi: 4 kg x 96 rows x 8 bf16 | lo] (projection chunk c = input channels 32c .. 32c+31), then 3 x [hi: 4 kg x 32 rows x 8 | lo]
+// (reprojection source block s = input channels 32s .. 32s+31: tri | f2d | f3d)
+__global__ void k_pack_front(const float* __restrict__ wp, const float* __restrict__ wr, __nv_bfloat16* __restrict__ blob) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int kProjHalf = 4 * 96 * 8, kReHalf = 4 * 32 * 8;
+  if (i < 6 * kProjHalf) {
+    const int c = i / kProjHalf, r = i % kProjHalf;
+    const int e = r & 7, n = (r >> 3) % 96, kg = (r >> 3) / 96;
+    const float v = wp[n * 192 + 32 * c + 8 * kg + e];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    blob[c * 2 * kProjHalf + r] = h;
+    blob[c * 2 * kProjHalf + kProjHalf + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+  } else if (i < 6 * kProjHalf + 3 * kReHalf) {
+    const int j = i - 6 * kProjHalf;
+    const int s = j / kReHalf, r = j % kReHalf;
+    const int e = r & 7, n = (r >> 3) % 32, kg = (r >> 3) / 32;
+    const float v = wr[n * 96 + 32 * s + 8 * kg + e];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16* dst = blob + 6 * 2 * kProjHalf + s * 2 * kReHalf;
+    dst[r] = h;
+    dst[kReHalf + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+size_t front_blob_bytes() { return (size_t)6 * fr::kWpStage + 3 * fr::kWrBlock; }
+
+int run_pack_front(const SherfWeights& w, unsigned char* blob, cudaStream_t st) {
+  const int total = 6 * 4 * 96 * 8 + 3 * 4 * 32 * 8;
+  k_pack_front<<<ceil_div(total, 256), 256, 0, st>>>(w.proj_w, w.reproj_w, reinterpret_cast<__nv_bfloat16*>(blob));
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+int run_front_fused(const GatherParams& G, const SherfWeights& w, const unsigned char* blob, float* tok, cudaStream_t st) {
+  if (G.np <= 0) return SHERF_OK;
+  if (!G.t_vertices) { set_error("internal: the front kernel needs the seeded canonical-vertex search"); return SHERF_E_INVALID; }
+  FrontArgs a;
+  a.G = G; a.wblob = blob; a.bp = w.proj_b; a.br = w.reproj_b; a.tok = tok;
+  static bool attr_done = false;
+  static int num_sms = 148;
+  if (!attr_done) {
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_front_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr::kSmemBytes));
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_front_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr::kSmemBytes));
+    int dev = 0;
+    SHERF_CUDA_OK(cudaGetDevice(&dev));
+    SHERF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  const bool dbg = G.dbg_feat || G.dbg_vid3 || G.dbg_can || G.dbg_cdir || G.dbg_uv;
+  const int ntiles = (G.np + 127) / 128;
+  const int grid = ntiles < 2 * num_sms ? ntiles : 2 * num_sms;             // two co-resident CTAs per SM
+  if (dbg) k_front_fused<true><<<grid, fr::kThreads, fr::kSmemBytes, st>>>(a);
+  else k_front_fused<false><<<grid, fr::kThreads, fr::kSmemBytes, st>>>(a);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+}  // namespace sherf

@@ -523,7 +523,7 @@ void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb) {
 
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st, void (*span_begin)(int),
-            void (*span_end)()) {
+            void (*span_end)(), DevCount dc) {
   if (np <= 0) return SHERF_OK;
   const int rows3 = 3 * np;
   // SHERF_MLP_BF16X3: the decoder runs as bf16 split products (decoder_pp.cu); fusion conv and transformer stay 3xTF32
@@ -535,7 +535,9 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
     if (prec == SHERF_MLP_FP32) return launch_simt_linear(P, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
     return launch_umma_linear(prec == SHERF_MLP_TF32X3 ? 3 : 1, C, A, lda, Y, ldy, M, act, s, Res, ldr, yg, ygs);
   };
-  if (fused && prec != SHERF_MLP_FP32 && fused->ff_blob) {
+  if (pp && fused->fr_blob && fused->xb_blob) {
+    // the front kernel (front_fused.cu) already left the tokens in cb.tok; LayerNorm-1 happens in the transformer kernel
+  } else if (fused && prec != SHERF_MLP_FP32 && fused->ff_blob) {
     // conv1d_projection + conv1d_reprojection + LayerNorm-1 in one persistent tcgen05 kernel (fusion_fused.cu)
     if (span_begin) span_begin(7);
     RC(run_fusion_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->ff_blob, cb.f3raw, cb.comb, cb.tok, cb.ln, np, st));
@@ -555,7 +557,12 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
                             w.ln1_w, w.ln1_b, cb.ln, 32));
     }
   }
-  if (fused && prec != SHERF_MLP_FP32 && fused->xf_blob) {
+  if (pp && fused->xb_blob) {
+    // bf16x3: LayerNorm-1 + qkv -> attention -> to_out -> LN2 -> FeedForward -> packed decoder inputs, two CTAs per SM (xformer_bf16.cu)
+    if (span_begin) span_begin(6);
+    RC(run_xformer_bf16(w, fused->xb_blob, cb.tok, cb.geo, np, dbg_tok, p0, dbg_max, st, fused->pp->xp, fused->pp->vp, cb.qkv /* PE scratch */, dc));
+    if (span_end) span_end();
+  } else if (fused && prec != SHERF_MLP_FP32 && fused->xf_blob) {
     // qkv -> attention -> to_out -> LN2 -> FeedForward -> decoder inputs in one persistent tcgen05 kernel (xformer_fused.cu)
     if (span_begin) span_begin(6);
     RC(run_xformer_fused(prec == SHERF_MLP_TF32X3 ? 3 : 1, w, fused->xf_blob, cb.ln, cb.tok, cb.geo, cb.x, cb.fv, np, dbg_tok, p0, dbg_max, st,
@@ -576,8 +583,8 @@ int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const Cano
   if (pp) {
     // whole NeRFDecoder, two tiles in flight per SM, activations in tensor memory
     if (span_begin) span_begin(5);
-    if (!fused->xf_blob) RC(run_pack_xv(cb.x, 72, cb.fv, 188, np, fused->pp->xp, fused->pp->vp, st));   // else the transformer kernel wrote the packed tiles
-    RC(run_decoder_pp(*fused->pp, w, fused->pp->xp, fused->pp->vp, sigma_out + p0, rgb_out + p0 * 3, np, st));
+    if (!fused->xf_blob && !fused->xb_blob) RC(run_pack_xv(cb.x, 72, cb.fv, 188, np, fused->pp->xp, fused->pp->vp, st));   // else the transformer kernel wrote the packed tiles
+    RC(run_decoder_pp(*fused->pp, w, fused->pp->xp, fused->pp->vp, sigma_out + p0, rgb_out + p0 * 3, np, st, dc));
     if (span_end) span_end();
     return SHERF_OK;
   }

@@ -4,6 +4,15 @@
 
 namespace sherf {
 
+// Survivor count known only on the device when the kernel is ENQUEUED (the first chunk of a pass is issued before the host has read
+// the cull's total): np = clamp(*total - p0, 0, cap); total == NULL -> the host's np stands.
+struct DevCount { const int64_t* total; int64_t p0; int cap; };
+__device__ __forceinline__ int resolve_np(int np_host, const DevCount& dc) {
+  if (!dc.total) return np_host;
+  const int64_t r = *dc.total - dc.p0;
+  return r <= 0 ? 0 : (r > dc.cap ? dc.cap : (int)r);
+}
+
 struct GatherParams {
   // rays
   const float *origins, *dirs, *nearv, *farv;
@@ -12,6 +21,7 @@ struct GatherParams {
   // compacted points of this chunk
   const int *point_sample, *point_vid;
   int64_t p0; int np;
+  DevCount dc;            // optional device-side count (front_fused.cu only)
   // frame
   const FrameConst* fc;
   const VertexWarp *T1, *T3;
@@ -82,13 +92,14 @@ struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0
 struct FusedSchedule { FusedChunk ch[44]; uint16_t layer_np[10]; uint16_t pad[2]; };
 // Ping-pong bf16x3 decoder (decoder_pp.cu): weight chunk offsets, packed weights / biases, packed X|V input tiles of one chunk
 struct PpPlan { uint32_t w_off[23]; const unsigned char* blob; const float* bias; unsigned char* xp; unsigned char* vp; };
-struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; const float* ff_blob; const PpPlan* pp; };
+struct FusedPlan { FusedSchedule sch; const unsigned char* blob; const float* bias; const float* xf_blob; const float* ff_blob; const PpPlan* pp;
+                   const unsigned char* xb_blob; /* bf16 transformer weights (xformer_bf16.cu) */ const unsigned char* fr_blob; /* front kernel weights (front_fused.cu) */ };
 size_t pp_blob_bytes();
 size_t pp_xv_bytes(int cap);
 int run_pack_pp(const SherfWeights& w, unsigned char* blob, float* bias, PpPlan& plan, cudaStream_t st);
 int run_pack_xv(const float* x, int ldx, const float* fv, int ldfv, int np, unsigned char* xp, unsigned char* vp, cudaStream_t st);
 int run_decoder_pp(const PpPlan& plan, const SherfWeights& w, const unsigned char* xp, const unsigned char* vp, float* sigma, float* rgb, int np,
-                   cudaStream_t st);
+                   cudaStream_t st, DevCount dc = DevCount{nullptr, 0, 0});
 size_t fused_blob_bytes();
 extern long long* g_fused_trace;
 int run_pack_fused_plan(const SherfWeights& w, unsigned char* blob, float* bias, FusedPlan& plan, cudaStream_t st);
@@ -108,11 +119,23 @@ int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const 
                       float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp,
                       float* pe_buf /* [np][64] scratch for the positional encodings */);
 
+// Front kernel: warp + gather + conv1d_projection / reprojection in one kernel (front_fused.cu); tok [np][3][32]
+size_t front_blob_bytes();
+int run_pack_front(const SherfWeights& w, unsigned char* blob, cudaStream_t st);
+int run_front_fused(const GatherParams& G, const SherfWeights& w, const unsigned char* blob, float* tok, cudaStream_t st);
+
+// bf16 split-product transformer, two CTAs per SM (xformer_bf16.cu)
+size_t xformer_bf16_blob_bytes();
+int run_pack_xformer_bf16(const SherfWeights& w, unsigned char* blob, cudaStream_t st);
+int run_xformer_bf16(const SherfWeights& w, const unsigned char* blob, const float* tok, const float* geo, int np, float* dbg_tok, int64_t p0,
+                     int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp, float* pe_buf, DevCount dc = DevCount{nullptr, 0, 0});
+int run_point_pe(const float* geo, float* pe, int np, cudaStream_t st, DevCount dc = DevCount{nullptr, 0, 0});
+
 // The fusion / transformer / decoder stack on one chunk.  renderer.py:350,423-432; triplane.py:285-316
 // prec: SHERF_MLP_FP32 (CUDA-core fp32 FMA) | SHERF_MLP_TF32 | SHERF_MLP_TF32X3 | SHERF_MLP_BF16X3 (tcgen05 tensor cores)
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st,
-            void (*span_begin)(int) = nullptr, void (*span_end)() = nullptr);
+            void (*span_begin)(int) = nullptr, void (*span_end)() = nullptr, DevCount dc = DevCount{nullptr, 0, 0});
 
 int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
                      int act, float* wscratch, cudaStream_t st);

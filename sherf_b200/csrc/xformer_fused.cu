@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(288, 1) k_xformer_fused(const XfArgs a) {
 // Positional encodings of the canonical position (pos_enc, 6 octaves) and view direction (view_enc, 4 octaves) of every point
 // (renderer.py:432, PositionalEncoding :900-916): pe[p][3*mm + c] = sin(phase(mm) + x_c * 2^(mm >> 1)), phase = 0 | pi/2 -- the same
 // separately rounded multiply and add as torch.addcmul.  One thread per value: the sixty sinf per point run at full occupancy here.
-__global__ void __launch_bounds__(256) k_point_pe(const float* __restrict__ geo, float* __restrict__ pe, int np) {
+__global__ void __launch_bounds__(256) k_point_pe(const float* __restrict__ geo, float* __restrict__ pe, int np_host, const DevCount dc) {
+  const int np = resolve_np(np_host, dc);
   // thread = (point, slot) with 32 slots per point: slot s < 18 -> position coordinate c = s % 3 at octave k = s / 3 (6 octaves),
   // 18 <= s < 30 -> direction coordinate at octave (s - 18) / 3 (4 octaves); each thread writes the phase-0 and the phase-pi/2 value
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,6 +386,13 @@ __global__ void __launch_bounds__(256) k_point_pe(const float* __restrict__ geo,
   float* o = row + (dir ? 36 : 0) + 6 * k + c;                     // pe[3 * mm + c], mm = 2k (phase 0) and 2k + 1 (phase pi/2)
   o[0] = sinf(__fadd_rn(0.f, y));                                  // torch.addcmul(0, x, f): 0 + y (turns -0 into +0)
   o[3] = sinf(__fadd_rn(kPi2, y));
+}
+
+int run_point_pe(const float* geo, float* pe, int np, cudaStream_t st, DevCount dc) {
+  if (np <= 0) return SHERF_OK;
+  k_point_pe<<<ceil_div((int64_t)np * 32, 256), 256, 0, st>>>(geo, pe, np, dc);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -429,8 +437,7 @@ int run_xformer_fused(int prec, const SherfWeights& w, const float* blob, const 
                       float* fv, int np, float* dbg_tok, int64_t p0, int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp,
                       float* pe_buf) {
   if (np <= 0) return SHERF_OK;
-  k_point_pe<<<ceil_div((int64_t)np * 32, 256), 256, 0, st>>>(geo, pe_buf, np);
-  SHERF_LAUNCH_CHECK();
+  { const int rc = run_point_pe(geo, pe_buf, np, st); if (rc) return rc; }
   XfArgs a;
   a.pe = pe_buf;
   a.ln1 = ln1; a.tok = tok; a.geo = geo; a.wblob = blob; a.bo = w.attn_out_b; a.ln_w = w.ln2_w; a.ln_b = w.ln2_b; a.b1 = w.ff1_b;

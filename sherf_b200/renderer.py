@@ -31,7 +31,7 @@ class _Runtime:
     module-level WeakKeyDictionary, NOT in the nn.Module's __dict__: the reference deep-copies and pickles the generator every tick
     (training_loop.py:196,572-579), and ctypes structures with pointers cannot be pickled (and a copied arena would double HBM).
     A copy / unpickled module simply starts with an empty runtime and rebuilds it lazily on its first forward."""
-    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', '__weakref__')
+    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', 'scene_sig', 'scene_epoch', '__weakref__')
 
     def __init__(self):
         self.smpl_dev = None
@@ -41,6 +41,8 @@ class _Runtime:
         self.dbg_keep = None
         self.faces_dev = None
         self.obs_scratch = None
+        self.scene_sig = None
+        self.scene_epoch = 0
 
 
 _RUNTIME = weakref.WeakKeyDictionary()
@@ -280,6 +282,13 @@ class ImportanceRenderer(nn.Module):
         rt.w_cache = None
         rt.w_epoch = next(_WEIGHT_EPOCH)
 
+    def invalidate_scene(self):
+        """Forget the channels-last copies of the feature tensors held by the arena (needed only after writing planes / feature map /
+        volumes in place through `.data`, which no signature can see)."""
+        rt = _runtime(self)
+        rt.scene_sig = None
+        rt.scene_epoch = next(_WEIGHT_EPOCH)
+
     def _smpl_struct(self, device):
         if self.SMPL_NEUTRAL is None:
             raise RuntimeError('no SMPL model: put assets/SMPL_NEUTRAL.pkl in the cwd or call set_smpl_model()')
@@ -491,8 +500,9 @@ class ImportanceRenderer(nn.Module):
             sc.obs_img, sc.img_h, sc.img_w = _ptr(im), im.shape[-2], im.shape[-1]
             ft = _dev32(obs_input_feature, device); keep.append(ft)
             sc.obs_feat, sc.feat_ch, sc.feat_h, sc.feat_w = _ptr(ft), ft.shape[-3], ft.shape[-2], ft.shape[-1]
+            keep_vols = []
             for l, v in enumerate(canonical_sp_conv_volume):
-                v = _dev32(v, device); keep.append(v)
+                v = _dev32(v, device); keep.append(v); keep_vols.append(v)
                 sc.vol[l], sc.vol_ch[l] = _ptr(v), v.shape[1]
                 for a in range(3):
                     sc.vol_dim[l][a] = v.shape[2 + a]
@@ -548,6 +558,19 @@ class ImportanceRenderer(nn.Module):
             # in training mode, or a hot-path parameter requires grad) reuse is off: EMA / clamp / init code writes through `.data`,
             # which no signature can see (weights_version 0 = "pack on this call").
             opts.weights_version = 0 if volatile_weights else rt.w_epoch
+            # same idea for the feature tensors: while planes / 2-D map / volumes are the same storage and were not written in place,
+            # the arena's channels-last copies are reused (one observation, many views / shards / poses).  Tensors that require grad or
+            # were produced under autograd (training: the encoders run every step) are never cached.
+            scene_ts = (pl, ft) + tuple(keep_vols)
+            # identity (object id, kept alive below so it cannot be recycled) + in-place version counter: a tensor the caching allocator
+            # re-issued at the same address is a different object and is copied again
+            sig = tuple((id(t), t._version) for t in scene_ts) + (rt.scratch.data_ptr(),)
+            if any(torch.is_tensor(t) and (t.requires_grad or t.grad_fn is not None) for t in (planes, obs_input_feature)):
+                opts.scene_version = 0
+            else:
+                if rt.scene_sig is None or sig != rt.scene_sig[0]:
+                    rt.scene_sig, rt.scene_epoch = (sig, scene_ts), next(_WEIGHT_EPOCH)
+                opts.scene_version = rt.scene_epoch
 
             dbg_p = None
             if debug is not None:
