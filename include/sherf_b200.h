@@ -133,10 +133,13 @@ typedef struct SherfOptions {
   float depth_clamp_min;     /* used only if use_external_clamp != 0: global min/max of ALL depths of the */
   float depth_clamp_max;     /*   full (unsharded) view, ray_marcher.py:57 -- needed when rays are sharded */
   int32_t use_external_clamp;
-  const float* density_noise; /* optional [N*S] additive sigma noise, already scaled (renderer.py:435-436); NULL = none */
+  const float* density_noise; /* optional additive sigma noise, already scaled, ONE VALUE PER SURVIVING POINT in compacted (row-major [N,S]
+                                 surviving) order, at least n_points long -- what `sigma += randn_like(sigma) * density_noise` adds at
+                                 renderer.py:435-436.  The count comes from sherf_count_survivors.  NULL = none */
   const float* importance_u;  /* [N*S_f] uniform draws in [0,1) standing for torch.rand at renderer.py:526; required when
                                  n_importance > 0 (the caller owns the RNG, SURVEY.md 8b "RNG") */
-  const float* density_noise_importance; /* optional [N*S_f] additive sigma noise of the fine samples; NULL = none */
+  const float* density_noise_importance; /* optional [N*S_f] additive sigma noise of the fine samples, per fine SAMPLE (their survivor count
+                                            depends on the coarse pass; the reference's own fine pass cannot run); NULL = none */
   uint64_t weights_version;   /* 0: the weights are re-packed into the scratch arena on every call.  Non-zero: the caller vouches
                                  that SherfWeights' contents are unchanged since the previous call THAT USED THE SAME scratch arena,
                                  mlp_precision and shapes with the same non-zero value; the packed copies made by that call are then
@@ -199,10 +202,21 @@ SHERF_API int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame*
                          const SherfOut* out, const SherfDebug* debug /* may be NULL */,
                          void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out);
 
+/* Stage 0 + 1 alone (renderer.py:299-321): the number of samples within 5 cm of the body, i.e. the length of the compacted point list
+ * the forward will process (what a caller needs to draw per-point density noise exactly like renderer.py:435-436).  Synchronises. */
+SHERF_API int sherf_count_survivors(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfRays* rays,
+                                    const SherfOptions* opts, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out);
+
 /* Replaces get_transform_params_torch (renderer.py:129-157) for one pose: writes the 24 rigid
  * transforms A[24,4,4] (device).  Exposed for tests and for the dataset-side SMPL forward. */
 SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* pose, float* A_out /* [24,16] device */,
                          void* scratch, size_t scratch_bytes, void* stream);
+
+/* Dataset-side SMPL forward: the posed vertices of one frame, replacing sherf/smpl/smpl_numpy.py:46-98
+ * (`SMPL.__call__`) and the `xyz @ R.T + Th` of RenderPeople_dataset.py:210 on the host.  verts_smpl [V,3] (SMPL space) and / or
+ * verts_world [V,3] (= input_data['vertices']); either may be NULL.  fp64 inside (as numpy), float32 out.  scratch >= 4 KB. */
+SHERF_API int sherf_smpl_vertices(const SherfSmplModel* smpl, const SherfPose* pose, float* verts_smpl, float* verts_world, void* scratch,
+                                  size_t scratch_bytes, void* stream);
 
 /* Global depth-clamp range of a full view: min/max over all rays of the first/last sample depth
  * (ray_marcher.py:57 via math_utils.py:101-118).  Host results; synchronises the stream. */

@@ -296,7 +296,7 @@ def unify_samples(d1, c1, s1, d2, c2, s2):
     return d, torch.gather(c, 1, idx[..., None].expand(-1, -1, 3)), torch.gather(s_, 1, idx)
 
 
-def evaluate_samples(weights: dict, smpl: dict, scene: dict, depths=None):
+def evaluate_samples(weights: dict, smpl: dict, scene: dict, depths=None, density_noise_points=None):
     """renderer.py:299-371: everything between the depth samples and the dense [N,S] colour / density arrays
     (cull, warps, three gathers, fusion, transformer, decoder, scatter-back with sigma = -80 where culled)."""
     idt, opts = scene['input_data'], scene['rendering_options']
@@ -317,14 +317,16 @@ def evaluate_samples(weights: dict, smpl: dict, scene: dict, depths=None):
         tri = gather_triplane(scene['planes'], can, idt['t_world_bounds'][0])
         dec = fuse_and_decode(weights, tri, f2d, f3d, can, cdir)
         colors[sel] = dec['rgb']
-        sigma[sel] = dec['sigma']
+        # renderer.py:435-436: sigma += randn_like(sigma) * density_noise on the surviving points (the draws are an input here)
+        sigma[sel] = dec['sigma'] if density_noise_points is None else dec['sigma'] + density_noise_points.reshape(-1)[:sel.numel()]
         st.update({'can': can, 'cdir': cdir, 'id3': id3, 'world_src': world, 'uv': uv, 'f2d': f2d, 'f3d_raw': f3d_raw,
                    'f3d': f3d, 'tri': tri, **dec})
     return colors.view(N, S, 3), sigma.view(N, S), st
 
 
 @torch.no_grad()
-def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool = False, importance_u=None, depth_clamp=None):
+def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool = False, importance_u=None, depth_clamp=None,
+                   density_noise_points=None):
     """The whole hot path.  `weights`: state-dict names prefixed 'renderer.' / 'decoder.' (SURVEY §8b).
     Returns rgb[1,N,3], depth[1,N,1], acc[1,N,1] (+ stages dict).
 
@@ -338,7 +340,7 @@ def render_forward(weights: dict, smpl: dict, scene: dict, return_stages: bool =
     opts = scene['rendering_options']
     assert opts['clamp_mode'] == 'relu'
     rays_d = scene['ray_directions'][0]
-    colors, sigma, st = evaluate_samples(weights, smpl, scene)
+    colors, sigma, st = evaluate_samples(weights, smpl, scene, density_noise_points=density_noise_points)
     n_imp = int(opts.get('depth_resolution_importance', 0) or 0)
     if n_imp > 0:
         assert importance_u is not None, 'the fine pass needs the uniform draws (torch.rand at renderer.py:526)'

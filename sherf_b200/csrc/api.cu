@@ -278,6 +278,16 @@ static int validate(const SherfSmplModel* smpl, const SherfFrame* fr, const Sher
     set_error("null device pointer in arguments");
     return SHERF_E_INVALID;
   }
+  {
+    const SherfPose* poses[3] = {&fr->target, &fr->canonical, &fr->obs};
+    bool ok = fr->vertices && fr->t_vertices && fr->t_world_bounds && fr->obs_K && fr->obs_R && fr->obs_T && fr->sp_bounds && smpl->v_template &&
+              smpl->shapedirs && smpl->j_regressor;
+    for (int i = 0; i < 3; ++i) ok = ok && poses[i]->poses && poses[i]->shapes;
+    ok = ok && fr->target.R && fr->target.Th && fr->obs.R && fr->obs.Th;
+    const float* const* wp = reinterpret_cast<const float* const*>(w);
+    for (size_t i = 0; i < sizeof(SherfWeights) / sizeof(const float*); ++i) ok = ok && wp[i] != nullptr;
+    if (!ok) { set_error("null device pointer in SherfFrame / SherfSmplModel / SherfWeights"); return SHERF_E_INVALID; }
+  }
   return SHERF_OK;
 }
 
@@ -303,6 +313,16 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   StageTimer tm;
   tm.init(g_profiling != 0, st);
   g_tm = &tm;
+  // every exit path (the RC / SHERF_CUDA_OK early returns included) clears the thread-local timer pointer and, if the side stream was
+  // forked and not yet joined, joins it into the caller's stream: the caller may free its tensors as soon as ITS stream has passed
+  struct Guard {
+    cudaStream_t st; bool forked = false, joined = false;
+    ~Guard() {
+      g_tm = nullptr;
+      if (forked && !joined && g_side.s) { cudaEventRecord(g_side.ldone, g_side.s); cudaStreamWaitEvent(st, g_side.ldone, 0); }
+    }
+  } guard;
+  guard.st = st;
 
   // ---- stage 0 + 1.  Per-frame work is split by consumer.  The caller's stream runs only what the cull needs (FrameConst, posed
   //      vertices in SMPL space, cull grid, depth range) and goes straight on to the cull + ordered compaction; an internal side stream
@@ -314,7 +334,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   cudaStream_t ls = side ? g_side.s : st;
   tm.begin(0);
   RC(run_prologue_frame(*frame, L.ft, st));
-  if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); }
+  if (side) { SHERF_CUDA_OK(cudaEventRecord(g_side.fork, st)); SHERF_CUDA_OK(cudaStreamWaitEvent(ls, g_side.fork, 0)); guard.forked = true; }
   RC(run_prologue_cull(*smpl, *frame, *rays, *opts, L.ft, st));
   tm.end();
   tm.begin(1);
@@ -450,7 +470,7 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   // (front_fused / xformer_bf16 / decoder_pp, i.e. the default bf16x3 path without debug taps).  The host then waits for the COUNT EVENT
   // only -- the GPU is already working on chunk 0 -- and enqueues the remaining chunks with exact counts.
   const bool async_first = fplan.fr_blob && fplan.xb_blob && use_pp && !dbg && !getenv("SHERF_SYNC_FIRST_CHUNK");
-  if (side) SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.ldone, 0));          // layouts + packed weights are ready
+  if (side) { SHERF_CUDA_OK(cudaStreamWaitEvent(st, g_side.ldone, 0)); guard.joined = true; }         // layouts + packed weights are ready
   if (async_first)
     RC(issue_chunk(L.point_sample, L.point_vid, 0, cb.cap, S, nullptr, L.sigma, L.rgb, nullptr, DevCount{L.total, 0, cb.cap}, 0, false, st));
   const double t_sync0 = now_us();
@@ -503,9 +523,36 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     tm.end();
   }
   tm.finish();
-  g_tm = nullptr;
   g_last_launches = g_launches.n;
   { const double t_exit = now_us(); g_host_us[0] = (float)(t_sync0 - t_enter); g_host_us[1] = (float)(t_sync1 - t_sync0); g_host_us[2] = (float)(t_exit - t_sync1); g_host_us[3] = (float)(t_exit - t_enter); }
+  return SHERF_OK;
+}
+
+int sherf_count_survivors(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfRays* rays, const SherfOptions* opts,
+                          void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {
+  g_err[0] = 0;
+  if (!smpl || !frame || !scene || !rays || !opts || !scratch || !n_points_out) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (rays->n_rays <= 0 || rays->n_samples < 2 || rays->n_samples > 256 || !rays->origins || !rays->dirs || !rays->near_ || !rays->far_) {
+    set_error("bad rays"); return SHERF_E_INVALID;
+  }
+  const int N = rays->n_rays, S = rays->n_samples, SF = rays->n_importance, V = smpl->n_verts;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a{(char*)scratch, scratch_bytes, 0, false};
+  const size_t mis = ((size_t)a.base) & 255;
+  if (mis) { a.base += 256 - mis; a.size -= 256 - mis; }
+  Layout L;
+  const size_t need = carve(a, *scene, N, S, SF, V, L);
+  if (need > a.size) { set_error("scratch arena too small: need %zu bytes, have %zu", need, scratch_bytes); return SHERF_E_SCRATCH; }
+  g_launches.n = 0;
+  RC(run_prologue_frame(*frame, L.ft, st));
+  RC(run_prologue_cull(*smpl, *frame, *rays, *opts, L.ft, st));
+  RC(run_cull(*rays, S, nullptr, L.ft, L.sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
+  int64_t* hcount = pinned_counts();
+  if (!hcount) { set_error("cudaHostAlloc failed for the survivor-count words"); return SHERF_E_CUDA; }
+  SHERF_CUDA_OK(cudaMemcpyAsync(&hcount[2], L.total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SHERF_CUDA_OK(cudaStreamSynchronize(st));
+  *n_points_out = hcount[2];
+  g_last_launches = g_launches.n;
   return SHERF_OK;
 }
 
@@ -613,6 +660,20 @@ int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* pose, floa
   float* pf = joints + kJoints * 3;
   g_launches.n = 0;
   RC(run_lbs_only(*smpl, *pose, A_out, joints, pf, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
+int sherf_smpl_vertices(const SherfSmplModel* smpl, const SherfPose* pose, float* verts_smpl, float* verts_world, void* scratch, size_t scratch_bytes,
+                        void* stream) {
+  g_err[0] = 0;
+  if (!smpl || !pose || !scratch || (!verts_smpl && !verts_world)) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (!smpl->v_template || !smpl->shapedirs || !smpl->posedirs || !smpl->j_regressor || !smpl->weights || !pose->poses || !pose->shapes || smpl->n_verts <= 0) {
+    set_error("null device pointer in SherfSmplModel / SherfPose"); return SHERF_E_INVALID;
+  }
+  if (verts_world && (!pose->R || !pose->Th)) { set_error("verts_world needs SherfPose.R and .Th"); return SHERF_E_INVALID; }
+  g_launches.n = 0;
+  RC(run_smpl_vertices(*smpl, *pose, verts_smpl, verts_world, scratch, scratch_bytes, (cudaStream_t)stream));
   g_last_launches = g_launches.n;
   return SHERF_OK;
 }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_composite(const float* __restrict__ dir
       t = sample_depth(nr, fr, i, S);
       const float delta = ((i == S - 1) ? 1e10f : (sample_depth(nr, fr, i + 1, S) - t)) * dnorm;   // ray_marcher.py:27-29
       float sg = sigma[p];
-      if (noise) sg += noise[s];                                            // renderer.py:435-436
+      if (noise) sg += noise[p];                                            // per SURVIVING point, compacted order: renderer.py:435-436
       alpha = 1.f - expf(-(fmaxf(sg, 0.f) * delta));                        // ray_marcher.py:39-45
       r = rgb[(size_t)p * 3]; g = rgb[(size_t)p * 3 + 1]; bl = rgb[(size_t)p * 3 + 2];
     }

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
   __shared__ __align__(8) uint64_t a_full[2], a_free[2], w_full[2], acc1, acc2, f3d_ready;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bp[96], s_br[32];
+  __shared__ float s_pt[128][8];      // per point: gn xyz | cn xyz | u v (see phase A)
   const GatherParams& P = a.G;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l8 = lane & 7, gbase = lane & 24;
   const int c4 = 4 * l8;
@@ -176,16 +177,19 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
     const bool has_next = tile + (int)gridDim.x < ntiles;
     // =========================== phase A: geometry of this lane group's two points ===========================
-    float can[2][3], uvp[2][2];
+    // The per-point coordinates every later chunk needs -- 3-D grid coordinates gn (renderer.py:544-556), tri-plane coordinates cn
+    // (renderer.py:218-243), observation pixel uv (renderer.py:686-704) -- go to shared memory (s_pt[row][8]); the chunk loop reloads
+    // what it needs, so nothing of a point stays in registers between chunks.
     int64_t gpt[2];
     bool act[2];
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) {
       const int lp_raw = tile * 128 + gi + 64 * p;
-      act[p] = lp_raw < np;
-      const int lp = act[p] ? lp_raw : np - 1;             // rows beyond the list shadow the last point; nothing of them is stored
+      const bool actp = lp_raw < np;
+      if (p == 0) act[0] = actp; else act[1] = actp;
+      const int lp = actp ? lp_raw : np - 1;                 // rows beyond the list shadow the last point; nothing of them is stored
       const int64_t gp = P.p0 + lp;
-      gpt[p] = gp;
+      if (p == 0) gpt[0] = gp; else gpt[1] = gp;
       const int s = P.point_sample[gp];
       const int n = s / P.S, i = s - n * P.S;
       const float t = P.depths ? P.depths[s] : sample_depth(P.nearv[n], P.farv[n], i, P.S);
@@ -209,9 +213,18 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       for (int k = 0; k < 3; ++k) cam[k] += fc.camT[k];
       mat3_vec(fc.camK, cam, pix);                                                     // renderer.py:686-704
       const float zz = pix[2] + 1e-5f;
-      uvp[p][0] = pix[0] / zz; uvp[p][1] = pix[1] / zz;
-      can[p][0] = cn[0]; can[p][1] = cn[1]; can[p][2] = cn[2];
-      if (act[p]) {
+      const float u = pix[0] / zz, v = pix[1] / zz;
+      {
+        // lane l8 < 3: gn_k = ((can_k - bounds_min_k) / 0.005) / out_sh[2-k] * 2 - 1; 3..5: cn_k = 2 (can_k - lo_k) / (hi_k - lo_k) - 1; 6, 7: u, v
+        const int k3 = l8 < 3 ? l8 : (l8 < 6 ? l8 - 3 : 0);
+        const float ck = k3 == 0 ? cn[0] : (k3 == 1 ? cn[1] : cn[2]);
+        float val;
+        if (l8 < 3) val = ((ck - fc.spb_min[k3]) / 0.005f) / fc.out_sh[2 - k3] * 2.f - 1.f;
+        else if (l8 < 6) val = 2.f * (ck - fc.twb_min[k3]) / (fc.twb_max[k3] - fc.twb_min[k3]) - 1.f;
+        else val = l8 == 6 ? u : v;
+        s_pt[gi + 64 * p][l8] = val;
+      }
+      if (actp) {
         float gval = 0.f;
         if (l8 == 0) gval = cn[0]; else if (l8 == 1) gval = cn[1]; else if (l8 == 2) gval = cn[2];
         else if (l8 == 3) gval = cdir[0]; else if (l8 == 4) gval = cdir[1]; else if (l8 == 5) gval = cdir[2];
@@ -220,151 +233,184 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
           if (P.dbg_vid3) P.dbg_vid3[gp] = vid3;
           if (P.dbg_can) { P.dbg_can[gp * 3] = cn[0]; P.dbg_can[gp * 3 + 1] = cn[1]; P.dbg_can[gp * 3 + 2] = cn[2]; }
           if (P.dbg_cdir) { P.dbg_cdir[gp * 3] = cdir[0]; P.dbg_cdir[gp * 3 + 1] = cdir[1]; P.dbg_cdir[gp * 3 + 2] = cdir[2]; }
-          if (P.dbg_uv) { P.dbg_uv[gp * 2] = uvp[p][0]; P.dbg_uv[gp * 2 + 1] = uvp[p][1]; }
+          if (P.dbg_uv) { P.dbg_uv[gp * 2] = u; P.dbg_uv[gp * 2 + 1] = v; }
         }
       }
     }
+    __syncwarp();                                            // s_pt rows of this lane group are read back by the same 8 lanes
 
-    // =========================== chunk plumbing ===========================
-    // chunk c (0..11) of this tile uses operand slot b = c & 1 for the (ti * 6 + c / 2)-th time
-    auto begin_chunk = [&](int c) -> unsigned char* {
-      const int b = c & 1;
-      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
-      umma::mbar_wait(&a_free[b], (u & 1u) ^ 1u);            // the MMAs that read this slot two chunks ago have completed
-      if (warp == 0 && lane == 0 && c >= 2 && c <= 7) {      // ... and so have the reads of weight stage b: refill it
-        const int wc = c <= 5 ? c : c - 6;                   // this tile's chunk c, or the next tile's chunk 0 / 1
-        if (c <= 5 || has_next) {
-          umma::mbar_arrive_expect_tx(&w_full[b], fr::kWpStage);
-          umma::bulk_g2s(smem + fr::kWp + b * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[b]);
-        }
-      }
-      return smem + (b ? fr::kA1 : fr::kA0);
-    };
-    auto store4 = [&](unsigned char* buf, int p, const float4& v) {   // 4 channels of row gi + 64p -> bf16 hi | lo halves of a 16-byte core-matrix row
-      uint2 h, l;
-      umma::split_bf16x2(v.x, v.y, h.x, l.x);
-      umma::split_bf16x2(v.z, v.w, h.y, l.y);
-      unsigned char* dst = buf + (size_t)(l8 >> 1) * fr::kLboA + (size_t)(gi + 64 * p) * 16 + (l8 & 1) * 8;
-      *reinterpret_cast<uint2*>(dst) = h;
-      *reinterpret_cast<uint2*>(dst + fr::kChunkHalf) = l;
-    };
-    auto issue_chunk = [&](int c) {                           // warp 0 only, converged
-      const int b = c & 1;
-      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
-      umma::mbar_wait(&a_full[b], u & 1u);
-      const uint32_t a_hi = sbase + (b ? fr::kA1 : fr::kA0), a_lo = a_hi + fr::kChunkHalf;
-      if (c < 6) {
-        umma::mbar_wait(&w_full[b], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
-        umma::tc_fence_after_sync();
-        const uint32_t w_hi = sbase + fr::kWp + (uint32_t)b * fr::kWpStage;
-        gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
-        umma::mma_commit_e(&a_free[b], el);
-        if (c == 5) umma::mma_commit_e(&acc1, el);
-      } else {
-        umma::tc_fence_after_sync();
-        const int tt = (c - 6) % 3, sblk = c < 9 ? 0 : 1;     // tri_t -> source block 0 (first MMA of token t), f2d_t -> block 1
-        if (c == 9) {                                         // all three tokens are initialised: add the projected 3-D feature (source block 2)
-          umma::mbar_wait(&f3d_ready, ti & 1u);
-          umma::tc_fence_after_sync();
-          const uint32_t w2 = sbase + fr::kWr + 2u * fr::kWrBlock;
-          for (int t3 = 0; t3 < 3; ++t3)
-            gemm32(sbase + fr::kF3d + (uint32_t)(4 * t3) * fr::kLboF, fr::kLboF, true, fr::kF3dLo + (uint32_t)(16 * t3), w2, w2 + fr::kWrBlock / 2, 32,
-                   fr::kD2 + (uint32_t)(32 * t3), 1u);
-        }
-        const uint32_t wb = sbase + fr::kWr + (uint32_t)sblk * fr::kWrBlock;
-        gemm32(a_hi, fr::kLboA, false, a_lo, wb, wb + fr::kWrBlock / 2, 32, fr::kD2 + (uint32_t)(32 * tt), c < 9 ? 0u : 1u);
-        umma::mma_commit_e(&a_free[b], el);
-        if (c == 11) umma::mma_commit_e(&acc2, el);
-      }
-    };
-    auto end_chunk = [&](int c) {
-      umma::fence_proxy_async_smem();
-      umma::tc_fence_before_sync();
-      fr_arrive(&a_full[c & 1]);
-      if (warp == 0) { issue_chunk(c); __syncwarp(); }
-    };
-
-    // =========================== phase B: the 3-D pyramid, chunks 0..5 (renderer.py:544-556,762-797) ===========================
-    {
-      int c = 0;
+    // =========================== the twelve chunks: ONE loop body (compact code: the unrolled form was 24 500 instructions) ===========================
+    //   c = 0..5  3-D pyramid (level, 32-channel group) = (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)   renderer.py:544-556,762-797
+    //   c = 6..8  tri-plane k = c - 6 (align_corners=False)                                     renderer.py:234-243
+    //   c = 9,10  2-D feature map channels 0-31 / 32-63, c = 11 rgb encoding (align_corners=True, uv normalised by the IMAGE size) renderer.py:331-340
+    int offT[2] = {-1, -1}, offI[2] = {-1, -1};
+    float wT[2] = {0.f, 0.f}, wI[2] = {0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 12; ++c) {
+      // ---- tap setup where a new sample set starts (lane l8 prepares corner l8 of both points) ----
+      if (c == 0 || c == 1 || c == 3) {
+        const int l = c == 0 ? 0 : (c == 1 ? 1 : 2);
+        const int D = P.vol_d[l], Hh = P.vol_h[l], Ww = P.vol_w[l], C = P.vol_ch[l];
 #pragma unroll
-      for (int l = 0; l < 3; ++l) {
-        int offB[2]; float wB[2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {                          // lane l8 prepares corner l8 (bit0 x, bit1 y, bit2 z) of level l
-          const int D = P.vol_d[l], Hh = P.vol_h[l], Ww = P.vol_w[l], C = P.vol_ch[l];
-          float gn[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) gn[k] = ((can[p][k] - fc.spb_min[k]) / 0.005f) / fc.out_sh[2 - k] * 2.f - 1.f;
-          const float ix = (gn[0] + 1.f) * 0.5f * (float)(Ww - 1), iy = (gn[1] + 1.f) * 0.5f * (float)(Hh - 1), iz = (gn[2] + 1.f) * 0.5f * (float)(D - 1);
+        for (int p = 0; p < 2; ++p) {
+          const float* pt = s_pt[gi + 64 * p];
+          const float ix = (pt[0] + 1.f) * 0.5f * (float)(Ww - 1), iy = (pt[1] + 1.f) * 0.5f * (float)(Hh - 1), iz = (pt[2] + 1.f) * 0.5f * (float)(D - 1);
           const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
           const int bx = l8 & 1, by = (l8 >> 1) & 1, bz = (l8 >> 2) & 1;
           const int xx = (int)fx + bx, yy = (int)fy + by, zz2 = (int)fz + bz;
           const float wx = bx ? ix - fx : (fx + 1.f) - ix, wy = by ? iy - fy : (fy + 1.f) - iy, wz = bz ? iz - fz : (fz + 1.f) - iz;
-          wB[p] = wx * wy * wz;
-          offB[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh && zz2 >= 0 && zz2 < D) ? ((zz2 * Hh + yy) * Ww + xx) * C : -1;
+          wT[p] = wx * wy * wz;
+          offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh && zz2 >= 0 && zz2 < D) ? ((zz2 * Hh + yy) * Ww + xx) * C : -1;
         }
+      } else if (c >= 6 && c <= 8) {
+        const int k = c - 6;
+        const int Ww = P.plane_w, Hh = P.plane_h;
 #pragma unroll
-        for (int gsel = 0; gsel < 3; ++gsel) {
-          if (gsel <= l) {                                     // level l has 32 * (l + 1) channels
-            unsigned char* buf = begin_chunk(c);
-            const float* vol = P.vol_cl[l] + c4 + 32 * gsel;
+        for (int p = 0; p < 2; ++p) {
+          const float* pt = s_pt[gi + 64 * p];
+          const float px = k == 2 ? pt[5] : pt[3], py = k == 1 ? pt[5] : pt[4];
+          const float ix = ((px + 1.f) * (float)Ww - 1.f) * 0.5f, iy = ((py + 1.f) * (float)Hh - 1.f) * 0.5f;
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
+          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+          wT[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+          offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
+        }
+      } else if (c == 9) {
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int tp = 0; tp < 8; ++tp) {
-                const int off = __shfl_sync(0xffffffffu, offB[p], gbase + tp);
-                const float w = __shfl_sync(0xffffffffu, wB[p], gbase + tp);
-                const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w;
-              }
-              store4(buf, p, acc);
-              if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 192 + 32 * c + c4) = acc;
-            }
-            end_chunk(c);
-            ++c;
+        for (int p = 0; p < 2; ++p) {
+          const float* pt = s_pt[gi + 64 * p];
+          const float gx = 2.0f * pt[6] / (float)P.img_w - 1.0f, gy = 2.0f * pt[7] / (float)P.img_h - 1.0f;
+          const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
+          {
+            const int Ww = P.feat_w, Hh = P.feat_h;
+            const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+            wT[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+            offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * P.feat_ch : -1;
+          }
+          {
+            const int Ww = P.img_w, Hh = P.img_h;
+            const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+            wI[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+            offI[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
           }
         }
       }
-    }
-    // =========================== chunks 6..8: tri-planes (renderer.py:234-243, align_corners=False) ===========================
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      int offA[2]; float wA[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {                            // lanes 0-3 of the group prepare the four corners (nw, ne, sw, se)
-        float cn[3];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) cn[e] = 2.f * (can[p][e] - fc.twb_min[e]) / (fc.twb_max[e] - fc.twb_min[e]) - 1.f;
-        const float px = k == 2 ? cn[2] : cn[0], py = k == 1 ? cn[2] : cn[1];
-        const int Ww = P.plane_w, Hh = P.plane_h;
-        const float ix = ((px + 1.f) * (float)Ww - 1.f) * 0.5f, iy = ((py + 1.f) * (float)Hh - 1.f) * 0.5f;
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
-        const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-        const float wx = cxb ? ix - fx : (fx + 1.f) - ix, wy = cyb ? iy - fy : (fy + 1.f) - iy;
-        wA[p] = wx * wy;
-        offA[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
+      // ---- operand slot b = c & 1, used for the (ti * 6 + c / 2)-th time: wait until the MMAs that read it two chunks ago have completed ----
+      const int b = c & 1;
+      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
+      umma::mbar_wait(&a_free[b], (u & 1u) ^ 1u);
+      if (warp == 0 && c >= 2 && c <= 7 && (c <= 5 || has_next)) {   // ... and so have the reads of weight stage b: refill it (predicated, no lane branch)
+        const int wc = c <= 5 ? c : c - 6;                    // this tile's chunk c, or the next tile's chunk 0 / 1
+        umma::mbar_arrive_expect_tx_e(&w_full[b], fr::kWpStage, el);
+        umma::bulk_g2s_e(smem + fr::kWp + b * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[b], el);
       }
-      unsigned char* buf = begin_chunk(6 + k);
-      const float* base = P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + c4;
+      unsigned char* buf = smem + (b ? fr::kA1 : fr::kA0);
+      // ---- gather the chunk's 32 channels of both points: 8 lanes x float4 per tap ----
+      const int ntap = c < 6 ? 8 : 4;
+      const float* src;
+      int dbg_col;
+      if (c < 6) { const int l = c == 0 ? 0 : (c < 3 ? 1 : 2); src = P.vol_cl[l] + 32 * (c - (l == 0 ? 0 : (l == 1 ? 1 : 3))); dbg_col = 192 + 32 * c; }
+      else if (c < 9) { src = P.planes_cl + (size_t)(c - 6) * P.plane_h * P.plane_w * 32; dbg_col = 32 * (c - 6); }
+      else { src = P.feat_cl + 32 * (c - 9); dbg_col = 96 + 32 * (c - 9); }
+      src += c4;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < 11) {
+          // all tap offsets / weights first (shuffles), then ALL loads back to back, then the blend: written this way so that the
+          // 4 or 8 16-byte loads of a point are in flight together (interleaved, every FMA group stalled on its own load: r2c profile,
+          // long-scoreboard 38 % of the stall samples)
+          int off[8]; float w[8];
 #pragma unroll
-        for (int tp = 0; tp < 4; ++tp) {
-          const int off = __shfl_sync(0xffffffffu, offA[p], gbase + tp);
-          const float w = __shfl_sync(0xffffffffu, wA[p], gbase + tp);
-          const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tp == 0) { acc.x = val.x * w; acc.y = val.y * w; acc.z = val.z * w; acc.w = val.w * w; }
-          else { acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w; }
+          for (int tp = 0; tp < 8; ++tp) {
+            off[tp] = __shfl_sync(0xffffffffu, offT[p], gbase + tp);
+            w[tp] = __shfl_sync(0xffffffffu, wT[p], gbase + tp);
+          }
+          float4 val[8];
+#pragma unroll
+          for (int tp = 0; tp < 8; ++tp)
+            val[tp] = (tp < ntap && off[tp] >= 0) ? __ldg(reinterpret_cast<const float4*>(src + off[tp])) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // grid_sample accumulates the corners in this order; the 2-D form starts from the first product, the 3-D form from zero
+          if (c >= 6) { acc.x = val[0].x * w[0]; acc.y = val[0].y * w[0]; acc.z = val[0].z * w[0]; acc.w = val[0].w * w[0]; }
+          else { acc.x += val[0].x * w[0]; acc.y += val[0].y * w[0]; acc.z += val[0].z * w[0]; acc.w += val[0].w * w[0]; }
+#pragma unroll
+          for (int tp = 1; tp < 8; ++tp) {
+            if (tp < ntap) { acc.x += val[tp].x * w[tp]; acc.y += val[tp].y * w[tp]; acc.z += val[tp].z * w[tp]; acc.w += val[tp].w * w[tp]; }
+          }
+        } else {
+          float rgbc = 0.f;
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {
+            const int offi = __shfl_sync(0xffffffffu, offI[p], gbase + tp);
+            const float wi = __shfl_sync(0xffffffffu, wI[p], gbase + tp);
+            const float vi = (l8 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l8 * P.img_h * P.img_w + offi) : 0.f;
+            rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
+          }
+          // rgb_enc outputs 4*l8 .. 4*l8+3 of the 32 kept ones: [r, g, b, sin(..) ...]                        renderer.py:339,900-916
+          const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
+                      r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
+          float enc[4];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int o = c4 + e4;
+            if (o < 3) enc[e4] = o == 0 ? r0 : (o == 1 ? r1 : r2);
+            else {
+              const int e = o - 3, m = e / 3, cc = e - 3 * m;
+              const float xc = cc == 0 ? r0 : (cc == 1 ? r1 : r2);
+              enc[e4] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+            }
+          }
+          acc = make_float4(enc[0], enc[1], enc[2], enc[3]);
+          dbg_col = 160;
         }
-        store4(buf, p, acc);
-        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 32 * k + c4) = acc;
+        {                                                      // 4 channels of row gi + 64p -> bf16 hi | lo halves of a 16-byte core-matrix row
+          uint2 h, l;
+          umma::split_bf16x2(acc.x, acc.y, h.x, l.x);
+          umma::split_bf16x2(acc.z, acc.w, h.y, l.y);
+          unsigned char* dst = buf + (size_t)(l8 >> 1) * fr::kLboA + (size_t)(gi + 64 * p) * 16 + (l8 & 1) * 8;
+          *reinterpret_cast<uint2*>(dst) = h;
+          *reinterpret_cast<uint2*>(dst + fr::kChunkHalf) = l;
+        }
+        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + dbg_col + c4) = acc;
       }
-      end_chunk(6 + k);
-      if (k == 0) {
+      // ---- hand the chunk over ----
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before_sync();
+      fr_arrive(&a_full[b]);
+      if (warp == 0) {                                         // MMA issue (warp-uniform branch; one elected lane issues)
+        umma::mbar_wait(&a_full[b], u & 1u);
+        const uint32_t a_hi = sbase + (b ? fr::kA1 : fr::kA0), a_lo = a_hi + fr::kChunkHalf;
+        if (c < 6) {
+          umma::mbar_wait(&w_full[b], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
+          umma::tc_fence_after_sync();
+          const uint32_t w_hi = sbase + fr::kWp + (uint32_t)b * fr::kWpStage;
+          gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
+          umma::mma_commit_e(&a_free[b], el);
+          if (c == 5) umma::mma_commit_e(&acc1, el);
+        } else {
+          umma::tc_fence_after_sync();
+          const int tt = (c - 6) % 3, sblk = c < 9 ? 0 : 1;     // tri_t -> source block 0 (first MMA of token t), f2d_t -> block 1
+          if (c == 9) {                                         // all three tokens are initialised: add the projected 3-D feature (source block 2)
+            umma::mbar_wait(&f3d_ready, ti & 1u);
+            umma::tc_fence_after_sync();
+            const uint32_t w2 = sbase + fr::kWr + 2u * fr::kWrBlock;
+#pragma unroll 1
+            for (int t3 = 0; t3 < 3; ++t3)
+              gemm32(sbase + fr::kF3d + (uint32_t)(4 * t3) * fr::kLboF, fr::kLboF, true, fr::kF3dLo + (uint32_t)(16 * t3), w2, w2 + fr::kWrBlock / 2, 32,
+                     fr::kD2 + (uint32_t)(32 * t3), 1u);
+          }
+          const uint32_t wb = sbase + fr::kWr + (uint32_t)sblk * fr::kWrBlock;
+          gemm32(a_hi, fr::kLboA, false, a_lo, wb, wb + fr::kWrBlock / 2, 32, fr::kD2 + (uint32_t)(32 * tt), c < 9 ? 0u : 1u);
+          umma::mma_commit_e(&a_free[b], el);
+          if (c == 11) umma::mma_commit_e(&acc2, el);
+        }
+      }
+      if (c == 6) {
         // =========================== E1: projected 3-D feature -> reprojection operand (on-chip only) ===========================
         umma::mbar_wait(&acc1, ti & 1u);
         umma::tc_fence_after_sync();
@@ -388,80 +434,6 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
         fr_arrive(&f3d_ready);
       }
     }
-    // =========================== chunks 9..11: pixel-aligned 2-D features + rgb encoding (renderer.py:331-340) ===========================
-    {
-      int offF[2], offI[2]; float wF[2], wI[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {                            // align_corners=True, uv normalised by the IMAGE size for both maps
-        const float gx = 2.0f * uvp[p][0] / (float)P.img_w - 1.0f, gy = 2.0f * uvp[p][1] / (float)P.img_h - 1.0f;
-        const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
-        {
-          const int Ww = P.feat_w, Hh = P.feat_h;
-          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
-          const float fx = floorf(ix), fy = floorf(iy);
-          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-          wF[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
-          offF[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * P.feat_ch : -1;
-        }
-        {
-          const int Ww = P.img_w, Hh = P.img_h;
-          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
-          const float fx = floorf(ix), fy = floorf(iy);
-          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-          wI[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
-          offI[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
-        }
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        unsigned char* buf = begin_chunk(9 + half);
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int tp = 0; tp < 4; ++tp) {
-            const int off = __shfl_sync(0xffffffffu, offF[p], gbase + tp);
-            const float w = __shfl_sync(0xffffffffu, wF[p], gbase + tp);
-            const float4 val = off >= 0 ? __ldg(reinterpret_cast<const float4*>(P.feat_cl + off + 32 * half + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp == 0) { acc.x = val.x * w; acc.y = val.y * w; acc.z = val.z * w; acc.w = val.w * w; }
-            else { acc.x += val.x * w; acc.y += val.y * w; acc.z += val.z * w; acc.w += val.w * w; }
-          }
-          store4(buf, p, acc);
-          if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 96 + 32 * half + c4) = acc;
-        }
-        end_chunk(9 + half);
-      }
-      unsigned char* buf = begin_chunk(11);
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        float rgbc = 0.f;
-#pragma unroll
-        for (int tp = 0; tp < 4; ++tp) {
-          const int offi = __shfl_sync(0xffffffffu, offI[p], gbase + tp);
-          const float wi = __shfl_sync(0xffffffffu, wI[p], gbase + tp);
-          const float vi = (l8 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l8 * P.img_h * P.img_w + offi) : 0.f;
-          rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
-        }
-        // rgb_enc outputs 4*l8 .. 4*l8+3 of the 32 kept ones: [r, g, b, sin(..) ...]                        renderer.py:339,900-916
-        const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
-                    r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
-        float enc[4];
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-          const int o = c4 + e4;
-          if (o < 3) enc[e4] = o == 0 ? r0 : (o == 1 ? r1 : r2);
-          else {
-            const int e = o - 3, m = e / 3, cc = e - 3 * m;
-            const float xc = cc == 0 ? r0 : (cc == 1 ? r1 : r2);
-            enc[e4] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
-          }
-        }
-        const float4 ev = make_float4(enc[0], enc[1], enc[2], enc[3]);
-        store4(buf, p, ev);
-        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + 160 + c4) = ev;
-      }
-      end_chunk(11);
-    }
     // =========================== E2: tokens = D2 + bias -> global ===========================
     {
       umma::mbar_wait(&acc2, ti & 1u);
@@ -484,6 +456,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
         }
       }
     }
+    __syncwarp();                                            // every lane has read its s_pt rows before the next tile overwrites them
   }
   umma::tc_fence_before_sync();
   __syncthreads();

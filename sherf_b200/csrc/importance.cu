@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) k_importance_sample(const float* __restri
         const float t = sample_depth(nr, fr, i, S);
         const float delta = ((i == S - 1) ? 1e10f : (sample_depth(nr, fr, i + 1, S) - t)) * dnorm;
         float sg = sigma[p];
-        if (noise) sg += noise[s];
+        if (noise) sg += noise[p];                                          // per SURVIVING point, compacted order (renderer.py:435-436)
         alpha = 1.f - expf(-(fmaxf(sg, 0.f) * delta));
       }
       const float f = (p < e) ? (1.f - alpha + 1e-10f) : 1.f;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) k_composite_merged(const float* __restric
     if (p >= 0) {
       float sg;
       if (p & (1 << 30)) { sg = sigma_f[p & ~(1 << 30)]; if (noise_f) sg += noise_f[(size_t)n * SF + (e - S)]; }
-      else { sg = sigma_c[p]; if (noise_c) sg += noise_c[(size_t)n * S + e]; }
+      else { sg = sigma_c[p]; if (noise_c) sg += noise_c[p]; }
       alpha = 1.f - expf(-(fmaxf(sg, 0.f) * delta));
     }
     key[e] = alpha;

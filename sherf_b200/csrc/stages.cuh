@@ -152,6 +152,11 @@ size_t sparse_encoder_scratch_bytes(int n, const int32_t* out_sh);
 int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
                       void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+// Dataset-side SMPL forward (smpl_forward.cu): smpl_numpy.py:46-98
+size_t smpl_forward_scratch_bytes();
+int run_smpl_vertices(const SherfSmplModel& smpl, const SherfPose& pose, float* verts_smpl, float* verts_world, void* scratch, size_t scratch_bytes,
+                      cudaStream_t st);
+
 // Observation preparation (observation.cu): triplane.py:105-137
 size_t observation_scratch_bytes(int V, int maxcell);
 int run_prepare_observation(const SherfSmplModel& smpl, const SherfObservation& ob, float* vert_feat, int32_t* coord, uint8_t* vmask_out,

@@ -44,7 +44,6 @@ constexpr uint32_t kD3 = 0, kD4 = 0, kD5 = 64, kLo1 = 144, kLo2 = 192;     // LN
 
 struct XbArgs {
   const float *tok, *geo;              // [3np][32] tokens (conv1d_reprojection output), [np][8] can / cdir
-  const float* pe;                     // [np][64] positional encodings made by k_point_pe
   const unsigned char* wblob;          // canonical bf16 hi | lo
   const float *ln1_w, *ln1_b, *bo, *ln_w, *ln_b, *b1, *b2;
   unsigned char *xp, *vp;              // packed bf16 hi/lo decoder-input tiles (decoder_pp.cu)
@@ -193,7 +192,6 @@ __global__ void __launch_bounds__(288, 2) k_xformer_bf16(const XbArgs a) {
         if (mn < np) {
           pf(a.tok + (size_t)(mn * 3 + t) * 32);
           if (t == 0) { pf(a.tok + (size_t)(mn * 3 + 2) * 32); pf(a.geo + (size_t)mn * 8); }
-          pf(a.pe + (size_t)mn * 64 + 32 * t);
         }
       }
       // ---- three heads: attention of query token t over the three tokens ----
@@ -282,6 +280,8 @@ __global__ void __launch_bounds__(288, 2) k_xformer_bf16(const XbArgs a) {
       }
       // ---- ff2 + residual -> packed decoder inputs ----
       {
+        const float g0 = row_ok ? a.geo[(size_t)m * 8 + 3 * t] : 0.f, g1 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 1] : 0.f,
+                    g2 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 2] : 0.f;
         umma::mbar_wait(&acc_bar, par_acc);
         par_acc ^= 1;
         umma::tc_fence_after_sync();
@@ -293,54 +293,45 @@ __global__ void __launch_bounds__(288, 2) k_xformer_bf16(const XbArgs a) {
         float tok3[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { tok3[i] = __uint_as_float(o0[i]) + s_b2[i] + tok2[i]; tok3[16 + i] = __uint_as_float(o1[i]) + s_b2[16 + i] + tok2[16 + i]; }
-        float4 pev[9];
-        {
-          const float4* pr = reinterpret_cast<const float4*>(a.pe + (size_t)m * 64 + (t == 0 ? 0 : 36));
-#pragma unroll
-          for (int i = 0; i < 9; ++i) pev[i] = (row_ok && (t == 0 || i < 6)) ? __ldg(pr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float g0 = row_ok ? a.geo[(size_t)m * 8 + 3 * t] : 0.f, g1 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 1] : 0.f,
-                    g2 = row_ok ? a.geo[(size_t)m * 8 + 3 * t + 2] : 0.f;
-        const float* pef = reinterpret_cast<const float*>(pev);              // pef[3 * mm + c] = sin(phase_mm + g_c * 2^(mm >> 1))
-        auto put8 = [&](unsigned char* tile_base, int kg, uint32_t lo_off, const float* v8) {
+        // decoder inputs, one 8-column core-matrix row at a time (nothing but tok3 and the point's xyz stays live):
+        //   t = 0: X = [can(3) | PE6(can)(36) | tok0(32)] = 71 -> 80 columns;  t = 1: V = [cdir(3) | PE4(cdir)(24) | tok1(32)] = 59 -> 64 columns
+        // PositionalEncoding (renderer.py:900-916): pe[3*mm + c] = sin(phase(mm) + x_c * 2^(mm >> 1)), phase = 0 | pi/2, computed here
+        // with torch.addcmul's separately rounded multiply and add (the round-1 k_point_pe pass and its 256 B per point are gone).
+        auto col_value = [&](int col, int npe) -> float {              // `col` is a compile-time constant after unrolling
+          if (col < 3) return col == 0 ? g0 : (col == 1 ? g1 : g2);
+          if (col < 3 + npe) {
+            const int o = col - 3, mm = o / 3, cc = o - 3 * mm;
+            const float x = cc == 0 ? g0 : (cc == 1 ? g1 : g2);
+            return sinf(__fadd_rn((mm & 1) ? kPi2 : 0.f, __fmul_rn(x, (float)(1 << (mm >> 1)))));
+          }
+          const int o = col - 3 - npe;
+          return o < 32 ? tok3[o] : 0.f;
+        };
+        auto put8 = [&](unsigned char* tile_base, int kg, uint32_t lo_off, const float (&v8)[8]) {
           uint4 h, l;
           umma::split_bf16x2(v8[0], v8[1], h.x, l.x); umma::split_bf16x2(v8[2], v8[3], h.y, l.y);
           umma::split_bf16x2(v8[4], v8[5], h.z, l.z); umma::split_bf16x2(v8[6], v8[7], h.w, l.w);
           *reinterpret_cast<uint4*>(tile_base + (size_t)(kg * 128 + row) * 16) = h;
           *reinterpret_cast<uint4*>(tile_base + lo_off + (size_t)(kg * 128 + row) * 16) = l;
         };
-        if (t == 0) {                                        // X = [can | PE6(can) | tok0] (71 -> 80 columns)
-          float vals[80];
-          vals[0] = g0; vals[1] = g1; vals[2] = g2;
-#pragma unroll
-          for (int o = 0; o < 36; ++o) vals[3 + o] = pef[o];
-#pragma unroll
-          for (int o = 0; o < 32; ++o) vals[39 + o] = tok3[o];
-#pragma unroll
-          for (int o = 71; o < 80; ++o) vals[o] = 0.f;
-          if (!row_ok) {
-#pragma unroll
-            for (int o = 0; o < 71; ++o) vals[o] = 0.f;
-          }
+        if (t == 0) {
           unsigned char* tb_ = a.xp + (size_t)tile * 40960;
 #pragma unroll
-          for (int kg = 0; kg < 10; ++kg) put8(tb_, kg, 20480u, vals + 8 * kg);
-        } else {                                             // V = [cdir | PE4(cdir) | tok1] (59 -> 64 columns)
-          float vals[64];
-          vals[0] = g0; vals[1] = g1; vals[2] = g2;
+          for (int kg = 0; kg < 10; ++kg) {
+            float v8[8];
 #pragma unroll
-          for (int o = 0; o < 24; ++o) vals[3 + o] = pef[o];
-#pragma unroll
-          for (int o = 0; o < 32; ++o) vals[27 + o] = tok3[o];
-#pragma unroll
-          for (int o = 59; o < 64; ++o) vals[o] = 0.f;
-          if (!row_ok) {
-#pragma unroll
-            for (int o = 0; o < 59; ++o) vals[o] = 0.f;
+            for (int e = 0; e < 8; ++e) v8[e] = row_ok ? col_value(8 * kg + e, 36) : 0.f;
+            put8(tb_, kg, 20480u, v8);
           }
+        } else {
           unsigned char* tb_ = a.vp + (size_t)tile * 32768;
 #pragma unroll
-          for (int kg = 0; kg < 8; ++kg) put8(tb_, kg, 16384u, vals + 8 * kg);
+          for (int kg = 0; kg < 8; ++kg) {
+            float v8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v8[e] = row_ok ? col_value(8 * kg + e, 24) : 0.f;
+            put8(tb_, kg, 16384u, v8);
+          }
         }
         if (row_ok && a.dbg_tok && a.p0 + m < a.dbg_max) {
 #pragma unroll
@@ -395,9 +386,9 @@ int run_pack_xformer_bf16(const SherfWeights& w, unsigned char* blob, cudaStream
 int run_xformer_bf16(const SherfWeights& w, const unsigned char* blob, const float* tok, const float* geo, int np, float* dbg_tok, int64_t p0,
                      int64_t dbg_max, cudaStream_t st, unsigned char* xp, unsigned char* vp, float* pe_buf, DevCount dc) {
   if (np <= 0) return SHERF_OK;
-  { const int rc = run_point_pe(geo, pe_buf, np, st, dc); if (rc) return rc; }
+  (void)pe_buf;                                             // positional encodings are computed in the last epilogue
   XbArgs a;
-  a.tok = tok; a.geo = geo; a.pe = pe_buf; a.wblob = blob; a.ln1_w = w.ln1_w; a.ln1_b = w.ln1_b; a.bo = w.attn_out_b; a.ln_w = w.ln2_w;
+  a.tok = tok; a.geo = geo; a.wblob = blob; a.ln1_w = w.ln1_w; a.ln1_b = w.ln1_b; a.bo = w.attn_out_b; a.ln_w = w.ln2_w;
   a.ln_b = w.ln2_b; a.b1 = w.ff1_b; a.b2 = w.ff2_b; a.xp = xp; a.vp = vp; a.dbg_tok = dbg_tok; a.p0 = p0; a.dbg_max = dbg_max; a.np = np; a.dc = dc;
   static bool attr_done = false;
   static int num_sms = 148;

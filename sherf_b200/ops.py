@@ -55,6 +55,26 @@ def lbs_transforms(renderer, params: dict) -> torch.Tensor:
     return A
 
 
+def smpl_vertices(renderer, params: dict, world: bool = True) -> torch.Tensor:
+    """Posed SMPL vertices [1,V,3] of one frame through `sherf_smpl_vertices` (replaces the host-side sherf/smpl/smpl_numpy.py:46-98 and,
+    with `world`, the `xyz @ R.T + Th` of RenderPeople_dataset.py:210, i.e. `input_data['vertices']`).  `params`: CUDA tensors poses [..,72],
+    shapes [..,10], R [..,3,3], Th [..,3]."""
+    lib = _lib.load()
+    device = params['poses'].device
+    if device.type != 'cuda':
+        raise RuntimeError('sherf_b200.ops.smpl_vertices runs on CUDA tensors only (no CPU fallback)')
+    with torch.cuda.device(device):
+        keep = []
+        smpl = renderer._smpl_struct(device)
+        pose = renderer._pose_struct(params, device, keep)
+        out = torch.empty(1, smpl.n_verts, 3, device=device, dtype=torch.float32)
+        scratch = torch.empty(8192, dtype=torch.uint8, device=device)
+        _lib.check(lib.sherf_smpl_vertices(C.byref(smpl), C.byref(pose), None if world else out.data_ptr(), out.data_ptr() if world else None,
+                                           scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream(device).cuda_stream))
+        del keep
+    return out
+
+
 def depth_range(near: torch.Tensor, far: torch.Tensor, n_samples: int):
     """(min, max) of all stratified sample depths of a view through `sherf_depth_range` (torch.min / torch.max(depths),
     ray_marcher.py:57); near / far: CUDA tensors with one value per ray."""

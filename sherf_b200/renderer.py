@@ -442,7 +442,7 @@ class ImportanceRenderer(nn.Module):
     # -- the hot path ----------------------------------------------------------------------------------------------
     def forward(self, planes, obs_input_img, obs_input_feature, canonical_sp_conv_volume, obs_smpl_vertex_mask, obs_sp_input,
                 decoder, ray_origins, ray_directions, near, far, input_data, rendering_options, debug: dict | None = None,
-                depth_clamp: tuple | None = None, importance_u: torch.Tensor | None = None):
+                depth_clamp: tuple | None = None, importance_u: torch.Tensor | None = None, density_noise_points: torch.Tensor | None = None):
         """Same positional signature and return value as renderer.py:286,398:
         (rgb[B,N,3] in (-1,1), depth[B,N,1], acc[B,N,1]).  `canonical_sp_conv_volume` is the list of the three densified
         pyramid levels [1,32,D/2..], [1,64,D/4..], [1,96,D/8..] (what SparseConvNet.forward densifies at renderer.py:762-782), or
@@ -450,7 +450,9 @@ class ImportanceRenderer(nn.Module):
         which is first run through self.encoder_3d (csrc/sparse_encoder.cu).
         Extra keyword-only hooks: `debug` (dict filled with stage-wise tensors), `depth_clamp` ((min,max) of the full
         view's depths when this call renders a shard of its rays, ray_marcher.py:57) and `importance_u` ([N,S_f] uniform
-        draws replacing the torch.rand of renderer.py:526; drawn here with torch.rand when omitted).
+        draws replacing the torch.rand of renderer.py:526; drawn here with torch.rand when omitted) and `density_noise_points`
+        (already scaled additive sigma noise, one value per surviving point in compacted order, replacing the torch.randn_like of
+        renderer.py:435-436; drawn here, per 700 000-point chunk like the reference, when rendering_options['density_noise'] > 0).
 
         rendering_options['depth_resolution_importance'] > 0 runs the fine pass of renderer.py:373-393 in its repaired form
         (the reference's own call sites :376 / :383 cannot execute; see include/sherf_b200.h)."""
@@ -529,15 +531,6 @@ class ImportanceRenderer(nn.Module):
             if depth_clamp is not None:
                 opts.use_external_clamp, opts.depth_clamp_min, opts.depth_clamp_max = 1, float(depth_clamp[0]), float(depth_clamp[1])
             noise_scale = float(rendering_options.get('density_noise', 0) or 0)
-            if noise_scale > 0:
-                # renderer.py:435-436; drawn per SAMPLE here (the reference draws per surviving point), same distribution
-                nz = torch.randn(N * S, device=device, dtype=torch.float32) * noise_scale
-                keep.append(nz)
-                opts.density_noise = _ptr(nz)
-                if SF > 0:
-                    nzf = torch.randn(N * SF, device=device, dtype=torch.float32) * noise_scale
-                    keep.append(nzf)
-                    opts.density_noise_importance = _ptr(nzf)
             if SF > 0:
                 uu = torch.rand(N, SF, device=device) if importance_u is None else _dev32(importance_u, device)      # renderer.py:526
                 assert uu.numel() == N * SF, 'importance_u must be [N, depth_resolution_importance]'
@@ -558,6 +551,25 @@ class ImportanceRenderer(nn.Module):
             # in training mode, or a hot-path parameter requires grad) reuse is off: EMA / clamp / init code writes through `.data`,
             # which no signature can see (weights_version 0 = "pack on this call").
             opts.weights_version = 0 if volatile_weights else rt.w_epoch
+            if noise_scale > 0 or density_noise_points is not None:
+                # renderer.py:435-436: `sigma += randn_like(sigma) * density_noise` on the SURVIVING points, chunk by chunk of 700 000
+                # (renderer.py:355-362).  The count comes from the cull (run once more inside the forward: training-only cost).
+                if density_noise_points is None:
+                    cnt = C.c_int64(0)
+                    _lib.check(lib.sherf_count_survivors(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(rays), C.byref(opts),
+                                                         rt.scratch.data_ptr(), rt.scratch.numel(),
+                                                         torch.cuda.current_stream(device).cuda_stream, C.byref(cnt)))
+                    P_ = int(cnt.value)
+                    parts = [torch.randn(1, min(700000, P_ - i), 1, device=device, dtype=torch.float32) for i in range(0, P_, 700000)]
+                    nz = (torch.cat(parts, 1).reshape(-1) if parts else torch.zeros(1, device=device)) * noise_scale
+                else:
+                    nz = _dev32(density_noise_points, device).reshape(-1)
+                keep.append(nz)
+                opts.density_noise = _ptr(nz)
+                if SF > 0 and noise_scale > 0:
+                    nzf = torch.randn(N * SF, device=device, dtype=torch.float32) * noise_scale
+                    keep.append(nzf)
+                    opts.density_noise_importance = _ptr(nzf)
             # same idea for the feature tensors: while planes / 2-D map / volumes are the same storage and were not written in place,
             # the arena's channels-last copies are reused (one observation, many views / shards / poses).  Tensors that require grad or
             # were produced under autograd (training: the encoders run every step) are never cached.

@@ -28,7 +28,7 @@ def _camera(H, W, seed):
     return K, R, T, bounds
 
 
-@pytest.mark.skipif(not ref_shim.available(), reason='reference tree is only mounted in the build container')
+@pytest.mark.skipif(not ref_shim.mounted(), reason='reference tree is only mounted in the build container')
 def test_restatement_matches_reference_dataset_code():
     sys.modules.setdefault('imageio', types.ModuleType('imageio'))
     if ref_shim.REF_ROOT not in sys.path:
@@ -148,3 +148,34 @@ def test_sampler_writes_test_loop_style_outputs(smpl_model, tmp_path):
         assert np.array_equal(png, to8b((o[:, :3].reshape(H, W, 3) / 2 + 0.5).cpu().numpy()))
         assert np.array_equal(np.load(tmp_path / f'frame0007_view{v:04d}_acc.npy'), o[:, 4].reshape(H, W).cpu().numpy())
     assert float(torch.stack([o[:, 4].max() for o in outs]).max()) > 0.2          # the body is visible from the orbit
+
+
+@pytest.mark.skipif(not ref_shim.mounted(), reason='reference tree is only mounted in the build container')
+def test_smpl_forward_restatement_matches_reference_class(smpl_model, tmp_path, monkeypatch):
+    """synthetic.smpl_forward_np (what the GPU SMPL forward, sherf_smpl_vertices, is checked against) == the reference's own
+    `SMPL.__call__` (sherf/smpl/smpl_numpy.py:46-98) on the synthetic body, loaded through its own pickle path."""
+    import pickle
+    import scipy.sparse
+    cv2 = pytest.importorskip('cv2')                                        # smpl_numpy.py imports cv2.Rodrigues
+    if ref_shim.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_shim.REF_ROOT)
+    sys.dont_write_bytecode = True
+    (tmp_path / 'assets').mkdir()
+    m = dict(smpl_model)
+    m['J_regressor'] = scipy.sparse.csc_matrix(np.asarray(smpl_model['J_regressor'], np.float64))
+    for k in ('v_template', 'shapedirs', 'posedirs', 'weights'):
+        m[k] = np.asarray(smpl_model[k], np.float64)
+    m['f'] = np.asarray(smpl_model['f'])
+    m['kintree_table'] = np.asarray(smpl_model['kintree_table'])
+    with open(tmp_path / 'assets' / 'SMPL_NEUTRAL.pkl', 'wb') as f:
+        pickle.dump(m, f)
+    monkeypatch.chdir(tmp_path)
+    from smpl.smpl_numpy import SMPL
+    body = SMPL('neutral', str(tmp_path))
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        poses = rng.normal(0, 0.3, 72).astype(np.float32)
+        shapes = rng.normal(0, 0.7, 10).astype(np.float32)
+        want, _ = body(poses, shapes)
+        got = S.smpl_forward_np(smpl_model, poses, shapes)
+        assert np.abs(got - want).max() <= 2e-7, np.abs(got - want).max()   # cv2.Rodrigues rounds R to float32, the restatement keeps float64
