@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       // ---- operand slot b = c & 1, used for the (ti * 6 + c / 2)-th time: wait until the MMAs that read it two chunks ago have completed ----
       const int b = c & 1;
       const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
-      umma::mbar_wait(&a_free[b], (u & 1u) ^ 1u);
+      umma::mbar_wait_backoff(&a_free[b], (u & 1u) ^ 1u);
       if (warp == 0 && c >= 2 && c <= 7 && (c <= 5 || has_next)) {   // ... and so have the reads of weight stage b: refill it (predicated, no lane branch)
         const int wc = c <= 5 ? c : c - 6;                    // this tile's chunk c, or the next tile's chunk 0 / 1
         umma::mbar_arrive_expect_tx_e(&w_full[b], fr::kWpStage, el);
@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       umma::fence_proxy_async_smem();
       umma::tc_fence_before_sync();
       fr_arrive(&a_full[b]);
-      if (warp == 0) {                                         // MMA issue (warp-uniform branch; one elected lane issues)
+      // MMA issue, ROTATING over the warps (chunk c -> warp c): the issuer has to wait until all 512 threads have delivered the chunk; with a
+      // fixed issuer that warp was always the slowest of the CTA and every other warp spun on a_free behind it (r2f profile: 10 % of all
+      // executed instructions were that spin).  tcgen05 ordering across the issuing threads is carried by the fence::before_thread_sync /
+      // mbarrier / fence::after_thread_sync chain every chunk hand-over already has.
+      if (warp == c) {                                         // warp-uniform branch; one elected lane issues
         umma::mbar_wait(&a_full[b], u & 1u);
         const uint32_t a_hi = sbase + (b ? fr::kA1 : fr::kA0), a_lo = a_hi + fr::kChunkHalf;
         if (c < 6) {

@@ -76,6 +76,14 @@ class _Finder(importlib.abc.MetaPathFinder):
             spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)      # namespace package stand-in
             spec.submodule_search_locations = []
             return spec
+        if fullname == 'imageio':                                     # imported, unused, by the reference's triplane.py:27
+            for f in sys.meta_path:
+                if f is self or not hasattr(f, 'find_spec'):
+                    continue
+                spec = f.find_spec(fullname, path, target)
+                if spec is not None:
+                    return spec
+            return importlib.machinery.ModuleSpec(fullname, _StubLoader(), is_package=True)
         if fullname == 'spconv' or fullname.startswith('spconv.'):
             for f in sys.meta_path:
                 if f is self or not hasattr(f, 'find_spec'):
@@ -119,7 +127,7 @@ def uninstall():
     if _finder is not None:
         sys.meta_path.remove(_finder)
         _finder = None
-    for name in list(SHADOWED) + ['spconv', 'spconv.pytorch', 'spconv.core']:
+    for name in list(SHADOWED) + [n for n in list(sys.modules) if n == 'imageio' or n == 'spconv' or n.startswith('spconv.')]:
         m = sys.modules.get(name)
         if m is not None and (name in SHADOWED or isinstance(m, _StubModule)):
             del sys.modules[name]
