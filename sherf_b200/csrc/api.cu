@@ -339,7 +339,9 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.end();
   tm.begin(1);
   int* sample_vid = (dbg && dbg->sample_vid) ? dbg->sample_vid : L.sample_vid;
-  RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st));
+  // dense per-sample ids of rays that miss the body are only needed by the debug taps and by the merged march of the fine pass
+  RC(run_cull(*rays, S, nullptr, L.ft, sample_vid, L.ray_count, L.block_sums, L.ray_start, L.total, L.point_sample, L.point_vid, st,
+              (dbg != nullptr || SF > 0) ? 1 : 0));
   tm.end();
   int64_t* hcount = pinned_counts();
   if (!hcount) { set_error("cudaHostAlloc failed for the survivor-count words"); return SHERF_E_CUDA; }

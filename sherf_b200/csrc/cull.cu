@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) k_cull_candidates(const float* __restrict
                                                          const float* __restrict__ nearv, const float* __restrict__ farv, int N, int S,
                                                          const FrameConst* __restrict__ fcp, const unsigned char* __restrict__ occ,
                                                          const float* __restrict__ depths, int* __restrict__ sample_vid,
-                                                         int* __restrict__ ray_count, int* __restrict__ queue, int* __restrict__ queue_count) {
+                                                         int* __restrict__ ray_count, int* __restrict__ queue, int* __restrict__ queue_count,
+                                                         int write_all) {
   __shared__ FrameConst fc;
   for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)fcp)[i];
   __syncthreads();
@@ -55,18 +56,49 @@ __global__ void __launch_bounds__(256) k_cull_candidates(const float* __restrict
   const float nr = nearv[n], fr = farv[n];
   const GridDesc& g = fc.g1;
   if (lane == 0) ray_count[n] = 0;
+  // Conservative parameter interval [t0, t1] in which the ray can be inside the cull grid's box (slab test in SMPL space, box grown by
+  // 1 mm to cover the fp32 rounding of the exactly-rounded query below): a sample outside it cannot fall into a grid cell, so it is a
+  // non-candidate without transforming it.  ~85 % of the rays of a 512x512 view miss the box altogether; when nobody reads the dense
+  // per-sample ids of such rays (no debug taps, no fine pass: k_compact skips rays without survivors) their -1 entries are not even written.
+  float t0 = -3.0e38f, t1 = 3.0e38f;
+  {
+    float po[3] = {origins[n * 3] - fc.Th_tgt[0], origins[n * 3 + 1] - fc.Th_tgt[1], origins[n * 3 + 2] - fc.Th_tgt[2]};
+    float pd[3] = {dirs[n * 3], dirs[n * 3 + 1], dirs[n * 3 + 2]}, qo[3], qd[3];
+    rowvec_mat3(po, fc.R_tgt, qo);
+    rowvec_mat3(pd, fc.R_tgt, qd);
+    const float tmag = fmaxf(fabsf(nr), fabsf(fr));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float margin = 1.0e-3f + 1.0e-5f * (fabsf(qo[k]) + tmag * fabsf(qd[k]));
+      const float lo = g.origin[k] - margin, hi = g.origin[k] + (float)g.dim[k] * g.cell + margin;
+      if (fabsf(qd[k]) < 1.0e-12f) {
+        if (qo[k] < lo || qo[k] > hi) { t0 = 1.f; t1 = 0.f; }
+      } else {
+        const float a = (lo - qo[k]) / qd[k], b = (hi - qo[k]) / qd[k];
+        t0 = fmaxf(t0, fminf(a, b));
+        t1 = fminf(t1, fmaxf(a, b));
+      }
+    }
+    const float slack = 1.0e-5f * (fabsf(t0) + fabsf(t1)) + 1.0e-6f;
+    t0 -= slack; t1 += slack;
+  }
+  const bool ray_misses = !(t0 <= t1) || t1 < fminf(nr, fr) || t0 > fmaxf(nr, fr);
+  if (ray_misses && !write_all && !depths) return;           // stratified depths lie in [near, far]: nothing of this ray can be a candidate
   for (int i0 = 0; i0 < S; i0 += 32) {
     const int i = i0 + lane;
     bool cand = false;
     if (i < S) {
       const float t = depths ? depths[(size_t)n * S + i] : sample_depth(nr, fr, i, S);   // fine pass: importance-sampled depths
       float q[3];
+      if (t < t0 || t > t1) { sample_vid[(size_t)n * S + i] = -1; }
+      else {
       cull_query(fc, origins, dirs, n, t, q);
       const int cx = grid_coord(q[0], g.origin[0], g.inv_cell, g.dim[0]);
       const int cy = grid_coord(q[1], g.origin[1], g.inv_cell, g.dim[1]);
       const int cz = grid_coord(q[2], g.origin[2], g.inv_cell, g.dim[2]);
       cand = cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2] && occ[(cz * g.dim[1] + cy) * g.dim[0] + cx];
       if (!cand) sample_vid[(size_t)n * S + i] = -1;
+      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, cand);
     if (m) {
@@ -192,7 +224,7 @@ int run_exclusive_scan(const int* cnt, int n, int* block_sums, int* start, int64
 #define RC_SCAN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
-             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st) {
+             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st, int write_all) {
   const int N = rays.n_rays;
   const float thr = (float)(0.05 * 0.05);        // `distance < 0.05 ** 2` compares in fp32 (renderer.py:318-319)
   // candidate queue = point_sample (written by k_compact only after the search), its counter = the first word of total_dev
@@ -200,7 +232,7 @@ int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTable
   int* queue_count = reinterpret_cast<int*>(total_dev);
   SHERF_CUDA_OK(cudaMemsetAsync(queue_count, 0, sizeof(int), st));
   k_cull_candidates<<<ceil_div(N, 8), 256, 0, st>>>(rays.origins, rays.dirs, rays.near_, rays.far_, N, S, ft.fc, ft.g1_occ, depths,
-                                                    sample_vid, ray_count, queue, queue_count);
+                                                    sample_vid, ray_count, queue, queue_count, write_all);
   SHERF_LAUNCH_CHECK();
   k_cull_search<<<148 * 8, 256, 0, st>>>(rays.origins, rays.dirs, rays.near_, rays.far_, S, ft.fc, ft.g1_cell_start, ft.g1_verts, thr, depths,
                                          queue, queue_count, sample_vid, ray_count);

@@ -44,7 +44,7 @@ int run_to_channels_last_multi(int n, const float* const* in, float* const* out,
 int run_point_gather(const GatherParams& P, cudaStream_t st);
 // S / depths: the sample set to cull -- (rays.n_samples, NULL) for the stratified coarse samples, (rays.n_importance, t_fine) for the fine pass
 int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
-             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st);
+             int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st, int write_all = 1);
 
 // Row-major activation buffers of one chunk of `cap` points (fp32).
 struct ChunkBuffers {
