@@ -7,10 +7,13 @@
 // points, profiles/r1_ab) now go from the gather lanes' registers straight into the tensor-core operand slots in shared memory.
 //
 // One CTA = one 128-point tile at a time, 16 warps, TWO CTAs per SM (one CTA's gather overlaps the other's MMA / epilogue phases).
-//   gather : as in gather.cu, 8 lanes per point (lane l8 owns channels 4*l8..4*l8+3 of every 32-channel group, one 16-byte load per
-//            tap); each lane group owns rows g and g + 64 of the tile.  The tile is produced in twelve 32-channel CHUNKS
-//            (six of the 3-D pyramid, three tri-planes, two feature-map halves, the rgb encoding); a chunk's values are split into
-//            bf16 hi / lo and stored as the K-major no-swizzle UMMA operand (8 B per lane: conflict-free with LBO = 2080).
+//   gather : FOUR lanes per point (lane l4 owns channels 8*l4..8*l4+7 of every 32-channel group: two 16-byte loads per tap), so a warp
+//            covers 8 points and the 16 warps exactly one 128-point tile -- every per-point instruction (geometry, tap set-up, shuffles,
+//            address arithmetic) serves 8 points (the kernel is instruction-issue bound, not memory bound: with the tap loads, the MMAs
+//            and the knn-#3 search knocked out it still took 73 % of its time, profiles/README.md r2 knock-outs).  The tile is produced
+//            in twelve 32-channel CHUNKS (six of the 3-D pyramid, three tri-planes, two feature-map halves, the rgb encoding); a chunk's
+//            values are split into bf16 hi / lo and stored as the K-major no-swizzle UMMA operand (one 16-byte core-matrix row per lane
+//            and part: conflict-free with LBO = 2080).
 //   MMA    : bf16 split products a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05 kind::f16, fp32 accumulators in TMEM; chunk c's MMAs
 //            run while chunk c+1 is gathered (two operand slots; projection weights stream through a two-stage TMA ring, 12 KB per
 //            chunk from L2; reprojection weights resident).  Warp 0 issues (after producing its own part of the chunk).
@@ -45,6 +48,7 @@ struct FrontArgs {
   const unsigned char* wblob;          // 6 projection chunks (hi | lo), then 3 reprojection blocks (hi | lo)
   const float *bp, *br;                // conv1d_projection bias [96], conv1d_reprojection bias [32]
   float* tok;                          // [np][3][32]
+  int knock;                           // diagnostics only (SHERF_FRONT_KNOCK): 1 no knn-#3 search, 2 no tap loads, 4 no MMAs, 8 no phase A geometry
 };
 
 __device__ __forceinline__ void fr_arrive(uint64_t* bar) {
@@ -72,18 +76,18 @@ __device__ __forceinline__ void fr_apply_warp(const VertexWarp* __restrict__ Tp,
   }
 }
 
-__device__ __forceinline__ void fr_grp_lexmin(float& d, int& id) {
+__device__ __forceinline__ void fr_grp_lexmin(float& d, int& id) {      // over the 4 lanes of a point
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = 2; o > 0; o >>= 1) {
     const float od = __shfl_xor_sync(0xffffffffu, d, o);
     const int oi = __shfl_xor_sync(0xffffffffu, id, o);
     if (od < d || (od == d && oi < id)) { d = od; id = oi; }
   }
 }
 
-// exact K=1 search over the canonical vertices seeded by the nearest posed vertex (gather.cu: nn_seeded8), 8 lanes per point
-__device__ __forceinline__ int fr_nn_seeded8(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
-                                             const float* __restrict__ t_vertices, float qx, float qy, float qz, int l8, int seed) {
+// exact K=1 search over the canonical vertices seeded by the nearest posed vertex (gather.cu: nn_seeded8), 4 lanes per point
+__device__ __forceinline__ int fr_nn_seeded4(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ gv,
+                                             const float* __restrict__ t_vertices, float qx, float qy, float qz, int l4, int seed) {
   float best = dist2_xyz(qx, qy, qz, t_vertices[seed * 3], t_vertices[seed * 3 + 1], t_vertices[seed * 3 + 2]);
   int bid = seed;
   const float rb = sqrtf(best) * 1.0001f + 1.0e-4f * g.cell;
@@ -94,7 +98,7 @@ __device__ __forceinline__ int fr_nn_seeded8(const GridDesc& g, const int* __res
   const int z0 = min(max(grid_coord(qz - rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
   const int z1 = min(max(grid_coord(qz + rb, g.origin[2], g.inv_cell, g.dim[2]), 0), g.dim[2] - 1);
   const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncells = nx * ny * (z1 - z0 + 1);
-  for (int cc = l8; cc < ncells; cc += 8) {
+  for (int cc = l4; cc < ncells; cc += 4) {
     const int xx = x0 + cc % nx, t = cc / nx;
     const int cell = ((z0 + t / ny) * g.dim[1] + (y0 + t % ny)) * g.dim[0] + xx;
     const int b = cell_start[cell], e = cell_start[cell + 1];
@@ -118,8 +122,8 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
   __shared__ float s_bp[96], s_br[32];
   __shared__ float s_pt[128][8];      // per point: gn xyz | cn xyz | u v (see phase A)
   const GatherParams& P = a.G;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l8 = lane & 7, gbase = lane & 24;
-  const int c4 = 4 * l8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l4 = lane & 3, gbase = lane & 28;
+  const int c8 = 8 * l4;
 
   for (int i = tid; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
   if (tid == 0) {
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
   const int np = resolve_np(P.np, P.dc);
   const int ntiles = (np + 127) / 128;
   const uint32_t el = umma::elect_one();                   // warp 0 stays converged in the issue code; one lane issues
-  const int gi = warp * 4 + (lane >> 3);                   // lane group 0..63: rows gi and gi + 64 of the tile
+  const int gi = warp * 8 + (lane >> 2);                   // lane group = row 0..127 of the tile
   // E1 / E2 role of this thread: TMEM lane quarter = warp & 3, 24-column group = warp >> 2
   const int erow = 32 * (warp & 3) + lane, ecg = warp >> 2;
   const uint32_t etb = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -176,20 +180,18 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
   uint32_t ti = 0;                                          // tile iteration of this CTA (barrier phase bookkeeping)
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
     const bool has_next = tile + (int)gridDim.x < ntiles;
-    // =========================== phase A: geometry of this lane group's two points ===========================
+    // =========================== phase A: geometry of this lane group's point (row gi of the tile) ===========================
     // The per-point coordinates every later chunk needs -- 3-D grid coordinates gn (renderer.py:544-556), tri-plane coordinates cn
     // (renderer.py:218-243), observation pixel uv (renderer.py:686-704) -- go to shared memory (s_pt[row][8]); the chunk loop reloads
     // what it needs, so nothing of a point stays in registers between chunks.
-    int64_t gpt[2];
-    bool act[2];
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-      const int lp_raw = tile * 128 + gi + 64 * p;
-      const bool actp = lp_raw < np;
-      if (p == 0) act[0] = actp; else act[1] = actp;
-      const int lp = actp ? lp_raw : np - 1;                 // rows beyond the list shadow the last point; nothing of them is stored
+    bool act;
+    int64_t gpt;
+    {
+      const int lp_raw = tile * 128 + gi;
+      act = lp_raw < np;
+      const int lp = act ? lp_raw : np - 1;                  // rows beyond the list shadow the last point; nothing of them is stored
       const int64_t gp = P.p0 + lp;
-      if (p == 0) gpt[0] = gp; else gpt[1] = gp;
+      gpt = gp;
       const int s = P.point_sample[gp];
       const int n = s / P.S, i = s - n * P.S;
       const float t = P.depths ? P.depths[s] : sample_depth(P.nearv[n], P.farv[n], i, P.S);
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       rowvec_mat3(dray, fc.R_tgt, vd);
       float cn[3] = {q[0], q[1], q[2]}, cdir[3] = {vd[0], vd[1], vd[2]};
       const int vid1 = P.point_vid[gp];
-      fr_apply_warp(P.T1 + vid1, cn, cdir, true);                                      // target -> canonical   renderer.py:558-621
-      const int vid3 = fr_nn_seeded8(fc.g3, P.g3_start, P.g3_verts, P.t_vertices, cn[0], cn[1], cn[2], l8, vid1);
+      if (!(a.knock & 8)) fr_apply_warp(P.T1 + vid1, cn, cdir, true);                  // target -> canonical   renderer.py:558-621
+      const int vid3 = (a.knock & 1) ? vid1 : fr_nn_seeded4(fc.g3, P.g3_start, P.g3_verts, P.t_vertices, cn[0], cn[1], cn[2], l4, vid1);
       float ps[3] = {cn[0], cn[1], cn[2]}, dummy[3] = {0.f, 0.f, 0.f};
       fr_apply_warp(P.T3 + vid3, ps, dummy, false);                                    // canonical -> observation   renderer.py:623-684
       float world[3], cam[3], pix[3];
@@ -215,21 +217,24 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       const float zz = pix[2] + 1e-5f;
       const float u = pix[0] / zz, v = pix[1] / zz;
       {
-        // lane l8 < 3: gn_k = ((can_k - bounds_min_k) / 0.005) / out_sh[2-k] * 2 - 1; 3..5: cn_k = 2 (can_k - lo_k) / (hi_k - lo_k) - 1; 6, 7: u, v
-        const int k3 = l8 < 3 ? l8 : (l8 < 6 ? l8 - 3 : 0);
+        // s_pt[row] = gn xyz | cn xyz | u v with gn_k = ((can_k - bounds_min_k) / 0.005) / out_sh[2-k] * 2 - 1 and
+        // cn_k = 2 (can_k - lo_k) / (hi_k - lo_k) - 1.  Lane l4 < 3 writes gn_l4 and cn_l4, lane 3 writes u and v.
+        const int k3 = l4 < 3 ? l4 : 0;
         const float ck = k3 == 0 ? cn[0] : (k3 == 1 ? cn[1] : cn[2]);
-        float val;
-        if (l8 < 3) val = ((ck - fc.spb_min[k3]) / 0.005f) / fc.out_sh[2 - k3] * 2.f - 1.f;
-        else if (l8 < 6) val = 2.f * (ck - fc.twb_min[k3]) / (fc.twb_max[k3] - fc.twb_min[k3]) - 1.f;
-        else val = l8 == 6 ? u : v;
-        s_pt[gi + 64 * p][l8] = val;
+        const float gnv = ((ck - fc.spb_min[k3]) / 0.005f) / fc.out_sh[2 - k3] * 2.f - 1.f;
+        const float cnv = 2.f * (ck - fc.twb_min[k3]) / (fc.twb_max[k3] - fc.twb_min[k3]) - 1.f;
+        s_pt[gi][l4 < 3 ? l4 : 6] = l4 < 3 ? gnv : u;
+        s_pt[gi][l4 < 3 ? 3 + l4 : 7] = l4 < 3 ? cnv : v;
       }
-      if (actp) {
-        float gval = 0.f;
-        if (l8 == 0) gval = cn[0]; else if (l8 == 1) gval = cn[1]; else if (l8 == 2) gval = cn[2];
-        else if (l8 == 3) gval = cdir[0]; else if (l8 == 4) gval = cdir[1]; else if (l8 == 5) gval = cdir[2];
-        P.geo[(size_t)lp * 8 + l8] = gval;
-        if (DBG && l8 == 0 && gp < P.dbg_max) {
+      if (act) {
+        if (l4 < 3) {
+          P.geo[(size_t)lp * 8 + l4] = l4 == 0 ? cn[0] : (l4 == 1 ? cn[1] : cn[2]);
+          P.geo[(size_t)lp * 8 + 3 + l4] = l4 == 0 ? cdir[0] : (l4 == 1 ? cdir[1] : cdir[2]);
+        } else {
+          P.geo[(size_t)lp * 8 + 6] = 0.f;
+          P.geo[(size_t)lp * 8 + 7] = 0.f;
+        }
+        if (DBG && l4 == 0 && gp < P.dbg_max) {
           if (P.dbg_vid3) P.dbg_vid3[gp] = vid3;
           if (P.dbg_can) { P.dbg_can[gp * 3] = cn[0]; P.dbg_can[gp * 3 + 1] = cn[1]; P.dbg_can[gp * 3 + 2] = cn[2]; }
           if (P.dbg_cdir) { P.dbg_cdir[gp * 3] = cdir[0]; P.dbg_cdir[gp * 3 + 1] = cdir[1]; P.dbg_cdir[gp * 3 + 2] = cdir[2]; }
@@ -237,67 +242,62 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
         }
       }
     }
-    __syncwarp();                                            // s_pt rows of this lane group are read back by the same 8 lanes
+    __syncwarp();                                            // s_pt rows of this lane group are read back by the same 4 lanes
 
     // =========================== the twelve chunks: ONE loop body (compact code: the unrolled form was 24 500 instructions) ===========================
     //   c = 0..5  3-D pyramid (level, 32-channel group) = (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)   renderer.py:544-556,762-797
     //   c = 6..8  tri-plane k = c - 6 (align_corners=False)                                     renderer.py:234-243
     //   c = 9,10  2-D feature map channels 0-31 / 32-63, c = 11 rgb encoding (align_corners=True, uv normalised by the IMAGE size) renderer.py:331-340
-    int offT[2] = {-1, -1}, offI[2] = {-1, -1};
-    float wT[2] = {0.f, 0.f}, wI[2] = {0.f, 0.f};
+    // Tap registers: lane l4 holds taps l4 and l4 + 4 of the current 8-tap set (3-D), or tap l4 of a 4-tap set (2-D) in slot 0.
+    int offT[2] = {-1, -1}, offI = -1;
+    float wT[2] = {0.f, 0.f}, wI = 0.f;
+    const float* pt = s_pt[gi];
 #pragma unroll 1
     for (int c = 0; c < 12; ++c) {
-      // ---- tap setup where a new sample set starts (lane l8 prepares corner l8 of both points) ----
+      // ---- tap setup where a new sample set starts ----
       if (c == 0 || c == 1 || c == 3) {
         const int l = c == 0 ? 0 : (c == 1 ? 1 : 2);
         const int D = P.vol_d[l], Hh = P.vol_h[l], Ww = P.vol_w[l], C = P.vol_ch[l];
+        const float ix = (pt[0] + 1.f) * 0.5f * (float)(Ww - 1), iy = (pt[1] + 1.f) * 0.5f * (float)(Hh - 1), iz = (pt[2] + 1.f) * 0.5f * (float)(D - 1);
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int bx = l4 & 1, by = (l4 >> 1) & 1;             // corner index = l4 + 4 * slot: bit0 x, bit1 y, bit2 z (= slot)
+        const int xx = (int)fx + bx, yy = (int)fy + by;
+        const float wxy = (bx ? ix - fx : (fx + 1.f) - ix) * (by ? iy - fy : (fy + 1.f) - iy);
+        const bool inxy = xx >= 0 && xx < Ww && yy >= 0 && yy < Hh;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const float* pt = s_pt[gi + 64 * p];
-          const float ix = (pt[0] + 1.f) * 0.5f * (float)(Ww - 1), iy = (pt[1] + 1.f) * 0.5f * (float)(Hh - 1), iz = (pt[2] + 1.f) * 0.5f * (float)(D - 1);
-          const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-          const int bx = l8 & 1, by = (l8 >> 1) & 1, bz = (l8 >> 2) & 1;
-          const int xx = (int)fx + bx, yy = (int)fy + by, zz2 = (int)fz + bz;
-          const float wx = bx ? ix - fx : (fx + 1.f) - ix, wy = by ? iy - fy : (fy + 1.f) - iy, wz = bz ? iz - fz : (fz + 1.f) - iz;
-          wT[p] = wx * wy * wz;
-          offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh && zz2 >= 0 && zz2 < D) ? ((zz2 * Hh + yy) * Ww + xx) * C : -1;
+        for (int sl = 0; sl < 2; ++sl) {
+          const int zz2 = (int)fz + sl;
+          wT[sl] = wxy * (sl ? iz - fz : (fz + 1.f) - iz);
+          offT[sl] = (inxy && zz2 >= 0 && zz2 < D) ? ((zz2 * Hh + yy) * Ww + xx) * C : -1;
         }
       } else if (c >= 6 && c <= 8) {
         const int k = c - 6;
         const int Ww = P.plane_w, Hh = P.plane_h;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const float* pt = s_pt[gi + 64 * p];
-          const float px = k == 2 ? pt[5] : pt[3], py = k == 1 ? pt[5] : pt[4];
-          const float ix = ((px + 1.f) * (float)Ww - 1.f) * 0.5f, iy = ((py + 1.f) * (float)Hh - 1.f) * 0.5f;
-          const float fx = floorf(ix), fy = floorf(iy);
-          const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
-          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-          wT[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
-          offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
-        }
+        const float px = k == 2 ? pt[5] : pt[3], py = k == 1 ? pt[5] : pt[4];
+        const float ix = ((px + 1.f) * (float)Ww - 1.f) * 0.5f, iy = ((py + 1.f) * (float)Hh - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int cxb = l4 & 1, cyb = (l4 >> 1) & 1;
+        const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+        wT[0] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+        offT[0] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
       } else if (c == 9) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const float* pt = s_pt[gi + 64 * p];
-          const float gx = 2.0f * pt[6] / (float)P.img_w - 1.0f, gy = 2.0f * pt[7] / (float)P.img_h - 1.0f;
-          const int cxb = l8 & 1, cyb = (l8 >> 1) & 1;
-          {
-            const int Ww = P.feat_w, Hh = P.feat_h;
-            const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
-            const float fx = floorf(ix), fy = floorf(iy);
-            const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-            wT[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
-            offT[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * P.feat_ch : -1;
-          }
-          {
-            const int Ww = P.img_w, Hh = P.img_h;
-            const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
-            const float fx = floorf(ix), fy = floorf(iy);
-            const int xx = (int)fx + cxb, yy = (int)fy + cyb;
-            wI[p] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
-            offI[p] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
-          }
+        const float gx = 2.0f * pt[6] / (float)P.img_w - 1.0f, gy = 2.0f * pt[7] / (float)P.img_h - 1.0f;
+        const int cxb = l4 & 1, cyb = (l4 >> 1) & 1;
+        {
+          const int Ww = P.feat_w, Hh = P.feat_h;
+          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+          wT[0] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+          offT[0] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * P.feat_ch : -1;
+        }
+        {
+          const int Ww = P.img_w, Hh = P.img_h;
+          const float ix = (gx + 1.f) * 0.5f * (float)(Ww - 1), iy = (gy + 1.f) * 0.5f * (float)(Hh - 1);
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int xx = (int)fx + cxb, yy = (int)fy + cyb;
+          wI = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
+          offI = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
         }
       }
       // ---- operand slot b = c & 1, used for the (ti * 6 + c / 2)-th time: wait until the MMAs that read it two chunks ago have completed ----
@@ -310,73 +310,85 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
         umma::bulk_g2s_e(smem + fr::kWp + b * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[b], el);
       }
       unsigned char* buf = smem + (b ? fr::kA1 : fr::kA0);
-      // ---- gather the chunk's 32 channels of both points: 8 lanes x float4 per tap ----
-      const int ntap = c < 6 ? 8 : 4;
+      // ---- gather the chunk's 32 channels of the point: 4 lanes x 2 float4 per tap ----
       const float* src;
       int dbg_col;
       if (c < 6) { const int l = c == 0 ? 0 : (c < 3 ? 1 : 2); src = P.vol_cl[l] + 32 * (c - (l == 0 ? 0 : (l == 1 ? 1 : 3))); dbg_col = 192 + 32 * c; }
       else if (c < 9) { src = P.planes_cl + (size_t)(c - 6) * P.plane_h * P.plane_w * 32; dbg_col = 32 * (c - 6); }
       else { src = P.feat_cl + 32 * (c - 9); dbg_col = 96 + 32 * (c - 9); }
-      src += c4;
+      src += c8;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1v = make_float4(0.f, 0.f, 0.f, 0.f);      // channels c8 .. c8+3 and c8+4 .. c8+7
+      if (c < 11) {
+        // taps in grid_sample's accumulation order (tap t sits in lane t & 3, register slot t >> 2); the four loads-pairs of a half set are
+        // issued back to back before the blend
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < 11) {
-          // all tap offsets / weights first (shuffles), then ALL loads back to back, then the blend: written this way so that the
-          // 4 or 8 16-byte loads of a point are in flight together (interleaved, every FMA group stalled on its own load: r2c profile,
-          // long-scoreboard 38 % of the stall samples)
-          int off[8]; float w[8];
+        for (int hs = 0; hs < 2; ++hs) {
+          if (hs == 0 || c < 6) {                               // 2-D sets have four taps only
+            int off[4]; float w[4];
 #pragma unroll
-          for (int tp = 0; tp < 8; ++tp) {
-            off[tp] = __shfl_sync(0xffffffffu, offT[p], gbase + tp);
-            w[tp] = __shfl_sync(0xffffffffu, wT[p], gbase + tp);
-          }
-          float4 val[8];
+            for (int tp = 0; tp < 4; ++tp) {
+              off[tp] = __shfl_sync(0xffffffffu, hs ? offT[1] : offT[0], gbase + tp);
+              w[tp] = __shfl_sync(0xffffffffu, hs ? wT[1] : wT[0], gbase + tp);
+            }
+            float4 v0[4], v1[4];
 #pragma unroll
-          for (int tp = 0; tp < 8; ++tp)
-            val[tp] = (tp < ntap && off[tp] >= 0) ? __ldg(reinterpret_cast<const float4*>(src + off[tp])) : make_float4(0.f, 0.f, 0.f, 0.f);
-          // grid_sample accumulates the corners in this order; the 2-D form starts from the first product, the 3-D form from zero
-          if (c >= 6) { acc.x = val[0].x * w[0]; acc.y = val[0].y * w[0]; acc.z = val[0].z * w[0]; acc.w = val[0].w * w[0]; }
-          else { acc.x += val[0].x * w[0]; acc.y += val[0].y * w[0]; acc.z += val[0].z * w[0]; acc.w += val[0].w * w[0]; }
+            for (int tp = 0; tp < 4; ++tp) {
+              const bool ok = off[tp] >= 0 && !(a.knock & 2);
+              v0[tp] = ok ? __ldg(reinterpret_cast<const float4*>(src + off[tp])) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v1[tp] = ok ? __ldg(reinterpret_cast<const float4*>(src + off[tp]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-          for (int tp = 1; tp < 8; ++tp) {
-            if (tp < ntap) { acc.x += val[tp].x * w[tp]; acc.y += val[tp].y * w[tp]; acc.z += val[tp].z * w[tp]; acc.w += val[tp].w * w[tp]; }
-          }
-        } else {
-          float rgbc = 0.f;
-#pragma unroll
-          for (int tp = 0; tp < 4; ++tp) {
-            const int offi = __shfl_sync(0xffffffffu, offI[p], gbase + tp);
-            const float wi = __shfl_sync(0xffffffffu, wI[p], gbase + tp);
-            const float vi = (l8 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l8 * P.img_h * P.img_w + offi) : 0.f;
-            rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
-          }
-          // rgb_enc outputs 4*l8 .. 4*l8+3 of the 32 kept ones: [r, g, b, sin(..) ...]                        renderer.py:339,900-916
-          const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
-                      r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
-          float enc[4];
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const int o = c4 + e4;
-            if (o < 3) enc[e4] = o == 0 ? r0 : (o == 1 ? r1 : r2);
-            else {
-              const int e = o - 3, m = e / 3, cc = e - 3 * m;
-              const float xc = cc == 0 ? r0 : (cc == 1 ? r1 : r2);
-              enc[e4] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+            for (int tp = 0; tp < 4; ++tp) {
+              if (tp == 0 && hs == 0 && c >= 6) {               // the 2-D form starts from the first product, the 3-D form from zero
+                acc0.x = v0[0].x * w[0]; acc0.y = v0[0].y * w[0]; acc0.z = v0[0].z * w[0]; acc0.w = v0[0].w * w[0];
+                acc1v.x = v1[0].x * w[0]; acc1v.y = v1[0].y * w[0]; acc1v.z = v1[0].z * w[0]; acc1v.w = v1[0].w * w[0];
+              } else {
+                acc0.x += v0[tp].x * w[tp]; acc0.y += v0[tp].y * w[tp]; acc0.z += v0[tp].z * w[tp]; acc0.w += v0[tp].w * w[tp];
+                acc1v.x += v1[tp].x * w[tp]; acc1v.y += v1[tp].y * w[tp]; acc1v.z += v1[tp].z * w[tp]; acc1v.w += v1[tp].w * w[tp];
+              }
             }
           }
-          acc = make_float4(enc[0], enc[1], enc[2], enc[3]);
-          dbg_col = 160;
         }
-        {                                                      // 4 channels of row gi + 64p -> bf16 hi | lo halves of a 16-byte core-matrix row
-          uint2 h, l;
-          umma::split_bf16x2(acc.x, acc.y, h.x, l.x);
-          umma::split_bf16x2(acc.z, acc.w, h.y, l.y);
-          unsigned char* dst = buf + (size_t)(l8 >> 1) * fr::kLboA + (size_t)(gi + 64 * p) * 16 + (l8 & 1) * 8;
-          *reinterpret_cast<uint2*>(dst) = h;
-          *reinterpret_cast<uint2*>(dst + fr::kChunkHalf) = l;
+      } else {
+        float rgbc = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          const int offi = __shfl_sync(0xffffffffu, offI, gbase + tp);
+          const float wi = __shfl_sync(0xffffffffu, wI, gbase + tp);
+          const float vi = (l4 < 3 && offi >= 0) ? __ldg(P.img + (size_t)l4 * P.img_h * P.img_w + offi) : 0.f;
+          rgbc = tp == 0 ? vi * wi : rgbc + vi * wi;
         }
-        if (DBG && P.dbg_feat && act[p] && gpt[p] < P.dbg_feat_max) *reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt[p] * 384 + dbg_col + c4) = acc;
+        // rgb_enc outputs 8*l4 .. 8*l4+7 of the 32 kept ones: [r, g, b, sin(..) ...]                        renderer.py:339,900-916
+        const float r0 = __shfl_sync(0xffffffffu, rgbc, gbase + 0), r1 = __shfl_sync(0xffffffffu, rgbc, gbase + 1),
+                    r2 = __shfl_sync(0xffffffffu, rgbc, gbase + 2);
+        float enc[8];
+#pragma unroll
+        for (int e8 = 0; e8 < 8; ++e8) {
+          const int o = c8 + e8;
+          if (o < 3) enc[e8] = o == 0 ? r0 : (o == 1 ? r1 : r2);
+          else {
+            const int e = o - 3, m = e / 3, cc = e - 3 * m;
+            const float xc = cc == 0 ? r0 : (cc == 1 ? r1 : r2);
+            enc[e8] = sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+          }
+        }
+        acc0 = make_float4(enc[0], enc[1], enc[2], enc[3]);
+        acc1v = make_float4(enc[4], enc[5], enc[6], enc[7]);
+        dbg_col = 160;
+      }
+      {                                                        // 8 channels of row gi -> one 16-byte core-matrix row of the hi part and of the lo part
+        uint4 h, l;
+        umma::split_bf16x2(acc0.x, acc0.y, h.x, l.x);
+        umma::split_bf16x2(acc0.z, acc0.w, h.y, l.y);
+        umma::split_bf16x2(acc1v.x, acc1v.y, h.z, l.z);
+        umma::split_bf16x2(acc1v.z, acc1v.w, h.w, l.w);
+        unsigned char* dst = buf + (size_t)l4 * fr::kLboA + (size_t)gi * 16;
+        *reinterpret_cast<uint4*>(dst) = h;
+        *reinterpret_cast<uint4*>(dst + fr::kChunkHalf) = l;
+      }
+      if (DBG && P.dbg_feat && act && gpt < P.dbg_feat_max) {
+        float4* d4 = reinterpret_cast<float4*>(P.dbg_feat + (size_t)gpt * 384 + dbg_col + c8);
+        d4[0] = acc0; d4[1] = acc1v;
       }
       // ---- hand the chunk over ----
       umma::fence_proxy_async_smem();
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
           umma::mbar_wait(&w_full[b], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
           umma::tc_fence_after_sync();
           const uint32_t w_hi = sbase + fr::kWp + (uint32_t)b * fr::kWpStage;
-          gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
+          if (!(a.knock & 4)) gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
           umma::mma_commit_e(&a_free[b], el);
           if (c == 5) umma::mma_commit_e(&acc1, el);
         } else {
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
                      fr::kD2 + (uint32_t)(32 * t3), 1u);
           }
           const uint32_t wb = sbase + fr::kWr + (uint32_t)sblk * fr::kWrBlock;
-          gemm32(a_hi, fr::kLboA, false, a_lo, wb, wb + fr::kWrBlock / 2, 32, fr::kD2 + (uint32_t)(32 * tt), c < 9 ? 0u : 1u);
+          if (!(a.knock & 4)) gemm32(a_hi, fr::kLboA, false, a_lo, wb, wb + fr::kWrBlock / 2, 32, fr::kD2 + (uint32_t)(32 * tt), c < 9 ? 0u : 1u);
           umma::mma_commit_e(&a_free[b], el);
           if (c == 11) umma::mma_commit_e(&acc2, el);
         }
@@ -506,6 +518,7 @@ int run_front_fused(const GatherParams& G, const SherfWeights& w, const unsigned
   if (!G.t_vertices) { set_error("internal: the front kernel needs the seeded canonical-vertex search"); return SHERF_E_INVALID; }
   FrontArgs a;
   a.G = G; a.wblob = blob; a.bp = w.proj_b; a.br = w.reproj_b; a.tok = tok;
+  { const char* e = getenv("SHERF_FRONT_KNOCK"); a.knock = e ? atoi(e) : 0; }
   static bool attr_done = false;
   static int num_sms = 148;
   if (!attr_done) {
