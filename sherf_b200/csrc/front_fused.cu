@@ -31,9 +31,9 @@ namespace fr {
 constexpr uint32_t kLboA = 2080;                          // streamed operand chunks: 8-byte stores from the gather lanes are conflict-free
 constexpr uint32_t kChunkHalf = 4 * kLboA;                // hi (or lo) part of one 32-channel chunk: 4 core-matrix columns
 constexpr uint32_t kChunk = 2 * kChunkHalf;
-constexpr uint32_t kA0 = 0, kA1 = kChunk;
-constexpr uint32_t kLboF = 2064;                          // projected 3-D feature (16-byte stores, thread = row)
-constexpr uint32_t kF3d = 2 * kChunk;                     // 12 core-matrix columns (96 channels), hi part
+constexpr int kSlots = 3;                                  // operand slots: a producer may run two chunks ahead of the slowest warp of the CTA
+constexpr uint32_t kLboF = 2048;                          // projected 3-D feature (16-byte stores, thread = row: conflict-free without padding)
+constexpr uint32_t kF3d = kSlots * kChunk;                // 12 core-matrix columns (96 channels), hi part
 constexpr uint32_t kWr = kF3d + 12 * kLboF;               // reprojection weights: 3 source blocks x (hi 2048 B | lo 2048 B)
 constexpr uint32_t kWrBlock = 4096;
 constexpr uint32_t kWp = kWr + 3 * kWrBlock;              // projection weight ring: 2 stages x (hi 6144 B | lo 6144 B)
@@ -117,17 +117,18 @@ template <bool DBG>
 __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ FrameConst fc;
-  __shared__ __align__(8) uint64_t a_full[2], a_free[2], w_full[2], acc1, acc2, f3d_ready;
+  __shared__ __align__(8) uint64_t a_full[fr::kSlots], a_free[fr::kSlots], w_full[2], w_free[2], acc1, acc2, f3d_ready;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bp[96], s_br[32];
-  __shared__ float s_pt[128][8];      // per point: gn xyz | cn xyz | u v (see phase A)
+  __shared__ float s_pt[128][6];      // per point: gn xyz | cn xyz (see phase A)
   const GatherParams& P = a.G;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l4 = lane & 3, gbase = lane & 28;
   const int c8 = 8 * l4;
 
   for (int i = tid; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { umma::mbar_init(&a_full[b], fr::kThreads); umma::mbar_init(&a_free[b], 1); umma::mbar_init(&w_full[b], 1); }
+    for (int b = 0; b < fr::kSlots; ++b) { umma::mbar_init(&a_full[b], fr::kThreads); umma::mbar_init(&a_free[b], 1); }
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(&w_full[b], 1); umma::mbar_init(&w_free[b], 1); }
     umma::mbar_init(&acc1, 1); umma::mbar_init(&acc2, 1); umma::mbar_init(&f3d_ready, fr::kThreads);
     umma::fence_mbar_init();
   }
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
     // what it needs, so nothing of a point stays in registers between chunks.
     bool act;
     int64_t gpt;
+    float pu, pv;                                            // observation pixel of the point (used by chunk 9's tap set-up)
     {
       const int lp_raw = tile * 128 + gi;
       act = lp_raw < np;
@@ -217,14 +219,14 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       const float zz = pix[2] + 1e-5f;
       const float u = pix[0] / zz, v = pix[1] / zz;
       {
-        // s_pt[row] = gn xyz | cn xyz | u v with gn_k = ((can_k - bounds_min_k) / 0.005) / out_sh[2-k] * 2 - 1 and
-        // cn_k = 2 (can_k - lo_k) / (hi_k - lo_k) - 1.  Lane l4 < 3 writes gn_l4 and cn_l4, lane 3 writes u and v.
+        // s_pt[row] = gn xyz | cn xyz with gn_k = ((can_k - bounds_min_k) / 0.005) / out_sh[2-k] * 2 - 1 and
+        // cn_k = 2 (can_k - lo_k) / (hi_k - lo_k) - 1.  Lane l4 < 3 writes gn_l4 and cn_l4.
         const int k3 = l4 < 3 ? l4 : 0;
         const float ck = k3 == 0 ? cn[0] : (k3 == 1 ? cn[1] : cn[2]);
         const float gnv = ((ck - fc.spb_min[k3]) / 0.005f) / fc.out_sh[2 - k3] * 2.f - 1.f;
         const float cnv = 2.f * (ck - fc.twb_min[k3]) / (fc.twb_max[k3] - fc.twb_min[k3]) - 1.f;
-        s_pt[gi][l4 < 3 ? l4 : 6] = l4 < 3 ? gnv : u;
-        s_pt[gi][l4 < 3 ? 3 + l4 : 7] = l4 < 3 ? cnv : v;
+        if (l4 < 3) { s_pt[gi][l4] = gnv; s_pt[gi][3 + l4] = cnv; }
+        pu = u; pv = v;
       }
       if (act) {
         if (l4 < 3) {
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
         wT[0] = (cxb ? ix - fx : (fx + 1.f) - ix) * (cyb ? iy - fy : (fy + 1.f) - iy);
         offT[0] = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) * 32 : -1;
       } else if (c == 9) {
-        const float gx = 2.0f * pt[6] / (float)P.img_w - 1.0f, gy = 2.0f * pt[7] / (float)P.img_h - 1.0f;
+        const float gx = 2.0f * pu / (float)P.img_w - 1.0f, gy = 2.0f * pv / (float)P.img_h - 1.0f;
         const int cxb = l4 & 1, cyb = (l4 >> 1) & 1;
         {
           const int Ww = P.feat_w, Hh = P.feat_h;
@@ -300,16 +302,20 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
           offI = (xx >= 0 && xx < Ww && yy >= 0 && yy < Hh) ? (yy * Ww + xx) : -1;
         }
       }
-      // ---- operand slot b = c & 1, used for the (ti * 6 + c / 2)-th time: wait until the MMAs that read it two chunks ago have completed ----
-      const int b = c & 1;
-      const uint32_t u = ti * 6u + (uint32_t)(c >> 1);
+      // ---- operand slot b = c % 3, used for the (ti * 4 + c / 3)-th time: wait until the MMAs that read it three chunks ago have completed ----
+      const int b = c % fr::kSlots;
+      const uint32_t u = ti * 4u + (uint32_t)(c / fr::kSlots);
       umma::mbar_wait_backoff(&a_free[b], (u & 1u) ^ 1u);
-      if (warp == 0 && c >= 2 && c <= 7 && (c <= 5 || has_next)) {   // ... and so have the reads of weight stage b: refill it (predicated, no lane branch)
-        const int wc = c <= 5 ? c : c - 6;                    // this tile's chunk c, or the next tile's chunk 0 / 1
-        umma::mbar_arrive_expect_tx_e(&w_full[b], fr::kWpStage, el);
-        umma::bulk_g2s_e(smem + fr::kWp + b * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[b], el);
+      if (warp == 0 && c >= 2 && c <= 7 && (c <= 5 || has_next)) {
+        // projection-weight stage ws = c & 1 is refilled once the MMAs of the chunk that used it last (two chunks ago) have completed:
+        // with this tile's chunk c, or the next tile's chunk 0 / 1 (predicated issue, no lane branch)
+        const int ws = c & 1, wc = c <= 5 ? c : c - 6;
+        const uint32_t fill = c <= 5 ? ti * 3u + (uint32_t)(c >> 1) : (ti + 1u) * 3u;
+        umma::mbar_wait(&w_free[ws], (fill - 1u) & 1u);
+        umma::mbar_arrive_expect_tx_e(&w_full[ws], fr::kWpStage, el);
+        umma::bulk_g2s_e(smem + fr::kWp + ws * fr::kWpStage, a.wblob + (size_t)wc * fr::kWpStage, fr::kWpStage, &w_full[ws], el);
       }
-      unsigned char* buf = smem + (b ? fr::kA1 : fr::kA0);
+      unsigned char* buf = smem + (uint32_t)b * fr::kChunk;
       // ---- gather the chunk's 32 channels of the point: 4 lanes x 2 float4 per tap ----
       const float* src;
       int dbg_col;
@@ -400,13 +406,15 @@ __global__ void __launch_bounds__(fr::kThreads, 2) k_front_fused(const FrontArgs
       // mbarrier / fence::after_thread_sync chain every chunk hand-over already has.
       if (warp == c) {                                         // warp-uniform branch; one elected lane issues
         umma::mbar_wait(&a_full[b], u & 1u);
-        const uint32_t a_hi = sbase + (b ? fr::kA1 : fr::kA0), a_lo = a_hi + fr::kChunkHalf;
+        const uint32_t a_hi = sbase + (uint32_t)b * fr::kChunk, a_lo = a_hi + fr::kChunkHalf;
         if (c < 6) {
-          umma::mbar_wait(&w_full[b], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
+          const int ws = c & 1;
+          umma::mbar_wait(&w_full[ws], (ti * 3u + (uint32_t)(c >> 1)) & 1u);
           umma::tc_fence_after_sync();
-          const uint32_t w_hi = sbase + fr::kWp + (uint32_t)b * fr::kWpStage;
+          const uint32_t w_hi = sbase + fr::kWp + (uint32_t)ws * fr::kWpStage;
           if (!(a.knock & 4)) gemm32(a_hi, fr::kLboA, false, a_lo, w_hi, w_hi + fr::kWpStage / 2, 96, fr::kD1, c == 0 ? 0u : 1u);
           umma::mma_commit_e(&a_free[b], el);
+          umma::mma_commit_e(&w_free[ws], el);
           if (c == 5) umma::mma_commit_e(&acc1, el);
         } else {
           umma::tc_fence_after_sync();
