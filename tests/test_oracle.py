@@ -1,5 +1,7 @@
 """CPU tests of the checker itself: oracle/port.py against the golden fixtures made from the reference's own code,
 and (only where /root/reference is mounted) against the live shimmed reference on a fresh scene."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -180,3 +182,38 @@ def test_composite_and_unify_match_reference_functions(white, smpl_model_t):
     ref2 = ren.ray_marcher(ac, as_, ad, rays_d[None], opts)
     got2 = port.composite(pc, ps, pd, rays_d, white)
     assert float((got2[0] - ref2[0][0]).abs().max()) <= 1e-6
+
+
+def test_branch_free_erf_of_the_transformer_kernel():
+    """csrc/xformer_bf16.cu: xb_erf -- the GELU's erf as 1 - exp(-|x| q(|x|)) with a degree-7 q on [0, 4].  The same fp32 arithmetic in numpy
+    against scipy's erf: absolute error <= 2e-7 everywhere (the kernel's header states 1.6e-7), and the GELU built from it within 5e-7
+    absolute of the exact one, and within 3e-7 relative for x > 0 (for x < 0 the `1 + erf` cancellation is the reference formula's own)."""
+    import re
+    from scipy.special import erf
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'sherf_b200', 'csrc', 'xformer_bf16.cu')).read()
+    body = src[src.index('float xb_erf(float x)'):src.index('return copysignf')]
+    coef = [np.float32(c) for c in re.findall(r'(-?\d+\.\d+(?:e-?\d+)?)f[;,)]', body) if c != '4.0']
+    assert len(coef) == 8, coef
+    x = np.linspace(-6, 6, 2000001).astype(np.float32)
+    t = np.minimum(np.abs(x), np.float32(4.0))
+    q = np.full_like(t, coef[0])
+    for c in coef[1:]:
+        q = (q * t + c).astype(np.float32)
+    e = np.copysign((np.float32(1.0) - np.exp((-t * q).astype(np.float32)).astype(np.float32)).astype(np.float32), x)
+    err = np.abs(e.astype(np.float64) - erf(x.astype(np.float64)))
+    assert err.max() <= 2e-7, err.max()
+    xs = x.astype(np.float64)
+    g_ref = 0.5 * xs * (1 + erf(xs / np.sqrt(2)))
+    arg = (x * np.float32(0.70710678118654752440)).astype(np.float32)
+    ta = np.minimum(np.abs(arg), np.float32(4.0))
+    qa = np.full_like(ta, coef[0])
+    for c in coef[1:]:
+        qa = (qa * ta + c).astype(np.float32)
+    ea = np.copysign((np.float32(1.0) - np.exp((-ta * qa).astype(np.float32)).astype(np.float32)).astype(np.float32), arg)
+    g = (np.float32(0.5) * x * (np.float32(1.0) + ea)).astype(np.float32)
+    d = np.abs(g.astype(np.float64) - g_ref)
+    assert d.max() <= 5e-7, d.max()
+    big = np.abs(g_ref) > 1e-3
+    assert (d[big] / np.abs(g_ref[big])).max() <= 2e-4          # the cancellation in 1 + erf(x) for x << 0 is the reference formula's own
+    pos = xs > 0                                                # no cancellation on this side: fp32-grade relative accuracy
+    assert (d[pos & big] / np.abs(g_ref[pos & big])).max() <= 3e-7
