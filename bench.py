@@ -521,10 +521,10 @@ def main():
             decoded_per_s = p_call * len(my_views) / (ms * 1e-3) if world == 1 else p_call / (ms * 1e-3)
             needed = N * NEEDED_DRAM_BYTES_PER_RAY + p_call * NEEDED_DRAM_BYTES_PER_POINT + SCENE_BYTES
             roof['path'] = {'achieved_tensor': decoded_per_s * FLOP_PER_POINT / 1e12 / pk['tensor_tflops'],
-                            'achieved_tensor_mlp_stage': (p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 / pk['tensor_tflops']) if mlp_ms > 0 else None,
+                            'achieved_tensor_point_stages': (p_call * FLOP_PER_POINT / ((per_stage[2] + mlp_ms) * 1e-3) / 1e12 / pk['tensor_tflops']) if mlp_ms > 0 else None,
                             'achieved_hbm': needed / (ms / len(my_views) * 1e-3 if world == 1 else ms * 1e-3) / 1e9 / pk['hbm_gbs'],
                             'needed_dram_bytes_per_view': needed,
-                            'note': 'achieved_tensor = decoded samples/s x 429 248 FLOP / measured bf16 peak (whole step; _mlp_stage: the point-stage kernels only); achieved_hbm = DRAM bytes the path needs per view / step time / measured copy bandwidth'}
+                            'note': 'achieved_tensor = decoded samples/s x 429 248 FLOP / measured bf16 peak (whole step; _point_stages: front + transformer + decoder kernels only -- the 429 248 FLOP include conv1d_projection / reprojection, which now run inside the front kernel next to the gathers); achieved_hbm = DRAM bytes the path needs per view / step time / measured copy bandwidth'}
         h2d_rank = sum(t_.numel() * 4 for sh in shard_host for t_ in sh.values()) + pose_host['vertices'].numel() * 4 * len(my_views)
         line = {
             'metric': 'ray_samples_per_sec', 'value': samples_per_step / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': world,
@@ -544,7 +544,7 @@ def main():
                                       'c_total': host_timed[3], 'python_forward_total': host_timed[4]},
             'clocks': clk,
             'stages_ms_per_view_call': {n: stage_ms[i] / calls for i, n in enumerate(['prologue+layout', 'cull+compact', 'front:warp+gather+fusion', 'point stages total', 'composite', 'mlp:decoder_kernel', 'mlp:transformer_kernel', 'mlp:fusion_kernel(legacy)'])},
-            'mlp_stage_tflops': p_call * FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,
+            'point_stages_tflops': p_call * FLOP_PER_POINT / ((per_stage[2] + mlp_ms) * 1e-3) / 1e12 if mlp_ms > 0 else 0.0,
             'roofline': roof,
             'decoded_samples_per_sec': points[0] / args.steps * world / (ms * 1e-3),      # surviving samples through the MLP stack (rank 0's count x ranks)
         }

@@ -45,13 +45,14 @@ def mounted() -> bool:
     return REF_ROOT == _MOUNTED
 
 
-def knn_points_bruteforce(p1, p2, K=1, chunk=4096, **_):
+def knn_points_bruteforce(p1, p2, K=1, chunk=None, **_):
     """Stand-in for pytorch3d.ops.knn.knn_points (call sites renderer.py:315,564,627)."""
     assert K == 1 and p1.shape[0] == 1 and p2.shape[0] == 1
     q, v = p1[0], p2[0]
+    chunk = chunk or (65536 if q.is_cuda else 4096)          # [chunk, V] temporaries: 1.8 GB each on the GPU, 113 MB on the CPU
     vx, vy, vz = v[:, 0][None], v[:, 1][None], v[:, 2][None]
-    d2_out = torch.empty(q.shape[0], dtype=torch.float32)
-    id_out = torch.empty(q.shape[0], dtype=torch.long)
+    d2_out = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+    id_out = torch.empty(q.shape[0], dtype=torch.long, device=q.device)
     for s in range(0, q.shape[0], chunk):
         c = q[s:s + chunk]
         dx = c[:, 0:1] - vx

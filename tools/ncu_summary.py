@@ -26,7 +26,7 @@ def main(path, only=None):
     names, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(names)}
     for vals in rows[2:]:
-        if len(vals) < len(names) or (only and only not in vals[col['Kernel Name']]):
+        if len(vals) < len(names) or (only and (only not in vals[col['Kernel Name']] or 'k_pack' in vals[col['Kernel Name']])):
             continue
         print('# kernel: %s' % vals[col['Kernel Name']][:120])
         for k in KEEP:
