@@ -7,6 +7,11 @@ render half.  No dataset or checkpoint is available offline, so the CLI renders 
 any scene dict with the layout of `sherf_b200.synthetic.make_scene`.
 
     python -m sherf_b200.sample --out out_dir --views 8 --res 512 --samples 64 [--importance 64] [--weights hot_path_state_dict.pt]
+    python -m sherf_b200.sample --out out_dir --network network-snapshot-000400.pkl --reference-root /path/to/SHERF/sherf
+
+`--network` loads a reference snapshot through `sherf_b200.checkpoint.load_generator` (legacy.load_network_pkl + the overlay) and renders
+with ITS renderer / decoder parameters; the observation tensors (planes, feature map, volumes) are still the seeded synthetic ones
+because no dataset is reachable offline.
 """
 from __future__ import annotations
 
@@ -67,6 +72,9 @@ def main():
     ap.add_argument('--importance', type=int, default=0)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--weights', default=None, help="torch-saved state dict with 'renderer.*' / 'decoder.*' hot-path names (default: seeded random init)")
+    ap.add_argument('--network', default=None, help='reference snapshot (network-snapshot-*.pkl, training_loop.py:563-579); needs --reference-root')
+    ap.add_argument('--reference-root', default=None, help="the reference's `sherf/` directory (dnnlib, torch_utils, legacy.py)")
+    ap.add_argument('--which', default='G_ema', help='entry of the snapshot dict to load (G or G_ema)')
     args = ap.parse_args()
     from . import synthetic as S
     from .triplane import hot_path_modules
@@ -84,7 +92,16 @@ def main():
             return [mv(v) for v in x]
         return x
     scene = {k: mv(v) for k, v in scene.items()}
-    ren, dec = hot_path_modules(model, seed=args.seed, dense_sigma=args.weights is None)
+    if args.network:
+        if not args.reference_root:
+            ap.error('--network needs --reference-root (the snapshot is unpickled with the reference\'s legacy.py / torch_utils)')
+        from .checkpoint import load_generator
+        G = load_generator(args.network, args.reference_root, which=args.which)
+        ren, dec = G.renderer, G.decoder
+        if ren.SMPL_NEUTRAL is None:
+            ren.set_smpl_model(model)
+    else:
+        ren, dec = hot_path_modules(model, seed=args.seed, dense_sigma=args.weights is None)
     if args.weights:
         sd = torch.load(args.weights, map_location='cpu')
         ren.load_state_dict({k[len('renderer.'):]: v for k, v in sd.items() if k.startswith('renderer.')}, strict=False)
