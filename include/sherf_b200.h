@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SHERF_ABI_VERSION 3
+#define SHERF_ABI_VERSION 4
 #if defined(__GNUC__)
 #define SHERF_API __attribute__((visibility("default")))
 #else
@@ -218,6 +218,49 @@ SHERF_API int sherf_lbs_transforms(const SherfSmplModel* smpl, const SherfPose* 
 SHERF_API int sherf_smpl_vertices(const SherfSmplModel* smpl, const SherfPose* pose, float* verts_smpl, float* verts_world, void* scratch,
                                   size_t scratch_bytes, void* stream);
 
+/* ---- Backward pass: what autograd derives through renderer.py:286-437, triplane.py:285-316 and ray_marcher.py:25-64
+ * when the reference calls loss.backward() (loss.py:175).  Same inputs as sherf_render_forward plus the gradient of the loss w.r.t. its
+ * three outputs; writes the gradients w.r.t. every hot-path parameter and w.r.t. the feature tensors the encoders produce.
+ * Recompute-in-backward: the library renders the view again inside the call (nothing has to be kept from the forward), then walks
+ * the surviving points back chunk by chunk in fp32.  Coarse pass only (n_importance must be 0: the reference's fine pass cannot
+ * execute).  Coordinates (warps, projections) carry no gradient -- SMPL parameters and cameras are data upstream. */
+typedef struct SherfOutGrads {   /* dL/d(out) of sherf_render_forward; NULL = zero */
+  const float* rgb;    /* [N,3] */
+  const float* depth;  /* [N]   (no gradient where the depth is clamped or 0/0, like torch.clamp / nan_to_num) */
+  const float* acc;    /* [N]   */
+} SherfOutGrads;
+
+typedef struct SherfWeightGrads {   /* same fields, shapes and order as SherfWeights; each is OVERWRITTEN with dL/d(param); NULL = not wanted */
+  float *proj_w, *proj_b;
+  float *reproj_w, *reproj_b;
+  float *ln1_w, *ln1_b;
+  float *qkv_w;
+  float *attn_out_w, *attn_out_b;
+  float *ln2_w, *ln2_b;
+  float *ff1_w, *ff1_b;
+  float *ff2_w, *ff2_b;
+  float *pts_w[8], *pts_b[8];
+  float *alpha_w, *alpha_b;
+  float *feature_w, *feature_b;
+  float *views_w, *views_b;
+  float *rgb_w, *rgb_b;
+} SherfWeightGrads;
+
+typedef struct SherfInputGrads {    /* same shapes / layouts as the SherfScene tensors; OVERWRITTEN; NULL = not wanted */
+  float* planes;                    /* [3,plane_ch,plane_h,plane_w]  (F.grid_sample backward of renderer.py:243) */
+  float* obs_feat;                  /* [feat_ch,feat_h,feat_w]       (renderer.py:333) */
+  float* vol[SHERF_NUM_LEVELS];     /* dense [C,D,H,W]               (renderer.py:790-797) */
+} SherfInputGrads;
+
+SHERF_API size_t sherf_backward_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_verts);
+/* Returns SHERF_OK or a negative code.  `scratch` must be an arena of its own (not the one a forward that is still in flight uses):
+ * >= sherf_backward_scratch_bytes.  n_points_out (optional, host): surviving samples.  Weight gradients are reduced in a fixed order
+ * (run-to-run identical); the grid gradients use floating-point reductions in memory like F.grid_sample's backward. */
+SHERF_API int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
+                                    const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out,
+                                    const SherfWeightGrads* grad_weights, const SherfInputGrads* grad_inputs, void* scratch,
+                                    size_t scratch_bytes, void* stream, int64_t* n_points_out);
+
 /* Global depth-clamp range of a full view: min/max over all rays of the first/last sample depth
  * (ray_marcher.py:57 via math_utils.py:101-118).  Host results; synchronises the stream. */
 SHERF_API int sherf_depth_range(const SherfRays* rays, float* min_out /* host */, float* max_out /* host */,
@@ -300,7 +343,7 @@ SHERF_API int sherf_debug_linear(int precision, const float* A, int lda, const f
 SHERF_API void sherf_debug_set_trace(long long* device_buf);
 
 SHERF_API const char* sherf_last_error(void);
-SHERF_API int sherf_abi_version(void);   /* == SHERF_ABI_VERSION (3) */
+SHERF_API int sherf_abi_version(void);   /* == SHERF_ABI_VERSION (4) */
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */
 SHERF_API int64_t sherf_last_launch_count(void);
 /* Number of FINE (importance) samples that survived the cull in the last sherf_render_forward on this thread

@@ -11,7 +11,7 @@ c_float_p = C.c_void_p          # device pointers travel as plain integers
 c_int_p = C.c_void_p
 
 MLP_FP32, MLP_TF32, MLP_TF32X3, MLP_BF16X3 = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SherfSmplModel(C.Structure):
@@ -44,6 +44,19 @@ class SherfWeights(C.Structure):
                 ('pts_b', c_float_p * 8), ('alpha_w', c_float_p), ('alpha_b', c_float_p), ('feature_w', c_float_p),
                 ('feature_b', c_float_p), ('views_w', c_float_p), ('views_b', c_float_p), ('rgb_w', c_float_p),
                 ('rgb_b', c_float_p)]
+
+
+class SherfWeightGrads(C.Structure):
+    """dL/d(param), same fields and order as SherfWeights (overwritten by sherf_render_backward; NULL = not wanted)."""
+    _fields_ = list(SherfWeights._fields_)
+
+
+class SherfOutGrads(C.Structure):
+    _fields_ = [('rgb', c_float_p), ('depth', c_float_p), ('acc', c_float_p)]
+
+
+class SherfInputGrads(C.Structure):
+    _fields_ = [('planes', c_float_p), ('obs_feat', c_float_p), ('vol', c_float_p * 3)]
 
 
 class SherfRays(C.Structure):
@@ -86,7 +99,7 @@ class SherfObservation(C.Structure):
                 ('proj_b', c_float_p)]
 
 
-EXPORTS = ['sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+EXPORTS = ['sherf_backward_scratch_bytes', 'sherf_render_backward', 'sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms', 'sherf_last_host_us']
 
 _lib = None
@@ -113,6 +126,13 @@ def load():
                                          C.POINTER(SherfWeights), C.POINTER(SherfRays), C.POINTER(SherfOptions),
                                          C.POINTER(SherfOut), C.POINTER(SherfDebug), C.c_void_p, C.c_size_t, C.c_void_p,
                                          C.POINTER(C.c_int64)]
+    lib.sherf_backward_scratch_bytes.restype = C.c_size_t
+    lib.sherf_backward_scratch_bytes.argtypes = [C.POINTER(SherfScene), C.c_int32, C.c_int32, C.c_int32]
+    lib.sherf_render_backward.restype = C.c_int
+    lib.sherf_render_backward.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfFrame), C.POINTER(SherfScene),
+                                          C.POINTER(SherfWeights), C.POINTER(SherfRays), C.POINTER(SherfOptions),
+                                          C.POINTER(SherfOutGrads), C.POINTER(SherfWeightGrads), C.POINTER(SherfInputGrads),
+                                          C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int64)]
     lib.sherf_count_survivors.restype = C.c_int
     lib.sherf_count_survivors.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfFrame), C.POINTER(SherfScene), C.POINTER(SherfRays),
                                           C.POINTER(SherfOptions), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int64)]

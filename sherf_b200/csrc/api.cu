@@ -228,6 +228,53 @@ struct SideStream {
   }
 };
 static thread_local SideStream g_side;
+// the per-call constants of the warp + gather kernels (forward chunks and the backward's recompute / scatter)
+static void fill_gather_params(GatherParams& G, const SherfRays& rays, const SherfFrame& frame, const SherfScene& scene, const Layout& L) {
+  G.origins = rays.origins; G.dirs = rays.dirs; G.nearv = rays.near_; G.farv = rays.far_; G.S = rays.n_samples; G.depths = nullptr;
+  G.point_sample = L.point_sample; G.point_vid = L.point_vid; G.p0 = 0; G.np = 0; G.dc = DevCount{nullptr, 0, 0};
+  G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
+  G.t_vertices = getenv("SHERF_KNN3_UNSEEDED") ? nullptr : frame.t_vertices;
+  G.planes_cl = L.planes_cl; G.plane_h = scene.plane_h; G.plane_w = scene.plane_w;
+  G.feat_cl = L.feat_cl; G.feat_h = scene.feat_h; G.feat_w = scene.feat_w; G.feat_ch = scene.feat_ch;
+  G.img = scene.obs_img; G.img_h = scene.img_h; G.img_w = scene.img_w;
+  for (int l = 0; l < 3; ++l) {
+    G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene.vol_ch[l];
+    G.vol_d[l] = scene.vol_dim[l][0]; G.vol_h[l] = scene.vol_dim[l][1]; G.vol_w[l] = scene.vol_dim[l][2];
+  }
+  G.comb = nullptr; G.f3raw = nullptr; G.geo = nullptr;
+  G.g_planes_cl = nullptr; G.g_feat_cl = nullptr; G.g_vol_cl[0] = G.g_vol_cl[1] = G.g_vol_cl[2] = nullptr;
+  G.dbg_vid3 = nullptr; G.dbg_can = nullptr; G.dbg_cdir = nullptr; G.dbg_uv = nullptr; G.dbg_feat = nullptr; G.dbg_max = 0; G.dbg_feat_max = 0;
+}
+
+// Backward arena = the forward arena (same carve, so the internal forward leaves its tables, layouts and per-point results where the backward
+// expects them) followed by the backward's own buffers.
+struct BwdLayout {
+  float* out;                 // rgb | depth | acc of the internal forward (5 N)
+  float* dsig; float* drgb;   // dL/d(sigma), dL/d(rgb) per surviving point
+  float* g_planes_cl; float* g_feat_cl; float* g_vol_cl[3];
+  float* chunk; int bcap;
+};
+static int bwd_chunk_cap(int N, int S) {
+  static int cap = 0;
+  if (!cap) { const char* e = getenv("SHERF_BWD_CHUNK_CAP"); const long v = e ? atol(e) : 0; cap = v >= 128 ? (int)(v / 128 * 128) : (1 << 17); }
+  const size_t NS = (size_t)N * S;
+  return (int)(NS < (size_t)cap ? (NS + 127) / 128 * 128 : (size_t)cap);
+}
+static size_t carve_backward(Arena& a, const SherfScene& sc, int N, int S, int V, Layout& L, BwdLayout& B, size_t* fwd_need) {
+  const size_t f = carve(a, sc, N, S, 0, V, L);
+  if (fwd_need) *fwd_need = f;
+  const size_t NS = (size_t)N * S;
+  B.out = a.take<float>((size_t)5 * N);
+  B.dsig = a.take<float>(NS);
+  B.drgb = a.take<float>(NS * 3);
+  B.g_planes_cl = a.take<float>((size_t)3 * sc.plane_ch * sc.plane_h * sc.plane_w);
+  B.g_feat_cl = a.take<float>((size_t)sc.feat_ch * sc.feat_h * sc.feat_w);
+  for (int l = 0; l < 3; ++l) B.g_vol_cl[l] = a.take<float>((size_t)sc.vol_ch[l] * sc.vol_dim[l][0] * sc.vol_dim[l][1] * sc.vol_dim[l][2]);
+  B.bcap = bwd_chunk_cap(N, S);
+  B.chunk = a.take<float>(bwd_chunk_floats(B.bcap));
+  return a.off;
+}
+
 static void nested_begin(int stage) { if (g_tm) g_tm->begin(stage); }
 static void nested_end() { if (g_tm) g_tm->end(); }
 
@@ -423,17 +470,8 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
     const int bsel = overlap ? (ci & 1) : 0;
     const ChunkBuffers& cbi = cbs[bsel];
     GatherParams G;
-    G.origins = rays->origins; G.dirs = rays->dirs; G.nearv = rays->near_; G.farv = rays->far_; G.S = Sn; G.depths = depths;
-    G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np; G.dc = dc;
-    G.fc = L.ft.fc; G.T1 = L.ft.T1; G.T3 = L.ft.T3; G.g3_start = L.ft.g3_cell_start; G.g3_verts = L.ft.g3_verts;
-    G.t_vertices = getenv("SHERF_KNN3_UNSEEDED") ? nullptr : frame->t_vertices;
-    G.planes_cl = L.planes_cl; G.plane_h = scene->plane_h; G.plane_w = scene->plane_w;
-    G.feat_cl = L.feat_cl; G.feat_h = scene->feat_h; G.feat_w = scene->feat_w; G.feat_ch = scene->feat_ch;
-    G.img = scene->obs_img; G.img_h = scene->img_h; G.img_w = scene->img_w;
-    for (int l = 0; l < 3; ++l) {
-      G.vol_cl[l] = L.vol_cl[l]; G.vol_ch[l] = scene->vol_ch[l];
-      G.vol_d[l] = scene->vol_dim[l][0]; G.vol_h[l] = scene->vol_dim[l][1]; G.vol_w[l] = scene->vol_dim[l][2];
-    }
+    fill_gather_params(G, *rays, *frame, *scene, L);
+    G.S = Sn; G.depths = depths; G.point_sample = point_sample; G.point_vid = point_vid; G.p0 = p0; G.np = np; G.dc = dc;
     G.comb = cbi.comb; G.f3raw = cbi.f3raw; G.geo = cbi.geo;
     G.dbg_vid3 = d ? d->point_vid3 : nullptr; G.dbg_can = d ? d->point_can : nullptr;
     G.dbg_cdir = d ? d->point_cdir : nullptr; G.dbg_uv = d ? d->point_uv : nullptr;
@@ -527,6 +565,110 @@ int sherf_render_forward(const SherfSmplModel* smpl, const SherfFrame* frame, co
   tm.finish();
   g_last_launches = g_launches.n;
   { const double t_exit = now_us(); g_host_us[0] = (float)(t_sync0 - t_enter); g_host_us[1] = (float)(t_sync1 - t_sync0); g_host_us[2] = (float)(t_exit - t_sync1); g_host_us[3] = (float)(t_exit - t_enter); }
+  return SHERF_OK;
+}
+
+size_t sherf_backward_scratch_bytes(const SherfScene* scene, int32_t n_rays, int32_t n_samples, int32_t n_verts) {
+  if (!scene || n_rays <= 0 || n_samples < 2 || n_verts <= 0) return 0;
+  Arena a{nullptr, 0, 0, true};
+  Layout L;
+  BwdLayout B;
+  return carve_backward(a, *scene, n_rays, n_samples, n_verts, L, B, nullptr) + 512;
+}
+
+int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
+                          const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out, const SherfWeightGrads* grad_weights,
+                          const SherfInputGrads* grad_inputs, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {
+  g_err[0] = 0;
+  if (!smpl || !frame || !scene || !weights || !rays || !opts || !grad_out || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (rays->n_importance != 0) {
+    set_error("sherf_render_backward covers the coarse pass only (n_importance must be 0; the reference's fine pass cannot execute, SURVEY a13)");
+    return SHERF_E_UNSUPPORTED;
+  }
+  const int N = rays->n_rays, S = rays->n_samples, V = smpl->n_verts;
+  if (N <= 0 || S < 2 || V <= 0) { set_error("bad sizes"); return SHERF_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a{(char*)scratch, scratch_bytes, 0, false};
+  const size_t mis = ((size_t)a.base) & 255;
+  if (mis) { a.base += 256 - mis; a.size -= 256 - mis; }
+  Layout L;
+  BwdLayout B;
+  size_t fwd_need = 0;
+  const size_t need = carve_backward(a, *scene, N, S, V, L, B, &fwd_need);
+  if (need > a.size) { set_error("backward scratch arena too small: need %zu bytes, have %zu", need, scratch_bytes); return SHERF_E_SCRATCH; }
+
+  // ---- the view once more on the fast path: leaves frame tables, channels-last layouts, the compacted point list and per-point sigma / rgb
+  //      in the first part of the arena ----
+  SherfOut fout; fout.rgb = B.out; fout.depth = B.out + (size_t)3 * N; fout.acc = B.out + (size_t)4 * N;
+  int64_t P = 0;
+  RC(sherf_render_forward(smpl, frame, scene, weights, rays, opts, &fout, nullptr, a.base, fwd_need + 256, stream, &P));
+  if (n_points_out) *n_points_out = P;
+  int64_t launches = g_launches.n;
+  g_launches.n = 0;
+
+  // ---- outputs start from zero ----
+  SherfWeightGrads gw;
+  if (grad_weights) gw = *grad_weights; else memset(&gw, 0, sizeof(gw));
+  {
+    float* const* gp = reinterpret_cast<float* const*>(&gw);
+    const int n_out[20] = {96, 32, 32, 144, 32, 32, 32, 32, 128, 128, 128, 128, 128, 128, 128, 128, 1, 128, 64, 3};
+    const int n_in[20] = {192, 96, 0, 32, 48, 0, 32, 32, 71, 128, 128, 128, 128, 199, 128, 128, 128, 128, 187, 64};
+    // struct order: proj w,b | reproj w,b | ln1 w,b | qkv w | attn_out w,b | ln2 w,b | ff1 w,b | ff2 w,b | pts_w[8] | pts_b[8] | alpha.. | feature.. | views.. | rgb..
+    size_t sizes[39]; int k = 0;
+    auto wb = [&](int layer, bool bias) { sizes[k++] = (size_t)n_out[layer] * (n_in[layer] ? n_in[layer] : 1); if (bias) sizes[k++] = n_out[layer]; };
+    wb(0, true); wb(1, true);
+    sizes[k++] = 32; sizes[k++] = 32;                 // ln1 weight, bias
+    wb(3, false); wb(4, true);
+    sizes[k++] = 32; sizes[k++] = 32;                 // ln2
+    wb(6, true); wb(7, true);
+    for (int i = 0; i < 8; ++i) sizes[k++] = (size_t)128 * n_in[8 + i];
+    for (int i = 0; i < 8; ++i) sizes[k++] = 128;
+    wb(16, true); wb(17, true); wb(18, true); wb(19, true);
+    if (k != 39 || sizeof(SherfWeightGrads) != 39 * sizeof(float*)) { set_error("internal: weight table mismatch"); return SHERF_E_INVALID; }
+    for (int i = 0; i < 39; ++i)
+      if (gp[i]) SHERF_CUDA_OK(cudaMemsetAsync(gp[i], 0, sizes[i] * sizeof(float), st));
+  }
+  const bool want_planes = grad_inputs && grad_inputs->planes, want_feat = grad_inputs && grad_inputs->obs_feat;
+  bool want_vol[3];
+  for (int l = 0; l < 3; ++l) want_vol[l] = grad_inputs && grad_inputs->vol[l];
+  const size_t plane = (size_t)scene->plane_ch * scene->plane_h * scene->plane_w;
+  if (want_planes) SHERF_CUDA_OK(cudaMemsetAsync(B.g_planes_cl, 0, 3 * plane * sizeof(float), st));
+  if (want_feat) SHERF_CUDA_OK(cudaMemsetAsync(B.g_feat_cl, 0, (size_t)scene->feat_ch * scene->feat_h * scene->feat_w * sizeof(float), st));
+  size_t vol_n[3];
+  for (int l = 0; l < 3; ++l) {
+    vol_n[l] = (size_t)scene->vol_ch[l] * scene->vol_dim[l][0] * scene->vol_dim[l][1] * scene->vol_dim[l][2];
+    if (want_vol[l]) SHERF_CUDA_OK(cudaMemsetAsync(B.g_vol_cl[l], 0, vol_n[l] * sizeof(float), st));
+  }
+
+  if (P > 0) {
+    PackedWeights pw;
+    g_pack_plan_only = false;
+    RC(run_pack_weights(*weights, L.packed_w, pw, st));
+    RC(run_composite_backward(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, grad_out->rgb,
+                              grad_out->depth, grad_out->acc, B.dsig, B.drgb, st));
+    BwdChunk bc;
+    carve_bwd_chunk(B.chunk, B.bcap, bc);
+    GatherParams G;
+    fill_gather_params(G, *rays, *frame, *scene, L);
+    for (int64_t p0 = 0; p0 < P; p0 += B.bcap) {
+      const int np = (int)((P - p0 < B.bcap) ? (P - p0) : B.bcap);
+      RC(run_backward_chunk(*weights, pw, gw, G, bc, np, p0, L.rgb, B.dsig, B.drgb, st));
+      GatherParams Gs = G;
+      Gs.g_planes_cl = want_planes ? B.g_planes_cl : nullptr;
+      Gs.g_feat_cl = want_feat ? B.g_feat_cl : nullptr;
+      for (int l = 0; l < 3; ++l) Gs.g_vol_cl[l] = want_vol[l] ? B.g_vol_cl[l] : nullptr;
+      RC(run_backward_chunk_inputs(*weights, Gs, bc, np, p0, st));
+    }
+  }
+  // ---- channels-last gradient grids -> the caller's PyTorch layouts ----
+  if (want_planes)
+    for (int k = 0; k < 3; ++k)
+      RC(run_from_channels_last(B.g_planes_cl + k * plane, grad_inputs->planes + k * plane, scene->plane_ch, (int64_t)scene->plane_h * scene->plane_w, st));
+  if (want_feat) RC(run_from_channels_last(B.g_feat_cl, grad_inputs->obs_feat, scene->feat_ch, (int64_t)scene->feat_h * scene->feat_w, st));
+  for (int l = 0; l < 3; ++l)
+    if (want_vol[l])
+      RC(run_from_channels_last(B.g_vol_cl[l], grad_inputs->vol[l], scene->vol_ch[l], (int64_t)(vol_n[l] / scene->vol_ch[l]), st));
+  g_last_launches = launches + g_launches.n;
   return SHERF_OK;
 }
 

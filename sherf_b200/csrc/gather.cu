@@ -420,7 +420,14 @@ __device__ int nn_unbounded8(const GridDesc& g, const int* __restrict__ cell_sta
   return bid;
 }
 
-template <bool DBG>
+// BWD = true turns the kernel into the ADJOINT of its three gathers (backward.cu): the warps, the knn #3 and the tap offsets / weights are
+// recomputed exactly as in the forward, P.comb / P.f3raw are READ as dL/d(comb) / dL/d(f3raw) and every tap adds weight x gradient into
+// the channels-last gradient grids P.g_* with one 16-byte vector reduction per lane and tap (red.global.add.v4.f32).
+__device__ __forceinline__ void red_add4(float* p, const float4& g, float w) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(g.x * w, g.y * w, g.z * w, g.w * w));
+}
+
+template <bool DBG, bool BWD>
 __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
   __shared__ FrameConst fc;
   for (int i = threadIdx.x; i < (int)(sizeof(FrameConst) / 4); i += blockDim.x) ((int*)&fc)[i] = ((const int*)P.fc)[i];
@@ -519,6 +526,19 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
     // ---- tri-planes ----
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+      if (BWD) {
+        if (P.g_planes_cl) {
+          float* gb = P.g_planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + c4;
+          const float4 g = *reinterpret_cast<const float4*>(comb + k * 96 + c4);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {
+            int off; float w;
+            tapA(4 * k + tp, off, w);
+            if (active && off >= 0) red_add4(gb + off, g, w);
+          }
+        }
+        continue;
+      }
       const float* base = P.planes_cl + (size_t)k * P.plane_h * P.plane_w * 32 + c4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -533,7 +553,17 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
       if (DBG && dbgf && active) *reinterpret_cast<float4*>(dbgf + k * 32 + c4) = acc;
     }
     // ---- pixel-aligned 2-D features + rgb positional encoding ----
-    {
+    if (BWD) {
+      if (P.g_feat_cl) {
+        const float4 g0 = *reinterpret_cast<const float4*>(comb + 0 * 96 + 32 + c4), g1 = *reinterpret_cast<const float4*>(comb + 1 * 96 + 32 + c4);
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          int off; float w;
+          tapA(12 + tp, off, w);
+          if (active && off >= 0) { red_add4(P.g_feat_cl + off + c4, g0, w); red_add4(P.g_feat_cl + off + 32 + c4, g1, w); }
+        }
+      }
+    } else {
       float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
       float rgbc = 0.f;
 #pragma unroll
@@ -583,6 +613,21 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
 #pragma unroll
         for (int tp = 0; tp < 8; ++tp) { off[tp] = __shfl_sync(0xffffffffu, offB[l], gbase + tp); w[tp] = __shfl_sync(0xffffffffu, wB[l], gbase + tp); }
         const float* vol = P.vol_cl[l] + c4;
+        if (BWD) {
+          if (P.g_vol_cl[l]) {
+#pragma unroll
+            for (int gsel = 0; gsel < 3; ++gsel) {
+              if (gsel <= l) {
+                const float4 g = *reinterpret_cast<const float4*>(f3 + coff + 32 * gsel + c4);
+#pragma unroll
+                for (int tp = 0; tp < 8; ++tp)
+                  if (active && off[tp] >= 0) red_add4(P.g_vol_cl[l] + c4 + off[tp] + 32 * gsel, g, w[tp]);
+              }
+            }
+          }
+          coff += 32 * (l + 1);
+          continue;
+        }
 #pragma unroll
         for (int gsel = 0; gsel < 3; ++gsel) {
           if (gsel <= l) {
@@ -599,7 +644,7 @@ __global__ void __launch_bounds__(256) k_point_gather4(const GatherParams P) {
         coff += 32 * (l + 1);
       }
     }
-    if (active) {
+    if (active && !BWD) {
       float gval = 0.f;
       if (l8 == 0) gval = can[0]; else if (l8 == 1) gval = can[1]; else if (l8 == 2) gval = can[2];
       else if (l8 == 3) gval = cdir[0]; else if (l8 == 4) gval = cdir[1]; else if (l8 == 5) gval = cdir[2];
@@ -623,9 +668,19 @@ int run_point_gather(const GatherParams& P, cudaStream_t st) {
     k_point_gather<<<blocks, 256, 0, st>>>(P);
   } else {
     const int blocks = min(ceil_div(P.np, 32), 148 * 8);
-    if (dbg) k_point_gather4<true><<<blocks, 256, 0, st>>>(P);
-    else k_point_gather4<false><<<blocks, 256, 0, st>>>(P);
+    if (dbg) k_point_gather4<true, false><<<blocks, 256, 0, st>>>(P);
+    else k_point_gather4<false, false><<<blocks, 256, 0, st>>>(P);
   }
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+// Adjoint of the three gathers: P.comb = dL/d(comb) [np][288], P.f3raw = dL/d(f3raw) [np][192]; P.g_* = channels-last gradient grids
+// (accumulated into; NULL = that input needs no gradient).  F.grid_sample's backward w.r.t. its input, renderer.py:243,333,790-797.
+int run_point_scatter(const GatherParams& P, cudaStream_t st) {
+  if (P.np <= 0) return SHERF_OK;
+  const int blocks = min(ceil_div(P.np, 32), 148 * 8);
+  k_point_gather4<false, true><<<blocks, 256, 0, st>>>(P);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
 }

@@ -519,6 +519,23 @@ void carve_chunk_buffers(float* base, int cap, ChunkBuffers& cb) {
   cb.vh = p; p += c * 64;
 }
 
+// host launchers of the small fp32 kernels for the recompute pass of the backward (backward.cu)
+int run_layernorm32(const float* x, const float* w, const float* b, float* y, int rows, cudaStream_t st) {
+  k_layernorm32<<<ceil_div(rows, 8), 256, 0, st>>>(x, w, b, y, rows);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+int run_attention3(const float* qkv, float* att, int np, cudaStream_t st) {
+  k_attention3<<<ceil_div(np * 3, 128), 128, 0, st>>>(qkv, att, np);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+int run_decoder_inputs(const float* geo, const float* tok3, float* x, float* hb, float* fv, int np, cudaStream_t st) {
+  k_decoder_inputs<<<ceil_div(np, 8), 256, 0, st>>>(geo, tok3, x, hb, fv, np, nullptr, 0, 0);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,

@@ -36,12 +36,15 @@ struct GatherParams {
   float* comb;      // [np][288]: token k at k*96: tri_k(32) | f2d_k(32) | (f3d_k written by the projection GEMM)
   float* f3raw;     // [np][192]
   float* geo;       // [np][8]: can xyz, cdir xyz, 0, 0
+  // backward only (run_point_scatter): channels-last gradient grids, same shapes as planes_cl / feat_cl / vol_cl; comb / f3raw are then inputs
+  float* g_planes_cl; float* g_feat_cl; float* g_vol_cl[3];
   // optional taps (absolute point index)
   int* dbg_vid3; float *dbg_can, *dbg_cdir, *dbg_uv, *dbg_feat; int64_t dbg_max, dbg_feat_max;
 };
 
 int run_to_channels_last_multi(int n, const float* const* in, float* const* out, const int* C, const int64_t* M, cudaStream_t st);
 int run_point_gather(const GatherParams& P, cudaStream_t st);
+int run_point_scatter(const GatherParams& P, cudaStream_t st);
 // S / depths: the sample set to cull -- (rays.n_samples, NULL) for the stratified coarse samples, (rays.n_importance, t_fine) for the fine pass
 int run_cull(const SherfRays& rays, int S, const float* depths, const FrameTables& ft, int* sample_vid, int* ray_count, int* block_sums,
              int* ray_start, int64_t* total_dev, int* point_sample, int* point_vid, cudaStream_t st, int write_all = 1);
@@ -136,6 +139,28 @@ int run_point_pe(const float* geo, float* pe, int np, cudaStream_t st, DevCount 
 int run_mlp(int prec, const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const FusedPlan* fused, const ChunkBuffers& cb, int np,
             int64_t p0, float* sigma_out, float* rgb_out, float* dbg_tok, int64_t dbg_max, cudaStream_t st,
             void (*span_begin)(int) = nullptr, void (*span_end)() = nullptr, DevCount dc = DevCount{nullptr, 0, 0});
+
+// Backward pass (backward.cu)
+struct BwdChunk {
+  int cap;
+  // activations kept by the recompute pass
+  float *comb, *f3raw, *geo, *tok, *ln1, *qkv, *att, *tok2, *ln2, *ffp, *ffa, *tok3, *x, *hb, *fv, *vh, *h[8];
+  // gradients
+  float *dvh, *dpre, *dfv, *dha, *dhb, *dx, *dtok3, *dff, *dln, *dtok2, *dtok, *datt, *dqkv, *dcomb, *df3raw;
+  float *part, *ln_part;
+};
+size_t bwd_chunk_floats(int cap);
+void carve_bwd_chunk(float* base, int cap, BwdChunk& b);
+int run_composite_backward(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample, const float* sigma,
+                           const float* rgb, const float* noise, int white_back, const float* g_rgb, const float* g_depth, const float* g_acc,
+                           float* dsig, float* drgb, cudaStream_t st);
+int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const SherfWeightGrads& gw, GatherParams G, const BwdChunk& b, int np, int64_t p0,
+                       const float* rgb, const float* dsig, const float* drgb, cudaStream_t st);
+int run_backward_chunk_inputs(const SherfWeights& w, GatherParams G, const BwdChunk& b, int np, int64_t p0, cudaStream_t st);
+int run_from_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
+int run_layernorm32(const float* x, const float* w, const float* b, float* y, int rows, cudaStream_t st);
+int run_attention3(const float* qkv, float* att, int np, cudaStream_t st);
+int run_decoder_inputs(const float* geo, const float* tok3, float* x, float* hb, float* fv, int np, cudaStream_t st);
 
 int run_debug_linear(int prec, const float* A, int lda, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
                      int act, float* wscratch, cudaStream_t st);

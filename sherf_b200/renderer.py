@@ -31,7 +31,8 @@ class _Runtime:
     module-level WeakKeyDictionary, NOT in the nn.Module's __dict__: the reference deep-copies and pickles the generator every tick
     (training_loop.py:196,572-579), and ctypes structures with pointers cannot be pickled (and a copied arena would double HBM).
     A copy / unpickled module simply starts with an empty runtime and rebuilds it lazily on its first forward."""
-    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', 'scene_sig', 'scene_epoch', '__weakref__')
+    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', 'scene_sig', 'scene_epoch', 'bwd_scratch',
+                 '__weakref__')
 
     def __init__(self):
         self.smpl_dev = None
@@ -43,6 +44,7 @@ class _Runtime:
         self.obs_scratch = None
         self.scene_sig = None
         self.scene_epoch = 0
+        self.bwd_scratch = None
 
 
 _RUNTIME = weakref.WeakKeyDictionary()
@@ -53,6 +55,23 @@ def _runtime(module) -> _Runtime:
     if rt is None:
         rt = _RUNTIME[module] = _Runtime()
     return rt
+
+class _RenderFn(torch.autograd.Function):
+    """Autograd node of one ImportanceRenderer.forward call.  `run_fwd()` performs the C-ABI forward and returns the
+    packed output [5N] (rgb | depth | acc); `run_bwd(grad[5N], needs)` calls sherf_render_backward (recompute-in-backward) and returns one
+    gradient (or None) per tensor in `tensors` = (planes, obs_input_feature, volume levels 0..2, the 39 hot-path parameters)."""
+
+    @staticmethod
+    def forward(ctx, run_fwd, run_bwd, *tensors):
+        ctx.run_bwd = run_bwd
+        return run_fwd()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        run_bwd, ctx.run_bwd = ctx.run_bwd, None
+        return (None, None) + tuple(run_bwd(grad, ctx.needs_input_grad[2:]))
+
 
 PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3, 'bf16x3': _lib.MLP_BF16X3,
               '_tf32x3_tmem_a': 99}      # diagnostic: 3xTF32 with the A_lo operand in tensor memory (sherf_debug_linear only)
@@ -511,13 +530,9 @@ class ImportanceRenderer(nn.Module):
 
             w = self._weights_struct(decoder, device, keep)
             hot_params = _runtime(self).w_cache[3]
-            wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in hot_params)
+            diff_inputs = [planes, obs_input_feature] + list(canonical_sp_conv_volume) + list(hot_params)
+            wants_grad = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in diff_inputs)
             volatile_weights = self.training or decoder.training or wants_grad
-            if wants_grad and not getattr(self, '_warned_no_grad', False):
-                warnings.warn('sherf_b200.ImportanceRenderer.forward is the inference kernel: its outputs carry no autograd graph. '
-                              'Use sherf_b200.autograd.render_with_grad (or wrap the call in torch.no_grad()) when gradients are needed.',
-                              stacklevel=2)
-                self._warned_no_grad = True
             rays = _lib.SherfRays()
             ro, rd = _dev32(ray_origins, device), _dev32(ray_directions, device)
             nr, fa = _dev32(near, device), _dev32(far, device)
@@ -610,15 +625,72 @@ class ImportanceRenderer(nn.Module):
                 dbg_p = C.byref(d)
                 rt.dbg_keep = (d, bufs)
 
-            npts = C.c_int64(0)
-            stream = torch.cuda.current_stream(device).cuda_stream
-            rc = lib.sherf_render_forward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(opts),
-                                          C.byref(out), dbg_p, rt.scratch.data_ptr(), rt.scratch.numel(), stream,
-                                          C.byref(npts))
-            _lib.check(rc)
-            self.last_num_points = int(npts.value)                               # coarse + fine survivors
-            self.last_num_fine_points = int(lib.sherf_last_importance_point_count())
-            self.last_launches = int(lib.sherf_last_launch_count())
+            def run_fwd():
+                npts = C.c_int64(0)
+                rc = lib.sherf_render_forward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(opts),
+                                              C.byref(out), dbg_p, rt.scratch.data_ptr(), rt.scratch.numel(),
+                                              torch.cuda.current_stream(device).cuda_stream, C.byref(npts))
+                _lib.check(rc)
+                self.last_num_points = int(npts.value)                               # coarse + fine survivors
+                self.last_num_fine_points = int(lib.sherf_last_importance_point_count())
+                self.last_launches = int(lib.sherf_last_launch_count())
+                return obuf
+
+            if wants_grad:
+                if SF > 0:
+                    raise NotImplementedError('gradients are implemented for the coarse pass (depth_resolution_importance = 0, what every '
+                                              'shipped SHERF configuration trains with; the reference\'s fine pass cannot execute)')
+                held = (smpl, fr, sc, w, rays, opts, list(keep), _runtime(self).w_cache)     # everything the structs point at stays alive
+                shapes = [tuple(t.shape) for t in (pl, ft) + tuple(keep_vols)]
+
+                def run_bwd(grad, needs, held=held):
+                    with torch.cuda.device(device):
+                        g = grad.detach().to(device=device, dtype=torch.float32).contiguous().reshape(-1)
+                        og = _lib.SherfOutGrads(_ptr(g[:3 * N]), _ptr(g[3 * N:4 * N]), _ptr(g[4 * N:]))
+                        grads = [None] * (5 + len(hot_params))
+                        ig = _lib.SherfInputGrads()
+                        if needs[0]:
+                            grads[0] = torch.empty(shapes[0], device=device, dtype=torch.float32); ig.planes = _ptr(grads[0])
+                        if needs[1]:
+                            grads[1] = torch.empty(shapes[1], device=device, dtype=torch.float32); ig.obs_feat = _ptr(grads[1])
+                        for l in range(3):
+                            if needs[2 + l]:
+                                grads[2 + l] = torch.empty(shapes[2 + l], device=device, dtype=torch.float32); ig.vol[l] = _ptr(grads[2 + l])
+                        gw = _lib.SherfWeightGrads()
+                        fields = (['proj_w', 'proj_b', 'reproj_w', 'reproj_b', 'ln1_w', 'ln1_b', 'qkv_w', 'attn_out_w', 'attn_out_b', 'ln2_w',
+                                   'ln2_b', 'ff1_w', 'ff1_b', 'ff2_w', 'ff2_b'] + [(n, i) for i in range(8) for n in ('pts_w', 'pts_b')] +
+                                  ['alpha_w', 'alpha_b', 'feature_w', 'feature_b', 'views_w', 'views_b', 'rgb_w', 'rgb_b'])
+                        for k, (f, p) in enumerate(zip(fields, hot_params)):
+                            if needs[5 + k]:
+                                t = torch.empty(p.shape, device=device, dtype=torch.float32)
+                                grads[5 + k] = t
+                                if isinstance(f, tuple):
+                                    getattr(gw, f[0])[f[1]] = _ptr(t)
+                                else:
+                                    setattr(gw, f, _ptr(t))
+                        rt_ = _runtime(self)
+                        need_b = lib.sherf_backward_scratch_bytes(C.byref(sc), N, S, smpl.n_verts)
+                        if rt_.bwd_scratch is None or rt_.bwd_scratch.numel() < need_b or rt_.bwd_scratch.device != device:
+                            rt_.bwd_scratch = None
+                            rt_.bwd_scratch = torch.empty(need_b, dtype=torch.uint8, device=device)
+                        o2 = _lib.SherfOptions.from_buffer_copy(opts)
+                        o2.weights_version = 0
+                        o2.scene_version = 0
+                        npb = C.c_int64(0)
+                        _lib.check(lib.sherf_render_backward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(o2),
+                                                             C.byref(og), C.byref(gw), C.byref(ig), rt_.bwd_scratch.data_ptr(),
+                                                             rt_.bwd_scratch.numel(), torch.cuda.current_stream(device).cuda_stream,
+                                                             C.byref(npb)))
+                        self.last_backward_launches = int(lib.sherf_last_launch_count())
+                        for k, t in enumerate(diff_inputs):
+                            if grads[k] is not None and torch.is_tensor(t) and t.dtype != torch.float32:
+                                grads[k] = grads[k].to(t.dtype)
+                        return grads
+
+                obuf = _RenderFn.apply(run_fwd, run_bwd, *diff_inputs)
+                rgb, depth, acc = obuf[:3 * N].view(1, N, 3), obuf[3 * N:4 * N].view(1, N, 1), obuf[4 * N:].view(1, N, 1)
+            else:
+                run_fwd()
             if debug is not None:
                 Pn = self.last_num_points - self.last_num_fine_points          # point-indexed taps describe the coarse pass
                 for k, v in rt.dbg_keep[1].items():

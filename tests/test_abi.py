@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f'{n} declared in the header but not exported'
-    assert lib.sherf_abi_version() == 3
+    assert lib.sherf_abi_version() == 4
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -161,7 +161,7 @@ def test_plain_c_client_binds_the_library(tmp_path, lib):
     subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.dirname(HEADER), src, '-o', str(exe), '-ldl'], check=True)
     r = subprocess.run([str(exe), _lib.lib_path()], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert r.stdout.startswith('ok abi=3')
+    assert r.stdout.startswith('ok abi=4')
     print(r.stdout.strip())
 
 

@@ -1,0 +1,151 @@
+"""GPU tests of the backward pass: `loss.backward()` through sherf_b200.ImportanceRenderer.forward against torch
+autograd through the CPU restatement of the reference (oracle/port.py is plain torch: differentiable once its no_grad is lifted).
+
+Loss = the reference's own reconstruction terms (loss.py:150-151,167): 100 * mse(image / 2 + 0.5, target) + 10 * mse(acc, mask), plus a
+depth term on rays whose depth is live (the reference itself never differentiates depth; 0/0 rays would poison torch's gradient).
+Gradients compared: all 39 hot-path parameters, tri-planes, 2-D feature map, the three dense volume levels."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import scene_to
+from sherf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(ren, dec, scene, **kw):
+    return ren(scene['planes'], scene['obs_input_img'], scene['obs_input_feature'], scene['volumes'], None, scene['obs_sp_input'],
+               dec, scene['ray_origins'], scene['ray_directions'], scene['near'], scene['far'], scene['input_data'],
+               scene['rendering_options'], **kw)
+
+
+def the_loss(rgb, depth, acc, tgt_img, tgt_acc, depth_w):
+    l = 100.0 * ((rgb / 2 + 0.5 - tgt_img) ** 2).mean() + 10.0 * ((acc - tgt_acc) ** 2).mean()
+    if depth_w is not None:
+        l = l + (depth * depth_w * (acc.detach() > 0)).sum()          # live rays only (see oracle_grads)
+    return l
+
+
+def oracle_grads(weights, smpl_t, scene, tgt_img, tgt_acc, depth_w, noise=None):
+    """torch autograd through oracle/port.py (the bodies of render_forward without its no_grad decorator)."""
+    from oracle import port
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    sc = dict(scene)
+    sc['planes'] = scene['planes'].clone().requires_grad_(True)
+    sc['obs_input_feature'] = scene['obs_input_feature'].clone().requires_grad_(True)
+    sc['volumes'] = [v.clone().requires_grad_(True) for v in scene['volumes']]
+    with torch.enable_grad():
+        colors, sigma, st = port.evaluate_samples(w, smpl_t, sc, density_noise_points=noise)
+        rays_d, wb = sc['ray_directions'][0], sc['rendering_options']['white_back']
+        rgb, depth, wts = port.composite(colors, sigma, st['depths'], rays_d, wb)
+        acc = wts.sum(1, keepdim=True)
+        loss = the_loss(rgb[None], depth[None].detach(), acc[None], tgt_img, tgt_acc, None)
+        if depth_w is not None:
+            # rays with zero accumulated weight give 0/0: torch propagates NaN through the division even under a zero upstream gradient;
+            # the CUDA path defines that gradient as 0, so the oracle's depth term is built from the live rays only
+            live = acc.detach()[:, 0] > 0
+            clamp = (st['depths'].min(), st['depths'].max())
+            _, depth_live, _ = port.composite(colors[live], sigma[live], st['depths'][live], rays_d[live], wb, clamp)
+            loss = loss + (depth_live * depth_w[0][live]).sum()
+    loss.backward()
+    g = {k: v.grad for k, v in w.items()}
+    g['planes'], g['obs_input_feature'] = sc['planes'].grad, sc['obs_input_feature'].grad
+    for l in range(3):
+        g[f'vol{l}'] = sc['volumes'][l].grad
+    return float(loss), g, int(st['sel'].numel())
+
+
+def cuda_grads(ren, dec, scene, tgt_img, tgt_acc, depth_w, **kw):
+    for p in list(ren.parameters()) + list(dec.parameters()):
+        p.grad = None
+    scene = dict(scene)
+    scene['planes'] = scene['planes'].clone().requires_grad_(True)
+    scene['obs_input_feature'] = scene['obs_input_feature'].clone().requires_grad_(True)
+    scene['volumes'] = [v.clone().requires_grad_(True) for v in scene['volumes']]
+    rgb, depth, acc = run_cuda(ren, dec, scene, **kw)
+    assert rgb.requires_grad and acc.requires_grad
+    loss = the_loss(rgb, depth, acc, tgt_img, tgt_acc, depth_w)
+    loss.backward()
+    g = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in named_hot_parameters(ren, dec).items()}
+    g['planes'], g['obs_input_feature'] = scene['planes'].grad, scene['obs_input_feature'].grad
+    for l in range(3):
+        g[f'vol{l}'] = scene['volumes'][l].grad
+    return float(loss), g
+
+
+def named_hot_parameters(ren, dec):
+    """checkpoint name -> nn.Parameter of the 39 hot-path tensors (SherfWeights); the sparse encoder's parameters are not on this path."""
+    d = {'renderer.' + k: p for k, p in ren.named_parameters() if not k.startswith('encoder_3d')}
+    d.update({'decoder.' + k: p for k, p in dec.named_parameters()})
+    return d
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30)), float((a - b).abs().max()), float(b.abs().max())
+
+
+@pytest.mark.parametrize('spec', [dict(H=24, W=24, samples=16, seed=2, white_back=False, depth=False, noise=0.0),
+                                  dict(H=32, W=20, samples=24, seed=5, white_back=True, depth=True, noise=0.0),
+                                  dict(H=16, W=16, samples=12, seed=7, white_back=False, depth=True, noise=0.5)])
+def test_backward_matches_autograd_through_the_oracle(spec, smpl_model, smpl_model_t):
+    from oracle import port
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene_c = S.make_scene(S.SceneSpec(H=spec['H'], W=spec['W'], samples=spec['samples'], seed=spec['seed']), smpl_model)
+    scene_c['rendering_options']['white_back'] = spec['white_back']
+    N = scene_c['ray_origins'].shape[1]
+    gen = torch.Generator().manual_seed(spec['seed'])
+    tgt_img, tgt_acc = torch.rand(1, N, 3, generator=gen), (torch.rand(1, N, 1, generator=gen) > 0.5).float()
+    depth_w = torch.randn(1, N, 1, generator=gen) * 0.1 if spec['depth'] else None
+    ren, dec = hot_path_modules(smpl_model, seed=3, dense_sigma=True)
+    ren.requires_grad_(True); dec.requires_grad_(True)
+    weights = {k: v.detach().clone() for k, v in port.hot_path_state_dict(ren, dec).items()}
+    noise = None
+    if spec['noise'] > 0:
+        noise = torch.randn(N * spec['samples'], generator=gen) * spec['noise']          # per surviving point, more than enough of them
+    loss_o, g_o, P = oracle_grads(weights, smpl_model_t, scene_c, tgt_img, tgt_acc, depth_w, noise)
+    assert P > 50, 'the synthetic view must hit the body'
+    ren, dec = ren.to(dev), dec.to(dev)
+    scene_g = scene_to(scene_c, dev)
+    kw = {'density_noise_points': noise.to(dev)} if noise is not None else {}
+    loss_g, g_g = cuda_grads(ren, dec, scene_g, tgt_img.to(dev), tgt_acc.to(dev), None if depth_w is None else depth_w.to(dev), **kw)
+    print(f'\n[backward {spec}] P = {P}, loss oracle {loss_o:.6f} cuda {loss_g:.6f}')
+    assert abs(loss_g - loss_o) <= 1e-4 * max(1.0, abs(loss_o))
+    worst = 0.0
+    keys = sorted(named_hot_parameters(ren, dec)) + ['planes', 'obs_input_feature', 'vol0', 'vol1', 'vol2']
+    assert len(keys) == 39 + 5
+    for k in keys:
+        assert k in g_g, f'no CUDA gradient for {k}'
+        assert g_g[k] is not None and g_o[k] is not None, k
+        assert tuple(g_g[k].shape) == tuple(g_o[k].shape), (k, g_g[k].shape, g_o[k].shape)
+        r, mx, ref = rel_err(g_g[k], g_o[k])
+        print(f'   {k:58s} rel L2 {r:.2e}   max abs {mx:.2e} of {ref:.2e}')
+        assert np.isfinite(r)
+        worst = max(worst, r)
+        assert r <= 1e-3, f'{k}: relative L2 error {r:.3e}'
+    print(f'   worst relative L2 error {worst:.2e}')
+
+
+def test_backward_is_deterministic_for_weights_and_frozen_inputs_get_none(smpl_model):
+    """Weight gradients are reduced in a fixed order: two backward passes give identical bits.  Tensors that do not require grad get None."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=32, W=32, samples=16, seed=4), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=1, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dec.requires_grad_(True)                       # the renderer's own parameters stay frozen
+    outs = []
+    for _ in range(2):
+        for p in dec.parameters():
+            p.grad = None
+        rgb, depth, acc = run_cuda(ren, dec, scene)
+        (rgb.square().sum() + acc.sum()).backward()
+        outs.append([p.grad.clone() for p in dec.parameters()])
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+    assert all(p.grad is None for p in ren.parameters())
+    assert any(float(g.abs().max()) > 0 for g in outs[0])
+    with torch.no_grad():
+        rgb, _, _ = run_cuda(ren, dec, scene)
+    assert not rgb.requires_grad
