@@ -37,7 +37,8 @@ def test_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header(tmp_path):
     structs = ['SherfSmplModel', 'SherfPose', 'SherfFrame', 'SherfScene', 'SherfWeights', 'SherfRays', 'SherfOptions', 'SherfOut',
-               'SherfDebug', 'SherfSparseConv', 'SherfSparseEncoder', 'SherfObservation']
+               'SherfDebug', 'SherfSparseConv', 'SherfSparseEncoder', 'SherfObservation', 'SherfOutGrads', 'SherfWeightGrads',
+               'SherfInputGrads']
     prog = '#include <stdio.h>\n#include "sherf_b200.h"\nint main(){' + ''.join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + 'return 0;}'
     c = tmp_path / 'sz.c'
@@ -65,6 +66,13 @@ def test_scratch_bytes_and_argument_validation(lib):
     assert lib.sherf_scratch_bytes(ctypes.byref(sc), 0, 16, 0, 6890) == 0
     rc = lib.sherf_render_forward(None, None, None, None, None, None, None, None, None, 0, None, None)
     assert rc == -1 and b'null' in lib.sherf_last_error()
+    # backward arena = forward arena + its own buffers; argument checks run before any CUDA call
+    bsmall = lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 4096, 16, 6890)
+    bbig = lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 512 * 512, 64, 6890)
+    assert small < bsmall < bbig < 16 << 30
+    assert lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 0, 16, 6890) == 0
+    assert lib.sherf_render_backward(None, None, None, None, None, None, None, None, None, None, 0, None, None) == -1
+    assert ctypes.sizeof(_lib.SherfWeightGrads) == ctypes.sizeof(_lib.SherfWeights) == 39 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_no_cpu_fallback(smpl_model):
