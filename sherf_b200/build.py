@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libsherf_b200.so')
-SOURCES = ['api.cu', 'prologue.cu', 'cull.cu', 'gather.cu', 'mlp_simt.cu', 'mlp_umma.cu', 'decoder_fused.cu', 'decoder_pp.cu', 'xformer_fused.cu', 'xformer_bf16.cu', 'front_fused.cu', 'fusion_fused.cu', 'composite.cu', 'importance.cu', 'rays.cu', 'sparse_encoder.cu', 'observation.cu', 'smpl_forward.cu', 'backward.cu']
+SOURCES = ['api.cu', 'prologue.cu', 'cull.cu', 'gather.cu', 'mlp_simt.cu', 'mlp_umma.cu', 'decoder_fused.cu', 'decoder_pp.cu', 'xformer_fused.cu', 'xformer_bf16.cu', 'front_fused.cu', 'fusion_fused.cu', 'composite.cu', 'importance.cu', 'rays.cu', 'sparse_encoder.cu', 'observation.cu', 'smpl_forward.cu', 'backward.cu', 'backward_umma.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

@@ -252,11 +252,12 @@ struct BwdLayout {
   float* out;                 // rgb | depth | acc of the internal forward (5 N)
   float* dsig; float* drgb;   // dL/d(sigma), dL/d(rgb) per surviving point
   float* g_planes_cl; float* g_feat_cl; float* g_vol_cl[3];
+  float* canon_w; float* canon_bwd;   // tf32 hi / lo weights of the recompute pass and, transposed, of the dX products
   float* chunk; int bcap;
 };
 static int bwd_chunk_cap(int N, int S) {
   static int cap = 0;
-  if (!cap) { const char* e = getenv("SHERF_BWD_CHUNK_CAP"); const long v = e ? atol(e) : 0; cap = v >= 128 ? (int)(v / 128 * 128) : (1 << 17); }
+  if (!cap) { const char* e = getenv("SHERF_BWD_CHUNK_CAP"); const long v = e ? atol(e) : 0; cap = v >= 128 ? (int)(v / 128 * 128) : (1 << 18); }
   const size_t NS = (size_t)N * S;
   return (int)(NS < (size_t)cap ? (NS + 127) / 128 * 128 : (size_t)cap);
 }
@@ -270,6 +271,8 @@ static size_t carve_backward(Arena& a, const SherfScene& sc, int N, int S, int V
   B.g_planes_cl = a.take<float>((size_t)3 * sc.plane_ch * sc.plane_h * sc.plane_w);
   B.g_feat_cl = a.take<float>((size_t)sc.feat_ch * sc.feat_h * sc.feat_w);
   for (int l = 0; l < 3; ++l) B.g_vol_cl[l] = a.take<float>((size_t)sc.vol_ch[l] * sc.vol_dim[l][0] * sc.vol_dim[l][1] * sc.vol_dim[l][2]);
+  B.canon_w = a.take<float>(canonical_weight_floats());
+  B.canon_bwd = a.take<float>(canonical_bwd_weight_floats());
   B.bcap = bwd_chunk_cap(N, S);
   B.chunk = a.take<float>(bwd_chunk_floats(B.bcap));
   return a.off;
@@ -644,6 +647,10 @@ int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, c
     PackedWeights pw;
     g_pack_plan_only = false;
     RC(run_pack_weights(*weights, L.packed_w, pw, st));
+    CanonWeights cw;
+    CanonBwdWeights cbw;
+    RC(run_pack_canonical(*weights, B.canon_w, cw, st));
+    RC(run_pack_canonical_bwd(*weights, B.canon_bwd, cbw, st));
     RC(run_composite_backward(*rays, L.ft.fc, L.ray_start, L.point_sample, L.sigma, L.rgb, opts->density_noise, opts->white_back, grad_out->rgb,
                               grad_out->depth, grad_out->acc, B.dsig, B.drgb, st));
     BwdChunk bc;
@@ -652,12 +659,12 @@ int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, c
     fill_gather_params(G, *rays, *frame, *scene, L);
     for (int64_t p0 = 0; p0 < P; p0 += B.bcap) {
       const int np = (int)((P - p0 < B.bcap) ? (P - p0) : B.bcap);
-      RC(run_backward_chunk(*weights, pw, gw, G, bc, np, p0, L.rgb, B.dsig, B.drgb, st));
+      RC(run_backward_chunk(*weights, pw, cw, cbw, gw, G, bc, np, p0, L.rgb, B.dsig, B.drgb, st));
       GatherParams Gs = G;
       Gs.g_planes_cl = want_planes ? B.g_planes_cl : nullptr;
       Gs.g_feat_cl = want_feat ? B.g_feat_cl : nullptr;
       for (int l = 0; l < 3; ++l) Gs.g_vol_cl[l] = want_vol[l] ? B.g_vol_cl[l] : nullptr;
-      RC(run_backward_chunk_inputs(*weights, Gs, bc, np, p0, st));
+      RC(run_backward_chunk_inputs(*weights, cbw, Gs, bc, np, p0, st));
     }
   }
   // ---- channels-last gradient grids -> the caller's PyTorch layouts ----

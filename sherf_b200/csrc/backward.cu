@@ -83,6 +83,8 @@ int run_composite_backward(const SherfRays& rays, const FrameConst* fc, const in
   return SHERF_OK;
 }
 
+#define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
 // ------------------------------------------------------------------------------------------------- GEMMs
 // column map of an operand: logical column c -> (c / group) * gstride + c % group   (group = 0: identity); used for the 96 outputs of
 // conv1d_projection, which live at columns 64..95 of each token's 96-wide slice of comb (renderer.py:350,423)
@@ -246,31 +248,53 @@ __global__ void __launch_bounds__(256) k_gemm_tn(const TnArgs g) {
   }
 }
 
-// dW[n][k] += sum_s part[s][n][k]  (k < K),  db[n] += sum_s part[s][n][K]; splits added in order: the result does not depend on scheduling
-__global__ void k_reduce_parts(const float* __restrict__ part, int splits, int N, int K, float* __restrict__ dW, float* __restrict__ db) {
-  const int K1 = K + 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * K1) return;
-  const int n = idx / K1, k = idx - n * K1;
+// dW[n][k] += sum_s part[s][n][k]  (k < K),  db[n] += sum_s part[s][n][K].  32 outputs per block; warp w adds the splits w, w + 8, ... in
+// order (128 contiguous bytes per split), the eight warp sums are added in warp order: the result does not depend on scheduling
+__global__ void __launch_bounds__(256) k_reduce_parts(const float* __restrict__ part, int splits, int N, int K, float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ float red[8][32];
+  const int K1 = K + 1, total = N * K1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += part[(size_t)sp * N * K1 + idx];
-  if (k < K) dW[(size_t)n * K + k] += s;
-  else if (db) db[n] += s;
+  if (idx < total)
+    for (int sp = w; sp < splits; sp += 8) s += part[(size_t)sp * total + idx];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && idx < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    const int n = idx / K1, k = idx - n * K1;
+    if (k < K) dW[(size_t)n * K + k] += t;
+    else if (db) db[n] += t;
+  }
 }
 
-constexpr int kRowsPerSplit = 1024;
+constexpr int kRowsPerSplit = kGradWRowsPerSplit;
+
+// SHERF_BWD_SIMT=1: every product of the backward on the CUDA cores in fp32 FMA (the first version; kept as the anchor of the tensor-core path)
+static bool bwd_simt() {
+  const char* e = getenv("SHERF_BWD_SIMT");        // read per call: the tests switch it between two backward passes of one process
+  return e && e[0] == '1';
+}
 
 // dW[N][K] += dY^T X, db[N] += column sums of dY     (dY = A [M][N], X = B [M][K])
 static int grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* dW, float* db, float* part, cudaStream_t st,
                   int agroup = 0, int agstride = 0) {
   if (!dW && !db) return SHERF_OK;
+  if (!bwd_simt()) {
+    RC(launch_umma_grad_w(dY, lda, N, X, ldb, K, M, part, st, agroup, agstride));
+    k_reduce_parts<<<ceil_div(N * (K + 1), 32), 256, 0, st>>>(part, ceil_div(M, kRowsPerSplit), N, K, dW, db);
+    SHERF_LAUNCH_CHECK();
+    return SHERF_OK;
+  }
   TnArgs g;
   g.A = dY; g.lda = lda; g.agroup = agroup; g.agstride = agstride; g.N = N; g.B = X; g.ldb = ldb; g.K = K; g.part = part; g.M = M;
   g.rows_per_split = kRowsPerSplit;
   const int splits = ceil_div(M, kRowsPerSplit);
   k_gemm_tn<<<dim3(ceil_div(N, 128), ceil_div(K + 1, 64), splits), 256, 0, st>>>(g);
   SHERF_LAUNCH_CHECK();
-  k_reduce_parts<<<ceil_div(N * (K + 1), 256), 256, 0, st>>>(part, splits, N, K, dW, db);
+  k_reduce_parts<<<ceil_div(N * (K + 1), 32), 256, 0, st>>>(part, splits, N, K, dW, db);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
 }
@@ -377,13 +401,19 @@ __global__ void __launch_bounds__(128) k_attention3_bwd(const float* __restrict_
   const int p = idx / 3, h = idx - p * 3;
   const float* base = qkv + (size_t)p * 3 * 144 + h * 16;
   float q[3][16], k[3][16], v[3][16], go[3][16];
+  // every 16-float head slice is 64-byte aligned: four 16-byte loads instead of sixteen scalar ones
+  auto ld16 = [](float (&dst)[16], const float* src) {
 #pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      q[t][d] = base[t * 144 + d]; k[t][d] = base[t * 144 + 48 + d]; v[t][d] = base[t * 144 + 96 + d];
-      go[t][d] = datt[(size_t)(p * 3 + t) * 48 + h * 16 + d];
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+      dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
     }
+  };
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    ld16(q[t], base + t * 144); ld16(k[t], base + t * 144 + 48); ld16(v[t], base + t * 144 + 96);
+    ld16(go[t], datt + (size_t)(p * 3 + t) * 48 + h * 16);
+  }
   float P[3][3], dS[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -414,10 +444,18 @@ __global__ void __launch_bounds__(128) k_attention3_bwd(const float* __restrict_
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      ob[t * 144 + d] = 0.25f * (dS[t][0] * k[0][d] + dS[t][1] * k[1][d] + dS[t][2] * k[2][d]);            // dq_t
-      ob[t * 144 + 48 + d] = 0.25f * (dS[0][t] * q[0][d] + dS[1][t] * q[1][d] + dS[2][t] * q[2][d]);       // dk_t
-      ob[t * 144 + 96 + d] = P[0][t] * go[0][d] + P[1][t] * go[1][d] + P[2][t] * go[2][d];                 // dv_t
+    for (int d4 = 0; d4 < 4; ++d4) {
+      float dq[4], dk[4], dv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * d4 + e;
+        dq[e] = 0.25f * (dS[t][0] * k[0][d] + dS[t][1] * k[1][d] + dS[t][2] * k[2][d]);
+        dk[e] = 0.25f * (dS[0][t] * q[0][d] + dS[1][t] * q[1][d] + dS[2][t] * q[2][d]);
+        dv[e] = P[0][t] * go[0][d] + P[1][t] * go[1][d] + P[2][t] * go[2][d];
+      }
+      reinterpret_cast<float4*>(ob + t * 144)[d4] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+      reinterpret_cast<float4*>(ob + t * 144 + 48)[d4] = make_float4(dk[0], dk[1], dk[2], dk[3]);
+      reinterpret_cast<float4*>(ob + t * 144 + 96)[d4] = make_float4(dv[0], dv[1], dv[2], dv[3]);
     }
 }
 
@@ -469,39 +507,49 @@ void carve_bwd_chunk(float* base, int cap, BwdChunk& b) {
   b.ln_part = p; p += (size_t)kLnBlocks * 64;
 }
 
-#define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
-
 // G: the forward gather parameters of this chunk (comb / f3raw / geo pointing at b.comb / b.f3raw / b.geo); rgb / dsig / drgb: per-point
 // arrays of the whole pass (absolute indices).  gw entries may be NULL (no gradient wanted for that parameter).
-int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const SherfWeightGrads& gw, GatherParams G, const BwdChunk& b, int np, int64_t p0,
-                       const float* rgb, const float* dsig, const float* drgb, cudaStream_t st) {
+int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const CanonBwdWeights& cbw, const SherfWeightGrads& gw,
+                       GatherParams G, const BwdChunk& b, int np, int64_t p0, const float* rgb, const float* dsig, const float* drgb, cudaStream_t st) {
   if (np <= 0) return SHERF_OK;
   const int M = np, R = 3 * np;
   const int E = 256;
-  // ---- recompute the forward with every activation kept (fp32 FMA, the parity path of mlp_simt.cu) ----
+  const bool simt = bwd_simt();
+  // one forward layer / one dX product on the selected arithmetic
+  auto fwd = [&](const PackedLayer& P, const CanonLayer& C, const float* A, int lda, float* Y, int ldy, int rows, int act, const float* Res = nullptr,
+                 int ldr = 0, int yg = 0, int ygs = 0) -> int {
+    if (simt) return launch_simt_linear(P, A, lda, Y, ldy, rows, act, st, Res, ldr, yg, ygs);
+    return launch_umma_linear(3, C, A, lda, Y, ldy, rows, act, st, Res, ldr, yg, ygs);
+  };
+  auto dxp = [&](const CanonLayer& C, const float* dY, int lda, const float* W, int ldb, float* dX, int ldx, int rows, int Nc, int Kr,
+                 const float* Mask = nullptr, int ldm = 0, int accum = 0, int agroup = 0, int agstride = 0) -> int {
+    if (simt) return gemm_nn(dY, lda, W, ldb, dX, ldx, rows, Nc, Kr, st, Mask, ldm, accum, agroup, agstride);
+    return launch_umma_dx(C, dY, lda, dX, ldx, rows, st, Mask, ldm, accum, agroup, agstride);
+  };
+  // ---- recompute the forward with every activation kept (per-layer kernels: 3xTF32 on tcgen05, or fp32 FMA with SHERF_BWD_SIMT=1) ----
   G.comb = b.comb; G.f3raw = b.f3raw; G.geo = b.geo; G.p0 = p0; G.np = np; G.dc = DevCount{nullptr, 0, 0};
   G.dbg_vid3 = nullptr; G.dbg_can = nullptr; G.dbg_cdir = nullptr; G.dbg_uv = nullptr; G.dbg_feat = nullptr; G.dbg_max = 0; G.dbg_feat_max = 0;
   G.g_planes_cl = nullptr; G.g_feat_cl = nullptr; G.g_vol_cl[0] = G.g_vol_cl[1] = G.g_vol_cl[2] = nullptr;
   RC(run_point_gather(G, st));
-  RC(launch_simt_linear(pw.proj, b.f3raw, 192, b.comb + 64, 288, M, 0, st, nullptr, 0, 32, 96));
-  RC(launch_simt_linear(pw.reproj, b.comb, 96, b.tok, 32, R, 0, st, nullptr, 0, 0, 0));
+  RC(fwd(pw.proj, cw.proj, b.f3raw, 192, b.comb + 64, 288, M, 0, nullptr, 0, 32, 96));
+  RC(fwd(pw.reproj, cw.reproj, b.comb, 96, b.tok, 32, R, 0));
   RC(run_layernorm32(b.tok, w.ln1_w, w.ln1_b, b.ln1, R, st));
-  RC(launch_simt_linear(pw.qkv, b.ln1, 32, b.qkv, 144, R, 0, st, nullptr, 0, 0, 0));
+  RC(fwd(pw.qkv, cw.qkv, b.ln1, 32, b.qkv, 144, R, 0));
   RC(run_attention3(b.qkv, b.att, M, st));
-  RC(launch_simt_linear(pw.attn_out, b.att, 48, b.tok2, 32, R, 0, st, b.tok, 32, 0, 0));
+  RC(fwd(pw.attn_out, cw.attn_out, b.att, 48, b.tok2, 32, R, 0, b.tok, 32));
   RC(run_layernorm32(b.tok2, w.ln2_w, w.ln2_b, b.ln2, R, st));
-  RC(launch_simt_linear(pw.ff1, b.ln2, 32, b.ffp, 32, R, 0, st, nullptr, 0, 0, 0));
+  RC(fwd(pw.ff1, cw.ff1, b.ln2, 32, b.ffp, 32, R, 0));
   k_gelu_fwd<<<ceil_div(R * 32, E), E, 0, st>>>(b.ffp, b.ffa, (size_t)R * 32);
   SHERF_LAUNCH_CHECK();
-  RC(launch_simt_linear(pw.ff2, b.ffa, 32, b.tok3, 32, R, 0, st, b.tok2, 32, 0, 0));
+  RC(fwd(pw.ff2, cw.ff2, b.ffa, 32, b.tok3, 32, R, 0, b.tok2, 32));
   RC(run_decoder_inputs(b.geo, b.tok3, b.x, b.hb, b.fv, M, st));
   const float* hin[8] = {b.x, b.h[0], b.h[1], b.h[2], b.h[3], b.hb, b.h[5], b.h[6]};
   const int hld[8] = {72, 128, 128, 128, 128, 200, 128, 128};
   float* hout[8] = {b.h[0], b.h[1], b.h[2], b.h[3], b.hb + 71, b.h[5], b.h[6], b.h[7]};
   const int hold[8] = {128, 128, 128, 128, 200, 128, 128, 128};
-  for (int i = 0; i < 8; ++i) RC(launch_simt_linear(pw.pts[i], hin[i], hld[i], hout[i], hold[i], M, 1 /* ReLU */, st, nullptr, 0, 0, 0));
-  RC(launch_simt_linear(pw.feature, b.h[7], 128, b.fv, 188, M, 0, st, nullptr, 0, 0, 0));
-  RC(launch_simt_linear(pw.views, b.fv, 188, b.vh, 64, M, 1, st, nullptr, 0, 0, 0));
+  for (int i = 0; i < 8; ++i) RC(fwd(pw.pts[i], cw.pts[i], hin[i], hld[i], hout[i], hold[i], M, 1 /* ReLU */));
+  RC(fwd(pw.feature, cw.feature, b.h[7], 128, b.fv, 188, M, 0));
+  RC(fwd(pw.views, cw.views, b.fv, 188, b.vh, 64, M, 1));
 
   // ---- decoder backward (triplane.py:285-316) ----
   const float* dsg = dsig + p0;
@@ -509,41 +557,41 @@ int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const She
   SHERF_LAUNCH_CHECK();
   RC(grad_w(b.dpre, 4, 3, b.vh, 64, 64, M, gw.rgb_w, gw.rgb_b, b.part, st));
   RC(grad_w(b.dvh, 64, 64, b.fv, 188, 187, M, gw.views_w, gw.views_b, b.part, st));
-  RC(gemm_nn(b.dvh, 64, w.views_w, 187, b.dfv, 188, M, 187, 64, st));                              // d [feature | PE4(dir) | tok1]
+  RC(dxp(cbw.views, b.dvh, 64, w.views_w, 187, b.dfv, 188, M, 187, 64));                              // d [feature | PE4(dir) | tok1]
   RC(grad_w(b.dfv, 188, 128, b.h[7], 128, 128, M, gw.feature_w, gw.feature_b, b.part, st));
   RC(grad_w(dsg, 1, 1, b.h[7], 128, 128, M, gw.alpha_w, gw.alpha_b, b.part, st));
-  RC(gemm_nn(b.dfv, 188, w.feature_w, 128, b.dha, 128, M, 128, 128, st));
+  RC(dxp(cbw.feature, b.dfv, 188, w.feature_w, 128, b.dha, 128, M, 128, 128));
   k_dh7<<<ceil_div(M * 128, E), E, 0, st>>>(b.dha, b.h[7], dsg, w.alpha_w, M);
   SHERF_LAUNCH_CHECK();
   float* dcur = b.dha; float* dnext = b.dhb;
   for (int i = 7; i >= 6; --i) {                                                                    // layers 7, 6: 128 -> 128
     RC(grad_w(dcur, 128, 128, hin[i], hld[i], 128, M, gw.pts_w[i], gw.pts_b[i], b.part, st));
-    RC(gemm_nn(dcur, 128, w.pts_w[i], 128, dnext, 128, M, 128, 128, st, hin[i], hld[i]));
+    RC(dxp(cbw.pts[i], dcur, 128, w.pts_w[i], 128, dnext, 128, M, 128, 128, hin[i], hld[i]));
     float* t = dcur; dcur = dnext; dnext = t;
   }
   // layer 5 reads cat([x, h4]) (triplane.py:299-300): x part -> dx (no ReLU), h4 part -> dh4 masked by h4 > 0
   RC(grad_w(dcur, 128, 128, b.hb, 200, 199, M, gw.pts_w[5], gw.pts_b[5], b.part, st));
-  RC(gemm_nn(dcur, 128, w.pts_w[5], 199, b.dx, 72, M, 71, 128, st));
-  RC(gemm_nn(dcur, 128, w.pts_w[5] + 71, 199, dnext, 128, M, 128, 128, st, b.hb + 71, 200));
+  RC(dxp(cbw.pts5x, dcur, 128, w.pts_w[5], 199, b.dx, 72, M, 71, 128));
+  RC(dxp(cbw.pts[5], dcur, 128, w.pts_w[5] + 71, 199, dnext, 128, M, 128, 128, b.hb + 71, 200));
   { float* t = dcur; dcur = dnext; dnext = t; }
   for (int i = 4; i >= 1; --i) {
     RC(grad_w(dcur, 128, 128, hin[i], hld[i], 128, M, gw.pts_w[i], gw.pts_b[i], b.part, st));
-    RC(gemm_nn(dcur, 128, w.pts_w[i], 128, dnext, 128, M, 128, 128, st, hin[i], hld[i]));
+    RC(dxp(cbw.pts[i], dcur, 128, w.pts_w[i], 128, dnext, 128, M, 128, 128, hin[i], hld[i]));
     float* t = dcur; dcur = dnext; dnext = t;
   }
   RC(grad_w(dcur, 128, 128, b.x, 72, 71, M, gw.pts_w[0], gw.pts_b[0], b.part, st));
-  RC(gemm_nn(dcur, 128, w.pts_w[0], 71, b.dx, 72, M, 71, 128, st, nullptr, 0, 1 /* += the skip branch */));
+  RC(dxp(cbw.pts[0], dcur, 128, w.pts_w[0], 71, b.dx, 72, M, 71, 128, nullptr, 0, 1 /* += the skip branch */));
 
   // ---- transformer backward (renderer.py:920-993) ----
   k_tok3_grad<<<ceil_div(M * 96, E), E, 0, st>>>(b.dx, b.dfv, b.dtok3, M);
   SHERF_LAUNCH_CHECK();
   // x3 = ff2(gelu(ff1(LN2(x2)))) + x2
   RC(grad_w(b.dtok3, 32, 32, b.ffa, 32, 32, R, gw.ff2_w, gw.ff2_b, b.part, st));
-  RC(gemm_nn(b.dtok3, 32, w.ff2_w, 32, b.dff, 32, R, 32, 32, st));
+  RC(dxp(cbw.ff2, b.dtok3, 32, w.ff2_w, 32, b.dff, 32, R, 32, 32));
   k_gelu_bwd<<<ceil_div(R * 32, E), E, 0, st>>>(b.dff, b.ffp, (size_t)R * 32);
   SHERF_LAUNCH_CHECK();
   RC(grad_w(b.dff, 32, 32, b.ln2, 32, 32, R, gw.ff1_w, gw.ff1_b, b.part, st));
-  RC(gemm_nn(b.dff, 32, w.ff1_w, 32, b.dln, 32, R, 32, 32, st));
+  RC(dxp(cbw.ff1, b.dff, 32, w.ff1_w, 32, b.dln, 32, R, 32, 32));
   SHERF_CUDA_OK(cudaMemcpyAsync(b.dtok2, b.dtok3, sizeof(float) * (size_t)R * 32, cudaMemcpyDeviceToDevice, st));     // residual branch
   k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok2, w.ln2_w, b.dln, b.dtok2, 1, R, b.ln_part);
   SHERF_LAUNCH_CHECK();
@@ -551,11 +599,11 @@ int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const She
   SHERF_LAUNCH_CHECK();
   // x2 = to_out(attention(to_qkv(LN1(x)))) + x
   RC(grad_w(b.dtok2, 32, 32, b.att, 48, 48, R, gw.attn_out_w, gw.attn_out_b, b.part, st));
-  RC(gemm_nn(b.dtok2, 32, w.attn_out_w, 48, b.datt, 48, R, 48, 32, st));
+  RC(dxp(cbw.attn_out, b.dtok2, 32, w.attn_out_w, 48, b.datt, 48, R, 48, 32));
   k_attention3_bwd<<<ceil_div(M * 3, 128), 128, 0, st>>>(b.qkv, b.datt, b.dqkv, M);
   SHERF_LAUNCH_CHECK();
   RC(grad_w(b.dqkv, 144, 144, b.ln1, 32, 32, R, gw.qkv_w, nullptr, b.part, st));
-  RC(gemm_nn(b.dqkv, 144, w.qkv_w, 32, b.dln, 32, R, 32, 144, st));
+  RC(dxp(cbw.qkv, b.dqkv, 144, w.qkv_w, 32, b.dln, 32, R, 32, 144));
   SHERF_CUDA_OK(cudaMemcpyAsync(b.dtok, b.dtok2, sizeof(float) * (size_t)R * 32, cudaMemcpyDeviceToDevice, st));
   k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok, w.ln1_w, b.dln, b.dtok, 1, R, b.ln_part);
   SHERF_LAUNCH_CHECK();
@@ -564,18 +612,21 @@ int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const She
 
   // ---- fusion convolutions (renderer.py:350,423-424) ----
   RC(grad_w(b.dtok, 32, 32, b.comb, 96, 96, R, gw.reproj_w, gw.reproj_b, b.part, st));
-  RC(gemm_nn(b.dtok, 32, w.reproj_w, 96, b.dcomb, 96, R, 96, 32, st));
+  RC(dxp(cbw.reproj, b.dtok, 32, w.reproj_w, 96, b.dcomb, 96, R, 96, 32));
   // conv1d_projection: its 96 outputs are columns 64..95 of each token's slice
   RC(grad_w(b.dcomb + 64, 288, 96, b.f3raw, 192, 192, M, gw.proj_w, gw.proj_b, b.part, st, 32, 96));
   return SHERF_OK;
 }
 
 // second half of a chunk: input gradients (needs the gradient grids); split from run_backward_chunk so that G's grid pointers are explicit
-int run_backward_chunk_inputs(const SherfWeights& w, GatherParams G, const BwdChunk& b, int np, int64_t p0, cudaStream_t st) {
+int run_backward_chunk_inputs(const SherfWeights& w, const CanonBwdWeights& cbw, GatherParams G, const BwdChunk& b, int np, int64_t p0, cudaStream_t st) {
   if (np <= 0) return SHERF_OK;
   if (!G.g_planes_cl && !G.g_feat_cl && !G.g_vol_cl[0] && !G.g_vol_cl[1] && !G.g_vol_cl[2]) return SHERF_OK;
   if (G.g_vol_cl[0] || G.g_vol_cl[1] || G.g_vol_cl[2])
-    RC(gemm_nn(b.dcomb + 64, 288, w.proj_w, 192, b.df3raw, 192, np, 192, 96, st, nullptr, 0, 0, 32, 96));
+  {
+    if (bwd_simt()) RC(gemm_nn(b.dcomb + 64, 288, w.proj_w, 192, b.df3raw, 192, np, 192, 96, st, nullptr, 0, 0, 32, 96));
+    else RC(launch_umma_dx(cbw.proj, b.dcomb + 64, 288, b.df3raw, 192, np, st, nullptr, 0, 0, 32, 96));
+  }
   G.comb = b.dcomb; G.f3raw = b.df3raw; G.geo = b.geo; G.p0 = p0; G.np = np; G.dc = DevCount{nullptr, 0, 0};
   G.dbg_vid3 = nullptr; G.dbg_can = nullptr; G.dbg_cdir = nullptr; G.dbg_uv = nullptr; G.dbg_feat = nullptr; G.dbg_max = 0; G.dbg_feat_max = 0;
   RC(run_point_scatter(G, st));

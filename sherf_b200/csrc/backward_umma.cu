@@ -1,0 +1,198 @@
+// Weight gradients of the backward pass on the tensor cores:  dW[n][k] = sum_m dY[m][n] X[m][k],  db[n] = sum_m dY[m][n]
+// -- what torch.autograd derives for every nn.Linear / Conv1d(k=1) of renderer.py:350,423-424,920-993 and triplane.py:285-316.
+//
+// It is a GEMM whose REDUCTION runs over the surviving points: D[n][k] (128 x <=208, fp32 in TMEM) += A[n][p] . B[k][p]^T with p the
+// tcgen05 K dimension.  dY / X sit in HBM row-major over points, so a 32-point chunk is transposed on its way into shared memory: each
+// thread loads a 4-point x 4-feature block (four 16-byte loads), splits it into tf32 hi / lo and stores four 16-byte core-matrix rows
+// (feature-major) of the K-major no-swizzle canonical layout of umma.cuh.  The 8 lanes of a quarter-warp write the 8 point-quads of one
+// feature block: with the K-direction stride padded by 16 bytes their STS.128 are bank-conflict free, and a warp's loads cover 8 rows x 64
+// contiguous bytes.  Arithmetic: 3xTF32 split products (a_lo w_hi + a_hi w_lo + a_hi w_hi, fp32 accumulate) = fp32-grade sums.
+// The bias gradient rides along as column K of B (a column of ones).  One CTA reduces kGradWRowsPerSplit rows and writes its partial
+// [n][K + 1] tile; k_reduce_parts (backward.cu) adds the partials in split order, so the result does not depend on scheduling.
+#include "common.cuh"
+#include "stages.cuh"
+#include "umma.cuh"
+
+namespace sherf {
+
+struct GradWArgs {
+  const float* dY; int lda, agroup, agstride; int N;     // [M][N], logical column c at (c / agroup) * agstride + c % agroup
+  const float* X; int ldb; int K;                         // [M][K]; logical column K is the constant 1
+  float* part;                                            // [splits][N][K + 1]
+  int M, rows_per_split;
+  int Np;                                                 // round_up(K + 1, 16)
+  uint32_t tmem_cols;
+};
+
+// four consecutive logical columns c .. c+3 of row `row` (zeros outside [0, ncols)); 16-byte load when the address allows it
+__device__ __forceinline__ float4 load_cols4(const float* __restrict__ base, size_t row, int ld, int c, int ncols, int group, int gstride) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c >= ncols) return v;
+  const float* p = base + row * (size_t)ld + (group ? (c / group) * gstride + (c % group) : c);
+  if (c + 3 < ncols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  v.x = __ldg(p);
+  if (c + 1 < ncols) v.y = __ldg(p + 1);
+  if (c + 2 < ncols) v.z = __ldg(p + 2);
+  if (c + 3 < ncols) v.w = __ldg(p + 3);
+  return v;
+}
+
+__device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float a, float b, float c, float d) {
+  const float4 h = make_float4(umma::to_tf32(a), umma::to_tf32(b), umma::to_tf32(c), umma::to_tf32(d));
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = make_float4(umma::to_tf32(a - h.x), umma::to_tf32(b - h.y), umma::to_tf32(c - h.z), umma::to_tf32(d - h.w));
+}
+
+constexpr int kGwChunk = 32;                     // points per shared-memory chunk = 8 core-matrix columns = 4 MMA k-steps
+constexpr uint32_t kGwALbo = 128 * 16 + 16;      // K-direction stride of the A operand (128 feature rows), padded
+
+__global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * 128, K1 = g.K + 1;
+  const int mlo = blockIdx.x * g.rows_per_split, mhi = min(g.M, mlo + g.rows_per_split);
+  const uint32_t b_lbo = (uint32_t)g.Np * 16u + 16u;
+  const uint32_t a_bytes = 8 * kGwALbo, b_bytes = 8 * b_lbo;
+  unsigned char* A_hi = smem;
+  unsigned char* A_lo = smem + a_bytes;
+  unsigned char* B_hi = smem + 2 * a_bytes;
+  unsigned char* B_lo = smem + 2 * a_bytes + b_bytes;
+
+  if (tid == 0) { umma::mbar_init(&mma_bar, 1); umma::fence_mbar_init(); }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, g.tmem_cols);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = umma::make_idesc_tf32(128, g.Np);
+
+  const int p4 = tid & 7;                        // point quad of the chunk this thread transposes
+  const int fb0 = tid >> 3;                      // first feature block (4 features); A has 32 of them, B has Np / 4 <= 64
+  const int nbB = g.Np / 4;
+  // one chunk = a 4-point x 4-feature block of dY and up to two of [X | 1] per thread, held in registers between the loads (issued while
+  // the previous chunk's MMAs run) and the transposing stores
+  float4 va[4], vb[2][4];
+  auto load_chunk = [&](int mb) {
+    const int mrow = mb + p4 * 4;
+    const int ca = n0 + fb0 * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      va[j] = (mrow + j < mhi) ? load_cols4(g.dY, (size_t)(mrow + j), g.lda, ca, g.N, g.agroup, g.agstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int fb = fb0 + 32 * u, c = fb * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = fb < nbB && mrow + j < mhi;
+        float4 v = ok ? load_cols4(g.X, (size_t)(mrow + j), g.ldb, c, g.K, 0, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && g.K >= c && g.K < c + 4) {                                // the ones column (bias gradient)
+          const int e = g.K - c;
+          if (e == 0) v.x = 1.f; else if (e == 1) v.y = 1.f; else if (e == 2) v.z = 1.f; else v.w = 1.f;
+        }
+        vb[u][j] = v;
+      }
+    }
+  };
+  auto store_chunk = [&]() {
+    {
+      const uint32_t off = (uint32_t)p4 * kGwALbo + (uint32_t)(fb0 * 4) * 16u;
+      store_split(A_hi, A_lo, off, va[0].x, va[1].x, va[2].x, va[3].x);
+      store_split(A_hi, A_lo, off + 16, va[0].y, va[1].y, va[2].y, va[3].y);
+      store_split(A_hi, A_lo, off + 32, va[0].z, va[1].z, va[2].z, va[3].z);
+      store_split(A_hi, A_lo, off + 48, va[0].w, va[1].w, va[2].w, va[3].w);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int fb = fb0 + 32 * u;
+      if (fb < nbB) {
+        const uint32_t off = (uint32_t)p4 * b_lbo + (uint32_t)(fb * 4) * 16u;
+        store_split(B_hi, B_lo, off, vb[u][0].x, vb[u][1].x, vb[u][2].x, vb[u][3].x);
+        store_split(B_hi, B_lo, off + 16, vb[u][0].y, vb[u][1].y, vb[u][2].y, vb[u][3].y);
+        store_split(B_hi, B_lo, off + 32, vb[u][0].z, vb[u][1].z, vb[u][2].z, vb[u][3].z);
+        store_split(B_hi, B_lo, off + 48, vb[u][0].w, vb[u][1].w, vb[u][2].w, vb[u][3].w);
+      }
+    }
+  };
+  uint32_t parity = 0;
+  bool first = true;
+  if (mlo < mhi) load_chunk(mlo);
+  for (int mb = mlo; mb < mhi; mb += kGwChunk) {
+    if (!first) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }       // the previous chunk's MMAs have read the operands
+    store_chunk();
+    umma::fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      umma::tc_fence_after_sync();
+      const uint32_t a_hi_s = umma::smem_u32(A_hi), a_lo_s = umma::smem_u32(A_lo), b_hi_s = umma::smem_u32(B_hi), b_lo_s = umma::smem_u32(B_lo);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {                                         // MMA K = 8 points = two core-matrix columns
+        const uint32_t a_off = (uint32_t)s * 2u * kGwALbo, b_off = (uint32_t)s * 2u * b_lbo;
+        const uint64_t ah = umma::make_smem_desc(a_hi_s + a_off, kGwALbo, 128u), al = umma::make_smem_desc(a_lo_s + a_off, kGwALbo, 128u);
+        const uint64_t bh = umma::make_smem_desc(b_hi_s + b_off, b_lbo, 128u), bl = umma::make_smem_desc(b_lo_s + b_off, b_lbo, 128u);
+        umma::mma_tf32_ss_w(tmem_base, al, bh, idesc, (first && s == 0) ? 0u : 1u);      // small terms first
+        umma::mma_tf32_ss_w(tmem_base, ah, bl, idesc, 1u);
+        umma::mma_tf32_ss_w(tmem_base, ah, bh, idesc, 1u);
+      }
+      umma::mma_commit_w(&mma_bar);
+      __syncwarp();
+    }
+    first = false;
+    if (mb + kGwChunk < mhi) load_chunk(mb + kGwChunk);                     // in flight while the tensor cores work on this chunk
+  }
+  if (!first) {
+    umma::mbar_wait(&mma_bar, parity);
+    umma::tc_fence_after_sync();
+    // ---- epilogue: TMEM lane = output feature n, column = input feature k.  Warp w owns lane quarter (w & 3), column half (w >> 2). ----
+    const int q = warp & 3, hsel = warp >> 2;
+    const int n = n0 + 32 * q + lane;
+    const int half = g.Np / 2;                                             // Np % 16 == 0: a multiple of 8
+    float* out = g.part + ((size_t)blockIdx.x * g.N + n) * K1;
+    for (int j = 0; j < half / 8; ++j) {
+      const int c0 = hsel * half + 8 * j;
+      uint32_t v[8];
+      umma::tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      umma::tmem_ld_wait();
+      if (n < g.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + i < K1) out[c0 + i] = __uint_as_float(v[i]);
+      }
+    }
+  } else if (mlo >= mhi) {
+    // empty split (cannot happen with the launcher's grid, kept for safety): its partial tile must still be defined
+    for (int i = tid; i < min(128, g.N - n0) * K1; i += 256) g.part[((size_t)blockIdx.x * g.N + n0) * K1 + i] = 0.f;
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, cudaStream_t st, int agroup,
+                       int agstride) {
+  if (M <= 0) return SHERF_OK;
+  GradWArgs g;
+  g.dY = dY; g.lda = lda; g.agroup = agroup; g.agstride = agstride; g.N = N; g.X = X; g.ldb = ldb; g.K = K; g.part = part; g.M = M;
+  g.rows_per_split = kGradWRowsPerSplit;
+  g.Np = (K + 1 + 15) / 16 * 16;
+  if (g.Np > 256) { set_error("grad_w: K + 1 = %d exceeds one MMA tile", K + 1); return SHERF_E_INVALID; }
+  uint32_t cols = 32;
+  while ((int)cols < g.Np) cols <<= 1;
+  g.tmem_cols = cols;
+  size_t smem = 2 * (size_t)8 * kGwALbo + 2 * (size_t)8 * ((size_t)g.Np * 16 + 16);
+  // TMEM holds 512 columns per SM: never let shared memory admit more CTAs than tcgen05.alloc can serve without waiting
+  const size_t floor_smem = (size_t)220 * 1024 / (512 / cols) - 1024;
+  if (cols >= 128 && smem < floor_smem) smem = floor_smem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_grad_w, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const int splits = ceil_div(M, kGradWRowsPerSplit);
+  k_umma_grad_w<<<dim3(splits, ceil_div(N, 128)), 256, smem, st>>>(g);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+}  // namespace sherf

@@ -16,8 +16,10 @@ namespace sherf {
 constexpr int kKC = 64;                 // k per shared-memory chunk (16 core-matrix columns)
 
 // W[N][K] (PyTorch) -> canonical chunks, hi (tf32-rounded) and lo (tf32-rounded residual) parts.
-struct CanonJob { const float* w; float* hi; float* lo; int N, K, Np, nchunks; };
-struct CanonJobs { CanonJob j[17]; int n; };
+// trans = 0: W is [N][K] with row stride ldw (PyTorch [out][in]); trans = 1: the packed operand is W^T, i.e. element (n, k) = w[k * ldw + n]
+// (the backward's dX = dY . W needs the weight matrix with the roles of its two axes swapped).  ldw = 0 means K (dense [N][K]).
+struct CanonJob { const float* w; float* hi; float* lo; int N, K, Np, nchunks, ldw, trans; };
+struct CanonJobs { CanonJob j[18]; int n; };
 
 __global__ void k_pack_canonical(const CanonJobs jobs) {
   const CanonJob jb = jobs.j[blockIdx.y];
@@ -25,7 +27,8 @@ __global__ void k_pack_canonical(const CanonJobs jobs) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 3, n = (i >> 2) % jb.Np, kg = (i >> 2) / jb.Np;     // kg counts core-matrix columns over all chunks
     const int k = kg * 4 + e;
-    const float v = (n < jb.N && k < jb.K) ? jb.w[(size_t)n * jb.K + k] : 0.f;
+    const int ldw = jb.ldw ? jb.ldw : jb.K;
+    const float v = (n < jb.N && k < jb.K) ? (jb.trans ? jb.w[(size_t)k * ldw + n] : jb.w[(size_t)n * ldw + k]) : 0.f;
     const float h = umma::to_tf32(v);
     jb.hi[i] = h;
     jb.lo[i] = umma::to_tf32(v - h);
@@ -42,6 +45,10 @@ struct UmmaArgs {
   int M, N, K;
   uint32_t tmem_cols;
   const float *ln_w, *ln_b; float* Y2; int ldy2;      // optional fused LayerNorm(32) of the output rows -> Y2 (N == 32 only)
+  // backward use (dX = dY . W): logical column k of A lives at (k / agroup) * agstride + k % agroup (agroup = 0: identity; agroup % 4 == 0);
+  // the result is forced to 0 where Mask <= 0 (the ReLU of the layer whose input gradient this is), applied after the residual add
+  int agroup, agstride;
+  const float* Mask; int ldm;
 };
 
 // Padded K-direction stride of the A operand: 2048 B of data + 16 B so that the 8 lanes of a quarter-warp that write 8
@@ -76,31 +83,49 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   const int nchunks = (g.K + KC - 1) / KC;
   const int kgl = tid & 7, rsub = tid >> 3;          // loader mapping: 8 lanes = 8 consecutive float4 of one row (128 B)
   uint32_t parity = 0;
+  // A chunk c: coalesced global reads -> registers (issued while chunk c - 1's MMAs run) -> tf32 hi (/lo) -> canonical smem
+  constexpr int NPASS = NKG / 8;
+  float4 pre[NPASS][4];
+  auto load_a = [&](int c) {
+    const int k0 = c * KC;
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ++ps) {
+      const int k = k0 + (ps * 8 + kgl) * 4;
+#pragma unroll
+      for (int rq = 0; rq < 4; ++rq) {
+        const int row = rq * 32 + rsub;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + row < g.M && k < g.K) {
+          const float* ap = g.A + (size_t)(m0 + row) * g.lda + (g.agroup ? (k / g.agroup) * g.agstride + (k % g.agroup) : k);
+          if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(ap);
+          else { v.x = ap[0]; if (k + 1 < g.K) v.y = ap[1]; if (k + 2 < g.K) v.z = ap[2]; }
+        }
+        pre[ps][rq] = v;
+      }
+    }
+  };
+  load_a(0);
   for (int c = 0; c < nchunks; ++c) {
     const int k0 = c * KC;
     const int used_kg = min(NKG, (g.K - k0 + 3) / 4);
     const int mma_steps = (used_kg + 1) / 2;         // MMA K = 8 = two core-matrix columns
     if (c > 0) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }
-    // ---- A chunk: coalesced global reads -> tf32 hi (/lo) -> canonical smem ----
-    for (int kgb = 0; kgb < 2 * mma_steps; kgb += 8) {
-      const int kg = kgb + kgl;
-      if (kg < 2 * mma_steps) {
-        const int k = k0 + kg * 4;
+    {
 #pragma unroll
-        for (int rb = 0; rb < 128; rb += 32) {
-          const int row = rb + rsub;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m0 + row < g.M && k < g.K) {
-            const float* ap = g.A + (size_t)(m0 + row) * g.lda + k;
-            if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(ap);
-            else { v.x = ap[0]; if (k + 1 < g.K) v.y = ap[1]; if (k + 2 < g.K) v.z = ap[2]; }
-          }
-          const float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
-          *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_hi) + kg * kALbo + row * 16) = h;
-          if (PREC == 3) {
-            const float4 l = make_float4(umma::to_tf32(v.x - h.x), umma::to_tf32(v.y - h.y), umma::to_tf32(v.z - h.z),
-                                         umma::to_tf32(v.w - h.w));
-            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_lo) + kg * kALbo + row * 16) = l;
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int kg = ps * 8 + kgl;
+        if (kg < 2 * mma_steps) {
+#pragma unroll
+          for (int rq = 0; rq < 4; ++rq) {
+            const int row = rq * 32 + rsub;
+            const float4 v = pre[ps][rq];
+            const float4 h = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
+            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_hi) + kg * kALbo + row * 16) = h;
+            if (PREC == 3) {
+              const float4 l = make_float4(umma::to_tf32(v.x - h.x), umma::to_tf32(v.y - h.y), umma::to_tf32(v.z - h.z),
+                                           umma::to_tf32(v.w - h.w));
+              *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A_lo) + kg * kALbo + row * 16) = l;
+            }
           }
         }
       }
@@ -164,6 +189,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
       umma::mma_commit_w(&mma_bar);
       __syncwarp();
     }
+    if (c + 1 < nchunks) load_a(c + 1);
   }
   umma::mbar_wait(&mma_bar, parity);
   umma::tc_fence_after_sync();
@@ -196,7 +222,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   if (warp == 0) umma::tmem_dealloc(tmem_base, g.tmem_cols);
   // ---- epilogue 2: coalesced copy-out (+ residual), consecutive lanes -> consecutive columns of a row ----
   {
-    const int n4 = g.N / 4;                          // every layer of the stack has N % 16 == 0
+    const int n4 = (g.N + 3) / 4;                    // forward layers: N % 16 == 0; backward dX layers: N = 71 / 187 write one zero pad column
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0) && (g.ldy % 4 == 0) && (g.ygroup % 4 == 0) && (g.ygstride % 4 == 0);
     for (int idx = tid; idx < 128 * n4; idx += 256) {
       const int row = idx / n4, c4 = idx - row * n4;
@@ -224,6 +250,13 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         }
       }
       if (!valid) continue;
+      if (g.Mask) {
+        const float* mp = g.Mask + (size_t)m * g.ldm + n;
+        if (!(mp[0] > 0.f)) v.x = 0.f;
+        if (n + 1 < g.N && !(mp[1] > 0.f)) v.y = 0.f;
+        if (n + 2 < g.N && !(mp[2] > 0.f)) v.z = 0.f;
+        if (n + 3 < g.N && !(mp[3] > 0.f)) v.w = 0.f;
+      }
       const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
       float* yp = g.Y + (size_t)m * g.ldy + col;
       if (vec_ok) *reinterpret_cast<float4*>(yp) = v;
@@ -251,7 +284,7 @@ int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cud
     const size_t sz = (size_t)L.nchunks * kKC * L.Np;
     L.hi = cur; L.lo = cur + sz;
     CanonJob& j = jobs.j[jobs.n++];
-    j.w = W; j.hi = cur; j.lo = cur + sz; j.N = N; j.K = K; j.Np = L.Np; j.nchunks = L.nchunks;
+    j.w = W; j.hi = cur; j.lo = cur + sz; j.N = N; j.K = K; j.Np = L.Np; j.nchunks = L.nchunks; j.ldw = 0; j.trans = 0;
     cur += 2 * sz;
   };
   add(cw.proj, w.proj_w, w.proj_b, 96, 192);
@@ -271,6 +304,10 @@ int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cud
   return SHERF_OK;
 }
 
+// extra operands of the backward's dX launches (set around one launch_umma_linear call by launch_umma_dx; zero otherwise)
+struct UmmaEx { int agroup, agstride; const float* Mask; int ldm; };
+static thread_local UmmaEx g_umma_ex = {0, 0, nullptr, 0};
+
 int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
                        const float* Res, int ldr, int ygroup, int ygstride, const float* ln_w, const float* ln_b, float* Y2, int ldy2) {
   UmmaArgs g;
@@ -278,6 +315,7 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
   g.Y = Y; g.ldy = ldy; g.ygroup = ygroup; g.ygstride = ygstride; g.Res = Res; g.ldr = ldr; g.act = act;
   g.M = M; g.N = L.N; g.K = L.K;
   g.ln_w = (L.N == 32) ? ln_w : nullptr; g.ln_b = ln_b; g.Y2 = Y2; g.ldy2 = ldy2;
+  g.agroup = g_umma_ex.agroup; g.agstride = g_umma_ex.agstride; g.Mask = g_umma_ex.Mask; g.ldm = g_umma_ex.ldm;
   uint32_t cols = 32;
   while ((int)cols < L.Np) cols <<= 1;
   g.tmem_cols = cols;
@@ -328,10 +366,65 @@ int run_debug_linear(int prec, const float* A, int lda, const float* W, const fl
   L.hi = wscratch; L.lo = wscratch + sz;
   jobs.n = 1;
   jobs.j[0].w = W; jobs.j[0].hi = wscratch; jobs.j[0].lo = wscratch + sz; jobs.j[0].N = N; jobs.j[0].K = K; jobs.j[0].Np = L.Np;
-  jobs.j[0].nchunks = L.nchunks;
+  jobs.j[0].nchunks = L.nchunks; jobs.j[0].ldw = 0; jobs.j[0].trans = 0;
   k_pack_canonical<<<dim3(16, 1), 256, 0, st>>>(jobs);
   SHERF_LAUNCH_CHECK();
   return launch_umma_linear(prec == 99 ? 4 : (prec == SHERF_MLP_TF32X3 ? 3 : 1), L, A, lda, Y, ldy, M, act, st, nullptr, 0, 0, 0);
+}
+
+}  // namespace sherf
+
+// ------------------------------------------------------------------------------------------------- backward: dX = dY . W on the tensor cores
+// The same kernel with the weight matrix packed transposed: "output feature" n = the layer's INPUT feature, reduction k = its OUTPUT feature.
+namespace sherf {
+
+size_t canonical_bwd_weight_floats() {
+  // (in, out) of the 17 dX products of backward.cu
+  const int dims[17][2] = {{187, 64}, {128, 128}, {71, 128}, {128, 128}, {128, 128}, {128, 128}, {128, 128}, {128, 128}, {128, 128}, {128, 128},
+                           {71, 128}, {32, 32}, {32, 32}, {48, 32}, {32, 144}, {96, 32}, {192, 96}};
+  size_t t = 0;
+  for (int i = 0; i < 17; ++i) t += (size_t)round_up_i(dims[i][1], kKC) * round_up_i(dims[i][0], 16);
+  return 2 * t;
+}
+
+int run_pack_canonical_bwd(const SherfWeights& w, float* base, CanonBwdWeights& cb, cudaStream_t st) {
+  CanonJobs jobs;
+  jobs.n = 0;
+  float* cur = base;
+  // W: [out][ldw] PyTorch layout, columns col0 .. col0 + in - 1 of it
+  auto add = [&](CanonLayer& L, const float* W, int out, int in, int ldw) {
+    L.N = in; L.K = out; L.Np = round_up_i(in, 16); L.nchunks = round_up_i(out, kKC) / kKC; L.bias = nullptr;
+    const size_t sz = (size_t)L.nchunks * kKC * L.Np;
+    L.hi = cur; L.lo = cur + sz;
+    CanonJob& j = jobs.j[jobs.n++];
+    j.w = W; j.hi = cur; j.lo = cur + sz; j.N = in; j.K = out; j.Np = L.Np; j.nchunks = L.nchunks; j.ldw = ldw; j.trans = 1;
+    cur += 2 * sz;
+  };
+  add(cb.views, w.views_w, 64, 187, 187);
+  add(cb.feature, w.feature_w, 128, 128, 128);
+  add(cb.pts[0], w.pts_w[0], 128, 71, 71);
+  for (int i = 1; i < 8; ++i) {
+    if (i == 5) add(cb.pts[5], w.pts_w[5] + 71, 128, 128, 199);      // the h4 half of cat([x, h4]) (triplane.py:299-300)
+    else add(cb.pts[i], w.pts_w[i], 128, 128, 128);
+  }
+  add(cb.pts5x, w.pts_w[5], 128, 71, 199);                           // the x half
+  add(cb.ff2, w.ff2_w, 32, 32, 32);
+  add(cb.ff1, w.ff1_w, 32, 32, 32);
+  add(cb.attn_out, w.attn_out_w, 32, 48, 48);
+  add(cb.qkv, w.qkv_w, 144, 32, 32);
+  add(cb.reproj, w.reproj_w, 32, 96, 96);
+  add(cb.proj, w.proj_w, 96, 192, 192);
+  k_pack_canonical<<<dim3(16, jobs.n), 256, 0, st>>>(jobs);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+int launch_umma_dx(const CanonLayer& L, const float* dY, int lda, float* dX, int ldx, int M, cudaStream_t st, const float* Mask, int ldm,
+                   int accum, int agroup, int agstride) {
+  g_umma_ex = UmmaEx{agroup, agstride, Mask, ldm};
+  const int rc = launch_umma_linear(3, L, dY, lda, dX, ldx, M, 0, st, accum ? dX : nullptr, ldx, 0, 0);
+  g_umma_ex = UmmaEx{0, 0, nullptr, 0};
+  return rc;
 }
 
 }  // namespace sherf

@@ -89,6 +89,16 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
                        float* Y2 = nullptr, int ldy2 = 0);
 int launch_simt_linear(const PackedLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
                        const float* Res, int ldr, int ygroup, int ygstride);
+// Backward on the tensor cores (3xTF32): weights packed transposed for dX = dY . W (mlp_umma.cu), dW = dY^T [X | 1] (backward_umma.cu)
+struct CanonBwdWeights { CanonLayer views, feature, pts[8] /* [5] = the h4 half */, pts5x, ff2, ff1, attn_out, qkv, reproj, proj; };
+size_t canonical_bwd_weight_floats();
+int run_pack_canonical_bwd(const SherfWeights& w, float* base, CanonBwdWeights& cb, cudaStream_t st);
+int launch_umma_dx(const CanonLayer& L, const float* dY, int lda, float* dX, int ldx, int M, cudaStream_t st, const float* Mask = nullptr,
+                   int ldm = 0, int accum = 0, int agroup = 0, int agstride = 0);
+constexpr int kGradWRowsPerSplit = 512;
+// part[s][n][K + 1] = sum over the rows of split s of dY[m][n] . [X | 1][m][k]
+int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, cudaStream_t st, int agroup = 0,
+                       int agstride = 0);
 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
@@ -154,9 +164,9 @@ void carve_bwd_chunk(float* base, int cap, BwdChunk& b);
 int run_composite_backward(const SherfRays& rays, const FrameConst* fc, const int* ray_start, const int* point_sample, const float* sigma,
                            const float* rgb, const float* noise, int white_back, const float* g_rgb, const float* g_depth, const float* g_acc,
                            float* dsig, float* drgb, cudaStream_t st);
-int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const SherfWeightGrads& gw, GatherParams G, const BwdChunk& b, int np, int64_t p0,
-                       const float* rgb, const float* dsig, const float* drgb, cudaStream_t st);
-int run_backward_chunk_inputs(const SherfWeights& w, GatherParams G, const BwdChunk& b, int np, int64_t p0, cudaStream_t st);
+int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const CanonWeights& cw, const CanonBwdWeights& cbw, const SherfWeightGrads& gw,
+                       GatherParams G, const BwdChunk& b, int np, int64_t p0, const float* rgb, const float* dsig, const float* drgb, cudaStream_t st);
+int run_backward_chunk_inputs(const SherfWeights& w, const CanonBwdWeights& cbw, GatherParams G, const BwdChunk& b, int np, int64_t p0, cudaStream_t st);
 int run_from_channels_last(const float* in, float* out, int C, int64_t M, cudaStream_t st);
 int run_layernorm32(const float* x, const float* w, const float* b, float* y, int rows, cudaStream_t st);
 int run_attention3(const float* qkv, float* att, int np, cudaStream_t st);

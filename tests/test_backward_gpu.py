@@ -4,6 +4,8 @@ autograd through the CPU restatement of the reference (oracle/port.py is plain t
 Loss = the reference's own reconstruction terms (loss.py:150-151,167): 100 * mse(image / 2 + 0.5, target) + 10 * mse(acc, mask), plus a
 depth term on rays whose depth is live (the reference itself never differentiates depth; 0/0 rays would poison torch's gradient).
 Gradients compared: all 39 hot-path parameters, tri-planes, 2-D feature map, the three dense volume levels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -86,9 +88,17 @@ def rel_err(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30)), float((a - b).abs().max()), float(b.abs().max())
 
 
-@pytest.mark.parametrize('spec', [dict(H=24, W=24, samples=16, seed=2, white_back=False, depth=False, noise=0.0),
-                                  dict(H=32, W=20, samples=24, seed=5, white_back=True, depth=True, noise=0.0),
-                                  dict(H=16, W=16, samples=12, seed=7, white_back=False, depth=True, noise=0.5)])
+# Tolerances (relative L2 per gradient tensor), frozen from the B200 measurements in profiles/r2_pytest_backward.log:
+#   * tensor-core (3xTF32) backward vs the same backward in fp32 FMA on the CUDA cores (same inputs, pure arithmetic): <= 1e-3 (measured <= 4.3e-4)
+#   * vs torch autograd through the oracle: <= 1e-3 on the small views (measured <= 4.8e-4).  The 64 x 64 x 32 view allows 3e-3: a weight gradient
+#     of conv1d_projection is a sum over 5 907 points of (output gradient) x (gathered 3-D feature) with random-sign N(0,1) features -- it cancels
+#     to ~ sqrt(P) of its terms, which amplifies the <= 2.6e-4 input difference of the gathered features (fp32 re-association of the warps,
+#     tests/test_parity_gpu.py) to 1.6e-3; the fp32 FMA path sits at the same distance (1.7e-3), so this is input conditioning, not arithmetic.
+@pytest.mark.parametrize('spec', [dict(H=24, W=24, samples=16, seed=2, white_back=False, depth=False, noise=0.0, tol=1e-3),
+                                  dict(H=32, W=20, samples=24, seed=5, white_back=True, depth=True, noise=0.0, tol=1e-3),
+                                  dict(H=16, W=16, samples=12, seed=7, white_back=False, depth=True, noise=0.5, tol=1e-3),
+                                  # several thousand surviving points: more than one reduction split per weight gradient, partial last tiles
+                                  dict(H=64, W=64, samples=32, seed=11, white_back=False, depth=False, noise=0.0, tol=3e-3)])
 def test_backward_matches_autograd_through_the_oracle(spec, smpl_model, smpl_model_t):
     from oracle import port
     from sherf_b200.triplane import hot_path_modules
@@ -111,9 +121,15 @@ def test_backward_matches_autograd_through_the_oracle(spec, smpl_model, smpl_mod
     scene_g = scene_to(scene_c, dev)
     kw = {'density_noise_points': noise.to(dev)} if noise is not None else {}
     loss_g, g_g = cuda_grads(ren, dec, scene_g, tgt_img.to(dev), tgt_acc.to(dev), None if depth_w is None else depth_w.to(dev), **kw)
+    # the same backward with every product on the CUDA cores in fp32 FMA (SHERF_BWD_SIMT=1): the anchor of the 3xTF32 tensor-core path
+    os.environ['SHERF_BWD_SIMT'] = '1'
+    try:
+        _, g_s = cuda_grads(ren, dec, scene_g, tgt_img.to(dev), tgt_acc.to(dev), None if depth_w is None else depth_w.to(dev), **kw)
+    finally:
+        os.environ.pop('SHERF_BWD_SIMT', None)
     print(f'\n[backward {spec}] P = {P}, loss oracle {loss_o:.6f} cuda {loss_g:.6f}')
     assert abs(loss_g - loss_o) <= 1e-4 * max(1.0, abs(loss_o))
-    worst = 0.0
+    worst, worst_ts = 0.0, 0.0
     keys = sorted(named_hot_parameters(ren, dec)) + ['planes', 'obs_input_feature', 'vol0', 'vol1', 'vol2']
     assert len(keys) == 39 + 5
     for k in keys:
@@ -121,11 +137,14 @@ def test_backward_matches_autograd_through_the_oracle(spec, smpl_model, smpl_mod
         assert g_g[k] is not None and g_o[k] is not None, k
         assert tuple(g_g[k].shape) == tuple(g_o[k].shape), (k, g_g[k].shape, g_o[k].shape)
         r, mx, ref = rel_err(g_g[k], g_o[k])
-        print(f'   {k:58s} rel L2 {r:.2e}   max abs {mx:.2e} of {ref:.2e}')
-        assert np.isfinite(r)
-        worst = max(worst, r)
-        assert r <= 1e-3, f'{k}: relative L2 error {r:.3e}'
-    print(f'   worst relative L2 error {worst:.2e}')
+        r_s = rel_err(g_s[k], g_o[k])[0]
+        r_ts = rel_err(g_g[k], g_s[k])[0]
+        print(f'   {k:58s} rel L2 {r:.2e}   max abs {mx:.2e} of {ref:.2e}   fp32-FMA path vs oracle {r_s:.2e}   tensor vs fp32-FMA {r_ts:.2e}')
+        assert np.isfinite(r) and np.isfinite(r_ts)
+        worst, worst_ts = max(worst, r), max(worst_ts, r_ts)
+        assert r <= spec['tol'], f'{k}: relative L2 error {r:.3e} vs the oracle'
+        assert r_ts <= 1e-3, f'{k}: tensor-core backward {r_ts:.3e} from the fp32 FMA backward'
+    print(f'   worst relative L2 error {worst:.2e} vs the oracle, {worst_ts:.2e} tensor-core vs fp32 FMA')
 
 
 def test_backward_is_deterministic_for_weights_and_frozen_inputs_get_none(smpl_model):

@@ -15,7 +15,7 @@ from sherf_b200.triplane import hot_path_modules           # noqa: E402
 def main():
     H = W = int(os.environ.get('BWD_RES', '512'))
     samples = int(os.environ.get('BWD_SAMPLES', '64'))
-    steps, warmup = int(os.environ.get('BWD_STEPS', '5')), 2
+    steps, warmup = int(os.environ.get('BWD_STEPS', '5')), int(os.environ.get('BWD_WARMUP', '2'))
     dev = torch.device('cuda:0')
     model = S.make_smpl_model(0)
     scene = S.make_scene(S.SceneSpec(H=H, W=W, samples=samples, seed=0), model)
@@ -60,7 +60,7 @@ def main():
     ms = e0.elapsed_time(e1) / steps
     print(json.dumps({'what': 'forward + loss + backward per view', 'H': H, 'W': W, 'samples': samples, 'surviving_points': ren.last_num_points,
                       'ms_per_step': ms, 'ray_samples_per_sec_training': N * samples / ms * 1e3, 'input_grads': inputs_grad,
-                      'backward_launches': getattr(ren, 'last_backward_launches', None), 'loss': float(loss),
+                      'backward_launches': getattr(ren, 'last_backward_launches', None), 'arithmetic': 'fp32 simt' if os.environ.get('SHERF_BWD_SIMT') == '1' else '3xTF32 tcgen05', 'loss': float(loss),
                       'peak_mem_GB': torch.cuda.max_memory_allocated() / 2**30}))
 
 
