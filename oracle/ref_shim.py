@@ -11,8 +11,9 @@ Shims (none of them touches reference arithmetic except #1, which replaces an ab
  1. pytorch3d.ops.knn.knn_points -> brute-force K=1 squared-L2 argmin, d2 = (dx*dx + dy*dy) + dz*dz
     in fp32, smallest index on ties.  pytorch3d is not vendored and its version is unpinned
     (README.md:48), so this formula IS our statement of its semantics ("parity unpinned").
- 2. spconv / spconv.pytorch -> constructor-only stubs that hold a zero `weight` of spconv 2.3.3's shape
-    (the sparse convs are outside the hot-path scope; the three densified volumes are inputs).
+ 2. spconv / spconv.pytorch -> oracle/spconv_shim.py: stand-ins that hold a zero `weight` of spconv 2.3.3's shape and evaluate
+    the three spconv ops the reference uses (rules restated there); the render fixtures still take the three densified volumes
+    as inputs (shim 6), the reference's SparseConvNet.forward runs under them in tests/test_sparse_encoder.py.
  3. torch.Tensor.cuda -> identity, torch.cuda.current_device -> 0 (the reference hard-codes .cuda()).
  4. renderer.read_pickle / SMPL_to_tensor -> return the synthetic SMPL-shaped model.
  5. imageio -> empty stub (imported, unused, by triplane.py:27).
@@ -76,20 +77,12 @@ class DenseVolumeGather(nn.Module):
         return feats.view(feats.size(0), -1, feats.size(4)).transpose(1, 2)
 
 
-class SpconvConvStub(nn.Module):
-    """Shim 2: constructor-only (Sub)MConv3d.  Holds `weight` in spconv 2.3.3's [out, k, k, k, in] layout (so that state-dict names and
-    shapes of the reference module can be compared) but computes nothing; zero-filled without touching torch's RNG stream.  Module
-    level so that the reference's persistence check can pickle modules that contain it."""
-
-    def __init__(self, in_channels=None, out_channels=None, kernel_size=3, *a, **k):
-        super().__init__()
-        if in_channels is not None and out_channels is not None:
-            ks = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
-            self.weight = nn.Parameter(torch.zeros(out_channels, ks, ks, ks, in_channels))
-
-
-class SpconvSequentialStub(nn.Sequential):
-    pass
+# Shim 2 (functional since round 2, oracle/spconv_shim.py): SubMConv3d / SparseConv3d / SparseSequential / SparseConvTensor stand-ins that
+# hold `weight` in spconv 2.3.3's [out, k, k, k, in] layout AND evaluate the convolutions (dense formulation), so that the reference's own
+# SparseConvNet.forward can run.  The old constructor-only names stay as aliases (tests/helpers/make_reference_snapshot.py subclasses them).
+from oracle import spconv_shim                                            # noqa: E402
+SpconvConvStub = spconv_shim.SparseConvolution
+SpconvSequentialStub = spconv_shim.SparseSequential
 
 
 _loaded = None
@@ -111,8 +104,9 @@ def load(smpl_model_torch: dict):
     sys.modules.update({'pytorch3d': p3d, 'pytorch3d.ops': ops_mod, 'pytorch3d.ops.knn': knn_mod})
 
     sp = types.ModuleType('spconv.pytorch')
-    sp.SparseSequential, sp.SubMConv3d, sp.SparseConv3d = SpconvSequentialStub, SpconvConvStub, SpconvConvStub
-    core = types.ModuleType('spconv.core'); core.SparseConvTensor = object
+    sp.SparseSequential, sp.SubMConv3d, sp.SparseConv3d = spconv_shim.SparseSequential, spconv_shim.SubMConv3d, spconv_shim.SparseConv3d
+    sp.SparseConvTensor = spconv_shim.SparseConvTensor
+    core = types.ModuleType('spconv.core'); core.SparseConvTensor = spconv_shim.SparseConvTensor
     sp.core = core
     spr = types.ModuleType('spconv'); spr.pytorch = sp; spr.core = core
     sys.modules.update({'spconv': spr, 'spconv.pytorch': sp, 'spconv.core': core})

@@ -1,5 +1,6 @@
-"""Sparse 3-D encoder.  "Parity unpinned": spconv 2.3.3 is absent, so the oracle states its semantics
-(oracle/sparse_encoder.py header).  CPU: the gather-form oracle == the dense conv3d + activity-mask formulation of the same network.
+"""Sparse 3-D encoder.  "Parity unpinned" for the per-convolution rules: spconv 2.3.3 is absent, so the oracle states
+its semantics (oracle/sparse_encoder.py, oracle/spconv_shim.py headers).  CPU: the gather-form oracle == the dense conv3d + activity-mask
+formulation of the same network == the reference's OWN SparseConvNet.forward run on functional spconv stand-ins.
 GPU: sherf_sparse_encode (through SparseConvNet.forward) == the oracle; then the render path fed with a SparseConvTensor == the
 render path fed with the oracle's dense volumes.  Tolerance: 2e-4 relative to each level's maximum (fp32, different summation order)."""
 import numpy as np
@@ -34,6 +35,37 @@ def test_oracle_sparse_equals_dense_formulation():
         assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max())
         assert int((x != 0).any(1).sum()) > 20
     assert len(SE.conv_list()) == 13 and SE.conv_list()[2][2] == 'down'
+
+
+def test_reference_sparse_conv_net_forward_under_the_functional_spconv_stand_ins(smpl_model_t):
+    """The reference's OWN SparseConvNet (renderer.py:707-797: layer order, the `.dense()` taps, grid_sample, concatenation) runs on the
+    spconv stand-ins of oracle/spconv_shim.py (dense conv3d formulation of the three spconv rules) and must agree with the gather-form oracle
+    that the CUDA kernels are checked against.  Pins the network topology and the weight / BatchNorm bookkeeping on the reference's code; the
+    per-convolution rules remain restated (spconv itself is absent): parity of f1 stays "unpinned" for them."""
+    import torch.nn.functional as F
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference files not present')
+    ref_renderer, _ = ref_shim.load(smpl_model_t)
+    import spconv                                                    # the stand-in package ref_shim.load registered
+    net = ref_renderer.SparseConvNet(num_layers=4).eval()
+    from sherf_b200.renderer import SparseConvNet
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in SparseConvNet(4).state_dict().items()}
+    sd = SE.random_state_dict(net, 1)
+    net.load_state_dict(sd)
+    for shape, n, seed in [((32, 64, 64), 200, 2), ((32, 32, 96), 60, 9)]:
+        coord, feat = _shell(n, shape, seed)
+        idx = torch.cat([torch.zeros(coord.shape[0], 1, dtype=torch.int32), coord], 1)
+        g = torch.Generator().manual_seed(seed)
+        grid = (torch.rand(1, 1, 1, 700, 3, generator=g) * 2 - 1) * 0.95                   # renderer.py:336 hands [1,1,1,P,3]
+        with torch.no_grad():
+            got = net(spconv.core.SparseConvTensor(feat, idx, list(shape), 1), grid)         # [1, P, 32 + 64 + 96]
+        dense = SE.encode_sparse(sd, coord, feat, shape)
+        feats = torch.cat([F.grid_sample(v, grid, padding_mode='zeros', align_corners=True) for v in dense], dim=1)
+        want = feats.view(1, -1, feats.size(4)).transpose(1, 2)
+        assert tuple(got.shape) == (1, 700, 192)
+        assert int((want != 0).sum()) > 1000
+        assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
 
 
 def test_duplicate_voxels_first_row_wins():
