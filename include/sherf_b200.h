@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SHERF_ABI_VERSION 4
+#define SHERF_ABI_VERSION 5
 #if defined(__GNUC__)
 #define SHERF_API __attribute__((visibility("default")))
 #else
@@ -295,6 +295,30 @@ SHERF_API int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* 
                                   const int32_t* out_sh /* host [3] */, float* vol1, float* vol2, float* vol3, void* scratch,
                                   size_t scratch_bytes, void* stream);
 
+/* Training mode of the sparse encoder: nn.BatchNorm1d(eps=1e-3, momentum=0.01) in train() normalises with the BATCH
+ * statistics of each layer's rows (renderer.py:822-871), and loss.backward() (loss.py:175) differentiates through SparseConvNet.forward.
+ * sherf_sparse_encode_train = sherf_sparse_encode with batch statistics; it keeps every activation in `scratch`, which must reach
+ * sherf_sparse_encode_backward unchanged (same enc / coord / n / out_sh).  batch_stats [13][2][96] (device, may be NULL): per conv the batch
+ * mean | biased batch variance per channel; row_counts [13] int32 (device, may be NULL): rows under each BatchNorm (spconv keeps duplicate
+ * input rows on the level-0 layers: they are counted) -- the caller updates running_mean / running_var / num_batches_tracked from them
+ * exactly like torch (unbiased variance = biased * n / (n - 1)).  use_running_stats != 0: the differentiable forward of eval() -- BatchNorm
+ * normalises with the running statistics (constants of the graph); nothing is written to batch_stats / row_counts. */
+typedef struct SherfSparseEncoderGrads {
+  float* weight[SHERF_SPARSE_CONVS];      /* [c_out,3,3,3,c_in] each, or NULL */
+  float* bn_weight[SHERF_SPARSE_CONVS];   /* [c_out] or NULL */
+  float* bn_bias[SHERF_SPARSE_CONVS];     /* [c_out] or NULL */
+} SherfSparseEncoderGrads;
+SHERF_API size_t sherf_sparse_encoder_train_scratch_bytes(int32_t n_voxels, const int32_t* out_sh /* host [3] */);
+SHERF_API int sherf_sparse_encode_train(const SherfSparseEncoder* enc, const int32_t* coord, const float* feat, int32_t n,
+                                        const int32_t* out_sh /* host [3] */, float* vol1, float* vol2, float* vol3, float* batch_stats,
+                                        int32_t* row_counts, int32_t use_running_stats, void* scratch, size_t scratch_bytes, void* stream);
+/* g_vol1/2/3: dL/d(vol1/2/3) in the layout of the outputs (any may be NULL = zero); grads: where to write dL/d(weights) (overwritten, not
+ * accumulated); g_feat [n,c_in] (may be NULL): dL/d(feat) -- rows that were merged into another row of the same voxel get zero. */
+SHERF_API int sherf_sparse_encode_backward(const SherfSparseEncoder* enc, const int32_t* coord, int32_t n, const int32_t* out_sh /* host [3] */,
+                                           const float* g_vol1, const float* g_vol2, const float* g_vol3, const SherfSparseEncoderGrads* grads,
+                                           float* g_feat, int32_t use_running_stats /* as in the forward */, void* scratch, size_t scratch_bytes,
+                                           void* stream);
+
 /* ---- Observation preparation ("vertex-feature splat"): what TriPlaneGenerator.synthesis computes once per
  * observation image before calling the renderer (triplane.py:105-137) -- the rows of the SparseConvTensor of triplane.py:137. ---- */
 typedef struct SherfObservation {
@@ -327,6 +351,13 @@ SHERF_API int sherf_prepare_observation(const SherfSmplModel* smpl, const SherfO
                                         uint8_t* vertex_mask, float* bounds, int32_t* out_sh_host, float* canonical_out, void* scratch,
                                         size_t scratch_bytes, void* stream);
 
+/* Backward of the vertex features (triplane.py:115-126) for training: g_vert_feat [V,32] = dL/d(vert_feat) -> g_proj_w [32,96], g_proj_b [32]
+ * (TriPlaneGenerator.conv1d_projection) and g_obs_feat [feat_ch,feat_h,feat_w] (adds the bilinear adjoint of triplane.py:115; the image
+ * and the vertex pixels are data).  Outputs are overwritten; any may be NULL.  scratch >= sherf_observation_scratch_bytes. */
+SHERF_API int sherf_prepare_observation_backward(const SherfSmplModel* smpl, const SherfObservation* obs, const float* g_vert_feat,
+                                                 float* g_proj_w, float* g_proj_b, float* g_obs_feat, void* scratch, size_t scratch_bytes,
+                                                 void* stream);
+
 /* sample_importance + sample_pdf (renderer.py:483-542) alone, on caller-supplied ray-marcher weights [N*S]
  * and uniform draws u [N*S_f]: writes the fine depths [N*S_f] and (optional) the searchsorted bin indices. */
 SHERF_API int sherf_debug_sample_importance(const SherfRays* rays, const float* weights, const float* u, float* t_fine_out,
@@ -343,7 +374,7 @@ SHERF_API int sherf_debug_linear(int precision, const float* A, int lda, const f
 SHERF_API void sherf_debug_set_trace(long long* device_buf);
 
 SHERF_API const char* sherf_last_error(void);
-SHERF_API int sherf_abi_version(void);   /* == SHERF_ABI_VERSION (4) */
+SHERF_API int sherf_abi_version(void);   /* == SHERF_ABI_VERSION (5) */
 /* Number of kernels launched by the last sherf_render_forward on this thread (bench's gpu_launches). */
 SHERF_API int64_t sherf_last_launch_count(void);
 /* Number of FINE (importance) samples that survived the cull in the last sherf_render_forward on this thread

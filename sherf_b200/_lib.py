@@ -11,7 +11,7 @@ c_float_p = C.c_void_p          # device pointers travel as plain integers
 c_int_p = C.c_void_p
 
 MLP_FP32, MLP_TF32, MLP_TF32X3, MLP_BF16X3 = 0, 1, 2, 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SherfSmplModel(C.Structure):
@@ -91,6 +91,10 @@ class SherfSparseEncoder(C.Structure):
     _fields_ = [('conv', SherfSparseConv * 13)]
 
 
+class SherfSparseEncoderGrads(C.Structure):
+    _fields_ = [('weight', c_float_p * 13), ('bn_weight', c_float_p * 13), ('bn_bias', c_float_p * 13)]
+
+
 class SherfObservation(C.Structure):
     _fields_ = [('obs', SherfPose), ('canonical', SherfPose), ('obs_vertices', c_float_p), ('t_vertices', c_float_p), ('obs_K', c_float_p),
                 ('obs_R', c_float_p), ('obs_T', c_float_p), ('faces', c_int_p), ('last_face', c_int_p), ('n_faces', C.c_int32),
@@ -99,7 +103,7 @@ class SherfObservation(C.Structure):
                 ('proj_b', c_float_p)]
 
 
-EXPORTS = ['sherf_backward_scratch_bytes', 'sherf_render_backward', 'sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+EXPORTS = ['sherf_sparse_encoder_train_scratch_bytes', 'sherf_sparse_encode_train', 'sherf_sparse_encode_backward', 'sherf_prepare_observation_backward', 'sherf_backward_scratch_bytes', 'sherf_render_backward', 'sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms', 'sherf_last_host_us']
 
 _lib = None
@@ -157,6 +161,17 @@ def load():
     lib.sherf_sparse_encode.restype = C.c_int
     lib.sherf_sparse_encode.argtypes = [C.POINTER(SherfSparseEncoder), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sherf_sparse_encoder_train_scratch_bytes.restype = C.c_size_t
+    lib.sherf_sparse_encoder_train_scratch_bytes.argtypes = [C.c_int32, C.POINTER(C.c_int32)]
+    lib.sherf_sparse_encode_train.restype = C.c_int
+    lib.sherf_sparse_encode_train.argtypes = [C.POINTER(SherfSparseEncoder), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sherf_sparse_encode_backward.restype = C.c_int
+    lib.sherf_sparse_encode_backward.argtypes = [C.POINTER(SherfSparseEncoder), C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.POINTER(SherfSparseEncoderGrads), C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sherf_prepare_observation_backward.restype = C.c_int
+    lib.sherf_prepare_observation_backward.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfObservation), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sherf_observation_scratch_bytes.restype = C.c_size_t
     lib.sherf_observation_scratch_bytes.argtypes = [C.c_int32]
     lib.sherf_prepare_observation.restype = C.c_int

@@ -757,6 +757,71 @@ int sherf_sparse_encode(const SherfSparseEncoder* enc, const int32_t* coord, con
   return SHERF_OK;
 }
 
+static int check_sparse_args(const SherfSparseEncoder* enc, const int32_t* coord, int32_t n, const int32_t* out_sh) {
+  if (!enc || !coord || !out_sh) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (n <= 0 || out_sh[0] <= 0 || out_sh[1] <= 0 || out_sh[2] <= 0 || (int64_t)out_sh[0] * out_sh[1] * out_sh[2] >= (1LL << 31)) {
+    set_error("bad sparse input: n = %d, out_sh = %d x %d x %d", n, out_sh[0], out_sh[1], out_sh[2]);
+    return SHERF_E_INVALID;
+  }
+  for (int c = 0; c < SHERF_SPARSE_CONVS; ++c)
+    if (!enc->conv[c].weight || !enc->conv[c].bn_weight || !enc->conv[c].bn_bias || !enc->conv[c].bn_mean || !enc->conv[c].bn_var) {
+      set_error("sparse conv %d: null parameter pointer", c);
+      return SHERF_E_INVALID;
+    }
+  return SHERF_OK;
+}
+
+size_t sherf_sparse_encoder_train_scratch_bytes(int32_t n_voxels, const int32_t* out_sh) {
+  if (n_voxels <= 0 || !out_sh || out_sh[0] <= 0 || out_sh[1] <= 0 || out_sh[2] <= 0) return 0;
+  return sparse_encoder_train_scratch_bytes(n_voxels, out_sh);
+}
+
+int sherf_sparse_encode_train(const SherfSparseEncoder* enc, const int32_t* coord, const float* feat, int32_t n, const int32_t* out_sh, float* vol1,
+                              float* vol2, float* vol3, float* batch_stats, int32_t* row_counts, int32_t use_running_stats, void* scratch,
+                              size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  RC(check_sparse_args(enc, coord, n, out_sh));
+  if (!feat || !vol1 || !vol2 || !vol3 || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  float* vols[3] = {vol1, vol2, vol3};
+  g_launches.n = 0;
+  RC(run_sparse_encode_train(*enc, coord, feat, n, out_sh, vols, batch_stats, row_counts, use_running_stats, scratch, scratch_bytes, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
+int sherf_sparse_encode_backward(const SherfSparseEncoder* enc, const int32_t* coord, int32_t n, const int32_t* out_sh, const float* g_vol1,
+                                 const float* g_vol2, const float* g_vol3, const SherfSparseEncoderGrads* grads, float* g_feat,
+                                 int32_t use_running_stats, void* scratch, size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  RC(check_sparse_args(enc, coord, n, out_sh));
+  if (!grads || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (!g_vol3) { set_error("the gradient of the last level (vol3) is required: nothing else reaches conv3"); return SHERF_E_INVALID; }
+  const float* gv[3] = {g_vol1, g_vol2, g_vol3};
+  g_launches.n = 0;
+  RC(run_sparse_encode_backward(*enc, coord, n, out_sh, gv, *grads, g_feat, use_running_stats, scratch, scratch_bytes, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
+int sherf_prepare_observation_backward(const SherfSmplModel* smpl, const SherfObservation* obs, const float* g_vert_feat, float* g_proj_w,
+                                       float* g_proj_b, float* g_obs_feat, void* scratch, size_t scratch_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!smpl || !obs || !g_vert_feat || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
+  if (smpl->n_verts <= 0 || !obs->obs_vertices || !obs->faces || !obs->last_face || !obs->obs_img || !obs->obs_feat || !obs->proj_w || !obs->obs_K ||
+      !obs->obs_R || !obs->obs_T || !obs->obs.R || !obs->obs.Th) {
+    set_error("null device pointer in SherfObservation / SherfSmplModel");
+    return SHERF_E_INVALID;
+  }
+  if (obs->feat_ch != 64 || obs->img_h <= 0 || obs->img_w <= 0 || obs->feat_h <= 0 || obs->feat_w <= 0) {
+    set_error("unsupported observation shapes (feature channels %d, expected 64)", obs->feat_ch);
+    return SHERF_E_UNSUPPORTED;
+  }
+  g_launches.n = 0;
+  RC(run_prepare_observation_backward(*smpl, *obs, g_vert_feat, g_proj_w, g_proj_b, g_obs_feat, scratch, scratch_bytes, (cudaStream_t)stream));
+  g_last_launches = g_launches.n;
+  return SHERF_OK;
+}
+
 size_t sherf_observation_scratch_bytes(int32_t n_verts) { return n_verts > 0 ? observation_scratch_bytes(n_verts, kMaxCell) + 512 : 0; }
 
 int sherf_prepare_observation(const SherfSmplModel* smpl, const SherfObservation* obs, float* vert_feat, int32_t* coord, uint8_t* vertex_mask,

@@ -24,19 +24,6 @@ struct GradWArgs {
   uint32_t tmem_cols;
 };
 
-// four consecutive logical columns c .. c+3 of row `row` (zeros outside [0, ncols)); 16-byte load when the address allows it
-__device__ __forceinline__ float4 load_cols4(const float* __restrict__ base, size_t row, int ld, int c, int ncols, int group, int gstride) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c >= ncols) return v;
-  const float* p = base + row * (size_t)ld + (group ? (c / group) * gstride + (c % group) : c);
-  if (c + 3 < ncols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
-  v.x = __ldg(p);
-  if (c + 1 < ncols) v.y = __ldg(p + 1);
-  if (c + 2 < ncols) v.z = __ldg(p + 2);
-  if (c + 3 < ncols) v.w = __ldg(p + 3);
-  return v;
-}
-
 __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float a, float b, float c, float d) {
   const float4 h = make_float4(umma::to_tf32(a), umma::to_tf32(b), umma::to_tf32(c), umma::to_tf32(d));
   *reinterpret_cast<float4*>(hi + off) = h;
@@ -72,46 +59,70 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
   const int fb0 = tid >> 3;                      // first feature block (4 features); A has 32 of them, B has Np / 4 <= 64
   const int nbB = g.Np / 4;
   // one chunk = a 4-point x 4-feature block of dY and up to two of [X | 1] per thread, held in registers between the loads (issued while
-  // the previous chunk's MMAs run) and the transposing stores
+  // the previous chunk's MMAs run) and the transposing stores.  The loads are branch-free in the common case and NOTHING consumes them
+  // before store_chunk (zero fill of rows past the split and the ones column are applied there): twelve 16-byte loads per thread stay in
+  // flight together (ncu on the first version: 48 % of the stall samples sat on a load whose value was patched right behind it).
+  // Per unit, decided once: mode 0 = all zeros / ones column only, 1 = one 16-byte load per row, 2 = guarded scalar loads (row tails).
   float4 va[4], vb[2][4];
-  auto load_chunk = [&](int mb) {
-    const int mrow = mb + p4 * 4;
-    const int ca = n0 + fb0 * 4;
+  const int ca = n0 + fb0 * 4;
+  const float* pa = g.dY + (g.agroup ? (ca / g.agroup) * g.agstride + (ca % g.agroup) : ca);
+  const int mode_a = ca >= g.N ? 0 : ((ca + 3 < g.N && (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(pa) & 15) == 0) ? 1 : 2);
+  const float* pb[2];
+  int mode_b[2], cb[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      va[j] = (mrow + j < mhi) ? load_cols4(g.dY, (size_t)(mrow + j), g.lda, ca, g.N, g.agroup, g.agstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = 0; u < 2; ++u) {
+    const int fb = fb0 + 32 * u;
+    cb[u] = fb * 4;
+    pb[u] = g.X + cb[u];
+    mode_b[u] = (fb >= nbB || cb[u] >= g.K) ? 0 : ((cb[u] + 3 < g.K && (g.ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(pb[u]) & 15) == 0) ? 1 : 2);
+  }
+  auto load_rows = [&](float4 (&v)[4], const float* p, int ld, int mode, int c, int ncols, int mrow) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int fb = fb0 + 32 * u, c = fb * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = fb < nbB && mrow + j < mhi;
-        float4 v = ok ? load_cols4(g.X, (size_t)(mrow + j), g.ldb, c, g.K, 0, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && g.K >= c && g.K < c + 4) {                                // the ones column (bias gradient)
-          const int e = g.K - c;
-          if (e == 0) v.x = 1.f; else if (e == 1) v.y = 1.f; else if (e == 2) v.z = 1.f; else v.w = 1.f;
-        }
-        vb[u][j] = v;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int row = min(mrow + j, g.M - 1);                                // clamped: always a valid address; masked in store_chunk
+      const float* q = p + (size_t)row * ld;
+      if (mode == 1) v[j] = __ldg(reinterpret_cast<const float4*>(q));
+      else if (mode == 2) {
+        v[j].x = __ldg(q);
+        v[j].y = c + 1 < ncols ? __ldg(q + 1) : 0.f;
+        v[j].z = c + 2 < ncols ? __ldg(q + 2) : 0.f;
+        v[j].w = c + 3 < ncols ? __ldg(q + 3) : 0.f;
+      } else v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto store_chunk = [&]() {
+  auto load_chunk = [&](int mb) {
+    const int mrow = mb + p4 * 4;
+    load_rows(va, pa, g.lda, mode_a, ca, g.N, mrow);
+    load_rows(vb[0], pb[0], g.ldb, mode_b[0], cb[0], g.K, mrow);
+    load_rows(vb[1], pb[1], g.ldb, mode_b[1], cb[1], g.K, mrow);
+  };
+  auto store_chunk = [&](int mb) {
+    const int mrow = mb + p4 * 4;
+    float rowok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rowok[j] = mrow + j < mhi ? 1.f : 0.f;
     {
       const uint32_t off = (uint32_t)p4 * kGwALbo + (uint32_t)(fb0 * 4) * 16u;
-      store_split(A_hi, A_lo, off, va[0].x, va[1].x, va[2].x, va[3].x);
-      store_split(A_hi, A_lo, off + 16, va[0].y, va[1].y, va[2].y, va[3].y);
-      store_split(A_hi, A_lo, off + 32, va[0].z, va[1].z, va[2].z, va[3].z);
-      store_split(A_hi, A_lo, off + 48, va[0].w, va[1].w, va[2].w, va[3].w);
+      store_split(A_hi, A_lo, off, va[0].x * rowok[0], va[1].x * rowok[1], va[2].x * rowok[2], va[3].x * rowok[3]);
+      store_split(A_hi, A_lo, off + 16, va[0].y * rowok[0], va[1].y * rowok[1], va[2].y * rowok[2], va[3].y * rowok[3]);
+      store_split(A_hi, A_lo, off + 32, va[0].z * rowok[0], va[1].z * rowok[1], va[2].z * rowok[2], va[3].z * rowok[3]);
+      store_split(A_hi, A_lo, off + 48, va[0].w * rowok[0], va[1].w * rowok[1], va[2].w * rowok[2], va[3].w * rowok[3]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int fb = fb0 + 32 * u;
       if (fb < nbB) {
+        const int e = g.K - cb[u];                                          // position of the ones column inside this block, if 0..3
+        float x[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          x[j][0] = e == 0 ? 1.f : vb[u][j].x; x[j][1] = e == 1 ? 1.f : vb[u][j].y;
+          x[j][2] = e == 2 ? 1.f : vb[u][j].z; x[j][3] = e == 3 ? 1.f : vb[u][j].w;
+        }
         const uint32_t off = (uint32_t)p4 * b_lbo + (uint32_t)(fb * 4) * 16u;
-        store_split(B_hi, B_lo, off, vb[u][0].x, vb[u][1].x, vb[u][2].x, vb[u][3].x);
-        store_split(B_hi, B_lo, off + 16, vb[u][0].y, vb[u][1].y, vb[u][2].y, vb[u][3].y);
-        store_split(B_hi, B_lo, off + 32, vb[u][0].z, vb[u][1].z, vb[u][2].z, vb[u][3].z);
-        store_split(B_hi, B_lo, off + 48, vb[u][0].w, vb[u][1].w, vb[u][2].w, vb[u][3].w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          store_split(B_hi, B_lo, off + 16 * i, x[0][i] * rowok[0], x[1][i] * rowok[1], x[2][i] * rowok[2], x[3][i] * rowok[3]);
       }
     }
   };
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
   if (mlo < mhi) load_chunk(mlo);
   for (int mb = mlo; mb < mhi; mb += kGwChunk) {
     if (!first) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }       // the previous chunk's MMAs have read the operands
-    store_chunk();
+    store_chunk(mb);
     umma::fence_proxy_async_smem();
     __syncthreads();
     if (warp == 0) {

@@ -257,4 +257,121 @@ int run_prepare_observation(const SherfSmplModel& smpl, const SherfObservation& 
   return SHERF_OK;
 }
 
+
+// ---- backward of the vertex features: what autograd derives through triplane.py:115-126 --------------------------------
+// out[v] = mask[v] (Wp [f64(uv_v) | pe32(rgb(uv_v))] + bp).  Gradients: Wp, bp (TriPlaneGenerator.conv1d_projection) and the 2-D feature
+// map (bilinear adjoint = F.grid_sample's backward, red.add like torch).  The image and the vertex pixels are data.  Blocks stride over
+// groups of 8 vertices (warp per vertex) and keep their share of dWp in registers: one atomicAdd per entry and block.
+constexpr int kObsBwdBlocks = 64;
+__global__ void __launch_bounds__(256) k_obs_features_bwd(const float* __restrict__ uv, const unsigned char* __restrict__ vmask, int V,
+                                                          const float* __restrict__ feat, int fh, int fw, const float* __restrict__ img, int ih, int iw,
+                                                          const float* __restrict__ Wp, const float* __restrict__ g_out, float* __restrict__ g_Wp,
+                                                          float* __restrict__ g_bp, float* __restrict__ g_feat) {
+  __shared__ float sW[32 * 97];
+  __shared__ float sx[8][96];
+  __shared__ float sg[8][32];
+  for (int i = threadIdx.x; i < 32 * 96; i += blockDim.x) sW[(i / 96) * 97 + (i % 96)] = Wp[i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float accW[12], accB = 0.f;                          // entries threadIdx.x + 256 e of the [32][96] matrix; bias: threads < 32
+#pragma unroll
+  for (int e = 0; e < 12; ++e) accW[e] = 0.f;
+  for (int v0 = blockIdx.x * 8; v0 < V; v0 += gridDim.x * 8) {
+    __syncthreads();
+    const int v = v0 + wid;
+    float g = 0.f;
+    if (v < V) {
+      const float gx = 2.0f * uv[v * 2] / (float)iw - 1.0f, gy = 2.0f * uv[v * 2 + 1] / (float)ih - 1.0f;
+      auto taps = [&](int H, int W, int (&xx)[4], int (&yy)[4], float (&w)[4]) {
+        const float ix = (gx + 1.f) * 0.5f * (float)(W - 1), iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+        const float fx = floorf(ix), fy = floorf(iy);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int cx = t & 1, cy = t >> 1;
+          xx[t] = (int)fx + cx; yy[t] = (int)fy + cy;
+          w[t] = (cx ? ix - fx : (fx + 1.f) - ix) * (cy ? iy - fy : (fy + 1.f) - iy);
+          if (xx[t] < 0 || xx[t] >= W || yy[t] < 0 || yy[t] >= H) w[t] = 0.f, xx[t] = 0, yy[t] = 0;
+        }
+      };
+      int fxx[4], fyy[4], ixx[4], iyy[4];
+      float fwt[4], iwt[4];
+      taps(fh, fw, fxx, fyy, fwt);
+      taps(ih, iw, ixx, iyy, iwt);
+      auto bil = [&](const float* __restrict__ plane, int W, const int (&xx)[4], const int (&yy)[4], const float (&w)[4]) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a += w[t] * __ldg(plane + (size_t)yy[t] * W + xx[t]);
+        return a;
+      };
+      sx[wid][lane] = bil(feat + (size_t)lane * fh * fw, fw, fxx, fyy, fwt);
+      sx[wid][32 + lane] = bil(feat + (size_t)(32 + lane) * fh * fw, fw, fxx, fyy, fwt);
+      const float rgbc = lane < 3 ? bil(img + (size_t)lane * ih * iw, iw, ixx, iyy, iwt) : 0.f;
+      {
+        const int e = lane - 3;
+        const int m = e >= 0 ? e / 3 : 0, c = e >= 0 ? e - 3 * m : lane;
+        const float xc = __shfl_sync(0xffffffffu, rgbc, c);
+        sx[wid][64 + lane] = lane < 3 ? xc : sinf(__fadd_rn((m & 1) ? kPi2 : 0.f, __fmul_rn(xc, (float)(1 << (m >> 1)))));
+      }
+      g = vmask[v] ? g_out[(size_t)v * 32 + lane] : 0.f;
+      // d f64[k] = sum_out Wp[out][k] g[out]  ->  bilinear adjoint into the feature map
+      if (g_feat) {
+        float d0 = 0.f, d1 = 0.f;
+        for (int o = 0; o < 32; ++o) {
+          const float go = __shfl_sync(0xffffffffu, g, o);
+          d0 = fmaf(sW[o * 97 + lane], go, d0);
+          d1 = fmaf(sW[o * 97 + 32 + lane], go, d1);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (fwt[t] != 0.f) {
+            atomicAdd(g_feat + ((size_t)lane * fh + fyy[t]) * fw + fxx[t], fwt[t] * d0);
+            atomicAdd(g_feat + ((size_t)(32 + lane) * fh + fyy[t]) * fw + fxx[t], fwt[t] * d1);
+          }
+      }
+    } else {
+      sx[wid][lane] = 0.f; sx[wid][32 + lane] = 0.f; sx[wid][64 + lane] = 0.f;
+    }
+    sg[wid][lane] = g;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const int idx = threadIdx.x + 256 * e, o = idx / 96, k = idx - o * 96;
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a = fmaf(sg[q][o], sx[q][k], a);
+      accW[e] += a;
+    }
+    if (threadIdx.x < 32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) accB += sg[q][threadIdx.x];
+    }
+  }
+  if (g_Wp)
+#pragma unroll
+    for (int e = 0; e < 12; ++e) atomicAdd(g_Wp + threadIdx.x + 256 * e, accW[e]);
+  if (g_bp && threadIdx.x < 32) atomicAdd(g_bp + threadIdx.x, accB);
+}
+
+int run_prepare_observation_backward(const SherfSmplModel& smpl, const SherfObservation& ob, const float* g_vert_feat, float* g_proj_w, float* g_proj_b,
+                                     float* g_obs_feat, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  const int V = smpl.n_verts;
+  char* base = (char*)scratch;
+  { const size_t mis = ((size_t)base) & 255; if (mis) base += 256 - mis; }
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* { off = (off + 255) & ~(size_t)255; void* p = base + off; off += bytes; return p; };
+  float* uv = (float*)take(sizeof(float) * (size_t)V * 2);
+  float* verts_smpl = (float*)take(sizeof(float) * (size_t)V * 3);
+  unsigned char* vmask = (unsigned char*)take(V);
+  if (off + 512 > scratch_bytes) { set_error("scratch arena too small for sherf_prepare_observation_backward"); return SHERF_E_SCRATCH; }
+  k_obs_geometry<<<ceil_div(V, 128), 128, 0, st>>>(ob.obs_vertices, V, ob.obs_R, ob.obs_T, ob.obs_K, ob.faces, ob.last_face, ob.obs.R, ob.obs.Th,
+                                                  uv, vmask, verts_smpl);
+  SHERF_LAUNCH_CHECK();
+  if (g_proj_w) SHERF_CUDA_OK(cudaMemsetAsync(g_proj_w, 0, sizeof(float) * 32 * 96, st));
+  if (g_proj_b) SHERF_CUDA_OK(cudaMemsetAsync(g_proj_b, 0, sizeof(float) * 32, st));
+  if (g_obs_feat) SHERF_CUDA_OK(cudaMemsetAsync(g_obs_feat, 0, sizeof(float) * (size_t)ob.feat_ch * ob.feat_h * ob.feat_w, st));
+  k_obs_features_bwd<<<kObsBwdBlocks, 256, 0, st>>>(uv, vmask, V, ob.obs_feat, ob.feat_h, ob.feat_w, ob.obs_img, ob.img_h, ob.img_w, ob.proj_w,
+                                                   g_vert_feat, g_proj_w, g_proj_b, g_obs_feat);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
 }  // namespace sherf

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_sp_conv(const int* __restrict__ coords,
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     const int co = lane + 32 * t;
-    if (co < cout) Fout[(size_t)r * cout + co] = fmaxf(acc[t] * scale_shift[co] + scale_shift[cout + co], 0.f);     // BN + ReLU
+    if (co < cout) Fout[(size_t)r * cout + co] = scale_shift ? fmaxf(acc[t] * scale_shift[co] + scale_shift[cout + co], 0.f) : acc[t];   // BN + ReLU | raw
   }
 }
 
@@ -208,6 +208,436 @@ int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const flo
       SHERF_LAUNCH_CHECK();
       ++emitted;
     }
+  }
+  return SHERF_OK;
+}
+
+
+// =====================================================================================================================================
+// Training mode: BatchNorm1d with BATCH statistics (nn.BatchNorm1d(eps=1e-3, momentum=0.01) in train(), renderer.py
+// :822,840,...) and the backward pass torch.autograd derives through SparseConvNet.forward (renderer.py:744-785) when loss.backward() runs
+// (loss.py:175).  Every activation is kept in the arena between the two calls.
+//
+// Rows and duplicates: spconv keeps one feature row per INPUT index, duplicates included, on the level-0 layers (SubMConv3d: output rows =
+// input rows), and BatchNorm1d normalises over those rows.  A duplicate row carries the same value as its voxel's representative after the
+// first convolution, so the statistics of the two level-0 BatchNorms weight every voxel by its multiplicity m (number of vertices in it);
+// after down0 rows are unique output sites (m = 1).  The duplicate rows' outputs are never read downstream (hash tables and .dense() see the
+// representative), but they do sit in the statistics, so in the backward pass a voxel hands  gamma rstd (dZ - m (dbeta + xhat dgamma) / N)
+// to the convolution below it: the sum over its m rows, of which only the representative has an upstream gradient.
+// =====================================================================================================================================
+
+// level-0 multiplicity: vertices per voxel (after k_sp_index0: idx holds rows)
+__global__ void k_sp_mult(const int* __restrict__ coord, int n, SpDims s, const int* __restrict__ idx, float* __restrict__ mult, int* __restrict__ nrows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int z = coord[i * 3], y = coord[i * 3 + 1], x = coord[i * 3 + 2];
+  if (!sp_inside(s, z, y, x)) return;
+  atomicAdd(&mult[idx[sp_cell(s, z, y, x)]], 1.f);
+  atomicAdd(nrows, 1);
+}
+
+// per-channel sums over rows in double: part[split][c][2] = (sum m x, sum m x^2); lane = channel (coalesced rows), warp = row slice
+constexpr int kSpStatSplits = 64;
+__global__ void __launch_bounds__(256) k_sp_bn_stats(const float* __restrict__ raw, const int* __restrict__ count, int cout, const float* __restrict__ mult,
+                                                     double* __restrict__ part) {
+  __shared__ double red[8][32][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int rows = *count;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < cout)
+    for (int r = blockIdx.y * 8 + w; r < rows; r += kSpStatSplits * 8) {
+      const double x = raw[(size_t)r * cout + c], m = mult ? mult[r] : 1.f;
+      s1 += m * x; s2 += m * x * x;
+    }
+  red[w][lane][0] = s1; red[w][lane][1] = s2;
+  __syncthreads();
+  if (w == 0 && c < cout) {
+    for (int k = 1; k < 8; ++k) { s1 += red[k][lane][0]; s2 += red[k][lane][1]; }
+    part[((size_t)blockIdx.y * cout + c) * 2] = s1;
+    part[((size_t)blockIdx.y * cout + c) * 2 + 1] = s2;
+  }
+}
+// stats[c] = mean, stats[96 + c] = biased variance, stats[192 + c] = rstd;  nrows: level-0 layers count duplicate rows (sum of m)
+__global__ void k_sp_bn_finalize(const double* __restrict__ part, int cout, const int* __restrict__ nrows, float* __restrict__ stats, float* __restrict__ out_stats,
+                                 int* __restrict__ out_rows) {
+  const int c = threadIdx.x;
+  if (c >= cout) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < kSpStatSplits; ++k) { s1 += part[((size_t)k * cout + c) * 2]; s2 += part[((size_t)k * cout + c) * 2 + 1]; }
+  const double n = (double)max(*nrows, 1);
+  const double mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[c] = (float)mean; stats[96 + c] = (float)var; stats[192 + c] = (float)(1.0 / sqrt(var + 1e-3));
+  if (out_stats) { out_stats[c] = (float)mean; out_stats[96 + c] = (float)var; }
+  if (out_rows && c == 0) *out_rows = *nrows;
+}
+// evaluation-mode statistics for a differentiable forward: mean / var = the running statistics (constants of the graph)
+__global__ void k_sp_bn_running(const float* __restrict__ mean, const float* __restrict__ var, int cout, float* __restrict__ stats) {
+  const int c = threadIdx.x;
+  if (c >= cout) return;
+  stats[c] = mean[c]; stats[96 + c] = var[c]; stats[192 + c] = 1.f / sqrtf(var[c] + 1e-3f);
+}
+// act = relu((raw - mean) rstd gamma + beta)
+__global__ void k_sp_bn_apply(const float* __restrict__ raw, const int* __restrict__ count, int cout, const float* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ act) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(t / cout), c = (int)(t % cout);
+  if (r >= *count) return;
+  act[t] = fmaxf((raw[t] - stats[c]) * stats[192 + c] * gamma[c] + beta[c], 0.f);
+}
+
+// dA[r][c] (+)= g_vol[c][cell(r)]: the adjoint of .dense()
+__global__ void k_sp_densify_bwd(const int* __restrict__ coords, const int* __restrict__ count, SpDims s, const float* __restrict__ gvol, int C, int accum,
+                                 float* __restrict__ dA) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(t / C), c = (int)(t % C);
+  if (r >= *count) return;
+  const float g = gvol ? gvol[(size_t)c * s.d[0] * s.d[1] * s.d[2] + sp_cell(s, coords[r * 3], coords[r * 3 + 1], coords[r * 3 + 2])] : 0.f;
+  dA[t] = accum ? dA[t] + g : g;
+}
+// part[split][c][2] = (sum dZ, sum dZ xhat), dZ = dA (act > 0), xhat = (raw - mean) rstd
+__global__ void __launch_bounds__(256) k_sp_bn_bwd_stats(const float* __restrict__ dA, const float* __restrict__ act, const float* __restrict__ raw,
+                                                         const int* __restrict__ count, int cout, const float* __restrict__ stats, double* __restrict__ part) {
+  __shared__ double red[8][32][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int rows = *count;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < cout) {
+    const float mean = stats[c], rstd = stats[192 + c];
+    for (int r = blockIdx.y * 8 + w; r < rows; r += kSpStatSplits * 8) {
+      const size_t i = (size_t)r * cout + c;
+      const float dz = act[i] > 0.f ? dA[i] : 0.f;
+      s1 += dz; s2 += (double)dz * (double)((raw[i] - mean) * rstd);
+    }
+  }
+  red[w][lane][0] = s1; red[w][lane][1] = s2;
+  __syncthreads();
+  if (w == 0 && c < cout) {
+    for (int k = 1; k < 8; ++k) { s1 += red[k][lane][0]; s2 += red[k][lane][1]; }
+    part[((size_t)blockIdx.y * cout + c) * 2] = s1;
+    part[((size_t)blockIdx.y * cout + c) * 2 + 1] = s2;
+  }
+}
+// dbeta / dgamma out (+ kept in dsum[c], dsum[96 + c] for the apply kernel)
+__global__ void k_sp_bn_bwd_finalize(const double* __restrict__ part, int cout, float* __restrict__ dsum, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+  const int c = threadIdx.x;
+  if (c >= cout) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < kSpStatSplits; ++k) { s1 += part[((size_t)k * cout + c) * 2]; s2 += part[((size_t)k * cout + c) * 2 + 1]; }
+  dsum[c] = (float)s1; dsum[96 + c] = (float)s2;
+  if (g_beta) g_beta[c] = (float)s1;
+  if (g_gamma) g_gamma[c] = (float)s2;
+}
+// dRaw = gamma rstd (dZ - m (dbeta + xhat dgamma) / N)
+__global__ void k_sp_bn_bwd_apply(const float* __restrict__ dA, const float* __restrict__ act, const float* __restrict__ raw, const int* __restrict__ count, int cout,
+                                  const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ dsum, const float* __restrict__ mult,
+                                  const int* __restrict__ nrows, float* __restrict__ dRaw) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(t / cout), c = (int)(t % cout);
+  if (r >= *count) return;
+  const float inv_n = nrows ? 1.f / (float)max(*nrows, 1) : 0.f;      // nrows == NULL: statistics were constants (evaluation mode)
+  const float xhat = (raw[t] - stats[c]) * stats[192 + c];
+  const float dz = act[t] > 0.f ? dA[t] : 0.f;
+  const float m = mult ? mult[r] : 1.f;
+  dRaw[t] = gamma[c] * stats[192 + c] * (dz - m * (dsum[c] + xhat * dsum[96 + c]) * inv_n);
+}
+
+// dX[j][ci] = sum over the outputs r that read input row j through offset o of  sum_co W[co][o][ci] dRaw[r][co].  Gather form from the INPUT
+// side (no atomics): one warp per input row, lanes = input channels (W is KRSC: ci contiguous).
+//   SubM: output at q = p - (k - 1);  strided: output at q with 2 q - 1 + k = p
+template <bool DOWN>
+__global__ void __launch_bounds__(256) k_sp_conv_bwd_x(const int* __restrict__ coords_in, const int* __restrict__ count_in, SpDims sout,
+                                                       const int* __restrict__ idx_out, const float* __restrict__ dRaw, int cin, int cout,
+                                                       const float* __restrict__ W, float* __restrict__ dX) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= *count_in) return;
+  const int z = coords_in[j * 3], y = coords_in[j * 3 + 1], x = coords_in[j * 3 + 2];
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int o = 0; o < 27; ++o) {
+    const int kz = o / 9, ky = (o / 3) % 3, kx = o % 3;
+    int qz, qy, qx;
+    if (DOWN) {
+      const int az = z + 1 - kz, ay = y + 1 - ky, ax = x + 1 - kx;
+      if (az < 0 || ay < 0 || ax < 0 || ((az | ay | ax) & 1)) continue;
+      qz = az >> 1; qy = ay >> 1; qx = ax >> 1;
+    } else {
+      qz = z - (kz - 1); qy = y - (ky - 1); qx = x - (kx - 1);
+    }
+    if (!sp_inside(sout, qz, qy, qx)) continue;
+    const int r = idx_out[sp_cell(sout, qz, qy, qx)];
+    if (r < 0) continue;
+    const float* g = dRaw + (size_t)r * cout;
+    for (int co = 0; co < cout; ++co) {
+      const float gv = g[co];
+      const float* w = W + ((size_t)co * 27 + o) * cin;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int ci = lane + 32 * t;
+        if (ci < cin) acc[t] = fmaf(gv, w[ci], acc[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int ci = lane + 32 * t;
+    if (ci < cin) dX[(size_t)j * cin + ci] = acc[t];
+  }
+}
+
+// dW[co][o][ci] += sum_r dRaw[r][co] x[nbr(r, o)][ci].  grid (27 offsets, row splits); a block stages 8 (row, neighbour) pairs in shared
+// memory, every thread owns up to 36 (co, ci) entries of the cout x cin tile; one atomicAdd per entry and block at the end.
+constexpr int kSpDwSplits = 48;
+template <bool DOWN>
+__global__ void __launch_bounds__(256) k_sp_conv_bwd_w(const int* __restrict__ coords_out, const int* __restrict__ count_out, SpDims sin,
+                                                       const int* __restrict__ idx_in, const float* __restrict__ dRaw, const float* __restrict__ X, int cin,
+                                                       int cout, float* __restrict__ dW) {
+  __shared__ float sg[8][96], sx[8][96];
+  __shared__ int sj[8];
+  const int o = blockIdx.x, kz = o / 9, ky = (o / 3) % 3, kx = o % 3;
+  const int rows = *count_out;
+  const int per = (rows + kSpDwSplits - 1) / kSpDwSplits;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  const int tci = threadIdx.x & 31, tco = threadIdx.x >> 5;      // ci = tci + 32 a (a < 3), co = tco + 8 b (b < 12)
+  float acc[3][12];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 12; ++b) acc[a][b] = 0.f;
+  for (int rb = r0; rb < r1; rb += 8) {
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int r = rb + threadIdx.x;
+      int j = -1;
+      if (r < r1) {
+        const int z = coords_out[r * 3], y = coords_out[r * 3 + 1], x = coords_out[r * 3 + 2];
+        const int pz = DOWN ? 2 * z - 1 + kz : z + kz - 1, py = DOWN ? 2 * y - 1 + ky : y + ky - 1, px = DOWN ? 2 * x - 1 + kx : x + kx - 1;
+        if (sp_inside(sin, pz, py, px)) j = idx_in[sp_cell(sin, pz, py, px)];
+      }
+      sj[threadIdx.x] = j;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 96; i += 256) {
+      const int q = i / 96, c = i - q * 96;
+      const int j = sj[q];
+      sg[q][c] = (j >= 0 && c < cout) ? dRaw[(size_t)(rb + q) * cout + c] : 0.f;
+      sx[q][c] = (j >= 0 && c < cin) ? X[(size_t)j * cin + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (sj[q] < 0) continue;
+      float xv[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) xv[a] = sx[q][tci + 32 * a];
+#pragma unroll
+      for (int b = 0; b < 12; ++b) {
+        const float gv = sg[q][tco + 8 * b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a][b] = fmaf(gv, xv[a], acc[a][b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 12; ++b) {
+    const int co = tco + 8 * b;
+    if (co >= cout) continue;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ci = tci + 32 * a;
+      if (ci < cin && acc[a][b] != 0.f) atomicAdd(&dW[((size_t)co * 27 + o) * cin + ci], acc[a][b]);
+    }
+  }
+}
+
+// g_feat[i] = dX0[row of vertex i] for the representative vertex of a voxel, 0 for the others (their rows are never read, renderer.py:756)
+__global__ void k_sp_feat_grad(const int* __restrict__ rowof, int n, int C, const float* __restrict__ dX, float* __restrict__ g_feat) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t / C), c = (int)(t % C);
+  if (i >= n) return;
+  const int row = rowof[i];
+  g_feat[t] = row >= 0 ? dX[(size_t)row * C + c] : 0.f;
+}
+
+// ---- arena of the training pass: the inference scratch + every layer's pre-BatchNorm output and activation + statistics ----
+struct SpTrain {
+  SpScratch s;
+  float* raw[SHERF_SPARSE_CONVS]; float* act[SHERF_SPARSE_CONVS];
+  float* stats;          // [13][288]: mean | biased var | rstd
+  float* mult;           // [cap0]
+  int* nrows;            // [13] rows under each BatchNorm (level 0: duplicates counted)
+  int* lvl_of;           // host-side only (not carved)
+  double* part;          // [kSpStatSplits][96][2]
+  float* dsum;           // [192]
+  float* dA; float* dB;  // [maxcap][96] gradient ping-pong
+};
+static const int kSpEmitAfter[SHERF_SPARSE_CONVS] = {0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+static const int kSpKind[SHERF_SPARSE_CONVS] = {0, 0, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+// output level of conv c
+static int sp_out_level(int c) { int l = 0; for (int i = 0; i <= c; ++i) l += kSpKind[i]; return l; }
+
+static size_t sp_carve_train(char* base, int n, const SpPlan& p, const SherfSparseEncoder* enc, SpTrain& t) {
+  size_t off = sp_carve(base, n, p, t.s);
+  auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; char* q = base ? base + off : nullptr; off += bytes; return q; };
+  int maxcap = 0;
+  for (int l = 0; l < 4; ++l) if (p.cap[l] > maxcap) maxcap = p.cap[l];
+  for (int c = 0; c < SHERF_SPARSE_CONVS; ++c) {
+    const int cout = enc ? enc->conv[c].c_out : 96;
+    const size_t rows = (size_t)p.cap[sp_out_level(c)];
+    t.raw[c] = (float*)take(rows * cout * sizeof(float));
+    t.act[c] = (float*)take(rows * cout * sizeof(float));
+  }
+  t.stats = (float*)take((size_t)SHERF_SPARSE_CONVS * 288 * sizeof(float));
+  t.mult = (float*)take((size_t)p.cap[0] * sizeof(float));
+  t.nrows = (int*)take(SHERF_SPARSE_CONVS * sizeof(int));
+  t.part = (double*)take((size_t)kSpStatSplits * 96 * 2 * sizeof(double));
+  t.dsum = (float*)take(192 * sizeof(float));
+  t.dA = (float*)take((size_t)maxcap * 96 * sizeof(float));
+  t.dB = (float*)take((size_t)maxcap * 96 * sizeof(float));
+  return off + 256;
+}
+
+size_t sparse_encoder_train_scratch_bytes(int n, const int32_t* out_sh) {
+  SpPlan p; sp_plan(n, out_sh, p);
+  SpTrain t;
+  return sp_carve_train(nullptr, n, p, nullptr, t) + 256;
+}
+
+static int sp_check_layers(const SherfSparseEncoder& enc) {
+  for (int c = 0; c < SHERF_SPARSE_CONVS; ++c) {
+    const SherfSparseConv& L = enc.conv[c];
+    if (L.c_in > 96 || L.c_out > 96 || L.c_in <= 0 || L.c_out <= 0 || L.kind != kSpKind[c]) {
+      set_error("sparse conv %d: unsupported layer (channels %d -> %d, kind %d)", c, L.c_in, L.c_out, L.kind);
+      return SHERF_E_UNSUPPORTED;
+    }
+  }
+  return SHERF_OK;
+}
+
+int run_sparse_encode_train(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
+                            float* batch_stats, int* row_counts, int use_running_stats, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  { const int rc = sp_check_layers(enc); if (rc) return rc; }
+  SpPlan p; sp_plan(n, out_sh, p);
+  char* base = (char*)scratch;
+  const size_t mis = ((size_t)base) & 255;
+  if (mis) base += 256 - mis;
+  SpTrain t;
+  const size_t need = sp_carve_train(base, n, p, &enc, t);
+  if (need + 256 > scratch_bytes) { set_error("sparse-encoder training scratch too small: need %zu bytes, have %zu", need + 256, scratch_bytes); return SHERF_E_SCRATCH; }
+  SpScratch& s = t.s;
+  for (int l = 0; l < 4; ++l) SHERF_CUDA_OK(cudaMemsetAsync(s.idx[l], 0xff, p.cells[l] * sizeof(int), st));
+  SHERF_CUDA_OK(cudaMemsetAsync(s.count, 0, 4 * sizeof(int), st));
+  SHERF_CUDA_OK(cudaMemsetAsync(t.mult, 0, (size_t)p.cap[0] * sizeof(float), st));
+  SHERF_CUDA_OK(cudaMemsetAsync(t.nrows, 0, SHERF_SPARSE_CONVS * sizeof(int), st));
+  const int C0 = enc.conv[0].c_in;
+  k_sp_claim<<<ceil_div(n, 256), 256, 0, st>>>(coord, n, p.dims[0], s.idx[0]);
+  SHERF_LAUNCH_CHECK();
+  k_sp_rows0<<<ceil_div(n, 256), 256, 0, st>>>(coord, feat, n, C0, p.dims[0], s.idx[0], s.count, s.rowof, s.coords[0], s.F[0]);
+  SHERF_LAUNCH_CHECK();
+  k_sp_index0<<<ceil_div(n, 256), 256, 0, st>>>(coord, n, p.dims[0], s.rowof, s.idx[0]);
+  SHERF_LAUNCH_CHECK();
+  k_sp_mult<<<ceil_div(n, 256), 256, 0, st>>>(coord, n, p.dims[0], s.idx[0], t.mult, t.nrows);      // nrows[0] = vertices inside the grid
+  SHERF_LAUNCH_CHECK();
+  int level = 0, emitted = 0;
+  const float* in = s.F[0];
+  for (int c = 0; c < SHERF_SPARSE_CONVS; ++c) {
+    const SherfSparseConv& L = enc.conv[c];
+    k_sp_pack<<<ceil_div(27 * L.c_in * L.c_out, 256), 256, 0, st>>>(L.weight, L.bn_weight, L.bn_bias, L.bn_mean, L.bn_var, L.c_in, L.c_out, s.Wt, s.ss);
+    SHERF_LAUNCH_CHECK();
+    if (L.kind == 0) {
+      k_sp_conv<false><<<ceil_div(p.cap[level], 8), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level], s.idx[level], in, L.c_in, L.c_out,
+                                                                  s.Wt, nullptr, t.raw[c]);
+      SHERF_LAUNCH_CHECK();
+    } else {
+      k_sp_down_sites<<<ceil_div((int64_t)p.cap[level] * 27, 256), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level + 1], s.idx[level + 1],
+                                                                               s.count + level + 1, s.coords[level + 1], p.cap[level + 1]);
+      SHERF_LAUNCH_CHECK();
+      k_sp_conv<true><<<ceil_div(p.cap[level + 1], 8), 256, 0, st>>>(s.coords[level + 1], s.count + level + 1, p.dims[level], s.idx[level], in, L.c_in,
+                                                                     L.c_out, s.Wt, nullptr, t.raw[c]);
+      SHERF_LAUNCH_CHECK();
+      ++level;
+    }
+    // rows under this BatchNorm: level 0 counts the duplicate rows (nrows[0], set by k_sp_mult), the other levels the unique output sites
+    const int* nr = level == 0 ? t.nrows : s.count + level;
+    if (use_running_stats) {
+      k_sp_bn_running<<<1, 96, 0, st>>>(L.bn_mean, L.bn_var, L.c_out, t.stats + (size_t)c * 288);
+      SHERF_LAUNCH_CHECK();
+    } else {
+      k_sp_bn_stats<<<dim3(ceil_div(L.c_out, 32), kSpStatSplits), 256, 0, st>>>(t.raw[c], s.count + level, L.c_out, level == 0 ? t.mult : nullptr, t.part);
+      SHERF_LAUNCH_CHECK();
+      k_sp_bn_finalize<<<1, 96, 0, st>>>(t.part, L.c_out, nr, t.stats + (size_t)c * 288, batch_stats ? batch_stats + (size_t)c * 192 : nullptr,
+                                         row_counts ? row_counts + c : nullptr);
+      SHERF_LAUNCH_CHECK();
+    }
+    k_sp_bn_apply<<<ceil_div((int64_t)p.cap[level] * L.c_out, 256), 256, 0, st>>>(t.raw[c], s.count + level, L.c_out, t.stats + (size_t)c * 288, L.bn_weight,
+                                                                               L.bn_bias, t.act[c]);
+    SHERF_LAUNCH_CHECK();
+    in = t.act[c];
+    if (kSpEmitAfter[c]) {
+      SHERF_CUDA_OK(cudaMemsetAsync(vols[emitted], 0, p.cells[level] * (size_t)L.c_out * sizeof(float), st));
+      k_sp_densify<<<ceil_div((int64_t)p.cap[level] * L.c_out, 256), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level], t.act[c], L.c_out,
+                                                                                 vols[emitted]);
+      SHERF_LAUNCH_CHECK();
+      ++emitted;
+    }
+  }
+  return SHERF_OK;
+}
+
+// scratch: the arena run_sparse_encode_train filled (same n / out_sh / encoder), untouched in between
+int run_sparse_encode_backward(const SherfSparseEncoder& enc, const int* coord, int n, const int32_t* out_sh, const float* const* g_vols,
+                               const SherfSparseEncoderGrads& gr, float* g_feat, int use_running_stats, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  { const int rc = sp_check_layers(enc); if (rc) return rc; }
+  SpPlan p; sp_plan(n, out_sh, p);
+  char* base = (char*)scratch;
+  const size_t mis = ((size_t)base) & 255;
+  if (mis) base += 256 - mis;
+  SpTrain t;
+  const size_t need = sp_carve_train(base, n, p, &enc, t);
+  if (need + 256 > scratch_bytes) { set_error("sparse-encoder training scratch too small: need %zu bytes, have %zu", need + 256, scratch_bytes); return SHERF_E_SCRATCH; }
+  SpScratch& s = t.s;
+  float* dA = t.dA;          // gradient w.r.t. the activation of layer c (rows of its output level)
+  float* dB = t.dB;          // dRaw of layer c, then (in dA's place) the gradient w.r.t. its input
+  bool have = false;         // dA holds the downstream convolution's input gradient
+  for (int c = SHERF_SPARSE_CONVS - 1; c >= 0; --c) {
+    const SherfSparseConv& L = enc.conv[c];
+    const int lo = sp_out_level(c), li = lo - kSpKind[c];
+    const int64_t elems = (int64_t)p.cap[lo] * L.c_out;
+    if (kSpEmitAfter[c]) {
+      const int e = lo - 1;                                           // levels 1, 2, 3 are emitted as volumes 0, 1, 2
+      k_sp_densify_bwd<<<ceil_div(elems, 256), 256, 0, st>>>(s.coords[lo], s.count + lo, p.dims[lo], g_vols[e], L.c_out, have ? 1 : 0, dA);
+      SHERF_LAUNCH_CHECK();
+      have = true;
+    }
+    if (!have) { set_error("sparse encoder backward: no gradient reaches layer %d", c); return SHERF_E_INVALID; }
+    const float* stats = t.stats + (size_t)c * 288;
+    const int* nr = use_running_stats ? nullptr : (lo == 0 ? t.nrows : s.count + lo);
+    k_sp_bn_bwd_stats<<<dim3(ceil_div(L.c_out, 32), kSpStatSplits), 256, 0, st>>>(dA, t.act[c], t.raw[c], s.count + lo, L.c_out, stats, t.part);
+    SHERF_LAUNCH_CHECK();
+    k_sp_bn_bwd_finalize<<<1, 96, 0, st>>>(t.part, L.c_out, t.dsum, gr.bn_weight[c], gr.bn_bias[c]);
+    SHERF_LAUNCH_CHECK();
+    k_sp_bn_bwd_apply<<<ceil_div(elems, 256), 256, 0, st>>>(dA, t.act[c], t.raw[c], s.count + lo, L.c_out, stats, L.bn_weight, t.dsum,
+                                                            lo == 0 ? t.mult : nullptr, nr, dB);
+    SHERF_LAUNCH_CHECK();
+    const float* X = c == 0 ? s.F[0] : t.act[c - 1];                  // the layer's input rows (level li)
+    if (gr.weight[c]) {
+      SHERF_CUDA_OK(cudaMemsetAsync(gr.weight[c], 0, (size_t)L.c_out * 27 * L.c_in * sizeof(float), st));
+      if (L.kind == 0) k_sp_conv_bwd_w<false><<<dim3(27, kSpDwSplits), 256, 0, st>>>(s.coords[lo], s.count + lo, p.dims[li], s.idx[li], dB, X, L.c_in, L.c_out, gr.weight[c]);
+      else k_sp_conv_bwd_w<true><<<dim3(27, kSpDwSplits), 256, 0, st>>>(s.coords[lo], s.count + lo, p.dims[li], s.idx[li], dB, X, L.c_in, L.c_out, gr.weight[c]);
+      SHERF_LAUNCH_CHECK();
+    }
+    if (c > 0 || g_feat) {
+      if (L.kind == 0) k_sp_conv_bwd_x<false><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
+      else k_sp_conv_bwd_x<true><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
+      SHERF_LAUNCH_CHECK();
+    }
+  }
+  if (g_feat) {
+    k_sp_feat_grad<<<ceil_div((int64_t)n * enc.conv[0].c_in, 256), 256, 0, st>>>(s.rowof, n, enc.conv[0].c_in, dA, g_feat);
+    SHERF_LAUNCH_CHECK();
   }
   return SHERF_OK;
 }

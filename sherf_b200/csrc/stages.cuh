@@ -187,6 +187,12 @@ size_t sparse_encoder_scratch_bytes(int n, const int32_t* out_sh);
 int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
                       void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+size_t sparse_encoder_train_scratch_bytes(int n, const int32_t* out_sh);
+int run_sparse_encode_train(const SherfSparseEncoder& enc, const int* coord, const float* feat, int n, const int32_t* out_sh, float* const* vols,
+                            float* batch_stats, int* row_counts, int use_running_stats, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int run_sparse_encode_backward(const SherfSparseEncoder& enc, const int* coord, int n, const int32_t* out_sh, const float* const* g_vols,
+                               const SherfSparseEncoderGrads& gr, float* g_feat, int use_running_stats, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
 // Dataset-side SMPL forward (smpl_forward.cu): smpl_numpy.py:46-98
 size_t smpl_forward_scratch_bytes();
 int run_smpl_vertices(const SherfSmplModel& smpl, const SherfPose& pose, float* verts_smpl, float* verts_world, void* scratch, size_t scratch_bytes,
@@ -196,6 +202,9 @@ int run_smpl_vertices(const SherfSmplModel& smpl, const SherfPose& pose, float* 
 size_t observation_scratch_bytes(int V, int maxcell);
 int run_prepare_observation(const SherfSmplModel& smpl, const SherfObservation& ob, float* vert_feat, int32_t* coord, uint8_t* vmask_out,
                             float* bounds_out, int32_t* out_sh_host, float* can_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+int run_prepare_observation_backward(const SherfSmplModel& smpl, const SherfObservation& ob, const float* g_vert_feat, float* g_proj_w, float* g_proj_b,
+                                     float* g_obs_feat, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // Importance (fine) pass, importance.cu (renderer.py:373-393, 446-456, 483-542)
 int run_importance_sample(const SherfRays& rays, const int* ray_start, const int* point_sample, const float* sigma, const float* noise,

@@ -73,6 +73,39 @@ class _RenderFn(torch.autograd.Function):
         return (None, None) + tuple(run_bwd(grad, ctx.needs_input_grad[2:]))
 
 
+class _SparseEncodeFn(torch.autograd.Function):
+    """Autograd node of one training-mode SparseConvNet.forward (SURVEY.md 8 f1 / f2).  `run_fwd()` -> (vol1, vol2, vol3);
+    `run_bwd((g1, g2, g3), needs)` -> one gradient (or None) per tensor in `tensors` = (features, then weight / BatchNorm weight / BatchNorm
+    bias of the 13 convolutions)."""
+
+    @staticmethod
+    def forward(ctx, run_fwd, run_bwd, *tensors):
+        ctx.run_bwd = run_bwd
+        return run_fwd()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        run_bwd, ctx.run_bwd = ctx.run_bwd, None
+        return (None, None) + tuple(run_bwd(grads, ctx.needs_input_grad[2:]))
+
+
+class _ObservationFn(torch.autograd.Function):
+    """Autograd node of the vertex features of prepare_observation (triplane.py:115-126): tensors = (obs_input_feature, conv1d_projection
+    weight, bias) -> vert_feat [V,32]."""
+
+    @staticmethod
+    def forward(ctx, run_fwd, run_bwd, *tensors):
+        ctx.run_bwd = run_bwd
+        return run_fwd()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        run_bwd, ctx.run_bwd = ctx.run_bwd, None
+        return (None, None) + tuple(run_bwd(grad, ctx.needs_input_grad[2:]))
+
+
 PRECISIONS = {'fp32': _lib.MLP_FP32, 'tf32': _lib.MLP_TF32, 'tf32x3': _lib.MLP_TF32X3, 'bf16x3': _lib.MLP_BF16X3,
               '_tf32x3_tmem_a': 99}      # diagnostic: 3xTF32 with the A_lo operand in tensor memory (sherf_debug_linear only)
 
@@ -181,7 +214,10 @@ class SparseConvNet(nn.Module):
     """The sparse 3-D encoder of renderer.py:708-742 (parameter names included).  forward() evaluates the convolutions of
     SparseConvNet.forward (renderer.py:756-782) and returns the three densified levels [net1.dense(), net2.dense(), net3.dense()]
     -- the grid_sample calls of :764,773,782 happen inside the render kernels.  The arithmetic runs in libsherf_b200.so
-    (csrc/sparse_encoder.cu); semantics of the spconv ops: oracle/sparse_encoder.py.  Evaluation-mode BatchNorm only."""
+    (csrc/sparse_encoder.cu); semantics of the spconv ops: oracle/sparse_encoder.py, oracle/spconv_shim.py.
+    eval(): BatchNorm running statistics (sherf_sparse_encode).  train(): batch statistics over each layer's rows, running statistics
+    updated like nn.BatchNorm1d(momentum=0.01), and -- when the features or a parameter require grad -- an autograd node whose backward
+    is sherf_sparse_encode_backward (what loss.backward() of loss.py:175 does through spconv in the reference)."""
 
     def __init__(self, num_layers=4):
         super().__init__()
@@ -203,8 +239,7 @@ class SparseConvNet(nn.Module):
     def forward(self, x, point_normalied_coords=None):
         if self.num_layers != 4:
             raise NotImplementedError('the CUDA encoder implements num_layers = 4 (renderer.py:270)')
-        if self.training:
-            raise NotImplementedError('sherf_b200 SparseConvNet: evaluation-mode BatchNorm only (training needs batch statistics + backward)')
+        feats_in = x.features
         feats, idx, out_sh = x.features, x.indices, [int(v) for v in x.spatial_shape]
         device = feats.device
         if device.type != 'cuda':
@@ -214,10 +249,12 @@ class SparseConvNet(nn.Module):
         lib = _lib.load()
         keep = []
         enc = _lib.SherfSparseEncoder()
+        params = []
         for c, (conv, bn, kind) in enumerate(self._convs()):
             w = _dev32(conv.weight, device)
             ts = [w, _dev32(bn.weight, device), _dev32(bn.bias, device), _dev32(bn.running_mean, device), _dev32(bn.running_var, device)]
             keep += ts
+            params += [conv.weight, bn.weight, bn.bias]
             e = enc.conv[c]
             e.weight, e.bn_weight, e.bn_bias, e.bn_mean, e.bn_var = (_ptr(t) for t in ts)
             e.c_out, e.c_in, e.kind = w.shape[0], w.shape[-1], kind
@@ -225,6 +262,7 @@ class SparseConvNet(nn.Module):
         feats = _dev32(feats, device)
         n = coord.shape[0]
         sh = (C.c_int32 * 3)(*out_sh)
+        wants_grad = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in [feats_in] + params)
         with torch.cuda.device(device):
             vols = []
             for lvl, ch in ((1, 32), (2, 64), (3, 96)):
@@ -232,6 +270,9 @@ class SparseConvNet(nn.Module):
                 for _ in range(lvl):
                     dims = [(d + 2 - 3) // 2 + 1 for d in dims]
                 vols.append(torch.empty(1, ch, *dims, device=device, dtype=torch.float32))
+            if self.training or wants_grad:
+                # train(): batch statistics.  eval() under autograd: the same differentiable kernels on the running statistics
+                return self._forward_train(lib, enc, keep, params, feats_in, feats, coord, n, sh, vols, device, wants_grad)
             need = lib.sherf_sparse_encoder_scratch_bytes(n, sh)
             rt = _runtime(self)
             if rt.scratch is None or rt.scratch.numel() < need or rt.scratch.device != device:
@@ -241,6 +282,77 @@ class SparseConvNet(nn.Module):
                                                torch.cuda.current_stream(device).cuda_stream))
         del keep
         return vols
+
+
+def _sparse_forward_train(self, lib, enc, keep, params, feats_in, feats, coord, n, sh, vols, device, wants_grad):
+    """train(): batch-statistics BatchNorm + running-statistics update + (optionally) the autograd node."""
+    running = 0 if self.training else 1
+    stats = torch.empty(13, 2, 96, device=device, dtype=torch.float32)
+    rows = torch.empty(13, device=device, dtype=torch.int32)
+    need = lib.sherf_sparse_encoder_train_scratch_bytes(n, sh)
+    # the arena carries every activation from the forward to the backward: one per call while a graph is being recorded
+    if wants_grad:
+        scratch = torch.empty(need, dtype=torch.uint8, device=device)
+    else:
+        rt = _runtime(self)
+        if rt.scratch is None or rt.scratch.numel() < need or rt.scratch.device != device:
+            rt.scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        scratch = rt.scratch
+
+    def run_fwd():
+        _lib.check(lib.sherf_sparse_encode_train(C.byref(enc), coord.data_ptr(), feats.data_ptr(), n, sh, vols[0].data_ptr(), vols[1].data_ptr(),
+                                                 vols[2].data_ptr(), stats.data_ptr(), rows.data_ptr(), running, scratch.data_ptr(), scratch.numel(),
+                                                 torch.cuda.current_stream(device).cuda_stream))
+        return tuple(vols)
+
+    def run_bwd(grads, needs, held=(enc, keep, coord, feats, scratch)):
+        with torch.cuda.device(device):
+            gv = [None if g is None else g.detach().to(device=device, dtype=torch.float32).contiguous() for g in grads]
+            if gv[2] is None:
+                gv[2] = torch.zeros_like(vols[2])
+            out = [None] * (1 + len(params))
+            gr = _lib.SherfSparseEncoderGrads()
+            g_feat = None
+            if needs[0]:
+                g_feat = torch.empty(n, feats.shape[1], device=device, dtype=torch.float32)
+                out[0] = g_feat.view(feats_in.shape).to(feats_in.dtype)
+            for c in range(13):
+                for k, arr in enumerate((gr.weight, gr.bn_weight, gr.bn_bias)):
+                    if needs[1 + 3 * c + k]:
+                        t = torch.empty(params[3 * c + k].shape, device=device, dtype=torch.float32)
+                        out[1 + 3 * c + k] = t
+                        arr[c] = _ptr(t)
+            _lib.check(lib.sherf_sparse_encode_backward(C.byref(enc), coord.data_ptr(), n, sh, None if gv[0] is None else gv[0].data_ptr(),
+                                                        None if gv[1] is None else gv[1].data_ptr(), gv[2].data_ptr(), C.byref(gr),
+                                                        None if g_feat is None else g_feat.data_ptr(), running, scratch.data_ptr(), scratch.numel(),
+                                                        torch.cuda.current_stream(device).cuda_stream))
+            if out[0] is not None:
+                out[0] = g_feat.view(feats_in.shape).to(feats_in.dtype)
+            return out
+
+    if wants_grad:
+        outs = _SparseEncodeFn.apply(run_fwd, run_bwd, feats_in, *params)
+    else:
+        outs = run_fwd()
+    if running:
+        return list(outs)
+    # running statistics, like nn.BatchNorm1d in train(): momentum blend with the batch mean and the UNBIASED batch variance
+    with torch.no_grad():
+        nrow = rows.to(torch.float32)
+        for c, (conv, bn, kind) in enumerate(self._convs()):
+            if not bn.track_running_stats or bn.running_mean is None:
+                continue
+            co = bn.num_features
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+            unb = nrow[c] / torch.clamp(nrow[c] - 1.0, min=1.0)
+            bn.running_mean.mul_(1.0 - m).add_(stats[c, 0, :co].to(bn.running_mean.dtype), alpha=m)
+            bn.running_var.mul_(1.0 - m).add_((stats[c, 1, :co] * unb).to(bn.running_var.dtype), alpha=m)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+    return list(outs)
+
+
+SparseConvNet._forward_train = _sparse_forward_train
 
 
 # ---- pointer plumbing -------------------------------------------------------------------------------------------
@@ -447,11 +559,36 @@ class ImportanceRenderer(nn.Module):
             need = lib.sherf_observation_scratch_bytes(V)
             if rt.obs_scratch is None or rt.obs_scratch.numel() < need or rt.obs_scratch.device != device:
                 rt.obs_scratch = torch.empty(need, dtype=torch.uint8, device=device)
-            _lib.check(lib.sherf_prepare_observation(C.byref(smpl), C.byref(ob), feat.data_ptr(), coord.data_ptr(), vmask.data_ptr(),
-                                                     bounds.data_ptr(), out_sh, can.data_ptr() if can is not None else None,
-                                                     rt.obs_scratch.data_ptr(), rt.obs_scratch.numel(),
-                                                     torch.cuda.current_stream(device).cuda_stream))
-            del keep
+            def run_fwd():
+                _lib.check(lib.sherf_prepare_observation(C.byref(smpl), C.byref(ob), feat.data_ptr(), coord.data_ptr(), vmask.data_ptr(),
+                                                         bounds.data_ptr(), out_sh, can.data_ptr() if can is not None else None,
+                                                         rt.obs_scratch.data_ptr(), rt.obs_scratch.numel(),
+                                                         torch.cuda.current_stream(device).cuda_stream))
+                return feat
+
+            diff = [obs_input_feature, projection_conv.weight, projection_conv.bias]
+            if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in diff):
+                # training: the vertex features carry a graph back to the 2-D encoder's feature map and the generator's conv1d_projection
+                def run_bwd(grad, needs, held=(smpl, ob, keep)):
+                    with torch.cuda.device(device):
+                        g = grad.detach().to(device=device, dtype=torch.float32).contiguous()
+                        g_ft = torch.empty_like(ft) if needs[0] else None
+                        g_w = torch.empty(32, 96, device=device, dtype=torch.float32) if needs[1] else None
+                        g_b = torch.empty(32, device=device, dtype=torch.float32) if needs[2] else None
+                        rt_ = _runtime(self)
+                        if rt_.obs_scratch is None or rt_.obs_scratch.numel() < need or rt_.obs_scratch.device != device:
+                            rt_.obs_scratch = torch.empty(need, dtype=torch.uint8, device=device)
+                        _lib.check(lib.sherf_prepare_observation_backward(
+                            C.byref(smpl), C.byref(ob), g.data_ptr(), None if g_w is None else g_w.data_ptr(), None if g_b is None else g_b.data_ptr(),
+                            None if g_ft is None else g_ft.data_ptr(), rt_.obs_scratch.data_ptr(), rt_.obs_scratch.numel(),
+                            torch.cuda.current_stream(device).cuda_stream))
+                        return [None if g_ft is None else g_ft.view(obs_input_feature.shape).to(obs_input_feature.dtype),
+                                None if g_w is None else g_w.view(projection_conv.weight.shape).to(projection_conv.weight.dtype),
+                                None if g_b is None else g_b.to(projection_conv.bias.dtype)]
+                feat = _ObservationFn.apply(run_fwd, run_bwd, *diff)
+            else:
+                run_fwd()
+                del keep
         sp_input = {'coord': coord, 'out_sh': [int(out_sh[0]), int(out_sh[1]), int(out_sh[2])], 'batch_size': 1, 'bounds': bounds}
         vol = SparseConvTensor(feat, coord, sp_input['out_sh'], 1)
         if return_canonical:

@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f'{n} declared in the header but not exported'
-    assert lib.sherf_abi_version() == 4
+    assert lib.sherf_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):

@@ -132,3 +132,80 @@ def test_render_from_sparse_tensor(smpl_model):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     assert float(a[2].max()) > 0.2 and float(vols[0].abs().max()) > 0
     print(f'\\n[render from SparseConvTensor] {coord.shape[0]} vertices -> active level-1 sites {int((vols[0][0] != 0).any(0).sum())}')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape,n,dup,train', [((32, 64, 64), 300, 20, True), ((32, 32, 96), 60, 0, True), ((32, 64, 64), 200, 10, False)])
+def test_cuda_encoder_training_step_against_the_reference_module(shape, n, dup, train, smpl_model_t):
+    """train(): batch-statistics BatchNorm, running-statistics update and the backward pass (sherf_sparse_encode_train / _backward) against
+    torch autograd through the REFERENCE's own SparseConvNet (renderer.py:707-797) in train() on the functional spconv stand-ins
+    (oracle/spconv_shim.py; duplicate rows stay rows of the level-0 BatchNorms like in spconv).  Loss = <the features the reference forward
+    returns (grid_sample of the three dense levels, renderer.py:764-785), a fixed random cotangent>.  Gradients: 13 conv weights, 26
+    BatchNorm parameters, the input features.  Tolerance 2e-4 relative L2 (fp32, different summation orders; measured in the log).
+    train = False: the same gradients in eval() (BatchNorm on its running statistics, which then do not move)."""
+    import torch.nn.functional as F
+    from oracle import ref_shim
+    from sherf_b200.renderer import SparseConvNet, SparseConvTensor
+    if not ref_shim.available():
+        pytest.skip('reference files not present')
+    ref_renderer, _ = ref_shim.load(smpl_model_t)
+    import spconv
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    ref = ref_renderer.SparseConvNet(num_layers=4)
+    sd = SE.random_state_dict(ref, 7)
+    ref.load_state_dict(sd)
+    ours = SparseConvNet(4)
+    ours.load_state_dict(sd)
+    coord, feat = _shell(n, shape, 13, dup=dup)
+    idx = torch.cat([torch.zeros(coord.shape[0], 1, dtype=torch.int32), coord], 1)
+    g = torch.Generator().manual_seed(17)
+    grid = (torch.rand(1, 1, 1, 900, 3, generator=g) * 2 - 1) * 0.95
+    cot = torch.randn(1, 900, 192, generator=g)
+
+    # ---- the reference module, train() ----
+    ref.train(train).requires_grad_(True)
+    f_ref = feat.clone().requires_grad_(True)
+    out_ref = ref(spconv.core.SparseConvTensor(f_ref, idx, list(shape), 1), grid)
+    (out_ref * cot).sum().backward()
+    want = {k: p.grad for k, p in ref.named_parameters() if not (k.startswith('down3') or k.startswith('conv4'))}
+    want_stats = {k: v.clone() for k, v in ref.state_dict().items() if 'running' in k or 'num_batches' in k}
+
+    # ---- the CUDA path, train() ----
+    ours = ours.to(dev).train(train).requires_grad_(True)
+    f_our = feat.to(dev).requires_grad_(True)
+    vols = ours(SparseConvTensor(f_our, idx.to(dev), list(shape), 1))
+    assert all(v.requires_grad for v in vols)
+    feats = torch.cat([F.grid_sample(v, grid.to(dev), padding_mode='zeros', align_corners=True) for v in vols], dim=1)
+    out_our = feats.view(1, -1, feats.size(4)).transpose(1, 2)
+    (out_our * cot.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+        return float((a - b).norm() / (b.norm() + 1e-30))
+    e_out = rel(out_our, out_ref)
+    print(f'\n[sparse encoder {"train" if train else "eval"}() {shape} n={n} dup={dup}] output rel L2 {e_out:.2e}')
+    assert e_out <= 2e-5
+    worst = 0.0
+    got = dict(ours.named_parameters())
+    assert len(want) == 39
+    for k, gw in want.items():
+        assert got[k].grad is not None, k
+        r = rel(got[k].grad, gw)
+        worst = max(worst, r)
+        assert r <= 2e-4, f'{k}: gradient relative L2 {r:.3e}'
+    r_f = rel(f_our.grad, f_ref.grad)
+    print(f'   worst parameter-gradient rel L2 {worst:.2e}; input-feature gradient {r_f:.2e}')
+    assert r_f <= 2e-4
+    # running statistics after one step (momentum 0.01, unbiased variance) and the batch counter
+    osd = ours.state_dict()
+    for k, v in want_stats.items():
+        if k.startswith('down3') or k.startswith('conv4'):
+            continue
+        if 'num_batches' in k:
+            assert int(osd[k]) == int(v) == (1 if train else 0), k
+        else:
+            assert float((osd[k].cpu() - v).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+    # the layers the reference never evaluates for num_layers = 4 stay untouched
+    assert all(p.grad is None for k, p in got.items() if k.startswith('down3') or k.startswith('conv4'))
