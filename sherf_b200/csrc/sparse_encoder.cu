@@ -6,6 +6,8 @@
 // encoder is a few GFLOP and latency-bound.  Semantics and the duplicate-voxel convention: oracle/sparse_encoder.py (header).
 #include "common.cuh"
 #include "stages.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace sherf {
 
@@ -587,6 +589,20 @@ int run_sparse_encode_train(const SherfSparseEncoder& enc, const int* coord, con
   return SHERF_OK;
 }
 
+// SHERF_SP_DEBUG=1: per layer, sums of the incoming gradient, of its gated part and the number of open gates (host printout; diagnostics)
+__global__ void k_sp_debug_sums(const float* __restrict__ dA, const float* __restrict__ act, const int* __restrict__ count, int cout, double* __restrict__ out) {
+  double a = 0, b = 0, g = 0, n = 0;
+  const int total = *count * cout;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) { a += dA[i]; b += fabs((double)dA[i]); if (act[i] > 0.f) { g += dA[i]; n += 1; } }
+  __shared__ double red[4][256];
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = b; red[2][threadIdx.x] = g; red[3][threadIdx.x] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) { double s = 0; for (int i = 0; i < 256; ++i) s += red[k][i]; out[k] = s; }
+    out[4] = *count;
+  }
+}
+
 // scratch: the arena run_sparse_encode_train filled (same n / out_sh / encoder), untouched in between
 int run_sparse_encode_backward(const SherfSparseEncoder& enc, const int* coord, int n, const int32_t* out_sh, const float* const* g_vols,
                                const SherfSparseEncoderGrads& gr, float* g_feat, int use_running_stats, void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -613,6 +629,13 @@ int run_sparse_encode_backward(const SherfSparseEncoder& enc, const int* coord, 
       have = true;
     }
     if (!have) { set_error("sparse encoder backward: no gradient reaches layer %d", c); return SHERF_E_INVALID; }
+    if (getenv("SHERF_SP_DEBUG")) {
+      double h[5];
+      k_sp_debug_sums<<<1, 256, 0, st>>>(dA, t.act[c], s.count + lo, L.c_out, t.part);
+      cudaMemcpyAsync(h, t.part, sizeof(h), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[sp bwd] layer %2d rows %4.0f sum dA % .6e  sum|dA| %.6e  gated sum % .6e  open gates %.0f\n", c, h[4], h[0], h[1], h[2], h[3]);
+    }
     const float* stats = t.stats + (size_t)c * 288;
     const int* nr = use_running_stats ? nullptr : (lo == 0 ? t.nrows : s.count + lo);
     k_sp_bn_bwd_stats<<<dim3(ceil_div(L.c_out, 32), kSpStatSplits), 256, 0, st>>>(dA, t.act[c], t.raw[c], s.count + lo, L.c_out, stats, t.part);
