@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32', 'tf32x3', 'bf16x3'],
                     help="MLP arithmetic: tf32x3 = error-compensated 3xTF32 on tcgen05 (fp32-grade parity, default); fp32 = CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-training-step', action='store_true', help='skip the (untimed) forward + backward measurement of the line\'s `training_step` key')
     ap.add_argument('--gpu-eager-baseline', action='store_true',
                     help='also time oracle/port.py (the reference path written as eager PyTorch) on this GPU for one full view (BASELINE.md 3.4)')
     ap.add_argument('--importance', type=int, default=0,
@@ -580,6 +581,38 @@ def main():
                                          'pixels': int(idx.numel()), 'mask_at_box_pixels': int(hit.sum()),
                                          'rgb_linf': float((got - ref_img).abs().max()), 'against': ref['kind'],
                                          'note': 'our render vs the cpu_baseline arm\'s image on its ray sample (test_loop.py:36-37,222-223 metric)'}
+        if world == 1 and not args.importance and not args.no_training_step:
+            # the training use of the same path, outside the timed region: forward + the reference's reconstruction loss
+            # (loss.py:150-151,167) + loss.backward() with every hot-path parameter and the five feature tensors requiring grad
+            import copy
+            ren_t, dec_t = copy.deepcopy(ren).train().requires_grad_(True), copy.deepcopy(dec).train().requires_grad_(True)
+            leaves = [scene['planes'].clone().requires_grad_(True), scene['obs_input_feature'].clone().requires_grad_(True)] + \
+                     [v.clone().requires_grad_(True) for v in scene['volumes']]
+            tgt = torch.rand(1, N, 3, device=dev)
+
+            def train_step():
+                rgb, depth, acc = ren_t(leaves[0], scene['obs_input_img'], leaves[1], leaves[2:], None, scene['obs_sp_input'], dec_t,
+                                        shard_dev[0]['ray_origins'], shard_dev[0]['ray_directions'], shard_dev[0]['near'], shard_dev[0]['far'],
+                                        scene['input_data'], scene['rendering_options'])
+                loss = 100 * ((rgb / 2 + 0.5 - tgt) ** 2).mean() + 10 * ((acc - 1) ** 2).mean()
+                loss.backward()
+                return loss
+            for _ in range(2):
+                train_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                loss_t = train_step()
+            e1.record()
+            e1.synchronize()
+            ms_t = e0.elapsed_time(e1) / 3
+            line['training_step'] = {'ms_per_view': ms_t, 'ray_samples_per_sec': N * S / (ms_t * 1e-3), 'backward_launches': getattr(ren_t, 'last_backward_launches', None),
+                                     'loss': float(loss_t), 'gradients': '39 hot-path parameters + tri-planes + 2-D feature map + 3 volume levels',
+                                     'arithmetic': 'recompute-in-backward; GEMMs 3xTF32 on tcgen05 (csrc/backward_umma.cu, mlp_umma.cu)',
+                                     'note': 'forward + loss (loss.py:150-151,167) + loss.backward() through ImportanceRenderer.forward, same view and weights; '
+                                             'CUDA-event timed over 3 steps after 2 warm-up steps, outside the timed region of `value`'}
+            del ren_t, dec_t, leaves
         if world == 1 and args.gpu_eager_baseline:
             # "the reference on the same box in GPU-eager mode": the reference's own ImportanceRenderer.forward (oracle/_ref
             # under the shims; knn_points = chunked brute force where the real reference calls pytorch3d's CUDA KNN), eager PyTorch on this GPU

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_reduce_parts(const float* __restrict__ 
   }
 }
 
-constexpr int kRowsPerSplit = kGradWRowsPerSplit;
+constexpr int kRowsPerSplit = 1024;          // rows per split of the fp32 FMA anchor path (SHERF_BWD_SIMT=1)
 
 // SHERF_BWD_SIMT=1: every product of the backward on the CUDA cores in fp32 FMA (the first version; kept as the anchor of the tensor-core path)
 static bool bwd_simt() {
@@ -283,8 +283,9 @@ static int grad_w(const float* dY, int lda, int N, const float* X, int ldb, int 
                   int agroup = 0, int agstride = 0) {
   if (!dW && !db) return SHERF_OK;
   if (!bwd_simt()) {
-    RC(launch_umma_grad_w(dY, lda, N, X, ldb, K, M, part, st, agroup, agstride));
-    k_reduce_parts<<<ceil_div(N * (K + 1), 32), 256, 0, st>>>(part, ceil_div(M, kRowsPerSplit), N, K, dW, db);
+    int splits = 0;
+    RC(launch_umma_grad_w(dY, lda, N, X, ldb, K, M, part, &splits, st, agroup, agstride));
+    k_reduce_parts<<<ceil_div(N * (K + 1), 32), 256, 0, st>>>(part, splits, N, K, dW, db);
     SHERF_LAUNCH_CHECK();
     return SHERF_OK;
   }
@@ -349,33 +350,49 @@ __global__ void __launch_bounds__(256) k_tok3_grad(const float* __restrict__ dx,
   dtok3[idx] = t == 0 ? dx[(size_t)p * 72 + 39 + c] : (t == 1 ? dfv[(size_t)p * 188 + 155 + c] : 0.f);
 }
 
-// LayerNorm(32) backward, warp per row: dx (+)= rstd (g - mean(g) - xhat mean(g xhat)), g = dy w; per-block partial sums of dw = dy xhat, db = dy
+// LayerNorm(32) backward, eight lanes per row (16 bytes each, four rows per warp pass):
+//   dx = res + rstd (g - mean(g) - xhat mean(g xhat)), g = dy w   (res = the residual branch's gradient: x + f(LN(x)), renderer.py:980-993)
+// and per-block partial sums of dw = dy xhat, db = dy (added in block order by k_ln_reduce).
 __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy,
-                                                float* __restrict__ dx, int accum, int rows, float* __restrict__ partial) {
+                                                const float* __restrict__ res, float* __restrict__ dx, int rows, float* __restrict__ partial) {
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const float wl = w[lane];
-  float sw = 0.f, sb = 0.f;
-  for (int r = blockIdx.x * 8 + wid; r < rows; r += gridDim.x * 8) {
-    const float v = x[(size_t)r * 32 + lane];
-    float s = v;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.f / 32.f);
-    const float d = v - mean;
-    float q = d * d;
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * (1.f / 32.f) + 1e-5f);
-    const float xh = d * rstd;
-    const float gy = dy[(size_t)r * 32 + lane];
-    sw += gy * xh; sb += gy;
-    const float gl = gy * wl;
-    float m1 = gl, m2 = gl * xh;
-    for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
-    const float val = rstd * (gl - m1 * (1.f / 32.f) - xh * (m2 * (1.f / 32.f)));
-    float* o = dx + (size_t)r * 32 + lane;
-    *o = accum ? *o + val : val;
+  const int sub = lane >> 3, c4 = lane & 7;
+  const float4 w4 = *reinterpret_cast<const float4*>(w + c4 * 4);
+  float sw[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  auto sum8 = [](float v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4); return v; };
+  for (int rb = (blockIdx.x * 8 + wid) * 4; rb < rows; rb += gridDim.x * 32) {      // warp-uniform trip count: the shuffles stay converged
+    const int r = rb + sub;
+    const bool ok = r < rows;
+    const size_t o = (size_t)(ok ? r : 0) * 32 + c4 * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + o);
+    float4 gy = *reinterpret_cast<const float4*>(dy + o);
+    if (!ok) gy = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float mean = sum8((v.x + v.y) + (v.z + v.w)) * (1.f / 32.f);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float rstd = rsqrtf(sum8((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) * (1.f / 32.f) + 1e-5f);
+    const float h0 = d0 * rstd, h1 = d1 * rstd, h2 = d2 * rstd, h3 = d3 * rstd;
+    sw[0] += gy.x * h0; sw[1] += gy.y * h1; sw[2] += gy.z * h2; sw[3] += gy.w * h3;
+    sb[0] += gy.x; sb[1] += gy.y; sb[2] += gy.z; sb[3] += gy.w;
+    const float g0 = gy.x * w4.x, g1 = gy.y * w4.y, g2 = gy.z * w4.z, g3 = gy.w * w4.w;
+    const float m1 = sum8((g0 + g1) + (g2 + g3)) * (1.f / 32.f);
+    const float m2 = sum8((g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3)) * (1.f / 32.f);
+    if (ok) {
+      float4 out = res ? *reinterpret_cast<const float4*>(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      out.x += rstd * (g0 - m1 - h0 * m2); out.y += rstd * (g1 - m1 - h1 * m2);
+      out.z += rstd * (g2 - m1 - h2 * m2); out.w += rstd * (g3 - m1 - h3 * m2);
+      *reinterpret_cast<float4*>(dx + o) = out;
+    }
   }
-  red[wid][lane] = sw; red[wid][32 + lane] = sb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                              // the four rows of a warp pass share a channel quad: add them (xor 8, 16)
+    sw[i] += __shfl_xor_sync(0xffffffffu, sw[i], 8); sw[i] += __shfl_xor_sync(0xffffffffu, sw[i], 16);
+    sb[i] += __shfl_xor_sync(0xffffffffu, sb[i], 8); sb[i] += __shfl_xor_sync(0xffffffffu, sb[i], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { red[wid][c4 * 4 + i] = sw[i]; red[wid][32 + c4 * 4 + i] = sb[i]; }
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     float s = 0.f;
@@ -503,7 +520,7 @@ void carve_bwd_chunk(float* base, int cap, BwdChunk& b) {
   b.dvh = p; p += c * 64; b.dpre = p; p += c * 4; b.dfv = p; p += c * 188; b.dha = p; p += c * 128; b.dhb = p; p += c * 128;
   b.dx = p; p += c * 72; b.dtok3 = p; p += c * 96; b.dff = p; p += c * 96; b.dln = p; p += c * 96; b.dtok2 = p; p += c * 96;
   b.dtok = p; p += c * 96; b.datt = p; p += c * 144; b.dqkv = p; p += c * 432; b.dcomb = p; p += c * 288; b.df3raw = p; p += c * 192;
-  b.part = p; p += (size_t)(ceil_div(cap * 3, kRowsPerSplit) + 1) * 128 * 200;
+  b.part = p; p += (size_t)(max(ceil_div(cap * 3, kRowsPerSplit) + 1, kGradWMaxSplits + 1)) * 144 * 200;
   b.ln_part = p; p += (size_t)kLnBlocks * 64;
 }
 
@@ -592,8 +609,7 @@ int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const Can
   SHERF_LAUNCH_CHECK();
   RC(grad_w(b.dff, 32, 32, b.ln2, 32, 32, R, gw.ff1_w, gw.ff1_b, b.part, st));
   RC(dxp(cbw.ff1, b.dff, 32, w.ff1_w, 32, b.dln, 32, R, 32, 32));
-  SHERF_CUDA_OK(cudaMemcpyAsync(b.dtok2, b.dtok3, sizeof(float) * (size_t)R * 32, cudaMemcpyDeviceToDevice, st));     // residual branch
-  k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok2, w.ln2_w, b.dln, b.dtok2, 1, R, b.ln_part);
+  k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok2, w.ln2_w, b.dln, b.dtok3 /* residual branch */, b.dtok2, R, b.ln_part);
   SHERF_LAUNCH_CHECK();
   k_ln_reduce<<<1, 64, 0, st>>>(b.ln_part, kLnBlocks, gw.ln2_w, gw.ln2_b);
   SHERF_LAUNCH_CHECK();
@@ -604,8 +620,7 @@ int run_backward_chunk(const SherfWeights& w, const PackedWeights& pw, const Can
   SHERF_LAUNCH_CHECK();
   RC(grad_w(b.dqkv, 144, 144, b.ln1, 32, 32, R, gw.qkv_w, nullptr, b.part, st));
   RC(dxp(cbw.qkv, b.dqkv, 144, w.qkv_w, 32, b.dln, 32, R, 32, 144));
-  SHERF_CUDA_OK(cudaMemcpyAsync(b.dtok, b.dtok2, sizeof(float) * (size_t)R * 32, cudaMemcpyDeviceToDevice, st));
-  k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok, w.ln1_w, b.dln, b.dtok, 1, R, b.ln_part);
+  k_ln_bwd<<<kLnBlocks, 256, 0, st>>>(b.tok, w.ln1_w, b.dln, b.dtok2 /* residual branch */, b.dtok, R, b.ln_part);
   SHERF_LAUNCH_CHECK();
   k_ln_reduce<<<1, 64, 0, st>>>(b.ln_part, kLnBlocks, gw.ln1_w, gw.ln1_b);
   SHERF_LAUNCH_CHECK();

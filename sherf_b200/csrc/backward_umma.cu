@@ -7,8 +7,9 @@
 // (feature-major) of the K-major no-swizzle canonical layout of umma.cuh.  The 8 lanes of a quarter-warp write the 8 point-quads of one
 // feature block: with the K-direction stride padded by 16 bytes their STS.128 are bank-conflict free, and a warp's loads cover 8 rows x 64
 // contiguous bytes.  Arithmetic: 3xTF32 split products (a_lo w_hi + a_hi w_lo + a_hi w_hi, fp32 accumulate) = fp32-grade sums.
-// The bias gradient rides along as column K of B (a column of ones).  One CTA reduces kGradWRowsPerSplit rows and writes its partial
-// [n][K + 1] tile; k_reduce_parts (backward.cu) adds the partials in split order, so the result does not depend on scheduling.
+// The bias gradient (column sums of dY) is accumulated in fp32 registers by the threads that stage dY and written as column K of the
+// partial tile.  The launcher deals the 32-point chunks to one wave of CTAs in equal contiguous ranges (no tail wave); every CTA writes its
+// partial [n][K + 1] tile and k_reduce_parts (backward.cu) adds the partials in split order: the result does not depend on scheduling.
 #include "common.cuh"
 #include "stages.cuh"
 #include "umma.cuh"
@@ -17,10 +18,10 @@ namespace sherf {
 
 struct GradWArgs {
   const float* dY; int lda, agroup, agstride; int N;     // [M][N], logical column c at (c / agroup) * agstride + c % agroup
-  const float* X; int ldb; int K;                         // [M][K]; logical column K is the constant 1
+  const float* X; int ldb; int K;                         // [M][K]
   float* part;                                            // [splits][N][K + 1]
   int M, rows_per_split;
-  int Np;                                                 // round_up(K + 1, 16)
+  int Np;                                                 // round_up(K, 16)
   uint32_t tmem_cols;
 };
 
@@ -33,7 +34,9 @@ __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo
 constexpr int kGwChunk = 32;                     // points per shared-memory chunk = 8 core-matrix columns = 4 MMA k-steps
 constexpr uint32_t kGwALbo = 128 * 16 + 16;      // K-direction stride of the A operand (128 feature rows), padded
 
-__global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
+// NU = feature blocks of X per thread: 1 for K <= 128 (three CTAs per SM), 2 up to K = 256
+template <int NU>
+__global__ void __launch_bounds__(256, NU == 1 ? 3 : 2) k_umma_grad_w(const GradWArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
@@ -63,14 +66,15 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
   // before store_chunk (zero fill of rows past the split and the ones column are applied there): twelve 16-byte loads per thread stay in
   // flight together (ncu on the first version: 48 % of the stall samples sat on a load whose value was patched right behind it).
   // Per unit, decided once: mode 0 = all zeros / ones column only, 1 = one 16-byte load per row, 2 = guarded scalar loads (row tails).
-  float4 va[4], vb[2][4];
+  float4 va[4], vb[NU][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};            // column sums of this thread's dY block over all its chunks (bias gradient)
   const int ca = n0 + fb0 * 4;
   const float* pa = g.dY + (g.agroup ? (ca / g.agroup) * g.agstride + (ca % g.agroup) : ca);
   const int mode_a = ca >= g.N ? 0 : ((ca + 3 < g.N && (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(pa) & 15) == 0) ? 1 : 2);
-  const float* pb[2];
-  int mode_b[2], cb[2];
+  const float* pb[NU];
+  int mode_b[NU], cb[NU];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < NU; ++u) {
     const int fb = fb0 + 32 * u;
     cb[u] = fb * 4;
     pb[u] = g.X + cb[u];
@@ -93,8 +97,8 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
   auto load_chunk = [&](int mb) {
     const int mrow = mb + p4 * 4;
     load_rows(va, pa, g.lda, mode_a, ca, g.N, mrow);
-    load_rows(vb[0], pb[0], g.ldb, mode_b[0], cb[0], g.K, mrow);
-    load_rows(vb[1], pb[1], g.ldb, mode_b[1], cb[1], g.K, mrow);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) load_rows(vb[u], pb[u], g.ldb, mode_b[u], cb[u], g.K, mrow);
   };
   auto store_chunk = [&](int mb) {
     const int mrow = mb + p4 * 4;
@@ -107,22 +111,21 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
       store_split(A_hi, A_lo, off + 16, va[0].y * rowok[0], va[1].y * rowok[1], va[2].y * rowok[2], va[3].y * rowok[3]);
       store_split(A_hi, A_lo, off + 32, va[0].z * rowok[0], va[1].z * rowok[1], va[2].z * rowok[2], va[3].z * rowok[3]);
       store_split(A_hi, A_lo, off + 48, va[0].w * rowok[0], va[1].w * rowok[1], va[2].w * rowok[2], va[3].w * rowok[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bsum[0] = fmaf(va[j].x, rowok[j], bsum[0]); bsum[1] = fmaf(va[j].y, rowok[j], bsum[1]);
+        bsum[2] = fmaf(va[j].z, rowok[j], bsum[2]); bsum[3] = fmaf(va[j].w, rowok[j], bsum[3]);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NU; ++u) {
       const int fb = fb0 + 32 * u;
       if (fb < nbB) {
-        const int e = g.K - cb[u];                                          // position of the ones column inside this block, if 0..3
-        float x[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          x[j][0] = e == 0 ? 1.f : vb[u][j].x; x[j][1] = e == 1 ? 1.f : vb[u][j].y;
-          x[j][2] = e == 2 ? 1.f : vb[u][j].z; x[j][3] = e == 3 ? 1.f : vb[u][j].w;
-        }
         const uint32_t off = (uint32_t)p4 * b_lbo + (uint32_t)(fb * 4) * 16u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          store_split(B_hi, B_lo, off + 16 * i, x[0][i] * rowok[0], x[1][i] * rowok[1], x[2][i] * rowok[2], x[3][i] * rowok[3]);
+        store_split(B_hi, B_lo, off, vb[u][0].x * rowok[0], vb[u][1].x * rowok[1], vb[u][2].x * rowok[2], vb[u][3].x * rowok[3]);
+        store_split(B_hi, B_lo, off + 16, vb[u][0].y * rowok[0], vb[u][1].y * rowok[1], vb[u][2].y * rowok[2], vb[u][3].y * rowok[3]);
+        store_split(B_hi, B_lo, off + 32, vb[u][0].z * rowok[0], vb[u][1].z * rowok[1], vb[u][2].z * rowok[2], vb[u][3].z * rowok[3]);
+        store_split(B_hi, B_lo, off + 48, vb[u][0].w * rowok[0], vb[u][1].w * rowok[1], vb[u][2].w * rowok[2], vb[u][3].w * rowok[3]);
       }
     }
   };
@@ -168,8 +171,16 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
       if (n < g.N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (c0 + i < K1) out[c0 + i] = __uint_as_float(v[i]);
+          if (c0 + i < g.K) out[c0 + i] = __uint_as_float(v[i]);
       }
+    }
+    // bias column: add the eight point-quad lanes of a feature block (xor 1, 2, 4 stay inside the quarter-warp), lane p4 == 0 writes
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float b = bsum[i];
+      b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2); b += __shfl_xor_sync(0xffffffffu, b, 4);
+      const int nn = n0 + fb0 * 4 + i;
+      if (p4 == 0 && nn < g.N) g.part[((size_t)blockIdx.x * g.N + nn) * K1 + g.K] = b;
     }
   } else if (mlo >= mhi) {
     // empty split (cannot happen with the launcher's grid, kept for safety): its partial tile must still be defined
@@ -180,28 +191,38 @@ __global__ void __launch_bounds__(256, 2) k_umma_grad_w(const GradWArgs g) {
   if (warp == 0) umma::tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
-int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, cudaStream_t st, int agroup,
-                       int agstride) {
+int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, int* splits_out, cudaStream_t st,
+                       int agroup, int agstride) {
+  if (splits_out) *splits_out = 0;
   if (M <= 0) return SHERF_OK;
   GradWArgs g;
   g.dY = dY; g.lda = lda; g.agroup = agroup; g.agstride = agstride; g.N = N; g.X = X; g.ldb = ldb; g.K = K; g.part = part; g.M = M;
-  g.rows_per_split = kGradWRowsPerSplit;
-  g.Np = (K + 1 + 15) / 16 * 16;
-  if (g.Np > 256) { set_error("grad_w: K + 1 = %d exceeds one MMA tile", K + 1); return SHERF_E_INVALID; }
+  g.Np = (K + 15) / 16 * 16;
+  if (g.Np > 256) { set_error("grad_w: K = %d exceeds one MMA tile", K); return SHERF_E_INVALID; }
   uint32_t cols = 32;
   while ((int)cols < g.Np) cols <<= 1;
   g.tmem_cols = cols;
-  size_t smem = 2 * (size_t)8 * kGwALbo + 2 * (size_t)8 * ((size_t)g.Np * 16 + 16);
-  // TMEM holds 512 columns per SM: never let shared memory admit more CTAs than tcgen05.alloc can serve without waiting
-  const size_t floor_smem = (size_t)220 * 1024 / (512 / cols) - 1024;
-  if (cols >= 128 && smem < floor_smem) smem = floor_smem;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_grad_w, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+  const size_t smem = 2 * (size_t)8 * kGwALbo + 2 * (size_t)8 * ((size_t)g.Np * 16 + 16);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    SHERF_CUDA_OK(cudaGetDevice(&dev));
+    SHERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_grad_w<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_grad_w<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  const int splits = ceil_div(M, kGradWRowsPerSplit);
-  k_umma_grad_w<<<dim3(splits, ceil_div(N, 128)), 256, smem, st>>>(g);
+  // one wave: the 32-point chunks are dealt to (SMs x resident CTAs) splits in equal contiguous ranges.  Residency: registers admit three
+  // CTAs of the one-block variant (TMEM: 3 x <= 128 columns) and two of the two-block variant (2 x 256 columns): tcgen05.alloc never waits.
+  const int nu = g.Np > 128 ? 2 : 1;
+  const int ntiles = ceil_div(N, 128);
+  const int slots = max(1, sms * (nu == 1 ? 3 : 2) / ntiles);
+  const int nchunks = ceil_div(M, kGwChunk);
+  const int min_rows = ceil_div(ceil_div(M, kGradWMaxSplits), kGwChunk) * kGwChunk;       // never more partial tiles than the buffer holds
+  g.rows_per_split = max(ceil_div(nchunks, slots) * kGwChunk, min_rows);
+  const int splits = ceil_div(M, g.rows_per_split);
+  if (splits_out) *splits_out = splits;
+  if (nu == 1) k_umma_grad_w<1><<<dim3(splits, ntiles), 256, smem, st>>>(g);
+  else k_umma_grad_w<2><<<dim3(splits, ntiles), 256, smem, st>>>(g);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
 }

@@ -95,10 +95,10 @@ size_t canonical_bwd_weight_floats();
 int run_pack_canonical_bwd(const SherfWeights& w, float* base, CanonBwdWeights& cb, cudaStream_t st);
 int launch_umma_dx(const CanonLayer& L, const float* dY, int lda, float* dX, int ldx, int M, cudaStream_t st, const float* Mask = nullptr,
                    int ldm = 0, int accum = 0, int agroup = 0, int agstride = 0);
-constexpr int kGradWRowsPerSplit = 512;
-// part[s][n][K + 1] = sum over the rows of split s of dY[m][n] . [X | 1][m][k]
-int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, cudaStream_t st, int agroup = 0,
-                       int agstride = 0);
+constexpr int kGradWMaxSplits = 1024;      // capacity of the partial-sum buffer; the launcher uses one wave of CTAs (<= 444 on a B200)
+// part[s][n][K + 1] = sum over the rows of split s of dY[m][n] . [X | 1][m][k];  *splits_out = number of splits written
+int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, int* splits_out, cudaStream_t st,
+                       int agroup = 0, int agstride = 0);
 
 // Fused tensor-core decoder trunk (decoder_fused.cu)
 struct FusedChunk { uint32_t w_off; uint32_t w_bytes; uint16_t src; uint16_t kg0; uint16_t nkg; uint16_t layer; uint16_t first; uint16_t last; };
