@@ -439,6 +439,9 @@ static int build_grid(int g, const SherfFrame& fr, const FrameTables& ft, int V,
 //   run_prologue_tables : what only the warp + gather stage needs -- SMPL chain of the three pose sets, pose / shape offsets,
 //                         per-vertex warp tables, the canonical-vertex grid
 int run_prologue_frame(const SherfFrame& fr, const FrameTables& ft, cudaStream_t st) {
+  // consumers copy the whole struct to shared memory before the later stages have filled their part (grid descriptors, depth range):
+  // define every byte first
+  SHERF_CUDA_OK(cudaMemsetAsync(ft.fc, 0, sizeof(FrameConst), st));
   k_frame_const<<<1, 32, 0, st>>>(fr, make_float3((float)fr.out_sh[0], (float)fr.out_sh[1], (float)fr.out_sh[2]), ft.fc);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;

@@ -135,7 +135,10 @@ def test_render_from_sparse_tensor(smpl_model):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('shape,n,dup,train', [((32, 64, 64), 300, 20, True), ((32, 32, 96), 60, 0, True), ((32, 64, 64), 260, 10, False)])
+# the third case is DENSE (every voxel has active neighbours on all sides, strided convolutions merge several inputs per output): the shells of
+# the other cases mostly exercise the centre tap
+@pytest.mark.parametrize('shape,n,dup,train', [((32, 64, 64), 300, 20, True), ((32, 32, 96), 60, 0, True), ((16, 32, 32), 4000, 60, True),
+                                               ((32, 64, 64), 260, 10, False)])
 def test_cuda_encoder_training_step_against_the_reference_module(shape, n, dup, train, smpl_model_t):
     """train(): batch-statistics BatchNorm, running-statistics update and the backward pass (sherf_sparse_encode_train / _backward) against
     torch autograd through the REFERENCE's own SparseConvNet (renderer.py:707-797) in train() on the functional spconv stand-ins
