@@ -27,6 +27,7 @@ from oracle import ref_shim, sparse_encoder as SE
 
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 SUBSAMPLE_ABOVE, SUBSAMPLE_STRIDE = 100000, 5
+VOL_ROW_STRIDE = 4
 CASES = {'training_step_32x32x16': dict(spec=S.SceneSpec(H=32, W=32, samples=16, seed=17), weight_seed=5, enc_seed=6, proj_seed=7, target_seed=3)}
 
 
@@ -67,6 +68,14 @@ def state_checksum(state) -> str:
     return h.hexdigest()
 
 
+def _synthesis_and_backward(ref_tp, fake, scene, tgt_img, tgt_mask):
+    out = dict(ref_tp.TriPlaneGenerator.synthesis(fake, None, scene['input_data'], None, use_sr_module=False, test_flag=False))
+    loss = the_loss(out, tgt_img, tgt_mask)
+    loss.backward()
+    out['loss'] = loss
+    return out
+
+
 def run_case(name, cfg, model, model_t):
     spec = cfg['spec']
     scene = S.make_scene(spec, model)
@@ -94,10 +103,26 @@ def run_case(name, cfg, model, model_t):
         finally:
             torch.set_num_threads(nthreads)
     ren.projection = projection_single_thread
-    out = ref_tp.TriPlaneGenerator.synthesis(fake, None, scene['input_data'], None, use_sr_module=False, test_flag=False)
+    # the gradients of the three `.dense()` volumes (renderer.py:762,771,780) at every VOL_ROW_STRIDE-th active voxel: what the render hands to
+    # the sparse encoder's backward
+    from oracle import spconv_shim
+    taps, orig_dense = [], spconv_shim.SparseConvTensor.dense
+
+    def tapped_dense(self, channels_first=True):
+        v = orig_dense(self, channels_first)
+        if v.requires_grad:
+            keep = spconv_shim._first_rows(self.indices)[::VOL_ROW_STRIDE]
+            idx = self.indices[keep][:, 1:]
+            taps.append(idx)
+            v.register_hook(lambda g_, idx=idx, slot=len(taps) - 1: taps.__setitem__(slot, (idx, g_[0][:, idx[:, 0], idx[:, 1], idx[:, 2]].t().clone())))
+        return v
+    spconv_shim.SparseConvTensor.dense = tapped_dense
+    try:
+        out = _synthesis_and_backward(ref_tp, fake, scene, tgt_img, tgt_mask)
+    finally:
+        spconv_shim.SparseConvTensor.dense = orig_dense
+    loss = out.pop('loss')
     ren.projection = o_proj
-    loss = the_loss(out, tgt_img, tgt_mask)
-    loss.backward()
     res = {
         'spec': np.array([spec.H, spec.W, spec.samples, spec.seed, int(spec.random_global_R), int(spec.white_back)], np.int64),
         'weight_seed': np.int64(cfg['weight_seed']), 'enc_seed': np.int64(cfg['enc_seed']), 'proj_seed': np.int64(cfg['proj_seed']),
@@ -119,6 +144,9 @@ def run_case(name, cfg, model, model_t):
             else:
                 res['nograd/' + prefix + k] = np.zeros(0, np.float32)
     res['g/planes'], res['g/obs_input_feature'] = planes.grad.numpy(), feat.grad.numpy()
+    assert len(taps) == 3 and all(isinstance(t, tuple) for t in taps), 'expected the gradients of three dense levels'
+    for l, (idx, gv) in enumerate(taps):
+        res[f'gvol{l}/zyx'], res[f'gvol{l}/g'] = idx.numpy().astype(np.int32), gv.numpy()
     for k, v in ren.state_dict().items():
         if 'running_' in k or 'num_batches_tracked' in k:
             res['stat/renderer.' + k] = v.numpy()

@@ -93,7 +93,7 @@ class SparseConvolution(nn.Module):
 
     def forward(self, x: SparseConvTensor) -> SparseConvTensor:
         w = self.weight.permute(0, 4, 1, 2, 3).contiguous()                      # KRSC -> [out, in, kz, ky, kx]
-        vol, act = x.dense(), x.activity()
+        vol, act = x._scatter(x.features), x.activity()           # (not .dense(): that name stays the reference's own call)
         if self.subm:
             # output sites = input sites (duplicates included: each row reads the value at its own coordinate)
             out = F.conv3d(vol, w, padding=self.kernel_size // 2)

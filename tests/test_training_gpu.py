@@ -125,6 +125,15 @@ def test_one_training_step_against_the_reference_generator(smpl_model):
         for k, v in state0.items():
             sd[k].copy_(v)
     G = G.to(dev).train().requires_grad_(True)                            # training_loop.py:193: the generator lives in train()
+    # tap what the render hands to the sparse encoder's backward: the gradients of the three dense levels
+    vol_grads, enc_forward = {}, G.renderer.encoder_3d.forward
+
+    def tapped_forward(x, *a, **k):
+        vols = enc_forward(x, *a, **k)
+        for l, v in enumerate(vols):
+            v.register_hook(lambda g_, l=l: vol_grads.__setitem__(l, g_.detach().clone()))
+        return vols
+    G.renderer.encoder_3d.forward = tapped_forward
     out = G.synthesis(None, scene['input_data'], None, use_sr_module=False, test_flag=False)
     assert out['image'].requires_grad and out['weights_image'].requires_grad
     loss = the_loss(out, tgt_img.to(dev), tgt_mask.to(dev))
@@ -134,6 +143,13 @@ def test_one_training_step_against_the_reference_generator(smpl_model):
     e_img = float((out['image'].detach().cpu() - torch.from_numpy(g['image'])).abs().max())
     print(f'\n[training step] loss reference {loss_ref:.6f} cuda {float(loss):.6f}; image max abs difference {e_img:.2e}')
     assert abs(float(loss) - loss_ref) <= 2e-4 * max(1.0, abs(loss_ref))
+    del G.renderer.encoder_3d.forward
+    for l in range(3):                                                   # the fixture holds them at every 4th active voxel of each level
+        zyx = torch.from_numpy(g[f'gvol{l}/zyx']).long()
+        mine = vol_grads[l][0][:, zyx[:, 0], zyx[:, 1], zyx[:, 2]].t()
+        r = rel(mine, torch.from_numpy(g[f'gvol{l}/g']))
+        print(f'   gradient of dense level {l + 1} at {zyx.shape[0]} active voxels: rel L2 {r:.2e}')
+        assert r <= 2e-3, f'volume gradient level {l + 1}: {r:.3e}'
     got = {k: p.grad for k, p in G.named_parameters()}
     got['planes'], got['obs_input_feature'] = G.backbone.planes.grad, G.encoder_2d_feature.feat.grad
     worst, n_cmp, over = 0.0, 0, []
