@@ -28,7 +28,16 @@ __global__ void k_pack_canonical(const CanonJobs jobs) {
     const int e = i & 3, n = (i >> 2) % jb.Np, kg = (i >> 2) / jb.Np;     // kg counts core-matrix columns over all chunks
     const int k = kg * 4 + e;
     const int ldw = jb.ldw ? jb.ldw : jb.K;
-    const float v = (n < jb.N && k < jb.K) ? (jb.trans ? jb.w[(size_t)k * ldw + n] : jb.w[(size_t)n * ldw + k]) : 0.f;
+    float v = 0.f;
+    if (n < jb.N && k < jb.K) {
+      if (jb.trans >= 2) {
+        // sparse-convolution input gradient: n = input channel, k = (kernel offset o, output channel co); the source is spconv's KRSC
+        // weight [c_out][27][c_in]; trans == 2 reads the mirrored offset 26 - o (SubMConv3d: the output that saw input p through offset o
+        // sits at p - (o - 1), i.e. at neighbour slot 26 - o of p)
+        const int cout = jb.K / 27, o = k / cout, co = k - o * cout;
+        v = jb.w[((size_t)co * 27 + (jb.trans == 2 ? 26 - o : o)) * jb.N + n];
+      } else v = jb.trans ? jb.w[(size_t)k * ldw + n] : jb.w[(size_t)n * ldw + k];
+    }
     const float h = umma::to_tf32(v);
     jb.hi[i] = h;
     jb.lo[i] = umma::to_tf32(v - h);
@@ -49,6 +58,13 @@ struct UmmaArgs {
   // the result is forced to 0 where Mask <= 0 (the ReLU of the layer whose input gradient this is), applied after the residual add
   int agroup, agstride;
   const float* Mask; int ldm;
+  // sparse-convolution use (sparse_encoder.cu): the layer is Y = A_virtual . W_flat^T with K = 27 * kin and A_virtual[r][o * kin + k] =
+  // A[rowtab[r * 27 + o]][k] (zero where the table holds -1): the A rows of chunk c are gathered through the neighbour table.  Mdev: the row
+  // count lives on the device (the grid is sized by its upper bound M).  csplit > 0: split-K -- blockIdx.y handles the chunks
+  // [blockIdx.y * csplit, ...) and writes its partial tile to Y + blockIdx.y * ysplit (summed in split order by the caller: deterministic)
+  const int* rowtab; int kin;
+  const int* Mdev;
+  int csplit; size_t ysplit;
 };
 
 // Padded K-direction stride of the A operand: 2048 B of data + 16 B so that the 8 lanes of a quarter-warp that write 8
@@ -64,6 +80,8 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128;
+  const int Meff = g.Mdev ? min(g.M, *g.Mdev) : g.M;
+  if (m0 >= Meff) return;                            // (whole CTA, before any barrier or TMEM allocation)
   const uint32_t a_bytes = NKG * kALbo, w_bytes = (uint32_t)NKG * g.Np * 16u;
   float* A_hi = reinterpret_cast<float*>(smem);
   float* W_hi = reinterpret_cast<float*>(smem + a_bytes);
@@ -80,7 +98,10 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   const uint32_t tmem_base = tmem_base_s;
 
   const uint32_t idesc = umma::make_idesc_tf32(128, g.Np);
-  const int nchunks = (g.K + KC - 1) / KC;
+  const int nchunks_all = (g.K + KC - 1) / KC;
+  const int c_begin = g.csplit > 0 ? (int)blockIdx.y * g.csplit : 0;
+  const int nchunks = g.csplit > 0 ? min(nchunks_all, c_begin + g.csplit) : nchunks_all;      // this CTA's chunks: [c_begin, nchunks)
+  float* const Yout = g.Y + (size_t)blockIdx.y * g.ysplit;
   const int kgl = tid & 7, rsub = tid >> 3;          // loader mapping: 8 lanes = 8 consecutive float4 of one row (128 B)
   uint32_t parity = 0;
   // A chunk c: coalesced global reads -> registers (issued while chunk c - 1's MMAs run) -> tf32 hi (/lo) -> canonical smem
@@ -95,7 +116,12 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
       for (int rq = 0; rq < 4; ++rq) {
         const int row = rq * 32 + rsub;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m0 + row < g.M && k < g.K) {
+        if (g.rowtab) {
+          // gathered row: chunk -> kernel offset o and channel offset inside the neighbour's feature row (kin % KC == 0)
+          const int o = k0 / g.kin;
+          const int j = (m0 + row < Meff) ? __ldg(g.rowtab + (size_t)(m0 + row) * 27 + o) : -1;
+          if (j >= 0) v = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)j * g.lda + (k - o * g.kin)));
+        } else if (m0 + row < Meff && k < g.K) {
           const float* ap = g.A + (size_t)(m0 + row) * g.lda + (g.agroup ? (k / g.agroup) * g.agstride + (k % g.agroup) : k);
           if (k + 3 < g.K) v = *reinterpret_cast<const float4*>(ap);
           else { v.x = ap[0]; if (k + 1 < g.K) v.y = ap[1]; if (k + 2 < g.K) v.z = ap[2]; }
@@ -104,12 +130,12 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
       }
     }
   };
-  load_a(0);
-  for (int c = 0; c < nchunks; ++c) {
+  load_a(c_begin);
+  for (int c = c_begin; c < nchunks; ++c) {
     const int k0 = c * KC;
     const int used_kg = min(NKG, (g.K - k0 + 3) / 4);
     const int mma_steps = (used_kg + 1) / 2;         // MMA K = 8 = two core-matrix columns
-    if (c > 0) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }
+    if (c > c_begin) { umma::mbar_wait(&mma_bar, parity); parity ^= 1; }
     {
 #pragma unroll
       for (int ps = 0; ps < NPASS; ++ps) {
@@ -139,7 +165,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int k = k0 + kg2 * 4 + e;
-          const float x = (m0 + row < g.M && k < g.K) ? g.A[(size_t)(m0 + row) * g.lda + k] : 0.f;
+          const float x = (m0 + row < Meff && k < g.K) ? g.A[(size_t)(m0 + row) * g.lda + k] : 0.f;
           lo[e] = __float_as_uint(umma::to_tf32(x - umma::to_tf32(x)));
         }
         umma::tmem_st8(tmem_base + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)(kg2 * 4), lo);
@@ -170,7 +196,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         const uint32_t a_off = (uint32_t)s * 2u * kALbo, w_off = (uint32_t)s * 2u * w_lbo;
         const uint64_t ah = umma::make_smem_desc(a_hi_s + a_off, kALbo, 128u);
         const uint64_t wh = umma::make_smem_desc(w_hi_s + w_off, w_lbo, 128u);
-        const uint32_t first = (c == 0 && s == 0) ? 0u : 1u;
+        const uint32_t first = (c == c_begin && s == 0) ? 0u : 1u;
         if (PREC == 3) {
           const uint64_t al = umma::make_smem_desc(a_lo_s + a_off, kALbo, 128u);
           const uint64_t wl = umma::make_smem_desc(w_lo_s + w_off, w_lbo, 128u);
@@ -226,7 +252,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
   {
     const int n4 = (g.N + 3) / 4;                    // forward layers: N % 16 == 0; backward dX layers: N = 71 / 187 write one zero pad column
     const int total = 128 * n4;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0) && (g.ldy % 4 == 0) && (g.ygroup % 4 == 0) && (g.ygstride % 4 == 0);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(Yout) & 15) == 0) && (g.ldy % 4 == 0) && (g.ygroup % 4 == 0) && (g.ygstride % 4 == 0);
     const bool mvec_ok = g.Mask && ((reinterpret_cast<uintptr_t>(g.Mask) & 15) == 0) && (g.ldm % 4 == 0);
     for (int idx0 = tid; idx0 < total; idx0 += 1024) {
       float4 v[4], rr[4], mk[4];
@@ -237,7 +263,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         const int idx = idx0 + 256 * u;
         const int row = idx / n4, c4 = idx - row * n4;
         mrow[u] = m0 + row; ncol[u] = c4 * 4;
-        valid[u] = idx < total && mrow[u] < g.M;
+        valid[u] = idx < total && mrow[u] < Meff;
         rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         mk[u] = make_float4(1.f, 1.f, 1.f, 1.f);
         if (idx < total) v[u] = *reinterpret_cast<const float4*>(stage + (size_t)row * sstride + ncol[u]);
@@ -280,7 +306,7 @@ __global__ void __launch_bounds__(256) k_umma_linear(const UmmaArgs g) {
         if (!(mk[u].z > 0.f)) x.z = 0.f;
         if (!(mk[u].w > 0.f)) x.w = 0.f;
         const int col = g.ygroup ? (n / g.ygroup) * g.ygstride + (n % g.ygroup) : n;
-        float* yp = g.Y + (size_t)m * g.ldy + col;
+        float* yp = Yout + (size_t)m * g.ldy + col;
         if (vec_ok) *reinterpret_cast<float4*>(yp) = x;
         else { yp[0] = x.x; yp[1] = x.y; yp[2] = x.z; yp[3] = x.w; }
       }
@@ -328,8 +354,8 @@ int run_pack_canonical(const SherfWeights& w, float* base, CanonWeights& cw, cud
 }
 
 // extra operands of the backward's dX launches (set around one launch_umma_linear call by launch_umma_dx; zero otherwise)
-struct UmmaEx { int agroup, agstride; const float* Mask; int ldm; };
-static thread_local UmmaEx g_umma_ex = {0, 0, nullptr, 0};
+struct UmmaEx { int agroup, agstride; const float* Mask; int ldm; const int* rowtab; int kin; const int* Mdev; int csplit; size_t ysplit; int nsplit; };
+static thread_local UmmaEx g_umma_ex = {0, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0};
 
 int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, float* Y, int ldy, int M, int act, cudaStream_t st,
                        const float* Res, int ldr, int ygroup, int ygstride, const float* ln_w, const float* ln_b, float* Y2, int ldy2) {
@@ -339,6 +365,8 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
   g.M = M; g.N = L.N; g.K = L.K;
   g.ln_w = (L.N == 32) ? ln_w : nullptr; g.ln_b = ln_b; g.Y2 = Y2; g.ldy2 = ldy2;
   g.agroup = g_umma_ex.agroup; g.agstride = g_umma_ex.agstride; g.Mask = g_umma_ex.Mask; g.ldm = g_umma_ex.ldm;
+  g.rowtab = g_umma_ex.rowtab; g.kin = g_umma_ex.kin; g.Mdev = g_umma_ex.Mdev; g.csplit = g_umma_ex.csplit; g.ysplit = g_umma_ex.ysplit;
+  const int gy = g_umma_ex.nsplit > 0 ? g_umma_ex.nsplit : 1;
   uint32_t cols = 32;
   while ((int)cols < L.Np) cols <<= 1;
   g.tmem_cols = cols;
@@ -356,9 +384,9 @@ int launch_umma_linear(int prec, const CanonLayer& L, const float* A, int lda, f
     static bool a4 = false;
     if (!a4) { SHERF_CUDA_OK(cudaFuncSetAttribute(k_umma_linear<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a4 = true; }
     g.tmem_cols = 512;
-    k_umma_linear<4><<<ceil_div(M, 128), 256, smem, st>>>(g);
-  } else if (prec == 3) k_umma_linear<3><<<ceil_div(M, 128), 256, smem, st>>>(g);
-  else k_umma_linear<1><<<ceil_div(M, 128), 256, smem, st>>>(g);
+    k_umma_linear<4><<<dim3(ceil_div(M, 128), gy), 256, smem, st>>>(g);
+  } else if (prec == 3) k_umma_linear<3><<<dim3(ceil_div(M, 128), gy), 256, smem, st>>>(g);
+  else k_umma_linear<1><<<dim3(ceil_div(M, 128), gy), 256, smem, st>>>(g);
   SHERF_LAUNCH_CHECK();
   return SHERF_OK;
 }
@@ -444,9 +472,38 @@ int run_pack_canonical_bwd(const SherfWeights& w, float* base, CanonBwdWeights& 
 
 int launch_umma_dx(const CanonLayer& L, const float* dY, int lda, float* dX, int ldx, int M, cudaStream_t st, const float* Mask, int ldm,
                    int accum, int agroup, int agstride) {
-  g_umma_ex = UmmaEx{agroup, agstride, Mask, ldm};
+  g_umma_ex = UmmaEx{agroup, agstride, Mask, ldm, nullptr, 0, nullptr, 0, 0, 0};
   const int rc = launch_umma_linear(3, L, dY, lda, dX, ldx, M, 0, st, accum ? dX : nullptr, ldx, 0, 0);
-  g_umma_ex = UmmaEx{0, 0, nullptr, 0};
+  g_umma_ex = UmmaEx{0, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0};
+  return rc;
+}
+
+// canonical pack of one sparse-convolution weight [c_out][27][c_in] (KRSC).  mode 0: forward, N = c_out, K = 27 c_in (the flattened weight);
+// mode 2 / 3: input gradient (N = c_in, K = 27 c_out), mirrored offsets (SubMConv3d) / plain offsets (strided convolution)
+size_t spconv_canon_floats() { return (size_t)2 * round_up_i(27 * 96, kKC) * 96; }
+int run_pack_spconv(const float* W, int cout, int cin, int mode, float* buf, CanonLayer& L, cudaStream_t st) {
+  CanonJobs jobs;
+  jobs.n = 1;
+  const int N = mode == 0 ? cout : cin, K = 27 * (mode == 0 ? cin : cout);
+  L.N = N; L.K = K; L.Np = round_up_i(N, 16); L.nchunks = round_up_i(K, kKC) / kKC; L.bias = nullptr;
+  const size_t sz = (size_t)L.nchunks * kKC * L.Np;
+  L.hi = buf; L.lo = buf + sz;
+  CanonJob& j = jobs.j[0];
+  j.w = W; j.hi = buf; j.lo = buf + sz; j.N = N; j.K = K; j.Np = L.Np; j.nchunks = L.nchunks; j.ldw = 0; j.trans = mode;
+  k_pack_canonical<<<dim3(64, 1), 256, 0, st>>>(jobs);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+
+// Sparse convolution as a gathered linear layer (sparse_encoder.cu): Y_part[s][r][n] = sum over the chunks of split s of
+// X[rowtab[r][o]][k] W[n][o][k].  L: canonical pack of W viewed as [N][27 * kin]; Mcap sizes the grid, *Mdev is the row count.
+int launch_umma_spconv(const CanonLayer& L, const float* X, int kin, const int* rowtab, const int* Mdev, int Mcap, float* Ypart, int nsplit,
+                       cudaStream_t st) {
+  const int nchunks = L.K / 32;                      // 27 * kin / 32 chunks of the 3xTF32 kernel
+  const int csplit = ceil_div(nchunks, nsplit);
+  g_umma_ex = UmmaEx{0, 0, nullptr, 0, rowtab, kin, Mdev, csplit, (size_t)Mcap * L.N, nsplit};
+  const int rc = launch_umma_linear(3, L, X, kin, Ypart, L.N, Mcap, 0, st, nullptr, 0, 0, 0);
+  g_umma_ex = UmmaEx{0, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0};
   return rc;
 }
 

@@ -123,6 +123,41 @@ __global__ void k_sp_densify(const int* __restrict__ coords, const int* __restri
   vol[(size_t)c * s.d[0] * s.d[1] * s.d[2] + sp_cell(s, coords[r * 3], coords[r * 3 + 1], coords[r * 3 + 2])] = F[(size_t)r * C + c];
 }
 
+// ---- the convolutions on the tensor cores: every layer is a linear layer with K = 27 c_in whose A rows are gathered through a neighbour
+//      table (mlp_umma.cu: launch_umma_spconv, 3xTF32 split products, split-K partial tiles summed in order) ----
+// MODE 0: SubMConv3d, table of the output (= input) sites of a level: slot o -> row at p + (k - 1)
+// MODE 1: strided convolution, table of the OUTPUT sites (coarse level): slot o -> fine row at 2 q - 1 + k
+// MODE 2: strided convolution, table of the INPUT sites (fine level): slot o -> coarse row q with 2 q - 1 + k = p (its gradient reaches p through W[:, o, :])
+template <int MODE>
+__global__ void k_sp_table(const int* __restrict__ coords, const int* __restrict__ count, SpDims ssrc, const int* __restrict__ idx_src, int* __restrict__ tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t / 27, o = t - r * 27;
+  if (r >= *count) return;
+  const int kz = o / 9, ky = (o / 3) % 3, kx = o % 3;
+  const int z = coords[r * 3], y = coords[r * 3 + 1], x = coords[r * 3 + 2];
+  int pz, py, px;
+  bool ok = true;
+  if (MODE == 0) { pz = z + kz - 1; py = y + ky - 1; px = x + kx - 1; }
+  else if (MODE == 1) { pz = 2 * z - 1 + kz; py = 2 * y - 1 + ky; px = 2 * x - 1 + kx; }
+  else {
+    const int az = z + 1 - kz, ay = y + 1 - ky, ax = x + 1 - kx;
+    ok = az >= 0 && ay >= 0 && ax >= 0 && !((az | ay | ax) & 1);
+    pz = az >> 1; py = ay >> 1; px = ax >> 1;
+  }
+  tab[t] = (ok && sp_inside(ssrc, pz, py, px)) ? idx_src[sp_cell(ssrc, pz, py, px)] : -1;
+}
+// out = sum of the split-K partial tiles (split order: deterministic); scale_shift != NULL: evaluation-mode BatchNorm + ReLU on the sum
+__global__ void k_sp_sum_parts(const float* __restrict__ part, int nsplit, size_t stride, const int* __restrict__ count, int cout,
+                               const float* __restrict__ scale_shift, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(t / cout), c = (int)(t % cout);
+  if (r >= *count) return;
+  float v = part[t];
+  for (int s = 1; s < nsplit; ++s) v += part[(size_t)s * stride + t];
+  out[t] = scale_shift ? fmaxf(v * scale_shift[c] + scale_shift[cout + c], 0.f) : v;
+}
+constexpr int kSpSplitK = 3;
+
 // level l = 0..3: dims, row capacity
 struct SpPlan { SpDims dims[4]; int cap[4]; size_t cells[4]; };
 static void sp_plan(int n, const int32_t* out_sh, SpPlan& p) {
@@ -136,7 +171,8 @@ static void sp_plan(int n, const int32_t* out_sh, SpPlan& p) {
   }
 }
 
-struct SpScratch { int* idx[4]; int* coords[4]; int* count; int* rowof; float* F[2]; float* Wt; float* ss; };
+struct SpScratch { int* idx[4]; int* coords[4]; int* count; int* rowof; float* F[2]; float* Wt; float* ss;
+                   int* tab_sub[4]; int* tab_down[3]; int* tab_downT[3]; float* part; float* canon; };
 static size_t sp_carve(char* base, int n, const SpPlan& p, SpScratch& s) {
   size_t off = 0;
   auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; char* q = base ? base + off : nullptr; off += bytes; return q; };
@@ -152,8 +188,45 @@ static size_t sp_carve(char* base, int n, const SpPlan& p, SpScratch& s) {
   s.F[1] = (float*)take((size_t)maxcap * 96 * sizeof(float));
   s.Wt = (float*)take((size_t)27 * 96 * 96 * sizeof(float));
   s.ss = (float*)take(2 * 96 * sizeof(float));
+  for (int l = 0; l < 4; ++l) s.tab_sub[l] = (int*)take((size_t)p.cap[l] * 27 * sizeof(int));
+  for (int l = 0; l < 3; ++l) {
+    s.tab_down[l] = (int*)take((size_t)p.cap[l + 1] * 27 * sizeof(int));
+    s.tab_downT[l] = (int*)take((size_t)p.cap[l] * 27 * sizeof(int));
+  }
+  s.part = (float*)take((size_t)kSpSplitK * maxcap * 96 * sizeof(float));
+  s.canon = (float*)take(spconv_canon_floats() * sizeof(float));
   return off + 256;
 }
+
+// one convolution on the tensor cores: out[rows of `lo`][c_out] = sum_o W[:, o, :] . in[neighbour o]  (raw, or BatchNorm(eval) + ReLU when ss != NULL)
+static int sp_conv_umma(const SherfSparseConv& L, const SpPlan& p, const SpScratch& s, int lo, const int* tab, const float* in, const float* ss,
+                        float* out, cudaStream_t st) {
+  CanonLayer cl;
+  int rc = run_pack_spconv(L.weight, L.c_out, L.c_in, 0, s.canon, cl, st);
+  if (rc) return rc;
+  rc = launch_umma_spconv(cl, in, L.c_in, tab, s.count + lo, p.cap[lo], s.part, kSpSplitK, st);
+  if (rc) return rc;
+  k_sp_sum_parts<<<ceil_div((int64_t)p.cap[lo] * L.c_out, 256), 256, 0, st>>>(s.part, kSpSplitK, (size_t)p.cap[lo] * L.c_out, s.count + lo, L.c_out, ss, out);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+// neighbour tables of a level (SubM) / of a strided convolution (forward table on the coarse rows, transposed table on the fine rows)
+static int sp_table_sub(const SpPlan& p, const SpScratch& s, int l, cudaStream_t st) {
+  k_sp_table<0><<<ceil_div((int64_t)p.cap[l] * 27, 256), 256, 0, st>>>(s.coords[l], s.count + l, p.dims[l], s.idx[l], s.tab_sub[l]);
+  SHERF_LAUNCH_CHECK();
+  return SHERF_OK;
+}
+static int sp_table_down(const SpPlan& p, const SpScratch& s, int l, bool transposed_too, cudaStream_t st) {
+  k_sp_table<1><<<ceil_div((int64_t)p.cap[l + 1] * 27, 256), 256, 0, st>>>(s.coords[l + 1], s.count + l + 1, p.dims[l], s.idx[l], s.tab_down[l]);
+  SHERF_LAUNCH_CHECK();
+  if (transposed_too) {
+    k_sp_table<2><<<ceil_div((int64_t)p.cap[l] * 27, 256), 256, 0, st>>>(s.coords[l], s.count + l, p.dims[l + 1], s.idx[l + 1], s.tab_downT[l]);
+    SHERF_LAUNCH_CHECK();
+  }
+  return SHERF_OK;
+}
+static bool sp_simt() { const char* e = getenv("SHERF_SP_SIMT"); return e && e[0] == '1'; }      // the warp-per-row fp32 FMA kernels (first version; anchor)
+
 
 size_t sparse_encoder_scratch_bytes(int n, const int32_t* out_sh) {
   SpPlan p; sp_plan(n, out_sh, p);
@@ -180,25 +253,41 @@ int run_sparse_encode(const SherfSparseEncoder& enc, const int* coord, const flo
   k_sp_index0<<<ceil_div(n, 256), 256, 0, st>>>(coord, n, p.dims[0], s.rowof, s.idx[0]);
   SHERF_LAUNCH_CHECK();
   int level = 0, cur = 0, emitted = 0;
+  const bool simt = sp_simt();
+  if (!simt) { const int rc = sp_table_sub(p, s, 0, st); if (rc) return rc; }
   // execution order and the levels emitted after conv1 / conv2 / conv3: renderer.py:756-782 (num_layers = 4)
   static const int emit_after[SHERF_SPARSE_CONVS] = {0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int c = 0; c < SHERF_SPARSE_CONVS; ++c) {
     const SherfSparseConv& L = enc.conv[c];
-    if (L.c_in > 96 || L.c_out > 96 || L.c_in <= 0 || L.c_out <= 0) { set_error("sparse conv %d: unsupported channels %d -> %d", c, L.c_in, L.c_out); return SHERF_E_UNSUPPORTED; }
+    if (L.c_in > 96 || L.c_out > 96 || L.c_in <= 0 || L.c_out <= 0 || (!simt && (L.c_in % 32 || L.c_out % 16))) {
+      set_error("sparse conv %d: unsupported channels %d -> %d", c, L.c_in, L.c_out); return SHERF_E_UNSUPPORTED;
+    }
     k_sp_pack<<<ceil_div(27 * L.c_in * L.c_out, 256), 256, 0, st>>>(L.weight, L.bn_weight, L.bn_bias, L.bn_mean, L.bn_var, L.c_in, L.c_out, s.Wt, s.ss);
     SHERF_LAUNCH_CHECK();
     if (L.kind == 0) {
-      k_sp_conv<false><<<ceil_div(p.cap[level], 8), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level], s.idx[level], s.F[cur], L.c_in,
-                                                                  L.c_out, s.Wt, s.ss, s.F[cur ^ 1]);
-      SHERF_LAUNCH_CHECK();
+      if (simt) {
+        k_sp_conv<false><<<ceil_div(p.cap[level], 8), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level], s.idx[level], s.F[cur], L.c_in,
+                                                                    L.c_out, s.Wt, s.ss, s.F[cur ^ 1]);
+        SHERF_LAUNCH_CHECK();
+      } else {
+        const int rc = sp_conv_umma(L, p, s, level, s.tab_sub[level], s.F[cur], s.ss, s.F[cur ^ 1], st);
+        if (rc) return rc;
+      }
     } else {
       if (level >= 3) { set_error("sparse encoder: too many strided convs"); return SHERF_E_INVALID; }
       k_sp_down_sites<<<ceil_div((int64_t)p.cap[level] * 27, 256), 256, 0, st>>>(s.coords[level], s.count + level, p.dims[level + 1], s.idx[level + 1],
                                                                                s.count + level + 1, s.coords[level + 1], p.cap[level + 1]);
       SHERF_LAUNCH_CHECK();
-      k_sp_conv<true><<<ceil_div(p.cap[level + 1], 8), 256, 0, st>>>(s.coords[level + 1], s.count + level + 1, p.dims[level], s.idx[level], s.F[cur],
-                                                                     L.c_in, L.c_out, s.Wt, s.ss, s.F[cur ^ 1]);
-      SHERF_LAUNCH_CHECK();
+      if (simt) {
+        k_sp_conv<true><<<ceil_div(p.cap[level + 1], 8), 256, 0, st>>>(s.coords[level + 1], s.count + level + 1, p.dims[level], s.idx[level], s.F[cur],
+                                                                       L.c_in, L.c_out, s.Wt, s.ss, s.F[cur ^ 1]);
+        SHERF_LAUNCH_CHECK();
+      } else {
+        int rc = sp_table_down(p, s, level, false, st);
+        if (!rc) rc = sp_conv_umma(L, p, s, level + 1, s.tab_down[level], s.F[cur], s.ss, s.F[cur ^ 1], st);
+        if (!rc) rc = sp_table_sub(p, s, level + 1, st);
+        if (rc) return rc;
+      }
       ++level;
     }
     cur ^= 1;
@@ -545,6 +634,12 @@ int run_sparse_encode_train(const SherfSparseEncoder& enc, const int* coord, con
   SHERF_LAUNCH_CHECK();
   int level = 0, emitted = 0;
   const float* in = s.F[0];
+  // The forward that a backward pass follows keeps the fp32 FMA convolutions: it decides the ReLU gates, and the 3xTF32 tensor-core
+  // products (2^-21 relative, 5e-6 on these outputs instead of 1e-6) flip ~ 5 x more near-zero units against the reference (measured,
+  // tests/test_sparse_encoder.py).  The tensor cores run the evaluation forward (run_sparse_encode) and the input-gradient convolutions of
+  // the backward, whose neighbour tables are built here.
+  const bool tables = !sp_simt();
+  if (tables) { const int rc = sp_table_sub(p, s, 0, st); if (rc) return rc; }
   for (int c = 0; c < SHERF_SPARSE_CONVS; ++c) {
     const SherfSparseConv& L = enc.conv[c];
     k_sp_pack<<<ceil_div(27 * L.c_in * L.c_out, 256), 256, 0, st>>>(L.weight, L.bn_weight, L.bn_bias, L.bn_mean, L.bn_var, L.c_in, L.c_out, s.Wt, s.ss);
@@ -560,6 +655,11 @@ int run_sparse_encode_train(const SherfSparseEncoder& enc, const int* coord, con
       k_sp_conv<true><<<ceil_div(p.cap[level + 1], 8), 256, 0, st>>>(s.coords[level + 1], s.count + level + 1, p.dims[level], s.idx[level], in, L.c_in,
                                                                      L.c_out, s.Wt, nullptr, t.raw[c]);
       SHERF_LAUNCH_CHECK();
+      if (tables) {
+        int rc = sp_table_down(p, s, level, true, st);
+        if (!rc) rc = sp_table_sub(p, s, level + 1, st);
+        if (rc) return rc;
+      }
       ++level;
     }
     // rows under this BatchNorm: level 0 counts the duplicate rows (nrows[0], set by k_sp_mult), the other levels the unique output sites
@@ -653,9 +753,20 @@ int run_sparse_encode_backward(const SherfSparseEncoder& enc, const int* coord, 
       SHERF_LAUNCH_CHECK();
     }
     if (c > 0 || g_feat) {
-      if (L.kind == 0) k_sp_conv_bwd_x<false><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
-      else k_sp_conv_bwd_x<true><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
-      SHERF_LAUNCH_CHECK();
+      if (sp_simt()) {
+        if (L.kind == 0) k_sp_conv_bwd_x<false><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
+        else k_sp_conv_bwd_x<true><<<ceil_div(p.cap[li], 8), 256, 0, st>>>(s.coords[li], s.count + li, p.dims[lo], s.idx[lo], dB, L.c_in, L.c_out, L.weight, dA);
+        SHERF_LAUNCH_CHECK();
+      } else {
+        // the adjoint is again a gathered linear layer: rows = the layer's INPUT sites, K = 27 c_out, weights with the two channel axes
+        // swapped (and the offsets mirrored for SubMConv3d, whose forward table serves both directions)
+        CanonLayer cl;
+        int rc = run_pack_spconv(L.weight, L.c_out, L.c_in, L.kind == 0 ? 2 : 3, s.canon, cl, st);
+        if (!rc) rc = launch_umma_spconv(cl, dB, L.c_out, L.kind == 0 ? s.tab_sub[li] : s.tab_downT[li], s.count + li, p.cap[li], s.part, kSpSplitK, st);
+        if (rc) return rc;
+        k_sp_sum_parts<<<ceil_div((int64_t)p.cap[li] * L.c_in, 256), 256, 0, st>>>(s.part, kSpSplitK, (size_t)p.cap[li] * L.c_in, s.count + li, L.c_in, nullptr, dA);
+        SHERF_LAUNCH_CHECK();
+      }
     }
   }
   if (g_feat) {

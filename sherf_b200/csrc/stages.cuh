@@ -95,6 +95,11 @@ size_t canonical_bwd_weight_floats();
 int run_pack_canonical_bwd(const SherfWeights& w, float* base, CanonBwdWeights& cb, cudaStream_t st);
 int launch_umma_dx(const CanonLayer& L, const float* dY, int lda, float* dX, int ldx, int M, cudaStream_t st, const float* Mask = nullptr,
                    int ldm = 0, int accum = 0, int agroup = 0, int agstride = 0);
+// sparse convolutions on the tensor cores (mlp_umma.cu): the layer as a gathered linear layer with K = 27 c_in, split-K partial tiles
+size_t spconv_canon_floats();
+int run_pack_spconv(const float* W, int cout, int cin, int mode, float* buf, CanonLayer& L, cudaStream_t st);
+int launch_umma_spconv(const CanonLayer& L, const float* X, int kin, const int* rowtab, const int* Mdev, int Mcap, float* Ypart, int nsplit,
+                       cudaStream_t st);
 constexpr int kGradWMaxSplits = 1024;      // capacity of the partial-sum buffer; the launcher uses one wave of CTAs (<= 444 on a B200)
 // part[s][n][K + 1] = sum over the rows of split s of dY[m][n] . [X | 1][m][k];  *splits_out = number of splits written
 int launch_umma_grad_w(const float* dY, int lda, int N, const float* X, int ldb, int K, int M, float* part, int* splits_out, cudaStream_t st,

@@ -76,9 +76,12 @@ def test_duplicate_voxels_first_row_wins():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('shape,n', [((32, 64, 64), 300), ((32, 32, 96), 40)])
-def test_cuda_encoder_against_oracle(shape, n):
+@pytest.mark.parametrize('shape,n,graph', [((32, 64, 64), 300, False), ((32, 32, 96), 40, False), ((16, 32, 32), 3000, False), ((32, 64, 64), 300, True)])
+def test_cuda_encoder_against_oracle(shape, n, graph):
+    """graph = False: the evaluation forward (torch.no_grad: convolutions as gathered linear layers on tcgen05, 3xTF32 split products).
+    graph = True: eval() under autograd (parameters require grad): the differentiable kernels on the running statistics, fp32 FMA convolutions."""
     from sherf_b200.renderer import SparseConvNet, SparseConvTensor
+    torch.set_grad_enabled(graph)
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
     enc = SparseConvNet(4)
@@ -89,13 +92,15 @@ def test_cuda_encoder_against_oracle(shape, n):
     idx = torch.cat([torch.zeros(coord.shape[0], 1, dtype=torch.int32), coord], 1)
     got = enc.to(dev).eval()(SparseConvTensor(feat.to(dev), idx.to(dev), list(shape), 1))
     torch.cuda.synchronize()
-    for lvl, (g, w) in enumerate(zip(got, want)):
+    for lvl, (g, w) in enumerate(zip([v.detach() for v in got], want)):
         assert g.shape == w.shape
         err = float((g.cpu() - w).abs().max()) / float(w.abs().max())
         same_sites = bool(torch.equal((g.cpu() != 0).any(1), (w != 0).any(1)))
         print(f'\\n[sparse encoder {shape} level {lvl + 1}] active sites {int((w != 0).any(1).sum())}, max err / max = {err:.2e}, same sites {same_sites}')
         assert err <= 2e-4
     again = enc(SparseConvTensor(feat.to(dev), idx.to(dev), list(shape), 1))
+    torch.set_grad_enabled(True)
+    assert all(v.requires_grad == graph for v in got)
     assert all(torch.equal(a, b) for a, b in zip(got, again)), 'the encoder must be deterministic'
 
 

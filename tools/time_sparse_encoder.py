@@ -21,6 +21,7 @@ feat = torch.randn(coord.shape[0], 32, device=dev)
 torch.manual_seed(0)
 enc = SparseConvNet(4).to(dev).eval()
 sp = SparseConvTensor(feat, idx, out_sh, 1)
+torch.set_grad_enabled(False)                                      # the evaluation forward (under autograd the differentiable kernels run instead)
 for _ in range(3):
     vols = enc(sp)
 torch.cuda.synchronize()
