@@ -103,7 +103,7 @@ class SherfObservation(C.Structure):
                 ('proj_b', c_float_p)]
 
 
-EXPORTS = ['sherf_sparse_encoder_train_scratch_bytes', 'sherf_sparse_encode_train', 'sherf_sparse_encode_backward', 'sherf_prepare_observation_backward', 'sherf_backward_scratch_bytes', 'sherf_render_backward', 'sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
+EXPORTS = ['sherf_render_backward_after_forward', 'sherf_sparse_encoder_train_scratch_bytes', 'sherf_sparse_encode_train', 'sherf_sparse_encode_backward', 'sherf_prepare_observation_backward', 'sherf_backward_scratch_bytes', 'sherf_render_backward', 'sherf_smpl_vertices', 'sherf_count_survivors', 'sherf_observation_scratch_bytes', 'sherf_prepare_observation', 'sherf_debug_set_trace', 'sherf_sparse_encoder_scratch_bytes', 'sherf_sparse_encode', 'sherf_generate_rays', 'sherf_debug_sample_importance', 'sherf_debug_linear', 'sherf_scratch_bytes', 'sherf_render_forward', 'sherf_lbs_transforms', 'sherf_depth_range', 'sherf_last_error',
            'sherf_abi_version', 'sherf_last_launch_count', 'sherf_last_importance_point_count', 'sherf_set_profiling', 'sherf_last_stage_ms', 'sherf_last_host_us']
 
 _lib = None
@@ -137,6 +137,8 @@ def load():
                                           C.POINTER(SherfWeights), C.POINTER(SherfRays), C.POINTER(SherfOptions),
                                           C.POINTER(SherfOutGrads), C.POINTER(SherfWeightGrads), C.POINTER(SherfInputGrads),
                                           C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.sherf_render_backward_after_forward.restype = C.c_int
+    lib.sherf_render_backward_after_forward.argtypes = lib.sherf_render_backward.argtypes[:-1] + [C.c_int64]
     lib.sherf_count_survivors.restype = C.c_int
     lib.sherf_count_survivors.argtypes = [C.POINTER(SherfSmplModel), C.POINTER(SherfFrame), C.POINTER(SherfScene), C.POINTER(SherfRays),
                                           C.POINTER(SherfOptions), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int64)]

@@ -582,9 +582,31 @@ size_t sherf_backward_scratch_bytes(const SherfScene* scene, int32_t n_rays, int
   return carve_backward(a, *scene, n_rays, n_samples, n_verts, L, B, nullptr) + 512;
 }
 
+static int render_backward_impl(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
+                                const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out, const SherfWeightGrads* grad_weights,
+                                const SherfInputGrads* grad_inputs, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out,
+                                int64_t forward_points /* >= 0: the forward already ran on this arena */);
+
 int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
                           const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out, const SherfWeightGrads* grad_weights,
                           const SherfInputGrads* grad_inputs, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {
+  return render_backward_impl(smpl, frame, scene, weights, rays, opts, grad_out, grad_weights, grad_inputs, scratch, scratch_bytes, stream, n_points_out, -1);
+}
+
+int sherf_render_backward_after_forward(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
+                                        const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out,
+                                        const SherfWeightGrads* grad_weights, const SherfInputGrads* grad_inputs, void* scratch, size_t scratch_bytes,
+                                        void* stream, int64_t n_points) {
+  if (n_points < 0) { g_err[0] = 0; set_error("n_points must be the survivor count the forward reported"); return SHERF_E_INVALID; }
+  return render_backward_impl(smpl, frame, scene, weights, rays, opts, grad_out, grad_weights, grad_inputs, scratch, scratch_bytes, stream, nullptr, n_points);
+}
+
+}  // extern "C"
+
+static int render_backward_impl(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfWeights* weights,
+                                const SherfRays* rays, const SherfOptions* opts, const SherfOutGrads* grad_out, const SherfWeightGrads* grad_weights,
+                                const SherfInputGrads* grad_inputs, void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out,
+                                int64_t forward_points) {
   g_err[0] = 0;
   if (!smpl || !frame || !scene || !weights || !rays || !opts || !grad_out || !scratch) { set_error("null argument"); return SHERF_E_INVALID; }
   if (rays->n_importance != 0) {
@@ -606,10 +628,13 @@ int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, c
   // ---- the view once more on the fast path: leaves frame tables, channels-last layouts, the compacted point list and per-point sigma / rgb
   //      in the first part of the arena ----
   SherfOut fout; fout.rgb = B.out; fout.depth = B.out + (size_t)3 * N; fout.acc = B.out + (size_t)4 * N;
-  int64_t P = 0;
-  RC(sherf_render_forward(smpl, frame, scene, weights, rays, opts, &fout, nullptr, a.base, fwd_need + 256, stream, &P));
+  int64_t P = forward_points;
+  int64_t launches = 0;
+  if (forward_points < 0) {
+    RC(sherf_render_forward(smpl, frame, scene, weights, rays, opts, &fout, nullptr, a.base, fwd_need + 256, stream, &P));
+    launches = g_launches.n;
+  } else if (forward_points > (int64_t)N * S) { set_error("n_points exceeds n_rays * n_samples"); return SHERF_E_INVALID; }
   if (n_points_out) *n_points_out = P;
-  int64_t launches = g_launches.n;
   g_launches.n = 0;
 
   // ---- outputs start from zero ----
@@ -681,6 +706,8 @@ int sherf_render_backward(const SherfSmplModel* smpl, const SherfFrame* frame, c
   g_last_launches = launches + g_launches.n;
   return SHERF_OK;
 }
+
+extern "C" {
 
 int sherf_count_survivors(const SherfSmplModel* smpl, const SherfFrame* frame, const SherfScene* scene, const SherfRays* rays, const SherfOptions* opts,
                           void* scratch, size_t scratch_bytes, void* stream, int64_t* n_points_out) {

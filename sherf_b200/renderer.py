@@ -31,7 +31,7 @@ class _Runtime:
     module-level WeakKeyDictionary, NOT in the nn.Module's __dict__: the reference deep-copies and pickles the generator every tick
     (training_loop.py:196,572-579), and ctypes structures with pointers cannot be pickled (and a copied arena would double HBM).
     A copy / unpickled module simply starts with an empty runtime and rebuilds it lazily on its first forward."""
-    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', 'scene_sig', 'scene_epoch', 'bwd_scratch',
+    __slots__ = ('smpl_dev', 'scratch', 'w_cache', 'w_epoch', 'dbg_keep', 'faces_dev', 'obs_scratch', 'scene_sig', 'scene_epoch', 'bwd_scratch', 'bwd_epoch',
                  '__weakref__')
 
     def __init__(self):
@@ -45,6 +45,7 @@ class _Runtime:
         self.scene_sig = None
         self.scene_epoch = 0
         self.bwd_scratch = None
+        self.bwd_epoch = 0            # bumped by every forward that runs in the backward arena (see ImportanceRenderer.forward)
 
 
 _RUNTIME = weakref.WeakKeyDictionary()
@@ -762,13 +763,26 @@ class ImportanceRenderer(nn.Module):
                 dbg_p = C.byref(d)
                 rt.dbg_keep = (d, bufs)
 
+            # A forward that records a graph runs in the BACKWARD arena (its first part is laid out exactly like the forward's): the compacted
+            # point list and per-point sigma / rgb are then still there when loss.backward() arrives, and the backward does not have to render
+            # the view a second time.  Any later forward of this module in that arena bumps the epoch; a stale graph falls back to re-rendering.
+            fwd_arena, my_epoch, n_points_fwd = rt.scratch, None, [0]
+            if wants_grad and SF == 0 and debug is None:
+                need_b = lib.sherf_backward_scratch_bytes(C.byref(sc), N, S, smpl.n_verts)
+                if rt.bwd_scratch is None or rt.bwd_scratch.numel() < need_b or rt.bwd_scratch.device != device:
+                    rt.bwd_scratch = None
+                    rt.bwd_scratch = torch.empty(need_b, dtype=torch.uint8, device=device)
+                rt.bwd_epoch += 1
+                fwd_arena, my_epoch = rt.bwd_scratch, rt.bwd_epoch
+
             def run_fwd():
                 npts = C.c_int64(0)
                 rc = lib.sherf_render_forward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(opts),
-                                              C.byref(out), dbg_p, rt.scratch.data_ptr(), rt.scratch.numel(),
+                                              C.byref(out), dbg_p, fwd_arena.data_ptr(), fwd_arena.numel(),
                                               torch.cuda.current_stream(device).cuda_stream, C.byref(npts))
                 _lib.check(rc)
                 self.last_num_points = int(npts.value)                               # coarse + fine survivors
+                n_points_fwd[0] = int(npts.value)
                 self.last_num_fine_points = int(lib.sherf_last_importance_point_count())
                 self.last_launches = int(lib.sherf_last_launch_count())
                 return obuf
@@ -813,11 +827,18 @@ class ImportanceRenderer(nn.Module):
                         o2 = _lib.SherfOptions.from_buffer_copy(opts)
                         o2.weights_version = 0
                         o2.scene_version = 0
-                        npb = C.c_int64(0)
-                        _lib.check(lib.sherf_render_backward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(o2),
-                                                             C.byref(og), C.byref(gw), C.byref(ig), rt_.bwd_scratch.data_ptr(),
-                                                             rt_.bwd_scratch.numel(), torch.cuda.current_stream(device).cuda_stream,
-                                                             C.byref(npb)))
+                        if my_epoch is not None and rt_.bwd_scratch is fwd_arena and rt_.bwd_epoch == my_epoch:
+                            # the forward of THIS graph was the last thing that ran in the arena: reuse its point list and per-point results
+                            _lib.check(lib.sherf_render_backward_after_forward(
+                                C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(o2), C.byref(og), C.byref(gw), C.byref(ig),
+                                rt_.bwd_scratch.data_ptr(), rt_.bwd_scratch.numel(), torch.cuda.current_stream(device).cuda_stream, n_points_fwd[0]))
+                        else:
+                            rt_.bwd_epoch += 1                                    # the re-render below overwrites whatever graph owned the arena
+                            npb = C.c_int64(0)
+                            _lib.check(lib.sherf_render_backward(C.byref(smpl), C.byref(fr), C.byref(sc), C.byref(w), C.byref(rays), C.byref(o2),
+                                                                 C.byref(og), C.byref(gw), C.byref(ig), rt_.bwd_scratch.data_ptr(),
+                                                                 rt_.bwd_scratch.numel(), torch.cuda.current_stream(device).cuda_stream,
+                                                                 C.byref(npb)))
                         self.last_backward_launches = int(lib.sherf_last_launch_count())
                         for k, t in enumerate(diff_inputs):
                             if grads[k] is not None and torch.is_tensor(t) and t.dtype != torch.float32:

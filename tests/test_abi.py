@@ -69,7 +69,7 @@ def test_scratch_bytes_and_argument_validation(lib):
     # backward arena = forward arena + its own buffers; argument checks run before any CUDA call
     bsmall = lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 4096, 16, 6890)
     bbig = lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 512 * 512, 64, 6890)
-    assert small < bsmall < bbig < 16 << 30
+    assert small < bsmall < bbig < 40 << 30          # one backward chunk of up to 2^20 points keeps 24 GB of activations
     assert lib.sherf_backward_scratch_bytes(ctypes.byref(sc), 0, 16, 6890) == 0
     assert lib.sherf_render_backward(None, None, None, None, None, None, None, None, None, None, 0, None, None) == -1
     assert ctypes.sizeof(_lib.SherfWeightGrads) == ctypes.sizeof(_lib.SherfWeights) == 39 * ctypes.sizeof(ctypes.c_void_p)

@@ -170,3 +170,28 @@ def test_backward_is_deterministic_for_weights_and_frozen_inputs_get_none(smpl_m
     with torch.no_grad():
         rgb, _, _ = run_cuda(ren, dec, scene)
     assert not rgb.requires_grad
+
+
+def test_a_graph_whose_forward_state_was_overwritten_still_gets_the_right_gradients(smpl_model):
+    """A forward that records a graph leaves its compacted point list and per-point results in the backward arena and the backward reuses them
+    (sherf_render_backward_after_forward).  A SECOND forward of the same module overwrites that state: the first graph's backward must notice
+    (arena epoch) and render its view again (sherf_render_backward) -- same gradients either way."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene_a = scene_to(S.make_scene(S.SceneSpec(H=24, W=24, samples=16, seed=2), smpl_model), dev)
+    scene_b = scene_to(S.make_scene(S.SceneSpec(H=20, W=28, samples=12, seed=9), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=3, dense_sigma=True)
+    ren, dec = ren.to(dev), dec.to(dev)
+    dec.requires_grad_(True)
+
+    def grads(interleave):
+        for p in dec.parameters():
+            p.grad = None
+        rgb, depth, acc = run_cuda(ren, dec, scene_a)
+        if interleave:
+            run_cuda(ren, dec, scene_b)                      # another graph-recording forward in the same arena
+        (rgb.square().sum() + acc.sum()).backward()
+        return [p.grad.clone() for p in dec.parameters()]
+    direct, stale = grads(False), grads(True)
+    assert any(float(g.abs().max()) > 0 for g in direct)
+    assert all(torch.equal(a, b) for a, b in zip(direct, stale))
