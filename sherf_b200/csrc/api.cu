@@ -259,8 +259,9 @@ struct BwdLayout {
 // (then-current kernels), 2^18 -> 39.6, 2^19 -> 37.1, 2^20 -> 35.6 ms per training view (fewer, fuller launches); 2^20 = 24 GB of the 180 GB.
 // SHERF_BWD_CHUNK_CAP lowers it; a view with fewer samples than the cap sizes the buffers by its own N x S.
 static int bwd_chunk_cap(int N, int S) {
-  static int cap = 0;
-  if (!cap) { const char* e = getenv("SHERF_BWD_CHUNK_CAP"); const long v = e ? atol(e) : 0; cap = v >= 128 ? (int)(v / 128 * 128) : (1 << 20); }
+  const char* e = getenv("SHERF_BWD_CHUNK_CAP");                    // read per call: tests switch it between two backward passes
+  const long v = e ? atol(e) : 0;
+  const int cap = v >= 128 ? (int)(v / 128 * 128) : (1 << 20);
   const size_t NS = (size_t)N * S;
   return (int)(NS < (size_t)cap ? (NS + 127) / 128 * 128 : (size_t)cap);
 }

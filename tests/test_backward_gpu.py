@@ -195,3 +195,26 @@ def test_a_graph_whose_forward_state_was_overwritten_still_gets_the_right_gradie
     direct, stale = grads(False), grads(True)
     assert any(float(g.abs().max()) > 0 for g in direct)
     assert all(torch.equal(a, b) for a, b in zip(direct, stale))
+
+
+def test_chunked_backward_equals_the_single_chunk_backward(smpl_model):
+    """The backward walks the surviving points in chunks (one chunk of up to 2^20 points by default).  Forcing 256-point chunks
+    (SHERF_BWD_CHUNK_CAP) must give the same gradients up to the order in which the per-chunk sums are added."""
+    from sherf_b200.triplane import hot_path_modules
+    dev = torch.device('cuda:0')
+    scene = scene_to(S.make_scene(S.SceneSpec(H=40, W=40, samples=24, seed=6), smpl_model), dev)
+    ren, dec = hot_path_modules(smpl_model, seed=3, dense_sigma=True)
+    ren, dec = ren.to(dev).requires_grad_(True), dec.to(dev).requires_grad_(True)
+    gen = torch.Generator().manual_seed(1)
+    N = scene['ray_origins'].shape[1]
+    tgt_img, tgt_acc = torch.rand(1, N, 3, generator=gen).to(dev), torch.ones(1, N, 1, device=dev)
+    _, g_one = cuda_grads(ren, dec, scene, tgt_img, tgt_acc, None)
+    os.environ['SHERF_BWD_CHUNK_CAP'] = '256'
+    try:
+        _, g_many = cuda_grads(ren, dec, scene, tgt_img, tgt_acc, None)
+    finally:
+        os.environ.pop('SHERF_BWD_CHUNK_CAP', None)
+    assert ren.last_num_points > 4 * 256, 'the view must span several chunks'
+    worst = max(rel_err(g_many[k], g_one[k])[0] for k in g_one)
+    print(f'\n[chunked backward] P = {ren.last_num_points}: worst relative L2 difference between 256-point chunks and one chunk {worst:.2e}')
+    assert worst <= 2e-5
