@@ -314,16 +314,31 @@ def main():
     points = [0]
     phase = {'render': [], 'collective': [], 'h2d': [], 'd2h': []}                  # (start, end) CUDA-event pairs, filled when `split` is on
     split = [False]
+    overlap_gather = [False]                                                          # on only inside the device-timed loop
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
+    pending = []                                                                      # all-gathers in flight: (work, output, source)
+
+    def drain_gathers():
+        while pending:
+            pending.pop(0)[0].wait()                                                    # the CURRENT STREAM waits (no host wait)
+
     def gather_views(local):
-        """view-granular sharding: one all-gather of the rendered [N,5] tiles -> every rank holds all `world` images"""
+        """view-granular sharding: one all-gather of the rendered [N,5] tiles -> every rank holds all `world` images.  In the timed loop the
+        all-gather of step i is left in flight while step i + 1 renders (views are independent; NCCL runs it on its own stream): the current
+        stream only waits for it behind the NEXT render, and the last one is drained inside the last step's timed window."""
         full = local.new_empty(world * N, 5)
-        dist.all_gather_into_tensor(full, local.contiguous())
+        src = local.contiguous()
+        if split[0] or not overlap_gather[0]:
+            drain_gathers()
+            dist.all_gather_into_tensor(full, src)
+            return full
+        drain_gathers()                                                                 # step i - 1's gather: it had this step's render to finish
+        pending.append((dist.all_gather_into_tensor(full, src, async_op=True), full, src))
         return full
 
     def step_device():
@@ -386,11 +401,13 @@ def main():
         (measured at N = 2: 3.36 ms per step against 3.0-3.05 ms of render + 0.1 ms of all-gather).  ImportanceRenderer.forward itself still
         waits for its survivor count inside every call; the end-to-end step reads its result on the host inside every step."""
         evs = []
-        for _ in range(k):
+        for i in range(k):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
+            if i == k - 1:
+                drain_gathers()                                                         # nothing escapes the K timed windows
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -419,7 +436,9 @@ def main():
     barrier()
     if clocks:
         clocks.mark()
+    overlap_gather[0] = world > 1 and not by_tiles
     ms = timed(step_device, args.steps)
+    overlap_gather[0] = False
     barrier()
     clk = clocks.stop() if clocks else None
     n_launch_timed, n_points_timed = launches[0], points[0]
@@ -540,7 +559,7 @@ def main():
             'config': common_config(world, args.importance),
             'arm': {'mlp_precision': args.precision, 'surviving_points_per_view': p_call * world if by_tiles else p_call,
                     'sharding': ('single GPU' if world == 1 else (f'256-ray tiles of every view dealt to {world} ranks, one all-gather per view' if by_tiles else
-                                 f'view granularity (rank r renders view r), one all_gather_into_tensor of the rendered [N,5] tiles per step'))},
+                                 f'view granularity (rank r renders view r), one all_gather_into_tensor of the rendered [N,5] tiles per step; in the device-timed loop the all-gather of step i overlaps the render of step i + 1 and the last one is drained inside the last timed window'))},
             'e2e': {'value': samples_per_step / (ms_e2e * 1e-3), 'unit': 'ray-samples/s', 'h2d_bytes_per_step': h2d_rank * world,
                     'd2h_bytes_per_step': world * N * 5 * 4, 'ms_per_step': ms_e2e,
                     'note': 'per step and rank: pinned-host rays/near/far/vertices -> device, ImportanceRenderer.forward via the C ABI, all-gather (N>1), the rank\'s own rendered rgb+depth+acc -> pinned host; bytes are totals over the ranks'},
