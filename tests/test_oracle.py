@@ -217,3 +217,29 @@ def test_branch_free_erf_of_the_transformer_kernel():
     assert (d[big] / np.abs(g_ref[big])).max() <= 2e-4          # the cancellation in 1 + erf(x) for x << 0 is the reference formula's own
     pos = xs > 0                                                # no cancellation on this side: fp32-grade relative accuracy
     assert (d[pos & big] / np.abs(g_ref[pos & big])).max() <= 3e-7
+
+
+def test_training_step_fixture_is_complete_and_its_weights_regenerate():
+    """tests/golden/training_step_32x32x16.npz (oracle/gen_golden_training.py: the reference's own synthesis + renderer + SparseConvNet + decoder in
+    train(), loss.backward()): 80 parameter gradients + tri-planes + feature map, the volume-gradient taps of the three dense levels, BatchNorm
+    statistics; the initial state it was produced from regenerates from the stored tensors + the encoder seed (checksum)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    from oracle import sparse_encoder as SE
+    from oracle.gen_golden_training import state_checksum
+    from sherf_b200.renderer import SparseConvNet
+    g = np.load(os.path.join(GOLDEN_DIR, 'training_step_32x32x16.npz'))
+    grads = [k for k in g.files if k.startswith('g/') or k.startswith('gs/')]
+    assert len(grads) == 39 + 39 + 2 + 2
+    assert sum(k.split('/', 1)[1].startswith('renderer.encoder_3d.') for k in grads) == 39
+    assert all(np.isfinite(g[k]).all() and np.abs(g[k]).max() > 0 for k in grads)
+    for l in range(3):
+        assert g[f'gvol{l}/zyx'].shape[0] == g[f'gvol{l}/g'].shape[0] > 100 and g[f'gvol{l}/g'].shape[1] == (32, 64, 96)[l]
+    assert len([k for k in g.files if k.startswith('stat/')]) >= 13 * 3          # running mean / var / batch counter of every BatchNorm the step ran
+    state = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('w/')}
+    torch.manual_seed(0)
+    enc = SparseConvNet(4)
+    enc.load_state_dict(SE.random_state_dict(enc, int(g['enc_seed'])))
+    state.update({'renderer.encoder_3d.' + k: v.clone() for k, v in enc.state_dict().items()})
+    assert state_checksum(state) == str(g['state_sha256'])
