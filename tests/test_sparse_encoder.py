@@ -238,3 +238,39 @@ def _training_step_case(shape, n, dup, train, smpl_model_t):
     # the layers the reference never evaluates for num_layers = 4 stay untouched
     assert all(p.grad is None for k, p in got.items() if k.startswith('down3') or k.startswith('conv4'))
     return worst
+
+
+def test_strided_sparse_conv_output_sites_known_answers():
+    """Hand-derived output sites of SparseConv3d(k=3, stride=2, padding=1) -- the rule of a regular strided convolution restricted to active
+    inputs (spconv `ops.get_conv_output_size` / `get_indice_pairs`): output o is active iff 2 o - 1 + k = p for an active input p, k in {0,1,2}.
+      p = (0,0,0): only k = 1, o = 0                      -> 1 site
+      p = (1,1,1): per axis (o, k) in {(0,2), (1,0)}      -> the 8 sites {0,1}^3
+      p = (2,0,1): axis values 2 -> o = 1 (k = 1); 0 -> o = 0; 1 -> o in {0,1}   -> (1,0,0), (1,0,1)
+    Both statements of the rule (the gather-form oracle and the functional spconv stand-in the reference module runs on) must produce them, with
+    out[o] = sum of W[:, k] . in[p] over exactly those pairs."""
+    from oracle import spconv_shim as SP
+    shape = (4, 4, 4)
+    cases = {(0, 0, 0): {(0, 0, 0)}, (1, 1, 1): {(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)}, (2, 0, 1): {(1, 0, 0), (1, 0, 1)}}
+    torch.manual_seed(0)
+    conv = SP.SparseConv3d(2, 3, 3, 2, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn_like(conv.weight))
+    for p, want_sites in cases.items():
+        feat = torch.tensor([[1.0, -2.0]])
+        x = SP.SparseConvTensor(feat, torch.tensor([[0, *p]]), list(shape), 1)
+        with torch.no_grad():
+            y = conv(x)
+        got_sites = {tuple(r[1:]) for r in y.indices.tolist()}
+        assert got_sites == want_sites, (p, got_sites)
+        assert y.spatial_shape == [2, 2, 2]                              # floor((4 + 2 - 3) / 2) + 1
+        for row, o in zip(y.features, [tuple(r[1:]) for r in y.indices.tolist()]):
+            k = tuple(p[a] - 2 * o[a] + 1 for a in range(3))             # the one offset that links p to o
+            assert all(0 <= kk <= 2 for kk in k)
+            assert torch.allclose(row, conv.weight[:, k[0], k[1], k[2]] @ feat[0], atol=1e-6)
+    # the same three inputs together through the gather-form oracle's site rule (first strided layer of the encoder: down0)
+    from sherf_b200.renderer import SparseConvNet
+    sd = SE.random_state_dict(SparseConvNet(4), 1)
+    coord = torch.tensor(list(cases), dtype=torch.int32)
+    vols = SE.encode_sparse(sd, coord, torch.randn(3, 32), (32, 32, 32))
+    active = {tuple(i) for i in torch.nonzero((vols[0][0] != 0).any(0)).tolist()}
+    assert active == set().union(*cases.values())
