@@ -1,11 +1,11 @@
-"""How errors of the dense-volume gradients propagate into the sparse encoder's parameter gradients, measured on the REFERENCE alone (CPU):
+"""TEST INFRASTRUCTURE.  How errors of the dense-volume gradients propagate into the sparse encoder's parameter gradients, measured on the REFERENCE alone (CPU):
 re-runs the reference training step of oracle/gen_golden_training.py with the gradients of the three `.dense()` volumes multiplied by
 (1 + eps * N(0,1)) elementwise and prints the relative change of the encoder gradients against the fixture.  usage: python
-tools/encoder_grad_conditioning.py [eps=5e-5].  Result (eps = 5e-5): conv3.7.* 5e-6 .. 7e-6, conv3.6.weight 2.9e-5, conv3.1.bias 7.3e-5,
+tests/helpers/encoder_grad_conditioning.py [eps=5e-5].  Result (eps = 5e-5): conv3.7.* 5e-6 .. 7e-6, conv3.6.weight 2.9e-5, conv3.1.bias 7.3e-5,
 conv0.* 1.5e-4 .. 2.1e-4 -- the train() BatchNorms subtract per-channel means of gradients that are far from zero-mean here, so a
 perturbation grows ~ 36 x from the last layer to the first.  tests/test_training_gpu.py sees the same profile (7.8e-5 -> 4.8e-3)."""
 import sys, types, torch, numpy as np
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from oracle import gen_golden_training as G, ref_shim, spconv_shim
 from sherf_b200 import synthetic as S
 import torch.nn as nn

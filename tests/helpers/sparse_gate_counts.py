@@ -1,6 +1,11 @@
+"""TEST INFRASTRUCTURE (GPU box).  Per-layer gradient sums and open ReLU-gate counts of one sparse-encoder training step, the reference module
+(oracle/ref_shim.py + oracle/spconv_shim.py, CPU) next to the CUDA encoder (SHERF_SP_DEBUG=1 prints its lines on stderr): a unit whose
+pre-activation is zero to rounding can open on one side only, which shows here as a gate count that differs by one and explains a ~ 1 / rows
+jump of every gradient below that layer.  usage: python tests/helpers/sparse_gate_counts.py [train]"""
 import os, sys, torch
 os.environ['SHERF_SP_DEBUG']='1'
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch.nn.functional as F
 from oracle import ref_shim, sparse_encoder as SE
 from sherf_b200 import synthetic as S

@@ -153,7 +153,7 @@ def test_cuda_encoder_training_step_against_the_reference_module(smpl_model_t):
     """Four voxel sets (see _training_step_case).  Every gradient must be within STRICT = 2e-4 relative L2 (measured <= 4e-6) -- except that ONE
     case may sit in the gate-flip regime (<= 2e-2): among the ~ 1e5-1e6 ReLU units of a case the smallest |pre-activation| is ~ 1e-6 (computed
     on the reference), the same size as the fp32 summation-order differences between the two implementations; a unit that opens on one side
-    only moves the gradients below it by ~ 1 / rows-per-channel (5.6e-3 seen with a fifth voxel set, n = 200 in eval(); tools/spdebug.py prints
+    only moves the gradients below it by ~ 1 / rows-per-channel (5.6e-3 seen with a fifth voxel set, n = 200 in eval(); tests/helpers/sparse_gate_counts.py prints
     both sides' per-layer gate counts).  The four sets below are flip-free on B200 with this build; the allowance covers a toolchain whose
     rounding differs."""
     worst = [_training_step_case(*case, smpl_model_t) for case in TRAINING_CASES]
@@ -170,7 +170,7 @@ def _training_step_case(shape, n, dup, train, smpl_model_t):
     BatchNorm parameters, the input features.  Tolerance 2e-4 relative L2 (fp32, different summation orders; measured in the log).
     train = False: the same gradients in eval() (BatchNorm on its running statistics, which then do not move).
     (A ReLU unit whose pre-activation is zero to rounding can open on one side and stay shut on the other: with ~ 200 rows per level-3
-    channel ONE such gate moves the gradients below it by ~ 5e-3 -- observed with n = 200, tools/spdebug.py prints the per-layer gate counts.)"""
+    channel ONE such gate moves the gradients below it by ~ 5e-3 -- observed with n = 200, tests/helpers/sparse_gate_counts.py prints the per-layer gate counts.)"""
     import torch.nn.functional as F
     from oracle import ref_shim
     from sherf_b200.renderer import SparseConvNet, SparseConvTensor

@@ -16,7 +16,7 @@ Tolerances (relative L2 per gradient tensor), with what was measured on B200 (pr
   * the 39 sparse-encoder tensors: 2e-2 (measured 2.3e-5 at the last BatchNorm growing to 4.8e-3 at the first convolution).  The CUDA encoder
     backward itself reproduces autograd through the reference module to 4e-6 on identical inputs (tests/test_sparse_encoder.py, sparse and
     dense voxel sets); what it receives here are the render's volume gradients, which carry the ~1e-4 differences of the gathers, and the
-    train() BatchNorms subtract per-channel means of gradients that are far from zero-mean: tools/encoder_grad_conditioning.py perturbs the
+    train() BatchNorms subtract per-channel means of gradients that are far from zero-mean: tests/helpers/encoder_grad_conditioning.py perturbs the
     volume gradients of the REFERENCE by 5e-5 and sees 5e-6 at conv3.7 grow to 2e-4 at conv0 -- the same ~40 x profile.
   * the generator's conv1d_projection: see below.
 
